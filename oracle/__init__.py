@@ -1,0 +1,297 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+ctypes bindings for the parity oracle:
+
+* ``libkmd_oracle.so``      — our plain-C restatement of the reference's `kmdiff diff` arithmetic
+                              (oracle/kmd_oracle.c, each function cites reference file:line);
+* ``_ref/libkmdiff_ref.so`` — the UNMODIFIED reference (PoissonLikelihood, LogFactorialTable,
+                              correctors, alglib chi-square) compiled from /root/reference behind
+                              oracle/ref_shim.cpp.
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl reference``
+legs may import this package — as the checker, never as the thing measured or shipped.  The
+product package ``kmdiff_b200`` never imports it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "libkmd_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libkmdiff_ref.so")
+REF_BIN = os.path.join(HERE, "_ref", "kmdiff")
+REF_BIN16 = os.path.join(HERE, "_ref", "kmdiff_c16")
+REFERENCE_ROOT = "/root/reference"
+
+CONTROL, CASE, NO = 0, 1, 2
+NOTHING, BONFERRONI, BENJAMINI, SIDAK, HOLM = 0, 1, 2, 3, 4
+CORRECTIONS = {"disabled": NOTHING, "nothing": NOTHING, "bonferroni": BONFERRONI,
+               "benjamini": BENJAMINI, "sidak": SIDAK, "holm": HOLM}
+
+
+def build(ref: bool | None = None, refbin: bool = False) -> None:
+    """Compile the C restatement and, when /root/reference is present, oracle/_ref."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if ref is None:
+        ref = os.path.isdir(REFERENCE_ROOT)
+    if ref:
+        targets = ["ref"] + (["refbin"] if refbin else [])
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE] + targets)
+
+
+class _Model(C.Structure):
+    _fields_ = [("nb_controls", C.c_uint32), ("nb_cases", C.c_uint32),
+                ("sum_controls", C.c_uint64), ("sum_cases", C.c_uint64),
+                ("lf_table", C.POINTER(C.c_double)), ("lf_size", C.c_uint64)]
+
+
+class _Corrector(C.Structure):
+    _fields_ = [("type", C.c_int), ("threshold", C.c_double), ("total", C.c_uint64),
+                ("rank", C.c_uint64)]
+
+
+SURVIVOR_DTYPE = np.dtype([("kmer", "<u8", (2,)), ("p", "<f8"), ("sign", "<i4"), ("pad_", "<i4"),
+                           ("mean_control", "<f8"), ("mean_case", "<f8"), ("row", "<u8")])
+
+_lib = None
+_ref = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        L = C.CDLL(ORACLE_SO)
+        d, u64, vp = C.c_double, C.c_uint64, C.c_void_p
+        L.kmo_log_factorial.restype = d
+        L.kmo_log_factorial.argtypes = [u64]
+        L.kmo_lf_table_fill.argtypes = [vp, u64]
+        L.kmo_lf_lookup.restype = d
+        L.kmo_lf_lookup.argtypes = [vp, u64, u64]
+        L.kmo_lngamma.restype = d
+        L.kmo_lngamma.argtypes = [d, C.POINTER(d)]
+        for f in (L.kmo_igam, L.kmo_igamc, L.kmo_chisqc):
+            f.restype = d
+            f.argtypes = [d, d]
+        L.kmo_model_rows.argtypes = [C.POINTER(_Model), vp, u64, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.kmo_diff_rows.restype = u64
+        L.kmo_diff_rows.argtypes = [C.POINTER(_Model), vp, u64, C.c_int, C.c_int, d, u64, vp, u64,
+                                    C.POINTER(u64), C.POINTER(u64)]
+        L.kmo_corrector_init.argtypes = [C.POINTER(_Corrector), C.c_int, d, u64]
+        L.kmo_corrector_apply.restype = C.c_int
+        L.kmo_corrector_apply.argtypes = [C.POINTER(_Corrector), d]
+        L.kmo_aggregate.restype = u64
+        L.kmo_aggregate.argtypes = [vp, u64, C.c_int, d, u64, vp]
+        L.kmo_kmer_to_string.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+def ref_available() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def ref() -> C.CDLL:
+    """The unmodified reference behind ref_shim.cpp (raises if oracle/_ref was never built)."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where "
+                                    f"{REFERENCE_ROOT} exists")
+        L = C.CDLL(REF_SO)
+        d, u64, vp, sz = C.c_double, C.c_uint64, C.c_void_p, C.c_size_t
+        L.ref_lf_table.argtypes = [sz, sz, vp, vp]
+        L.ref_chisqc.restype = d
+        L.ref_chisqc.argtypes = [d, d]
+        L.ref_model_create.restype = vp
+        L.ref_model_create.argtypes = [C.c_int, sz, sz, vp, sz]
+        L.ref_model_destroy.argtypes = [C.c_int, vp]
+        L.ref_model_rows.argtypes = [C.c_int, vp, vp, sz, sz, vp, vp, vp, vp, C.c_int]
+        L.ref_corrector_create.restype = vp
+        L.ref_corrector_create.argtypes = [C.c_int, d, sz]
+        L.ref_corrector_apply.restype = C.c_int
+        L.ref_corrector_apply.argtypes = [vp, d]
+        L.ref_corrector_destroy.argtypes = [vp]
+        _ref = L
+    return _ref
+
+
+# ------------------------------------------------------------------------------------------------
+# numpy-level helpers around the C restatement
+# ------------------------------------------------------------------------------------------------
+
+def lf_table(size: int) -> np.ndarray:
+    t = np.empty(size, dtype=np.float64)
+    lib().kmo_lf_table_fill(t.ctypes.data, size)
+    return t
+
+
+def lf_lookup(table: np.ndarray, i: int) -> float:
+    return lib().kmo_lf_lookup(table.ctypes.data, table.size, int(i))
+
+
+def chisqc(v: float, x: float) -> float:
+    return lib().kmo_chisqc(v, x)
+
+
+@dataclass
+class Model:
+    """PoissonLikelihood state (reference include/kmdiff/model.hpp:105-118)."""
+    nb_controls: int
+    nb_cases: int
+    totals: np.ndarray          # per-sample totals, controls first (get_total_kmer)
+    lf_size: int = 10000        # --log-factorial default (src/cli.cpp:354-357)
+
+    def __post_init__(self):
+        self.totals = np.ascontiguousarray(self.totals, dtype=np.uint64)
+        assert self.totals.size == self.nb_controls + self.nb_cases
+        self.sum_controls = int(self.totals[:self.nb_controls].sum())
+        self.sum_cases = int(self.totals[self.nb_controls:].sum())
+        self.table = lf_table(self.lf_size)
+        self._c = _Model(self.nb_controls, self.nb_cases, self.sum_controls, self.sum_cases,
+                         self.table.ctypes.data_as(C.POINTER(C.c_double)), self.lf_size)
+
+    def row_bytes(self, kmer_words: int, count_bytes: int) -> int:
+        return 8 * kmer_words + (self.nb_controls + self.nb_cases) * count_bytes
+
+    def rows(self, payload: np.ndarray, kmer_words: int, count_bytes: int):
+        """(p, sign, mean_control, mean_case) for every row of an AoS matrix payload."""
+        payload = np.ascontiguousarray(payload, dtype=np.uint8).ravel()
+        R = self.row_bytes(kmer_words, count_bytes)
+        n = payload.size // R
+        p = np.empty(n, np.float64)
+        sign = np.empty(n, np.int32)
+        mc = np.empty(n, np.float64)
+        kk = np.empty(n, np.float64)
+        lib().kmo_model_rows(C.byref(self._c), payload.ctypes.data, n, kmer_words, count_bytes,
+                             p.ctypes.data, sign.ctypes.data, mc.ctypes.data, kk.ctypes.data)
+        return p, sign, mc, kk
+
+    def diff(self, payload: np.ndarray, kmer_words: int, count_bytes: int, thr: float,
+             row_base: int = 0):
+        """Survivors of diff_observer::process (p <= thr) + (n_control, n_case)."""
+        payload = np.ascontiguousarray(payload, dtype=np.uint8).ravel()
+        R = self.row_bytes(kmer_words, count_bytes)
+        n = payload.size // R
+        cap = max(1024, n // 16)
+        while True:
+            out = np.zeros(cap, dtype=SURVIVOR_DTYPE)
+            nc, nk = C.c_uint64(), C.c_uint64()
+            found = lib().kmo_diff_rows(C.byref(self._c), payload.ctypes.data, n, kmer_words,
+                                        count_bytes, thr, row_base, out.ctypes.data, cap,
+                                        C.byref(nc), C.byref(nk))
+            if found <= cap:
+                return out[:found], nc.value, nk.value
+            cap = found
+
+
+class Corrector:
+    """Stateful corrector (reference src/corrector.cpp)."""
+
+    def __init__(self, kind: int, threshold: float, total: int):
+        self._c = _Corrector()
+        lib().kmo_corrector_init(C.byref(self._c), kind, threshold, total)
+
+    def apply(self, p: float) -> bool:
+        return bool(lib().kmo_corrector_apply(C.byref(self._c), p))
+
+
+def aggregate(p: np.ndarray, kind: int, threshold: float, total: int) -> np.ndarray:
+    """Indices of kept survivors in output order (reference aggregator.hpp run())."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    keep = np.empty(max(1, p.size), dtype=np.uint64)
+    n = lib().kmo_aggregate(p.ctypes.data, p.size, kind, threshold, total, keep.ctypes.data)
+    return keep[:n].astype(np.int64)
+
+
+def kmer_to_string(words, k: int) -> str:
+    w = np.ascontiguousarray(words, dtype=np.uint64).ravel()
+    buf = C.create_string_buffer(k + 1)
+    lib().kmo_kmer_to_string(w.ctypes.data, w.size, k, buf)
+    return buf.value.decode()
+
+
+# ------------------------------------------------------------------------------------------------
+# numpy-level helpers around the real reference (oracle/_ref)
+# ------------------------------------------------------------------------------------------------
+
+def ref_lf(size: int, idx) -> np.ndarray:
+    idx = np.ascontiguousarray(idx, dtype=np.uint64)
+    out = np.empty(idx.size, np.float64)
+    ref().ref_lf_table(size, idx.size, idx.ctypes.data, out.ctypes.data)
+    return out
+
+
+def ref_chisqc(v: float, x: float) -> float:
+    return ref().ref_chisqc(v, x)
+
+
+def ref_model_rows(nb_controls: int, nb_cases: int, totals, lf_size: int, payload: np.ndarray,
+                   kmer_words: int, count_bytes: int, threads: int = 1):
+    """kmdiff::PoissonLikelihood<MAX_C>::process on every row, through the real reference."""
+    totals = np.ascontiguousarray(totals, dtype=np.uint64)
+    payload = np.ascontiguousarray(payload, dtype=np.uint8).ravel()
+    R = 8 * kmer_words + (nb_controls + nb_cases) * count_bytes
+    n = payload.size // R
+    h = ref().ref_model_create(count_bytes, nb_controls, nb_cases, totals.ctypes.data, lf_size)
+    try:
+        p = np.empty(n, np.float64)
+        sign = np.empty(n, np.int32)
+        mc = np.empty(n, np.float64)
+        kk = np.empty(n, np.float64)
+        ref().ref_model_rows(count_bytes, h, payload.ctypes.data, n, 8 * kmer_words,
+                             p.ctypes.data, sign.ctypes.data, mc.ctypes.data, kk.ctypes.data,
+                             threads)
+    finally:
+        ref().ref_model_destroy(count_bytes, h)
+    return p, sign, mc, kk
+
+
+class RefCorrector:
+    def __init__(self, kind: int, threshold: float, total: int):
+        self._h = ref().ref_corrector_create(kind, threshold, total)
+
+    def apply(self, p: float) -> bool:
+        return bool(ref().ref_corrector_apply(self._h, p))
+
+    def __del__(self):
+        try:
+            ref().ref_corrector_destroy(self._h)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# Output formatting (reference include/kmdiff/aggregator.hpp:55-62, fmt 8.1.1, kseq++ 60-col wrap)
+# ------------------------------------------------------------------------------------------------
+
+def fmt_g(x: float) -> str:
+    """fmt `{:g}` == printf %g (6 significant digits, trailing zeros stripped)."""
+    return "%g" % x
+
+
+def fmt_shortest(x: float) -> str:
+    """fmt `{}` for double: shortest round-trip digits, fixed for 1e-4 <= |x| < 1e16."""
+    r = repr(float(x))
+    if r.endswith(".0"):
+        r = r[:-2]
+    if "e" in r:
+        mant, exp = r.split("e")
+        if mant.endswith(".0"):
+            mant = mant[:-2]
+        sign = "-" if exp.startswith("-") else "+"
+        digits = exp.lstrip("+-").rjust(2, "0")
+        r = f"{mant}e{sign}{digits}"
+    return r
+
+
+def fasta_record(index: int, p: float, mean_control: float, mean_case: float, seq: str) -> str:
+    head = f">{index}_pval={fmt_g(p)}_control={int(mean_control)}_case={fmt_shortest(mean_case)}"
+    lines = [seq[i:i + 60] for i in range(0, len(seq), 60)]
+    return head + "\n" + "\n".join(lines) + "\n"
