@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py — k-mer rows tested per second (Poisson LRT + correction) on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU `kmdiff diff`
+    torchrun ... bench.py --gpus N ...                       # N > 1: one rank per GPU (NCCL)
+
+One "step" = one pass of the hot path over one batch of synthetic kmtricks-format rows held by each
+GPU: reset -> LRT scan of the batch (screen + exact fp64 test of the candidates + prefilter) ->
+global row count (NCCL all-reduce when N > 1) -> significance correction on the device (sort /
+compaction) -> counts of significant control / case k-mers back on the host.
+
+Workload at N=1: BASELINE.json configs[1] ("synthetic 10 control + 10 case, k=31, 1e9 k-mer rows,
+Poisson LRT + Bonferroni"), 88 B/row = 88 GB resident in HBM.  Every rank holds its own 1e9-row
+partition set (weak scaling; partitions are disjoint, no data-path collective).
+
+`value`  : rows/s with the rows already resident in HBM (device generated, seeded).
+`e2e`    : rows/s through the C-ABI with HOST buffers (kmd_scan_host from pinned memory, survivors
+           and significant k-mers read back), H2D/D2H inside the timed region, on a smaller batch.
+`roofline`: lrt_scan kernel, algorithmic bytes R*rows / its CUDA-event duration vs measured HBM peak.
+`cpu_baseline`: the reference's own `kmdiff diff` binary (oracle/_ref/kmdiff) on the host cores,
+           on a bounded prefix of the same synthetic matrix written as a kmtricks run dir.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (nb_controls, nb_cases, k, count_bytes, rows, correction)
+    "c2": (10, 10, 31, 4, 1_000_000_000, "bonferroni"),
+    "c3": (100, 100, 31, 4, 150_000_000, "benjamini"),   # 2e9 rows = 1.6 TB do not fit one GPU
+    "c5": (50, 50, 63, 2, 500_000_000, "bonferroni"),    # per-GPU share of 4e9 rows over 8 GPUs
+}
+SIGNIFICANCE = 0.05
+CUTOFF = 100000
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons of one GPU through NVML while the timed region runs"""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm: the unmodified `kmdiff diff` binary on the host cores
+# ------------------------------------------------------------------------------------------------------
+
+def reference_available():
+    import oracle
+    return os.path.exists(oracle.REF_BIN)
+
+
+def make_reference_run_dir(cfg_name: str, sample_rows: int, partitions: int) -> tuple[str, int]:
+    """kmtricks run dir holding rows [0, sample_rows) of the workload's synthetic matrix"""
+    import kmdiff_b200 as K
+    from kmdiff_b200 import kmtricks_io as kio
+    nc, nk, k, b, rows, _ = CONFIGS[cfg_name]
+    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=rows, seed=42)
+    d = tempfile.mkdtemp(prefix="kmdiff_ref_run_", dir=os.environ.get("KMD_TMP", "/tmp"))
+    kio.write_run_dir(d, spec, sample_rows, partitions)
+    return d, spec.row_bytes
+
+
+def run_reference_once(run_dir: str, cfg_name: str, threads: int) -> float:
+    import oracle
+    nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
+    binary = oracle.REF_BIN if b == 4 else oracle.REF_BIN16
+    out = tempfile.mkdtemp(prefix="kmdiff_ref_out_", dir=os.environ.get("KMD_TMP", "/tmp"))
+    opt = os.path.join(run_dir, "kmdiff-count.opt")
+    if os.path.exists(opt):
+        os.remove(opt)   # reference quirk: matrix mode truncates it and the next run then fails
+    cmd = [binary, "diff", "--km-run", run_dir, "-1", str(nc), "-2", str(nk), "-o", out, "-t", str(threads),
+           "-c", corr, "-s", str(SIGNIFICANCE), "-u", str(CUTOFF)]
+    t0 = time.perf_counter()
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    shutil.rmtree(out, ignore_errors=True)
+    if r.returncode != 0 or "[error]" in r.stderr:
+        raise RuntimeError(f"reference kmdiff failed: {r.stderr[-500:]}")
+    return dt
+
+
+def reference_sample_rows(cfg_name: str, cores: int) -> int:
+    nc, nk, k, b, rows, _ = CONFIGS[cfg_name]
+    # ~3 M rows/s/core at N=20, scaling down with the row width; aim at ~5 s per run
+    per_core = int(3_000_000 * 20 / (nc + nk))
+    return int(min(rows, 32_000_000, max(200_000, per_core * min(cores, 64) * 2)))
+
+
+def bench_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg_name = args.config
+    nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
+    base = {"metric": "kmer_rows_tested_per_sec", "unit": "rows/s", "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    import oracle
+    binary = oracle.REF_BIN if b == 4 else oracle.REF_BIN16
+    if not os.path.exists(binary):
+        print(json.dumps({"impl": "reference", "unavailable": f"{binary} not built (make -C oracle refbin)"}))
+        return
+    cores = os.cpu_count() or 1
+    sample = reference_sample_rows(cfg_name, cores)
+    parts = max(cores, 8)
+    run_dir, R = make_reference_run_dir(cfg_name, sample, parts)
+    try:
+        for _ in range(args.warmup):
+            run_reference_once(run_dir, cfg_name, cores)
+        t = [run_reference_once(run_dir, cfg_name, cores) for _ in range(args.steps)]
+    finally:
+        shutil.rmtree(run_dir, ignore_errors=True)
+    total = sum(t)
+    value = sample * args.steps / total
+    line = dict(base)
+    line.update({
+        "value": value, "ms_per_step": 1e3 * total / args.steps,
+        "config": {"workload": f"{cfg_name}: synthetic {nc}+{nk} samples, k={k}, {b}-byte counts, {corr}",
+                   "rows_per_step": sample, "partitions": parts, "row_bytes": R,
+                   "note": "reference `kmdiff diff` binary (file read + LRT + correction + FASTA) on a "
+                           "bounded prefix of the workload's synthetic matrix, uncompressed matrices"},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "reference",
+                         "sample": f"{sample} rows in {parts} partitions per step"},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    })
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+
+def bench_b200(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import kmdiff_b200 as K
+    from kmdiff_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — kmdiff_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg_name = args.config
+    nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
+    if args.rows:
+        rows = args.rows
+    corr_kind = K.correction_from_str(corr)
+    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=rows * world, seed=42)
+    R = spec.row_bytes
+    totals = spec.totals()
+    thr = SIGNIFICANCE / CUTOFF
+
+    stream = torch.cuda.current_stream()
+    ctx = K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), kmer_size=k, count_bytes=b,
+                        threshold=thr, device=local_rank, max_survivors=max(1 << 22, rows // 200))
+    ctx.set_stream(stream.cuda_stream)
+
+    # ---- resident workload: this rank's rows, generated on the device (seeded, counter-based) ----
+    data = torch.empty(rows * R, dtype=torch.uint8, device=dev)
+    spec.rows_device(data.data_ptr(), rows, row_base=rank * rows, device=local_rank, stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+
+    counts_dev = torch.zeros(3, dtype=torch.int64, device=dev)
+
+    def step():
+        ctx.reset()
+        ctx.scan_device(data.data_ptr(), rows, row_base=rank * rows, partition=rank)
+        c = ctx.counters()
+        total_rows = c.rows
+        if world > 1:
+            counts_dev.copy_(torch.tensor([c.rows, c.n_control, c.n_case], dtype=torch.int64), non_blocking=True)
+            dist.all_reduce(counts_dev)
+            total_rows = int(counts_dev[0].item())
+        if corr_kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM) and world > 1:
+            # global ascending walk: exchange the ranks' sorted p-values, find the first rejection
+            p_loc = torch.from_numpy(ctx.sorted_pvalues()).to(dev)
+            n_loc = torch.tensor([p_loc.numel()], dtype=torch.int64, device=dev)
+            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(sizes, n_loc)
+            mx = int(max(int(s.item()) for s in sizes))
+            pad = torch.full((mx,), float("inf"), dtype=torch.float64, device=dev)
+            pad[:p_loc.numel()] = p_loc
+            allp = [torch.empty(mx, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(allp, pad)
+            merged = torch.sort(torch.cat([a[:int(s.item())] for a, s in zip(allp, sizes)])).values.cpu().numpy()
+            _, cut = K.first_reject(merged, corr_kind, SIGNIFICANCE, total_rows)
+            return ctx.keep_below(cut), c
+        return ctx.correct(corr_kind, SIGNIFICANCE, total_rows), c
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        res, c = step()
+    launches0 = ctx.launch_count()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms = []
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        res, c = step()
+        scan_ms.append(ctx.scan_kernel_ms())
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = (ctx.launch_count() - launches0) // args.steps
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = rows * world * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C-ABI with host buffers ----
+    e2e_rows = min(rows, args.e2e_rows)
+    L = _lib.load()
+    hptr = L.kmd_host_alloc(e2e_rows * R)
+    if not hptr:
+        raise SystemExit("kmd_host_alloc failed")
+    import ctypes
+    hbuf = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint8)), shape=(e2e_rows * R,))
+    torch.cuda.synchronize()
+    hbuf[:] = data[:e2e_rows * R].cpu().numpy()      # same rows as the resident workload's prefix
+    d2h = 0
+
+    def e2e_step():
+        nonlocal d2h
+        ctx.reset()
+        ctx.scan_host(hptr, e2e_rows, row_base=rank * rows, partition=rank)
+        cc = ctx.counters()
+        total = cc.rows * world
+        r = ctx.correct(corr_kind, SIGNIFICANCE, total)
+        sig = ctx.significant()
+        d2h = sig.nbytes + 48 * 3
+        return r, len(sig)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_res, n_sig = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_rows * world * args.e2e_steps / float(te.item())
+    L.kmd_host_free(hptr)
+
+    # ---- roofline of the dominant kernel (lrt_scan) ----
+    peak, peak_src = load_peaks()
+    scan_avg_ms = sum(scan_ms) / len(scan_ms)
+    achieved = rows * R / (scan_avg_ms * 1e-3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r01_lrt_scan_ncu.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                pj = json.load(f)
+            if pj.get("config") == cfg_name and pj.get("rows"):
+                traffic = pj["dram_bytes_per_launch"] * (rows / pj["rows"])
+        except Exception:
+            pass
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline: the reference binary on a bounded prefix of the same matrix (N=1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        try:
+            if reference_available():
+                sample = reference_sample_rows(cfg_name, cores)
+                parts = max(cores, 8)
+                run_dir, _ = make_reference_run_dir(cfg_name, sample, parts)
+                try:
+                    run_reference_once(run_dir, cfg_name, cores)           # warm the page cache
+                    dt = run_reference_once(run_dir, cfg_name, cores)
+                finally:
+                    shutil.rmtree(run_dir, ignore_errors=True)
+                cpu = {"value": sample / dt, "unit": "rows/s", "cores": cores, "kind": "reference",
+                       "sample": f"`kmdiff diff -t {cores}` (oracle/_ref/kmdiff) on the first {sample} rows of the "
+                                 f"workload, {parts} uncompressed partitions, {dt:.2f} s"}
+            else:
+                import oracle
+                sample = min(rows, 2_000_000)
+                hrows = data[:sample * R].cpu().numpy()
+                m = oracle.Model(nc, nk, totals)
+                t0 = time.perf_counter()
+                m.diff(hrows, spec.kmer_words, b, thr)
+                dt = time.perf_counter() - t0
+                cpu = {"value": sample / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                       "sample": f"oracle/kmd_oracle.c on the first {sample} rows, in memory, {dt:.2f} s"}
+        except Exception as e:  # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": "rows/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+
+    line = {
+        "metric": "kmer_rows_tested_per_sec", "value": value, "unit": "rows/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": f"{cfg_name}: synthetic {nc}+{nk} samples, k={k}, {b}-byte counts, Poisson LRT + {corr}",
+            "rows_per_gpu": rows, "row_bytes": R, "bytes_per_gpu": rows * R, "significance": SIGNIFICANCE,
+            "cutoff": CUTOFF, "partition_sharding": f"{world} ranks x {rows} rows, disjoint",
+            "l2": "inputs (>= 13 GB per step) far exceed the 126 MB L2; no flush needed",
+            "survivors_per_gpu": int(c.survivors), "significant": [int(res[0]), int(res[1])],
+            "screen_candidates": int(c.candidates),
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "lrt_scan_kernel", "ms_per_launch": scan_avg_ms,
+                     "algorithmic_bytes_per_launch": rows * R, "peak_source": peak_src},
+        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": e2e_rows * R,
+                "d2h_bytes_per_step": int(d2h), "rows_per_step": e2e_rows, "steps": args.e2e_steps,
+                "api": "kmd_scan_host + kmd_correct + kmd_significant (pinned host buffer)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the config's)")
+    ap.add_argument("--e2e-rows", type=int, default=1 << 25)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,214 @@
+/*
+ * kmdiff_b200 — C-ABI of the B200-native `kmdiff diff` hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ / torch types, integer status
+ * codes and a last-error string, no exceptions across it.  The reference (tlemane/kmdiff, pure
+ * C++17/CPU) has no FFI of its own for this path; each entry point below names the reference
+ * interface it replaces (file:line relative to the reference root; "kmtricks/" =
+ * thirdparty/kmtricks/include/kmtricks/).  INTEGRATION.md shows the binding a reference
+ * maintainer would add inside include/kmdiff/cmd/diff.hpp.
+ *
+ * Threading: a context is thread-compatible (one thread at a time per context); distinct
+ * contexts are independent.  All device work of a context is ordered on one CUDA stream
+ * (its own, or the caller's via kmd_set_stream).
+ *
+ * Row layout everywhere = the payload of a kmtricks count matrix (kmtricks/io/matrix_file.hpp:
+ * 144-154): per row kmer_words*8 bytes of k-mer (little-endian u64 words, word 0 least
+ * significant) followed by nb_controls+nb_cases counts of count_bytes each, controls first.
+ */
+#ifndef KMDIFF_B200_H
+#define KMDIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMD_ABI_VERSION 1
+
+/* status codes */
+enum
+{
+  KMD_OK = 0,
+  KMD_ERR_ARG = 1,      /* invalid argument / configuration                     */
+  KMD_ERR_CUDA = 2,     /* a CUDA runtime call failed (see kmd_last_error)       */
+  KMD_ERR_NOMEM = 3,    /* host or device allocation failed                      */
+  KMD_ERR_OVERFLOW = 4, /* more candidates/survivors than max_survivors          */
+  KMD_ERR_STATE = 5,    /* call order violated (e.g. fetch before correct)       */
+  KMD_ERR_NO_DEVICE = 6 /* no usable sm_100 device; there is NO CPU fallback     */
+};
+
+/* kmdiff::Significance (include/kmdiff/kmer.hpp:33-38) */
+enum { KMD_SIGN_CONTROL = 0, KMD_SIGN_CASE = 1, KMD_SIGN_NO = 2 };
+
+/* kmdiff::CorrectionType (include/kmdiff/correction.hpp) */
+enum
+{
+  KMD_CORR_NOTHING = 0,
+  KMD_CORR_BONFERRONI = 1,
+  KMD_CORR_BENJAMINI = 2,
+  KMD_CORR_SIDAK = 3,
+  KMD_CORR_HOLM = 4
+};
+
+typedef struct kmd_context kmd_context;
+
+/* Replaces the constructor arguments of PoissonLikelihood (include/kmdiff/model.hpp:105-118),
+ * diff_observer (include/kmdiff/merge.hpp:48-66) and global_merge (merge.hpp:211-236). */
+typedef struct kmd_config
+{
+  uint32_t abi_version;   /* KMD_ABI_VERSION                                               */
+  int32_t device;         /* CUDA device ordinal                                           */
+  uint32_t nb_controls;   /* -1/--nb-controls                                              */
+  uint32_t nb_cases;      /* -2/--nb-cases                                                 */
+  uint32_t kmer_size;     /* k                                                             */
+  uint32_t kmer_words;    /* on-disk k-mer words = ceil(k/32) (matrix_file.hpp:109); 1 or 2 */
+  uint32_t count_bytes;   /* 1, 2 or 4 (compile-time MAX_C in the reference)               */
+  uint32_t flags;         /* reserved, 0                                                   */
+  uint64_t sum_controls;  /* Σ per-sample totals of the controls (model.hpp:185-186)       */
+  uint64_t sum_cases;     /* Σ per-sample totals of the cases (model.hpp:188)              */
+  double threshold;       /* prefilter: significance / cutoff (cmd/diff.hpp:146)           */
+  const double* lf_table; /* host log-factorial table in reference order, or NULL: the     */
+  uint64_t lf_size;       /*   library then builds lf_size entries itself (--log-factorial) */
+  uint64_t max_survivors; /* capacity of the device survivor buffers; 0 = 1<<22            */
+} kmd_config;
+
+/* KmerSign (include/kmdiff/kmer.hpp:88-127) plus the global row index */
+typedef struct kmd_survivor
+{
+  uint64_t kmer[2];    /* kmer[0] = least-significant word                        */
+  double p_value;      /* PoissonLikelihood::process p-value                      */
+  int32_t sign;        /* KMD_SIGN_*                                              */
+  uint32_t partition;  /* partition tag given to kmd_scan_*                       */
+  double mean_control; /* sum(ctrl) * sum_cases / sum_controls (model.hpp:164)    */
+  double mean_case;    /* sum(case)                                               */
+  uint64_t row;        /* row_base + index inside the scanned batch               */
+} kmd_survivor;
+
+/* merge.hpp:105-113, 319-337 (total / nb_sign / signs) */
+typedef struct kmd_counters
+{
+  uint64_t rows;       /* rows tested so far = m for the correctors (merge.hpp:316) */
+  uint64_t candidates; /* rows that passed the fp32 screen (diagnostic)             */
+  uint64_t survivors;  /* rows with p <= threshold                                  */
+  uint64_t n_control;  /* survivors with sign CONTROL                               */
+  uint64_t n_case;     /* survivors with sign CASE or NO (merge.hpp:95-98)          */
+} kmd_counters;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+int kmd_abi_version(void);
+/* number of CUDA devices visible to the library; 0 => every compute entry point fails loudly */
+int kmd_device_count(void);
+
+int kmd_create(const kmd_config* cfg, kmd_context** out);
+void kmd_destroy(kmd_context* ctx);
+/* message of the last failing call on ctx (ctx == NULL: last failing kmd_create of this thread) */
+const char* kmd_last_error(const kmd_context* ctx);
+/* run all device work of ctx on the caller's cudaStream_t (NULL restores the context's own) */
+int kmd_set_stream(kmd_context* ctx, void* cuda_stream);
+int kmd_sync(kmd_context* ctx);
+/* forget survivors and counters (start of a new `diff` run, cmd/diff.hpp:66) */
+int kmd_reset(kmd_context* ctx);
+
+/* ---- the partition loop: global_merge::merge(paths) -> matrix_proxy::merge ->
+ *      diff_observer::process (merge.hpp:341-397, 194-203, 68-103) --------------------------- */
+
+/* Test every row of a device-resident batch (Poisson LRT + chi-square p-value + prefilter) and
+ * append the survivors to the context.  d_rows must be 16-byte aligned.  Asynchronous. */
+int kmd_scan_device(kmd_context* ctx, const void* d_rows, uint64_t n_rows, uint64_t row_base,
+                    uint32_t partition);
+/* Same for a HOST buffer: chunked host->device copies (async when h_rows is pinned, see
+ * kmd_host_alloc) overlapped with the scan of the previous chunk.  Returns after the last chunk
+ * has been enqueued and the host buffer is no longer needed. */
+int kmd_scan_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_t row_base,
+                  uint32_t partition);
+int kmd_counters_get(kmd_context* ctx, kmd_counters* out);
+/* prefilter survivors ordered by row (what the FileAccumulators hold, accumulator.hpp:156-285) */
+int kmd_survivors(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n);
+
+/* diagnostics for bench.py: kernels launched on behalf of ctx so far, and the device time of the
+ * most recent lrt_scan kernel launch (CUDA events on the context's stream) */
+uint64_t kmd_launch_count(const kmd_context* ctx);
+int kmd_scan_kernel_ms(kmd_context* ctx, float* ms);
+
+/* ---- IModel::process, batched (include/kmdiff/imodel.hpp:37, model.hpp:142-176) ------------ */
+
+/* p-value, sign and the two "means" of EVERY row (no screen, no prefilter); rows on the device
+ * (out arrays on the device too) or on the host (out arrays on the host). */
+int kmd_model_rows_device(kmd_context* ctx, const void* d_rows, uint64_t n_rows, double* d_p,
+                          int32_t* d_sign, double* d_mean_control, double* d_mean_case);
+int kmd_model_rows_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, double* p,
+                        int32_t* sign, double* mean_control, double* mean_case);
+
+/* ---- do_correction: make_corrector + (sorted_)aggregator::run
+ *      (cmd/diff.hpp:227-260, src/corrector.cpp, aggregator.hpp:137-322) --------------------- */
+
+/* Apply `correction` with significance level `significance` and m = total_rows to the prefilter
+ * survivors held by ctx.  NOTHING/BONFERRONI/SIDAK: independent strict `<` tests, output in row
+ * order.  BENJAMINI/HOLM: device radix sort by p, walk ascending, stop at the first rejection
+ * (the reference's step-down-with-break).  Returns counts of kept control / case k-mers. */
+int kmd_correct(kmd_context* ctx, int correction, double significance, uint64_t total_rows,
+                uint64_t* n_control, uint64_t* n_case);
+/* kept survivors in output order (row order, or ascending p for BENJAMINI/HOLM) */
+int kmd_significant(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n);
+
+/* Multi-GPU BENJAMINI/HOLM (partitions sharded over ranks): every rank exports its survivors'
+ * p-values ascending, the host side exchanges them (NCCL all-gather), computes the first
+ * rejected p-value with kmd_first_reject, and every rank keeps its survivors with p < p_cut. */
+int kmd_sorted_pvalues(kmd_context* ctx, double* out, uint64_t cap, uint64_t* n);
+int kmd_keep_below(kmd_context* ctx, double p_cut, uint64_t* n_control, uint64_t* n_case);
+/* host helper: walk p_sorted (ascending, all ranks merged) exactly like sorted_aggregator::run;
+ * returns the number accepted and writes the first rejected p-value (+inf if none) */
+uint64_t kmd_first_reject(const double* p_sorted, uint64_t n, int correction, double significance,
+                          uint64_t total_rows, double* p_cut);
+
+/* ---- host-side pieces of the path that stay on the CPU -------------------------------------- */
+
+/* LogFactorialTable (src/log_factorial_table.cpp:5-22): table[i] = log(i)+log(i-1)+...+log(2) */
+void kmd_lf_table_fill(double* table, uint64_t size);
+/* alglib::chisquarecdistribution(v, x) (thirdparty/alglib/src/specialfunctions.cpp:9559) */
+double kmd_chisqc(double v, double x);
+/* one corrector predicate (src/corrector.cpp): rank = 1-based rank for BENJAMINI, number of
+ * earlier applications for HOLM, ignored otherwise */
+int kmd_corrector_apply(int correction, double significance, uint64_t total_rows, uint64_t rank,
+                        double p);
+/* km::Kmer::to_string (kmtricks/kmer.hpp:38, 797-810); out holds k+1 bytes */
+void kmd_kmer_to_string(const uint64_t* words, uint32_t kmer_words, uint32_t k, char* out);
+/* one FASTA record exactly as aggregator.hpp:55-62 + kseq++ (60-column wrap) print it; returns
+ * the number of bytes written (excluding the NUL), or the size needed if cap is too small */
+size_t kmd_format_fasta(uint64_t index, const kmd_survivor* s, uint32_t kmer_words, uint32_t k,
+                        char* out, size_t cap);
+
+/* pinned host memory for kmd_scan_host / kmd_model_rows_host */
+void* kmd_host_alloc(size_t bytes);
+void kmd_host_free(void* p);
+
+/* ---- seeded synthetic kmtricks-format rows (bench / tests) ------------------ */
+
+typedef struct kmd_synth
+{
+  uint64_t seed;
+  uint64_t total_rows;  /* rows of the whole synthetic matrix (fixes the k-mer spacing)   */
+  uint32_t nb_controls;
+  uint32_t nb_cases;
+  uint32_t kmer_size;
+  uint32_t kmer_words;
+  uint32_t count_bytes;
+  uint32_t enriched_ppm; /* rows per million whose cases (or controls) are over-abundant  */
+} kmd_synth;
+
+/* rows [row_base, row_base+n_rows) of the synthetic matrix, bit-identical on host and device */
+int kmd_synth_fill_host(const kmd_synth* s, void* h_rows, uint64_t n_rows, uint64_t row_base,
+                        int threads);
+int kmd_synth_fill_device(const kmd_synth* s, int device, void* d_rows, uint64_t n_rows,
+                          uint64_t row_base, void* cuda_stream);
+/* per-sample totals the synthetic cohort declares (what the .hist files would hold) */
+void kmd_synth_totals(const kmd_synth* s, uint64_t* totals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMDIFF_B200_H */

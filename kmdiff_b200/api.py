@@ -1,0 +1,328 @@
+"""Python mirror of the reference's operator interface for the `kmdiff diff` path, over the C-ABI.
+
+Names and argument meaning follow the reference (file:line relative to the reference root):
+
+    LogFactorialTable      include/kmdiff/log_factorial_table.hpp:9-26
+    PoissonLikelihood      include/kmdiff/model.hpp:93-192   (IModel::process, imodel.hpp:37)
+    Significance           include/kmdiff/kmer.hpp:33-38
+    CorrectionType         include/kmdiff/correction.hpp
+    bonferroni / benjamini / sidak / holm / basic_threshold, make_corrector
+                           include/kmdiff/corrector.hpp, src/corrector.cpp
+    DiffContext            global_merge + diff_observer + accumulators + aggregators
+                           (include/kmdiff/merge.hpp, accumulator.hpp, aggregator.hpp)
+
+Everything that computes runs in the CUDA library; nothing here falls back to numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import SURVIVOR_DTYPE, Config, Counters
+
+
+class KmdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"kmdiff_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Significance(enum.IntEnum):
+    CONTROL = 0
+    CASE = 1
+    NO = 2
+
+
+class CorrectionType(enum.IntEnum):
+    NOTHING = 0
+    BONFERRONI = 1
+    BENJAMINI = 2
+    SIDAK = 3
+    HOLM = 4
+
+
+def correction_from_str(s: str) -> CorrectionType:
+    """-c/--correction values of the reference CLI (src/cli.cpp)."""
+    table = {"bonferroni": CorrectionType.BONFERRONI, "benjamini": CorrectionType.BENJAMINI,
+             "sidak": CorrectionType.SIDAK, "holm": CorrectionType.HOLM,
+             "disabled": CorrectionType.NOTHING}
+    if s not in table:
+        raise ValueError(f"unknown correction '{s}'")
+    return table[s]
+
+
+class LogFactorialTable:
+    """table[i] = log(i) + log(i-1) + ... + log(2); beyond the table the value is recomputed."""
+
+    def __init__(self, size: int):
+        self.size = int(size)
+        self.table = np.empty(self.size, dtype=np.float64)
+        _lib.load().kmd_lf_table_fill(self.table.ctypes.data, self.size)
+
+    def __getitem__(self, i: int) -> float:
+        if i < self.size:
+            return float(self.table[i])
+        t = np.empty(i + 1, dtype=np.float64)
+        _lib.load().kmd_lf_table_fill(t.ctypes.data, i + 1)
+        return float(t[i])
+
+
+# ---- correctors (host predicates, stateful like the reference) -----------------------------------
+
+class ICorrector:
+    kind = CorrectionType.NOTHING
+
+    def __init__(self, threshold: float, total: int = 0):
+        self.threshold = float(threshold)
+        self.total = int(total)
+        self._applied = 0   # benjamini: accepted so far; holm: applications so far
+
+    def type(self) -> CorrectionType:
+        return self.kind
+
+    def str_type(self) -> str:
+        return {0: "threshold", 1: "bonferroni", 2: "benjamini", 3: "sidak", 4: "holm"}[int(self.kind)]
+
+    def apply(self, pvalue: float) -> bool:
+        L = _lib.load()
+        rank = self._applied + 1 if self.kind == CorrectionType.BENJAMINI else self._applied
+        ok = bool(L.kmd_corrector_apply(int(self.kind), self.threshold, self.total, rank, pvalue))
+        if self.kind == CorrectionType.BENJAMINI:
+            self._applied += 1 if ok else 0
+        elif self.kind == CorrectionType.HOLM:
+            self._applied += 1
+        return ok
+
+
+class basic_threshold(ICorrector):
+    kind = CorrectionType.NOTHING
+
+
+class bonferroni(ICorrector):
+    kind = CorrectionType.BONFERRONI
+
+
+class benjamini(ICorrector):
+    kind = CorrectionType.BENJAMINI
+
+
+class sidak(ICorrector):
+    kind = CorrectionType.SIDAK
+
+
+class holm(ICorrector):
+    kind = CorrectionType.HOLM
+
+
+def make_corrector(kind: CorrectionType, threshold: float, kmers: int) -> ICorrector:
+    return {CorrectionType.BONFERRONI: bonferroni, CorrectionType.SIDAK: sidak,
+            CorrectionType.BENJAMINI: benjamini, CorrectionType.HOLM: holm,
+            CorrectionType.NOTHING: basic_threshold}[CorrectionType(kind)](threshold, kmers)
+
+
+# ---- the device context ---------------------------------------------------------------------------
+
+def _as_u8(buf) -> np.ndarray:
+    a = np.asarray(buf)
+    if a.dtype != np.uint8:
+        a = a.view(np.uint8)
+    return np.ascontiguousarray(a).ravel()
+
+
+class DiffContext:
+    """One GPU's share of `kmdiff diff`: the partition loop (scan), the survivor accumulators and
+    the correction, all device-side behind the C-ABI."""
+
+    def __init__(self, nb_controls: int, nb_cases: int, sum_controls: int, sum_cases: int,
+                 kmer_size: int = 31, count_bytes: int = 4, threshold: float = 0.05 / 100000,
+                 lf_size: int = 10000, lf_table: np.ndarray | None = None, device: int = 0,
+                 max_survivors: int = 0):
+        self._L = _lib.load()
+        self.nb_controls, self.nb_cases = int(nb_controls), int(nb_cases)
+        self.kmer_size = int(kmer_size)
+        self.kmer_words = (self.kmer_size + 31) // 32
+        self.count_bytes = int(count_bytes)
+        self.row_bytes = 8 * self.kmer_words + (self.nb_controls + self.nb_cases) * self.count_bytes
+        self.threshold = float(threshold)
+        self.device = int(device)
+        self._table = None if lf_table is None else np.ascontiguousarray(lf_table, dtype=np.float64)
+        cfg = Config(_lib.KMD_ABI_VERSION, self.device, self.nb_controls, self.nb_cases,
+                     self.kmer_size, self.kmer_words, self.count_bytes, 0, int(sum_controls),
+                     int(sum_cases), self.threshold,
+                     None if self._table is None else self._table.ctypes.data_as(C.POINTER(C.c_double)),
+                     int(lf_size if self._table is None else self._table.size), int(max_survivors))
+        h = C.c_void_p()
+        rc = self._L.kmd_create(C.byref(cfg), C.byref(h))
+        if rc:
+            raise KmdError(rc, self._L.kmd_last_error(None).decode())
+        self._h = h
+
+    # -- plumbing --
+    def _ck(self, rc: int) -> None:
+        if rc:
+            raise KmdError(rc, self._L.kmd_last_error(self._h).decode())
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.kmd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        self._ck(self._L.kmd_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self) -> None:
+        self._ck(self._L.kmd_sync(self._h))
+
+    def reset(self) -> None:
+        self._ck(self._L.kmd_reset(self._h))
+
+    # -- partition loop --
+    def scan_device(self, dev_ptr: int, n_rows: int, row_base: int = 0, partition: int = 0) -> None:
+        self._ck(self._L.kmd_scan_device(self._h, C.c_void_p(dev_ptr), n_rows, row_base, partition))
+
+    def scan_host(self, rows, n_rows: int | None = None, row_base: int = 0, partition: int = 0) -> None:
+        """rows: bytes-like / uint8 array holding a matrix payload, or an integer host address."""
+        if isinstance(rows, int):
+            assert n_rows is not None
+            ptr = rows
+        else:
+            a = _as_u8(rows)
+            if n_rows is None:
+                assert a.size % self.row_bytes == 0, "payload is not a whole number of rows"
+                n_rows = a.size // self.row_bytes
+            ptr = a.ctypes.data
+        self._ck(self._L.kmd_scan_host(self._h, C.c_void_p(ptr), n_rows, row_base, partition))
+
+    def counters(self) -> Counters:
+        c = Counters()
+        self._ck(self._L.kmd_counters_get(self._h, C.byref(c)))
+        return c
+
+    def launch_count(self) -> int:
+        return int(self._L.kmd_launch_count(self._h))
+
+    def scan_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self._L.kmd_scan_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def survivors(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._ck(self._L.kmd_survivors(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=SURVIVOR_DTYPE)
+        if n.value:
+            self._ck(self._L.kmd_survivors(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    # -- IModel::process, batched --
+    def model_rows(self, rows):
+        a = _as_u8(rows)
+        assert a.size % self.row_bytes == 0
+        n = a.size // self.row_bytes
+        p = np.empty(n, np.float64)
+        sign = np.empty(n, np.int32)
+        mc = np.empty(n, np.float64)
+        kk = np.empty(n, np.float64)
+        self._ck(self._L.kmd_model_rows_host(self._h, a.ctypes.data, n, p.ctypes.data, sign.ctypes.data,
+                                             mc.ctypes.data, kk.ctypes.data))
+        return p, sign, mc, kk
+
+    # -- correction --
+    def correct(self, correction: int, significance: float, total_rows: int) -> tuple[int, int]:
+        nc, nk = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.kmd_correct(self._h, int(correction), significance, total_rows, C.byref(nc), C.byref(nk)))
+        return nc.value, nk.value
+
+    def significant(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._ck(self._L.kmd_significant(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=SURVIVOR_DTYPE)
+        if n.value:
+            self._ck(self._L.kmd_significant(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def sorted_pvalues(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._ck(self._L.kmd_sorted_pvalues(self._h, None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float64)
+        if n.value:
+            self._ck(self._L.kmd_sorted_pvalues(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def keep_below(self, p_cut: float) -> tuple[int, int]:
+        nc, nk = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.kmd_keep_below(self._h, p_cut, C.byref(nc), C.byref(nk)))
+        return nc.value, nk.value
+
+
+def first_reject(p_sorted: np.ndarray, correction: int, significance: float, total_rows: int):
+    """Walk merged ascending p-values like sorted_aggregator::run; -> (n_accepted, p_cut)."""
+    p = np.ascontiguousarray(p_sorted, dtype=np.float64)
+    cut = C.c_double()
+    n = _lib.load().kmd_first_reject(p.ctypes.data, p.size, int(correction), significance, total_rows, C.byref(cut))
+    return int(n), cut.value
+
+
+class PoissonLikelihood:
+    """IModel implementation of the reference (model.hpp:93-192) evaluated on the GPU.
+
+    process(controls, cases) keeps the reference's per-row signature; process_rows() is the batched
+    form the GPU is meant for."""
+
+    def __init__(self, nb_controls: int, nb_cases: int, total_controls: Sequence[int],
+                 total_cases: Sequence[int], preload: int = 10000, count_bytes: int = 4,
+                 kmer_size: int = 31, device: int = 0):
+        assert len(total_controls) == nb_controls and len(total_cases) == nb_cases
+        self.nb_controls, self.nb_cases = nb_controls, nb_cases
+        self.count_bytes = count_bytes
+        self._dtype = {1: np.uint8, 2: np.uint16, 4: np.uint32}[count_bytes]
+        self._ctx = DiffContext(nb_controls, nb_cases, int(sum(int(t) for t in total_controls)),
+                                int(sum(int(t) for t in total_cases)), kmer_size=kmer_size,
+                                count_bytes=count_bytes, lf_size=preload, device=device,
+                                max_survivors=1024)
+
+    def configure(self, config: str) -> None:  # IModel::configure (model.hpp:121)
+        pass
+
+    def process(self, controls, cases):
+        c = np.concatenate([np.asarray(controls, dtype=self._dtype), np.asarray(cases, dtype=self._dtype)])
+        assert c.size == self.nb_controls + self.nb_cases
+        row = np.zeros(self._ctx.row_bytes, dtype=np.uint8)
+        row[8 * self._ctx.kmer_words:] = c.view(np.uint8)
+        p, sign, mc, kk = self._ctx.model_rows(row)
+        return float(p[0]), Significance(int(sign[0])), float(mc[0]), float(kk[0])
+
+    def process_rows(self, payload):
+        return self._ctx.model_rows(payload)
+
+
+def kmer_to_string(words, k: int) -> str:
+    w = np.ascontiguousarray(words, dtype=np.uint64).ravel()
+    buf = C.create_string_buffer(k + 1)
+    _lib.load().kmd_kmer_to_string(w.ctypes.data, w.size, k, buf)
+    return buf.value.decode()
+
+
+def format_fasta(index: int, record: np.void, kmer_size: int) -> str:
+    """One FASTA record as the reference's writer prints it (aggregator.hpp:55-62, 60-col wrap)."""
+    rec = np.array([record], dtype=SURVIVOR_DTYPE)
+    buf = C.create_string_buffer(512 + 2 * kmer_size)
+    n = _lib.load().kmd_format_fasta(index, rec.ctypes.data, (kmer_size + 31) // 32, kmer_size, buf, len(buf))
+    assert n < len(buf)
+    return buf.value.decode()

@@ -1,0 +1,1353 @@
+// C-ABI of the B200-native `kmdiff diff` hot path (include/kmdiff_b200.h) and the kernels behind it
+// that are not the streaming scan (kmd_scan.cuh) or the sort (kmd_sort.cuh).
+//
+// There is no CPU fallback in this file: every compute entry point needs a context, and a context
+// needs an sm_100 device.
+#include "../../include/kmdiff_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "kmd_math.cuh"
+#include "kmd_scan.cuh"
+#include "kmd_sort.cuh"
+#include "kmd_synth.cuh"
+
+namespace {
+
+using namespace kmd;
+
+thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+
+struct SurvivorArrays
+{
+  uint64_t* kmer0 = nullptr;
+  uint64_t* kmer1 = nullptr;
+  double* p = nullptr;
+  int32_t* sign = nullptr;
+  uint32_t* part = nullptr;
+  double* mc = nullptr;
+  double* kk = nullptr;
+  uint64_t* row = nullptr;
+};
+
+struct DeviceCounters
+{
+  uint32_t cand_count;      // candidates of the batch in flight
+  uint32_t surv_count;      // survivors appended so far
+  uint32_t n_control;
+  uint32_t n_case;
+  unsigned long long cand_total;
+  uint32_t overflow;        // 1: candidate buffer overflowed, 2: survivor buffer overflowed
+  uint32_t first_reject;    // scratch for first_reject_kernel
+  uint32_t keep_control;
+  uint32_t keep_case;
+  uint32_t keep_total;
+  uint32_t pad_;
+};
+
+}  // namespace
+
+struct kmd_context
+{
+  kmd_config cfg{};
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  std::string err;
+
+  // model
+  kmd::ModelConst model{};      // lf points to device memory
+  double* d_lf = nullptr;
+  double lr_cut = 0;            // LR*(threshold) on the host
+  // scan plan
+  kmd::ScanParams plan{};
+  uint32_t consumer_warps = kmd::kConsumerWarps;
+  size_t scan_smem = 0;
+  bool direct = false;          // stream rows with plain global loads instead of the TMA ring
+
+  // device state
+  uint64_t cap = 0;
+  DeviceCounters* d_cnt = nullptr;
+  DeviceCounters* h_cnt = nullptr;  // pinned
+  uint32_t* d_cand = nullptr;
+  SurvivorArrays surv;
+  uint64_t rows_tested = 0;
+  uint64_t launches = 0;          // kernels launched on behalf of this context
+  cudaEvent_t ev_k0 = nullptr;    // around the last lrt_scan kernel launch
+  cudaEvent_t ev_k1 = nullptr;
+  bool scan_timed = false;
+
+  // sort / correction state
+  uint64_t* d_keys[2] = {nullptr, nullptr};
+  uint32_t* d_vals[2] = {nullptr, nullptr};
+  uint32_t* d_hist = nullptr;
+  size_t hist_entries = 0;
+  double* d_p_sorted = nullptr;
+  kmd_survivor* d_out = nullptr;
+  uint64_t out_cap = 0;
+  uint32_t* d_order = nullptr;   // final order (survivor slots), valid after correct/keep_below
+  uint32_t n_final = 0;
+  int order_state = 0;           // 0 none, 1 row order over all survivors, 2 p order over all survivors
+  bool final_valid = false;
+
+  // host staging for kmd_scan_host / kmd_model_rows_host
+  uint8_t* d_stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  cudaEvent_t ev_scan[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+int fail(kmd_context* ctx, int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define KMD_CUDA(ctx, call)                                                                      \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? KMD_ERR_NOMEM : KMD_ERR_CUDA,           \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+  } while (0)
+
+uint32_t env_u32(const char* name, uint32_t dflt)
+{
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return static_cast<uint32_t>(strtoul(v, nullptr, 10));
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side model pieces
+// ------------------------------------------------------------------------------------------------
+
+// LogFactorialTable (reference src/log_factorial_table.cpp:5-22): entry k is log(k) + log(k-1) +
+// ... + log(2), accumulated in exactly that order.  log(j) is evaluated once per j instead of once
+// per (k, j) pair; the additions and their order are the reference's, so the table is bit-identical
+// to the reference's on the same libm.
+void lf_table_fill(double* table, uint64_t size)
+{
+  if (size == 0) return;
+  std::vector<double> logs(size);
+  for (uint64_t j = 2; j < size; j++) logs[j] = std::log(static_cast<double>(j));
+  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  unsigned nt = size < 4096 ? 1 : std::min(hw, 16u);
+  auto work = [&](unsigned t) {
+    // interleave so every thread gets short and long chains
+    for (uint64_t k = t; k < size; k += nt)
+    {
+      double acc = 0;
+      for (uint64_t j = k; j > 1; j--) acc += logs[j];
+      table[k] = acc;
+    }
+  };
+  if (nt == 1) { work(0); return; }
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < nt; t++) pool.emplace_back(work, t);
+  for (auto& th : pool) th.join();
+}
+
+double host_igamc_half(double x)
+{
+  static const double lg = kmd::lngamma_small(0.5);
+  return kmd::igamc_half(x, lg);
+}
+
+// Largest LR known to give p > thr (bisection on the monotone igamc); +inf if nothing can pass,
+// -1 if everything passes.
+double lr_cut_for(double thr)
+{
+  if (!(thr >= 0)) return std::numeric_limits<double>::infinity();  // negative or NaN: no survivor
+  if (thr >= 1) return -1;
+  double lo = 0, hi = 1;
+  while (host_igamc_half(hi) > thr)
+  {
+    lo = hi;
+    hi *= 2;
+    if (hi > 4096) return std::numeric_limits<double>::infinity();
+  }
+  for (int i = 0; i < 200; i++)
+  {
+    double mid = 0.5 * (lo + hi);
+    if (host_igamc_half(mid) > thr) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// scan plan: tile / stage / lanes-per-row geometry
+// ------------------------------------------------------------------------------------------------
+
+uint32_t conflict_degree(uint32_t R, uint32_t kmer_bytes, uint32_t g, bool fast, uint32_t B)
+{
+  uint32_t worst = 1;
+  if (fast)
+  {
+    for (uint32_t half = 0; half < 2; half++)
+    {
+      uint32_t cnt[16] = {0};
+      uint64_t seen[16][16];
+      for (uint32_t i = 0; i < 16; i++)
+      {
+        uint32_t lane = half * 16 + i;
+        uint64_t addr = static_cast<uint64_t>(lane / g) * R + kmer_bytes + 8 * (lane % g);
+        uint32_t bank = (addr / 8) % 16;
+        bool dup = false;
+        for (uint32_t k = 0; k < cnt[bank]; k++) dup |= seen[bank][k] == addr;
+        if (!dup) seen[bank][cnt[bank]++] = addr;
+      }
+      for (uint32_t b = 0; b < 16; b++) worst = std::max(worst, cnt[b]);
+    }
+  }
+  else
+  {
+    uint32_t cnt[32] = {0};
+    uint64_t seen[32][32];
+    for (uint32_t lane = 0; lane < 32; lane++)
+    {
+      uint64_t addr = (static_cast<uint64_t>(lane / g) * R + kmer_bytes + B * (lane % g)) / 4;
+      uint32_t bank = addr % 32;
+      bool dup = false;
+      for (uint32_t k = 0; k < cnt[bank]; k++) dup |= seen[bank][k] == addr;
+      if (!dup) seen[bank][cnt[bank]++] = addr;
+    }
+    for (uint32_t b = 0; b < 32; b++) worst = std::max(worst, cnt[b]);
+  }
+  return worst;
+}
+
+int make_plan(kmd_context* ctx)
+{
+  const kmd_config& c = ctx->cfg;
+  ScanParams& P = ctx->plan;
+  const uint32_t N = c.nb_controls + c.nb_cases;
+  const uint32_t B = c.count_bytes;
+  P.row_bytes = 8 * c.kmer_words + N * B;
+  P.kmer_bytes = 8 * c.kmer_words;
+  P.nb_controls = c.nb_controls;
+  P.nb_cases = c.nb_cases;
+  P.fast = (static_cast<uint64_t>(N) * B) % 8 == 0;
+  P.words_total = P.fast ? N * B / 8 : 0;
+  P.words_ctrl = P.fast ? c.nb_controls * B / 8 : 0;
+  P.straddle_elems = P.fast ? (c.nb_controls * B % 8) / B : 0;
+
+  const uint32_t warps = std::min<uint32_t>(kConsumerWarps, std::max<uint32_t>(1, env_u32("KMD_SCAN_WARPS", kConsumerWarps)));
+  ctx->consumer_warps = warps;
+
+  const uint32_t ring_budget = 200 * 1024;
+  const uint32_t target_tile = env_u32("KMD_SCAN_TILE_BYTES", 40 * 1024);
+  const uint32_t units = P.fast ? P.words_total : N;
+
+  // lanes per row: cheapest estimated issue cost among the choices whose full pass fits the ring
+  uint32_t best_g = 32;
+  double best_cost = 1e30;
+  for (uint32_t g = 1; g <= 32; g *= 2)
+  {
+    const uint64_t pass_rows = static_cast<uint64_t>(warps) * (32 / g);
+    if (pass_rows * P.row_bytes > ring_budget / 3 && g < 32) continue;
+    const uint32_t conf = conflict_degree(P.row_bytes, P.kmer_bytes, g, P.fast, B);
+    uint32_t lg = 0;
+    while ((1u << lg) < g) lg++;
+    const double per_pass = std::ceil(static_cast<double>(units) / g) * (2.0 + 2.0 * conf) + 8.0 * lg + 40.0;
+    const double cost = per_pass * g / 32.0;
+    if (cost < best_cost) { best_cost = cost; best_g = g; }
+  }
+  P.lanes_per_row = env_u32("KMD_SCAN_G", best_g);
+  if (P.lanes_per_row == 0 || (P.lanes_per_row & (P.lanes_per_row - 1)) || P.lanes_per_row > 32)
+    return fail(ctx, KMD_ERR_ARG, "KMD_SCAN_G must be a power of two in [1,32]");
+
+  // rows per tile: whole passes of all consumer warps, rounded to 16 rows so that tile bytes are a
+  // multiple of 16 for any R
+  uint32_t pass_rows = warps * (32 / P.lanes_per_row);
+  pass_rows = (pass_rows + 15) / 16 * 16;
+  uint32_t passes = std::max<uint32_t>(1, target_tile / (pass_rows * P.row_bytes));
+  P.tile_rows = env_u32("KMD_SCAN_TILE_ROWS", pass_rows * passes);
+  if (P.tile_rows % 16) return fail(ctx, KMD_ERR_ARG, "tile rows must be a multiple of 16");
+  const uint64_t tile_bytes = static_cast<uint64_t>(P.tile_rows) * P.row_bytes;
+  P.stage_bytes = static_cast<uint32_t>((tile_bytes + 127) / 128 * 128);
+  uint32_t stages = tile_bytes ? static_cast<uint32_t>(ring_budget / P.stage_bytes) : 0;
+  stages = std::min<uint32_t>(stages, kMaxStages);
+  stages = std::min<uint32_t>(stages, std::max<uint32_t>(1, env_u32("KMD_SCAN_STAGES", kMaxStages)));
+  P.stages = stages;
+  const char* mode = getenv("KMD_SCAN_MODE");
+  ctx->direct = stages < 2 || tile_bytes >= (1u << 20) || (mode && !strcmp(mode, "direct"));
+  ctx->scan_smem = ctx->direct ? 0 : kBarrierBytes + static_cast<size_t>(P.stages) * P.stage_bytes;
+
+  // screen
+  const double Sc = static_cast<double>(c.sum_controls), Sk = static_cast<double>(c.sum_cases);
+  const double S = static_cast<double>(c.sum_controls + c.sum_cases);
+  P.screen_off = (c.sum_controls == 0 || c.sum_cases == 0 || ctx->lr_cut < 0) ? 1 : 0;
+  if (env_u32("KMD_SCREEN_OFF", 0)) P.screen_off = 1;
+  P.frac_ctrl = static_cast<float>(Sc / S);
+  P.frac_case = static_cast<float>(Sk / S);
+  if (std::isinf(ctx->lr_cut))
+    P.lr2_cut = std::numeric_limits<float>::infinity();
+  else
+  {
+    const double cut2 = ctx->lr_cut * (1.0 - 1e-9) / 0.6931471805599453;
+    P.lr2_cut = std::nextafterf(static_cast<float>(cut2), -std::numeric_limits<float>::infinity());
+  }
+  return KMD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+
+// Same work as lrt_scan_kernel without the shared-memory ring: rows are read with plain global
+// loads.  Used for rows too large for the ring, and as the A/B baseline (KMD_SCAN_MODE=direct).
+template <int B>
+__global__ void __launch_bounds__(kScanThreads) lrt_scan_direct_kernel(const ScanParams P, uint32_t warps)
+{
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= warps) return;
+  const uint64_t n_chunks = (P.n_rows + P.tile_rows - 1) / P.tile_rows;
+  for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x)
+  {
+    const uint64_t first = chunk * P.tile_rows;
+    const uint32_t n = static_cast<uint32_t>(min(static_cast<uint64_t>(P.tile_rows), P.n_rows - first));
+    GmemLoader ld{P.rows + first * P.row_bytes};
+    scan_rows<B>(P, ld, n, static_cast<uint32_t>(first), warp, warps, lane);
+  }
+}
+
+struct ExactArgs
+{
+  const uint8_t* rows;
+  uint64_t row_base;
+  uint32_t partition;
+  double threshold;
+  ModelConst model;
+  ScanParams geom;        // lanes_per_row forced to 1
+  const uint32_t* cand;
+  DeviceCounters* cnt;
+  SurvivorArrays out;
+  uint32_t cap;
+  uint32_t kmer_words;
+};
+
+// diff_observer::process on the candidate rows: exact fp64 LRT in reference order, the `<=`
+// prefilter, sign counting (NO counted as case) and the KmerSign fields (merge.hpp:68-103).
+template <int B>
+__global__ void __launch_bounds__(256) lrt_exact_kernel(const ExactArgs A)
+{
+  const uint32_t n_cand = min(A.cnt->cand_count, A.geom.cand_cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    atomicAdd(&A.cnt->cand_total, static_cast<unsigned long long>(A.cnt->cand_count));
+    if (A.cnt->cand_count > A.geom.cand_cap) atomicOr(&A.cnt->overflow, 1u);
+  }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += gridDim.x * blockDim.x)
+  {
+    const uint32_t r = A.cand[i];
+    const uint8_t* row = A.rows + static_cast<uint64_t>(r) * A.geom.row_bytes;
+    GmemLoader ld{row};
+    uint64_t sc, sk;
+    row_partial<B>(A.geom, ld, 0, 0, 1, sc, sk);
+    const double* lf = A.model.lf;
+    const RowStat st = lrt_exact(A.model, sc, sk, [lf](uint64_t k) { return __ldg(lf + k); });
+    if (st.p <= A.threshold)
+    {
+      const uint32_t pos = atomicAdd(&A.cnt->surv_count, 1u);
+      if (st.sign == KMD_SIGN_CONTROL) atomicAdd(&A.cnt->n_control, 1u); else atomicAdd(&A.cnt->n_case, 1u);
+      if (pos < A.cap)
+      {
+        uint64_t k0 = 0, k1 = 0;
+        if ((A.geom.row_bytes & 7u) == 0)
+        {
+          k0 = ld.ld64(0);
+          if (A.kmer_words > 1) k1 = ld.ld64(8);
+        }
+        else
+        {
+          for (int b = 0; b < 8; b++) k0 |= static_cast<uint64_t>(ld.ld8(b)) << (8 * b);
+          if (A.kmer_words > 1)
+            for (int b = 0; b < 8; b++) k1 |= static_cast<uint64_t>(ld.ld8(8 + b)) << (8 * b);
+        }
+        A.out.kmer0[pos] = k0;
+        A.out.kmer1[pos] = k1;
+        A.out.p[pos] = st.p;
+        A.out.sign[pos] = st.sign;
+        A.out.part[pos] = A.partition;
+        A.out.mc[pos] = st.mean_control;
+        A.out.kk[pos] = st.mean_case;
+        A.out.row[pos] = A.row_base + r;
+      }
+      else
+        atomicOr(&A.cnt->overflow, 2u);
+    }
+  }
+}
+
+// IModel::process for every row (imodel.hpp:37): one thread per row, the log-factorial table
+// staged in shared memory (each row does four look-ups).
+template <int B>
+__global__ void __launch_bounds__(256) lrt_model_rows_kernel(const uint8_t* rows, uint64_t n_rows, ScanParams geom,
+                                                            ModelConst model, uint32_t lf_smem, double* p,
+                                                            int32_t* sign, double* mc, double* kk)
+{
+  extern __shared__ double lf_s[];
+  for (uint32_t i = threadIdx.x; i < lf_smem; i += blockDim.x) lf_s[i] = model.lf[i];
+  __syncthreads();
+  const double* lf = model.lf;
+  for (uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; r < n_rows;
+       r += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+  {
+    GmemLoader ld{rows + r * geom.row_bytes};
+    uint64_t sc, sk;
+    row_partial<B>(geom, ld, 0, 0, 1, sc, sk);
+    const RowStat st = lrt_exact(model, sc, sk, [lf, lf_smem](uint64_t k) {
+      return k < lf_smem ? lf_s[k] : __ldg(lf + k);
+    });
+    p[r] = st.p;
+    sign[r] = st.sign;
+    mc[r] = st.mean_control;
+    kk[r] = st.mean_case;
+  }
+}
+
+__global__ void iota_keys_kernel(uint32_t n, const uint64_t* row, const double* p, int by_p, const uint32_t* order_in,
+                                 uint64_t* keys, uint32_t* vals)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t slot = order_in ? order_in[i] : i;
+  keys[i] = by_p ? static_cast<uint64_t>(__double_as_longlong(p[slot])) : row[slot];
+  vals[i] = slot;
+}
+
+__global__ void set_u32_kernel(uint32_t* dst, uint32_t v) { *dst = v; }
+
+__global__ void gather_p_kernel(uint32_t n, const uint32_t* order, const double* p, double* out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = p[order[i]];
+}
+
+// keep flags of the stateless correctors / of keep_below, over survivors visited in `order`
+__global__ void flag_below_kernel(uint32_t n, const uint32_t* order, const double* p, double cut, uint32_t* flags)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = p[order[i]] < cut ? 1u : 0u;
+}
+
+// stable compaction given exclusive-scanned flags; also counts kept controls / cases
+__global__ void compact_kernel(uint32_t n, const uint32_t* order, const uint32_t* flags_scanned,
+                               const double* p, double cut, const int32_t* sign, uint32_t* out_order,
+                               DeviceCounters* cnt)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t slot = order[i];
+  if (p[slot] < cut)
+  {
+    out_order[flags_scanned[i]] = slot;
+    if (sign[slot] == KMD_SIGN_CONTROL) atomicAdd(&cnt->keep_control, 1u); else atomicAdd(&cnt->keep_case, 1u);
+  }
+}
+
+__global__ void count_prefix_kernel(uint32_t n, const uint32_t* order, const int32_t* sign, DeviceCounters* cnt)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (sign[order[i]] == KMD_SIGN_CONTROL) atomicAdd(&cnt->keep_control, 1u); else atomicAdd(&cnt->keep_case, 1u);
+}
+
+__global__ void gather_records_kernel(uint32_t n, const uint32_t* order, SurvivorArrays s, kmd_survivor* out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t slot = order[i];
+  kmd_survivor r;
+  r.kmer[0] = s.kmer0[slot];
+  r.kmer[1] = s.kmer1[slot];
+  r.p_value = s.p[slot];
+  r.sign = s.sign[slot];
+  r.partition = s.part[slot];
+  r.mean_control = s.mc[slot];
+  r.mean_case = s.kk[slot];
+  r.row = s.row[slot];
+  out[i] = r;
+}
+
+__global__ void synth_kernel(synth::Params p, const synth::Tables* t, uint8_t* dst, uint64_t n_rows, uint64_t row_base)
+{
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n_rows;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+    synth::make_row(p, *t, row_base + i, dst + i * p.row_bytes);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+
+template <int B>
+int launch_scan(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, uint64_t row_base, uint32_t partition)
+{
+  ScanParams P = ctx->plan;
+  P.rows = d_rows;
+  P.n_rows = n_rows;
+  P.cand_count = &ctx->d_cnt->cand_count;
+  P.cand = ctx->d_cand;
+  P.cand_cap = static_cast<uint32_t>(ctx->cap);
+  KMD_CUDA(ctx, cudaMemsetAsync(&ctx->d_cnt->cand_count, 0, sizeof(uint32_t), ctx->stream));
+  if (ctx->direct)
+  {
+    P.n_tiles = 0;
+    const uint64_t chunks = (n_rows + P.tile_rows - 1) / P.tile_rows;
+    const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(chunks, static_cast<uint64_t>(ctx->sm_count) * 2));
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
+    lrt_scan_direct_kernel<B><<<grid, kScanThreads, 0, ctx->stream>>>(P, ctx->consumer_warps);
+    cudaEventRecord(ctx->ev_k1, ctx->stream);
+  }
+  else
+  {
+    P.n_tiles = static_cast<uint32_t>(n_rows / P.tile_rows);
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(P.n_tiles, ctx->sm_count));
+    cudaEventRecord(ctx->ev_k0, ctx->stream);
+    lrt_scan_kernel<B><<<grid, kScanThreads, ctx->scan_smem, ctx->stream>>>(P);
+    cudaEventRecord(ctx->ev_k1, ctx->stream);
+  }
+  ctx->scan_timed = true;
+  ctx->launches += 2;
+  KMD_CUDA(ctx, cudaGetLastError());
+
+  ExactArgs A;
+  A.rows = d_rows;
+  A.row_base = row_base;
+  A.partition = partition;
+  A.threshold = ctx->cfg.threshold;
+  A.model = ctx->model;
+  A.geom = P;
+  A.geom.lanes_per_row = 1;
+  A.cand = ctx->d_cand;
+  A.cnt = ctx->d_cnt;
+  A.out = ctx->surv;
+  A.cap = static_cast<uint32_t>(ctx->cap);
+  A.kmer_words = ctx->cfg.kmer_words;
+  lrt_exact_kernel<B><<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(A);
+  KMD_CUDA(ctx, cudaGetLastError());
+  return KMD_OK;
+}
+
+int scan_device_impl(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, uint64_t row_base, uint32_t partition)
+{
+  // the kernels index rows of one launch with 32 bits
+  const uint64_t max_batch = (1ull << 31);
+  uint64_t done = 0;
+  while (done < n_rows)
+  {
+    uint64_t n = std::min(max_batch, n_rows - done);
+    if (n < n_rows - done) n -= n % 16;  // keep the next sub-batch 16-byte aligned for any row size
+    const uint8_t* base = d_rows + done * ctx->plan.row_bytes;
+    int rc;
+    switch (ctx->cfg.count_bytes)
+    {
+      case 1: rc = launch_scan<1>(ctx, base, n, row_base + done, partition); break;
+      case 2: rc = launch_scan<2>(ctx, base, n, row_base + done, partition); break;
+      default: rc = launch_scan<4>(ctx, base, n, row_base + done, partition); break;
+    }
+    if (rc) return rc;
+    done += n;
+  }
+  ctx->rows_tested += n_rows;
+  ctx->order_state = 0;
+  ctx->final_valid = false;
+  return KMD_OK;
+}
+
+int ensure_stage(kmd_context* ctx)
+{
+  if (ctx->d_stage[0]) return KMD_OK;
+  size_t want = static_cast<size_t>(env_u32("KMD_STAGE_MB", 64)) << 20;
+  const size_t unit = static_cast<size_t>(ctx->plan.row_bytes) * 16;
+  want = std::max(unit, want / unit * unit);
+  for (int b = 0; b < 2; b++)
+  {
+    KMD_CUDA(ctx, cudaMalloc(&ctx->d_stage[b], want));
+    KMD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy[b], cudaEventDisableTiming));
+    KMD_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_scan[b], cudaEventDisableTiming));
+  }
+  ctx->stage_bytes = want;
+  return KMD_OK;
+}
+
+int fetch_counters(kmd_context* ctx)
+{
+  KMD_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, ctx->stream));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_cnt->overflow)
+    return fail(ctx, KMD_ERR_OVERFLOW, "%s buffer overflow: raise kmd_config.max_survivors (now %llu)",
+                (ctx->h_cnt->overflow & 1) ? "candidate" : "survivor", static_cast<unsigned long long>(ctx->cap));
+  return KMD_OK;
+}
+
+// stable radix sort of (key, slot) pairs currently in d_keys[0]/d_vals[0]; result back in [0]
+int radix_sort(kmd_context* ctx, uint32_t n)
+{
+  if (n < 2) return KMD_OK;
+  const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
+  const size_t need = static_cast<size_t>(n_tiles) * 256;
+  if (need > ctx->hist_entries)
+  {
+    if (ctx->d_hist) cudaFree(ctx->d_hist);
+    ctx->d_hist = nullptr;
+    KMD_CUDA(ctx, cudaMalloc(&ctx->d_hist, need * sizeof(uint32_t)));
+    ctx->hist_entries = need;
+  }
+  const uint32_t blocks = (n_tiles + kSortWarps - 1) / kSortWarps;
+  int cur = 0;
+  for (int pass = 0; pass < 8; pass++)
+  {
+    const int shift = 8 * pass;
+    sort_hist_kernel<<<blocks, kSortWarps * 32, 0, ctx->stream>>>(ctx->d_keys[cur], n, shift, n_tiles, ctx->d_hist);
+    scan_exclusive_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, static_cast<uint32_t>(need), nullptr);
+    sort_scatter_kernel<<<blocks, kSortWarps * 32, 0, ctx->stream>>>(ctx->d_keys[cur], ctx->d_vals[cur], ctx->d_keys[cur ^ 1],
+                                                                      ctx->d_vals[cur ^ 1], n, shift, n_tiles, ctx->d_hist);
+    ctx->launches += 3;
+    cur ^= 1;
+  }
+  KMD_CUDA(ctx, cudaGetLastError());
+  // 8 passes: the result is back in buffer 0
+  return KMD_OK;
+}
+
+inline uint32_t blocks_for(uint32_t n) { return std::max<uint32_t>(1, (n + 255) / 256); }
+
+// order survivors by row (state 1) or by (p, row) (state 2); the order ends up in d_vals[0]
+int ensure_order(kmd_context* ctx, int want)
+{
+  int rc = fetch_counters(ctx);
+  if (rc) return rc;
+  const uint32_t n = ctx->h_cnt->surv_count;
+  if (ctx->order_state == want || n == 0) { ctx->order_state = want; return KMD_OK; }
+  if (ctx->order_state == 0)
+  {
+    iota_keys_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->surv.row, ctx->surv.p, 0, nullptr, ctx->d_keys[0], ctx->d_vals[0]);
+    ctx->launches++;
+    if ((rc = radix_sort(ctx, n))) return rc;
+    ctx->order_state = 1;
+  }
+  if (want == 2 && ctx->order_state == 1)
+  {
+    // stable sort by p of the row-ordered slots: ties in p keep row order
+    KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_vals[1], ctx->d_vals[0], n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    iota_keys_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->surv.row, ctx->surv.p, 1, ctx->d_vals[1], ctx->d_keys[0], ctx->d_vals[0]);
+    ctx->launches++;
+    if ((rc = radix_sort(ctx, n))) return rc;
+    ctx->order_state = 2;
+  }
+  else if (want == 1 && ctx->order_state == 2)
+  {
+    iota_keys_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->surv.row, ctx->surv.p, 0, nullptr, ctx->d_keys[0], ctx->d_vals[0]);
+    ctx->launches++;
+    if ((rc = radix_sort(ctx, n))) return rc;
+    ctx->order_state = 1;
+  }
+  KMD_CUDA(ctx, cudaGetLastError());
+  return KMD_OK;
+}
+
+int ensure_out(kmd_context* ctx, uint64_t n)
+{
+  if (n <= ctx->out_cap) return KMD_OK;
+  if (ctx->d_out) cudaFree(ctx->d_out);
+  ctx->d_out = nullptr;
+  ctx->out_cap = 0;
+  KMD_CUDA(ctx, cudaMalloc(&ctx->d_out, n * sizeof(kmd_survivor)));
+  ctx->out_cap = n;
+  return KMD_OK;
+}
+
+int download_records(kmd_context* ctx, const uint32_t* d_order, uint32_t n, kmd_survivor* out, uint64_t cap, uint64_t* n_out)
+{
+  if (n_out) *n_out = n;
+  if (n == 0 || !out) return KMD_OK;
+  if (cap < n) return fail(ctx, KMD_ERR_ARG, "output capacity %llu < %u records", static_cast<unsigned long long>(cap), n);
+  int rc = ensure_out(ctx, n);
+  if (rc) return rc;
+  gather_records_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, d_order, ctx->surv, ctx->d_out);
+  ctx->launches++;
+  KMD_CUDA(ctx, cudaGetLastError());
+  KMD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n * sizeof(kmd_survivor), cudaMemcpyDeviceToHost, ctx->stream));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KMD_OK;
+}
+
+// keep survivors (visited in the current order) with p < cut; stable
+int keep_below_impl(kmd_context* ctx, double cut, uint64_t* n_control, uint64_t* n_case)
+{
+  const uint32_t n = ctx->h_cnt->surv_count;
+  KMD_CUDA(ctx, cudaMemsetAsync(&ctx->d_cnt->keep_control, 0, 3 * sizeof(uint32_t), ctx->stream));
+  if (n)
+  {
+    uint32_t* flags = ctx->d_vals[1];
+    flag_below_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->d_vals[0], ctx->surv.p, cut, flags);
+    scan_exclusive_kernel<<<1, 1024, 0, ctx->stream>>>(flags, n, &ctx->d_cnt->keep_total);
+    compact_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->d_vals[0], flags, ctx->surv.p, cut, ctx->surv.sign, ctx->d_order, ctx->d_cnt);
+    ctx->launches += 3;
+    KMD_CUDA(ctx, cudaGetLastError());
+  }
+  int rc = fetch_counters(ctx);
+  if (rc) return rc;
+  ctx->n_final = n ? ctx->h_cnt->keep_total : 0;
+  ctx->final_valid = true;
+  if (n_control) *n_control = ctx->h_cnt->keep_control;
+  if (n_case) *n_case = ctx->h_cnt->keep_case;
+  return KMD_OK;
+}
+
+synth::Tables* build_synth_tables()
+{
+  static synth::Tables t;
+  static bool done = false;
+  if (!done)
+  {
+    for (int c = 0; c < synth::kClasses; c++)
+    {
+      const double lam = synth::kLambda[c];
+      double pmf = std::exp(-lam), cdf = 0;
+      for (int i = 0; i < synth::kCdfLen; i++)
+      {
+        cdf += pmf;
+        double v = std::floor(cdf * 4294967296.0);
+        t.cdf[c][i] = v >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(v);
+        pmf = pmf * lam / (i + 1);
+      }
+      t.cdf[c][synth::kCdfLen - 1] = 0xFFFFFFFFu;
+    }
+    done = true;
+  }
+  return &t;
+}
+
+int synth_params(const kmd_synth* s, synth::Params* p)
+{
+  if (!s || !s->nb_controls || !s->nb_cases || (s->kmer_words != 1 && s->kmer_words != 2) ||
+      (s->count_bytes != 1 && s->count_bytes != 2 && s->count_bytes != 4) || !s->total_rows)
+    return KMD_ERR_ARG;
+  p->seed = s->seed;
+  p->nb_controls = s->nb_controls;
+  p->nb_cases = s->nb_cases;
+  p->kmer_words = s->kmer_words;
+  p->count_bytes = s->count_bytes;
+  p->enriched_ppm = s->enriched_ppm;
+  p->row_bytes = 8 * s->kmer_words + (s->nb_controls + s->nb_cases) * s->count_bytes;
+  int bits = 2 * static_cast<int>(s->kmer_size) - (s->kmer_words == 2 ? 64 : 0);
+  bits = std::max(1, std::min(bits, 62));
+  p->kmer_stride = std::max<uint64_t>(1, (1ull << bits) / s->total_rows);
+  return KMD_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+
+extern "C" {
+
+int kmd_abi_version(void) { return KMD_ABI_VERSION; }
+
+int kmd_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* kmd_last_error(const kmd_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void kmd_destroy(kmd_context* ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+  cudaFree(ctx->d_lf);
+  cudaFree(ctx->d_cnt);
+  if (ctx->h_cnt) cudaFreeHost(ctx->h_cnt);
+  cudaFree(ctx->d_cand);
+  cudaFree(ctx->surv.kmer0); cudaFree(ctx->surv.kmer1); cudaFree(ctx->surv.p); cudaFree(ctx->surv.sign);
+  cudaFree(ctx->surv.part); cudaFree(ctx->surv.mc); cudaFree(ctx->surv.kk); cudaFree(ctx->surv.row);
+  for (int b = 0; b < 2; b++)
+  {
+    cudaFree(ctx->d_keys[b]); cudaFree(ctx->d_vals[b]); cudaFree(ctx->d_stage[b]);
+    if (ctx->ev_copy[b]) cudaEventDestroy(ctx->ev_copy[b]);
+    if (ctx->ev_scan[b]) cudaEventDestroy(ctx->ev_scan[b]);
+  }
+  cudaFree(ctx->d_hist); cudaFree(ctx->d_p_sorted); cudaFree(ctx->d_out); cudaFree(ctx->d_order);
+  if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+  if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+int kmd_create(const kmd_config* cfg, kmd_context** out)
+{
+  if (!cfg || !out) return fail(nullptr, KMD_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != KMD_ABI_VERSION) return fail(nullptr, KMD_ERR_ARG, "ABI version %u != %u", cfg->abi_version, KMD_ABI_VERSION);
+  if (!cfg->nb_controls || !cfg->nb_cases) return fail(nullptr, KMD_ERR_ARG, "nb_controls and nb_cases must be > 0");
+  if (cfg->kmer_words != 1 && cfg->kmer_words != 2) return fail(nullptr, KMD_ERR_ARG, "kmer_words must be 1 or 2 (k <= 64)");
+  if (cfg->count_bytes != 1 && cfg->count_bytes != 2 && cfg->count_bytes != 4) return fail(nullptr, KMD_ERR_ARG, "count_bytes must be 1, 2 or 4");
+  if (static_cast<uint64_t>(cfg->nb_controls) + cfg->nb_cases > 65536) return fail(nullptr, KMD_ERR_ARG, "more than 65536 samples");
+
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+  {
+    cudaGetLastError();
+    return fail(nullptr, KMD_ERR_NO_DEVICE, "no CUDA device visible: kmdiff_b200 has no CPU fallback");
+  }
+  if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, KMD_ERR_ARG, "device %d out of range (0..%d)", cfg->device, n_dev - 1);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, KMD_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major < 10)
+    return fail(nullptr, KMD_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+
+  kmd_context* ctx = new (std::nothrow) kmd_context;
+  if (!ctx) return fail(nullptr, KMD_ERR_NOMEM, "out of host memory");
+  ctx->cfg = *cfg;
+  ctx->device = cfg->device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cap = cfg->max_survivors ? cfg->max_survivors : (1ull << 22);
+  if (ctx->cap >= (1ull << 31)) { delete ctx; return fail(nullptr, KMD_ERR_ARG, "max_survivors must be < 2^31"); }
+
+  auto bail = [&](int rc) { g_create_error = ctx->err; kmd_destroy(ctx); return rc; };
+#define KMD_TRY(expr) do { int rc_ = (expr); if (rc_) return bail(rc_); } while (0)
+#define KMD_CUDA_C(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    fail(ctx, e_ == cudaErrorMemoryAllocation ? KMD_ERR_NOMEM : KMD_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    return bail(e_ == cudaErrorMemoryAllocation ? KMD_ERR_NOMEM : KMD_ERR_CUDA); } } while (0)
+
+  KMD_CUDA_C(cudaSetDevice(ctx->device));
+  KMD_CUDA_C(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  KMD_CUDA_C(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  KMD_CUDA_C(cudaEventCreate(&ctx->ev_k0));
+  KMD_CUDA_C(cudaEventCreate(&ctx->ev_k1));
+
+  // model constants + log-factorial table
+  std::vector<double> table;
+  const double* lf_host = cfg->lf_table;
+  if (!lf_host && cfg->lf_size)
+  {
+    table.resize(cfg->lf_size);
+    lf_table_fill(table.data(), cfg->lf_size);
+    lf_host = table.data();
+  }
+  if (cfg->lf_size)
+  {
+    KMD_CUDA_C(cudaMalloc(&ctx->d_lf, cfg->lf_size * sizeof(double)));
+    KMD_CUDA_C(cudaMemcpy(ctx->d_lf, lf_host, cfg->lf_size * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  ctx->model.sum_controls = static_cast<double>(cfg->sum_controls);
+  ctx->model.sum_cases = static_cast<double>(cfg->sum_cases);
+  ctx->model.sum_all = static_cast<double>(cfg->sum_controls + cfg->sum_cases);
+  ctx->model.lgam_half = kmd::lngamma_small(0.5);
+  ctx->model.lf = ctx->d_lf;
+  ctx->model.lf_size = cfg->lf_size;
+  ctx->lr_cut = lr_cut_for(cfg->threshold);
+
+  KMD_TRY(make_plan(ctx));
+  if (!ctx->direct)
+  {
+    KMD_CUDA_C(cudaFuncSetAttribute(lrt_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->scan_smem)));
+    KMD_CUDA_C(cudaFuncSetAttribute(lrt_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->scan_smem)));
+    KMD_CUDA_C(cudaFuncSetAttribute(lrt_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->scan_smem)));
+  }
+  const int lf_smem_bytes = static_cast<int>(std::min<uint64_t>(cfg->lf_size, 12288) * sizeof(double));
+  KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
+  KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
+  KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
+
+  // buffers
+  const size_t cap = ctx->cap;
+  KMD_CUDA_C(cudaMalloc(&ctx->d_cnt, sizeof(DeviceCounters)));
+  KMD_CUDA_C(cudaMemset(ctx->d_cnt, 0, sizeof(DeviceCounters)));
+  KMD_CUDA_C(cudaMallocHost(&ctx->h_cnt, sizeof(DeviceCounters)));
+  memset(ctx->h_cnt, 0, sizeof(DeviceCounters));
+  KMD_CUDA_C(cudaMalloc(&ctx->d_cand, cap * sizeof(uint32_t)));
+  KMD_CUDA_C(cudaMalloc(&ctx->surv.kmer0, cap * 8));
+  KMD_CUDA_C(cudaMalloc(&ctx->surv.kmer1, cap * 8));
+  KMD_CUDA_C(cudaMalloc(&ctx->surv.p, cap * 8));
+  KMD_CUDA_C(cudaMalloc(&ctx->surv.sign, cap * 4));
+  KMD_CUDA_C(cudaMalloc(&ctx->surv.part, cap * 4));
+  KMD_CUDA_C(cudaMalloc(&ctx->surv.mc, cap * 8));
+  KMD_CUDA_C(cudaMalloc(&ctx->surv.kk, cap * 8));
+  KMD_CUDA_C(cudaMalloc(&ctx->surv.row, cap * 8));
+  for (int b = 0; b < 2; b++)
+  {
+    KMD_CUDA_C(cudaMalloc(&ctx->d_keys[b], cap * 8));
+    KMD_CUDA_C(cudaMalloc(&ctx->d_vals[b], cap * 4));
+  }
+  KMD_CUDA_C(cudaMalloc(&ctx->d_p_sorted, cap * 8));
+  KMD_CUDA_C(cudaMalloc(&ctx->d_order, cap * 4));
+#undef KMD_TRY
+#undef KMD_CUDA_C
+  *out = ctx;
+  return KMD_OK;
+}
+
+int kmd_set_stream(kmd_context* ctx, void* cuda_stream)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return KMD_OK;
+}
+
+int kmd_sync(kmd_context* ctx)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KMD_OK;
+}
+
+int kmd_reset(kmd_context* ctx)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  KMD_CUDA(ctx, cudaMemsetAsync(ctx->d_cnt, 0, sizeof(DeviceCounters), ctx->stream));
+  ctx->rows_tested = 0;
+  ctx->order_state = 0;
+  ctx->final_valid = false;
+  ctx->n_final = 0;
+  return KMD_OK;
+}
+
+int kmd_scan_device(kmd_context* ctx, const void* d_rows, uint64_t n_rows, uint64_t row_base, uint32_t partition)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (n_rows == 0) return KMD_OK;
+  if (!d_rows) return fail(ctx, KMD_ERR_ARG, "null row pointer");
+  if (reinterpret_cast<uintptr_t>(d_rows) & 15u) return fail(ctx, KMD_ERR_ARG, "d_rows must be 16-byte aligned");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return scan_device_impl(ctx, static_cast<const uint8_t*>(d_rows), n_rows, row_base, partition);
+}
+
+int kmd_scan_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_t row_base, uint32_t partition)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (n_rows == 0) return KMD_OK;
+  if (!h_rows) return fail(ctx, KMD_ERR_ARG, "null row pointer");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx);
+  if (rc) return rc;
+  const uint64_t R = ctx->plan.row_bytes;
+  const uint64_t chunk_rows = ctx->stage_bytes / R;
+  const uint8_t* src = static_cast<const uint8_t*>(h_rows);
+  uint64_t done = 0;
+  for (uint64_t c = 0; done < n_rows; c++)
+  {
+    const int b = static_cast<int>(c & 1);
+    const uint64_t n = std::min(chunk_rows, n_rows - done);
+    if (c >= 2) KMD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_scan[b], 0));
+    KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage[b], src + done * R, n * R, cudaMemcpyHostToDevice, ctx->copy_stream));
+    KMD_CUDA(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
+    KMD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
+    if ((rc = scan_device_impl(ctx, ctx->d_stage[b], n, row_base + done, partition))) return rc;
+    KMD_CUDA(ctx, cudaEventRecord(ctx->ev_scan[b], ctx->stream));
+    done += n;
+  }
+  // the caller may reuse h_rows as soon as we return
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  return KMD_OK;
+}
+
+int kmd_counters_get(kmd_context* ctx, kmd_counters* out)
+{
+  if (!ctx || !out) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = fetch_counters(ctx);
+  out->rows = ctx->rows_tested;
+  out->candidates = ctx->h_cnt->cand_total;
+  out->survivors = ctx->h_cnt->surv_count;
+  out->n_control = ctx->h_cnt->n_control;
+  out->n_case = ctx->h_cnt->n_case;
+  return rc;
+}
+
+uint64_t kmd_launch_count(const kmd_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int kmd_scan_kernel_ms(kmd_context* ctx, float* ms)
+{
+  if (!ctx || !ms) return KMD_ERR_ARG;
+  if (!ctx->scan_timed) return fail(ctx, KMD_ERR_STATE, "no scan has been launched yet");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  KMD_CUDA(ctx, cudaEventSynchronize(ctx->ev_k1));
+  KMD_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_k0, ctx->ev_k1));
+  return KMD_OK;
+}
+
+int kmd_survivors(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_order(ctx, 1);
+  if (rc) return rc;
+  return download_records(ctx, ctx->d_vals[0], ctx->h_cnt->surv_count, out, cap, n);
+}
+
+static int model_rows_launch(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, double* p, int32_t* sign, double* mc, double* kk)
+{
+  ScanParams G = ctx->plan;
+  G.lanes_per_row = 1;
+  const uint32_t lf_smem = static_cast<uint32_t>(std::min<uint64_t>(ctx->cfg.lf_size, 12288));
+  const size_t smem = lf_smem * sizeof(double);
+  const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>((n_rows + 255) / 256, static_cast<uint64_t>(ctx->sm_count) * 8));
+  switch (ctx->cfg.count_bytes)
+  {
+    case 1: lrt_model_rows_kernel<1><<<grid, 256, smem, ctx->stream>>>(d_rows, n_rows, G, ctx->model, lf_smem, p, sign, mc, kk); break;
+    case 2: lrt_model_rows_kernel<2><<<grid, 256, smem, ctx->stream>>>(d_rows, n_rows, G, ctx->model, lf_smem, p, sign, mc, kk); break;
+    default: lrt_model_rows_kernel<4><<<grid, 256, smem, ctx->stream>>>(d_rows, n_rows, G, ctx->model, lf_smem, p, sign, mc, kk); break;
+  }
+  ctx->launches++;
+  KMD_CUDA(ctx, cudaGetLastError());
+  return KMD_OK;
+}
+
+int kmd_model_rows_device(kmd_context* ctx, const void* d_rows, uint64_t n_rows, double* d_p, int32_t* d_sign,
+                          double* d_mean_control, double* d_mean_case)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (n_rows == 0) return KMD_OK;
+  if (!d_rows || !d_p || !d_sign || !d_mean_control || !d_mean_case) return fail(ctx, KMD_ERR_ARG, "null pointer");
+  if (reinterpret_cast<uintptr_t>(d_rows) & 15u) return fail(ctx, KMD_ERR_ARG, "d_rows must be 16-byte aligned");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return model_rows_launch(ctx, static_cast<const uint8_t*>(d_rows), n_rows, d_p, d_sign, d_mean_control, d_mean_case);
+}
+
+int kmd_model_rows_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, double* p, int32_t* sign,
+                        double* mean_control, double* mean_case)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (n_rows == 0) return KMD_OK;
+  if (!h_rows || !p || !sign || !mean_control || !mean_case) return fail(ctx, KMD_ERR_ARG, "null pointer");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_stage(ctx);
+  if (rc) return rc;
+  const uint64_t R = ctx->plan.row_bytes;
+  // chunk so that rows + 28 bytes of results per row fit one staging buffer
+  const uint64_t chunk_rows = std::max<uint64_t>(1, ctx->stage_bytes / (R + 32));
+  double *d_p = nullptr, *d_mc = nullptr, *d_kk = nullptr;
+  int32_t* d_sign = nullptr;
+  KMD_CUDA(ctx, cudaMalloc(&d_p, chunk_rows * 8));
+  KMD_CUDA(ctx, cudaMalloc(&d_mc, chunk_rows * 8));
+  KMD_CUDA(ctx, cudaMalloc(&d_kk, chunk_rows * 8));
+  KMD_CUDA(ctx, cudaMalloc(&d_sign, chunk_rows * 4));
+  const uint8_t* src = static_cast<const uint8_t*>(h_rows);
+  for (uint64_t done = 0; done < n_rows && rc == KMD_OK; done += chunk_rows)
+  {
+    const uint64_t n = std::min(chunk_rows, n_rows - done);
+    cudaError_t e = cudaMemcpyAsync(ctx->d_stage[0], src + done * R, n * R, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = model_rows_launch(ctx, ctx->d_stage[0], n, d_p, d_sign, d_mc, d_kk);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p + done, d_p, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mean_control + done, d_mc, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(mean_case + done, d_kk, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sign + done, d_sign, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, KMD_ERR_CUDA, "model_rows_host: %s", cudaGetErrorString(e));
+  }
+  cudaFree(d_p); cudaFree(d_mc); cudaFree(d_kk); cudaFree(d_sign);
+  return rc;
+}
+
+int kmd_correct(kmd_context* ctx, int correction, double significance, uint64_t total_rows, uint64_t* n_control, uint64_t* n_case)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (correction < KMD_CORR_NOTHING || correction > KMD_CORR_HOLM) return fail(ctx, KMD_ERR_ARG, "unknown correction %d", correction);
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const bool sorted = correction == KMD_CORR_BENJAMINI || correction == KMD_CORR_HOLM;
+  int rc = ensure_order(ctx, sorted ? 2 : 1);
+  if (rc) return rc;
+  const uint32_t n = ctx->h_cnt->surv_count;
+  if (!sorted)
+  {
+    double cut;
+    switch (correction)
+    {
+      case KMD_CORR_BONFERRONI: cut = significance / static_cast<double>(total_rows); break;                    // corrector.cpp:11
+      case KMD_CORR_SIDAK: cut = 1 - std::pow(1 - significance, 1.0 / static_cast<double>(total_rows)); break;   // corrector.cpp:52
+      default: cut = significance; break;                                                                        // corrector.cpp:88
+    }
+    return keep_below_impl(ctx, cut, n_control, n_case);
+  }
+  // BENJAMINI / HOLM: ascending walk, stop at the first rejection (aggregator.hpp:282-310)
+  KMD_CUDA(ctx, cudaMemsetAsync(&ctx->d_cnt->keep_control, 0, 3 * sizeof(uint32_t), ctx->stream));
+  uint32_t n_keep = 0;
+  if (n)
+  {
+    gather_p_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->d_vals[0], ctx->surv.p, ctx->d_p_sorted);
+    set_u32_kernel<<<1, 1, 0, ctx->stream>>>(&ctx->d_cnt->first_reject, n);
+    first_reject_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(ctx->d_p_sorted, n, correction == KMD_CORR_HOLM, significance,
+                                                                total_rows, &ctx->d_cnt->first_reject);
+    KMD_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    if ((rc = fetch_counters(ctx))) return rc;
+    n_keep = ctx->h_cnt->first_reject;
+    if (n_keep)
+    {
+      KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, ctx->d_vals[0], n_keep * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+      count_prefix_kernel<<<blocks_for(n_keep), 256, 0, ctx->stream>>>(n_keep, ctx->d_order, ctx->surv.sign, ctx->d_cnt);
+      ctx->launches++;
+      KMD_CUDA(ctx, cudaGetLastError());
+    }
+  }
+  if ((rc = fetch_counters(ctx))) return rc;
+  ctx->n_final = n_keep;
+  ctx->final_valid = true;
+  if (n_control) *n_control = ctx->h_cnt->keep_control;
+  if (n_case) *n_case = ctx->h_cnt->keep_case;
+  return KMD_OK;
+}
+
+int kmd_significant(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (!ctx->final_valid) return fail(ctx, KMD_ERR_STATE, "kmd_significant called before kmd_correct / kmd_keep_below");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return download_records(ctx, ctx->d_order, ctx->n_final, out, cap, n);
+}
+
+int kmd_sorted_pvalues(kmd_context* ctx, double* out, uint64_t cap, uint64_t* n)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_order(ctx, 2);
+  if (rc) return rc;
+  const uint32_t cnt = ctx->h_cnt->surv_count;
+  if (n) *n = cnt;
+  if (!cnt || !out) return KMD_OK;
+  if (cap < cnt) return fail(ctx, KMD_ERR_ARG, "output capacity %llu < %u", static_cast<unsigned long long>(cap), cnt);
+  gather_p_kernel<<<blocks_for(cnt), 256, 0, ctx->stream>>>(cnt, ctx->d_vals[0], ctx->surv.p, ctx->d_p_sorted);
+  ctx->launches++;
+  KMD_CUDA(ctx, cudaGetLastError());
+  KMD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_p_sorted, cnt * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KMD_OK;
+}
+
+int kmd_keep_below(kmd_context* ctx, double p_cut, uint64_t* n_control, uint64_t* n_case)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_order(ctx, 2);
+  if (rc) return rc;
+  return keep_below_impl(ctx, p_cut, n_control, n_case);
+}
+
+int kmd_corrector_apply(int correction, double significance, uint64_t total_rows, uint64_t rank, double p)
+{
+  switch (correction)
+  {
+    case KMD_CORR_BONFERRONI: return p < (significance / static_cast<double>(total_rows));
+    case KMD_CORR_BENJAMINI: return p < ((static_cast<double>(rank) / static_cast<double>(total_rows)) * significance);
+    case KMD_CORR_SIDAK: return p < (1 - std::pow(1 - significance, 1.0 / static_cast<double>(total_rows)));
+    case KMD_CORR_HOLM: return p < (significance / static_cast<double>(total_rows - rank));
+    default: return p < significance;
+  }
+}
+
+uint64_t kmd_first_reject(const double* p_sorted, uint64_t n, int correction, double significance, uint64_t total_rows, double* p_cut)
+{
+  uint64_t i = 0;
+  for (; i < n; i++)
+  {
+    const uint64_t rank = correction == KMD_CORR_BENJAMINI ? i + 1 : i;
+    if (!kmd_corrector_apply(correction, significance, total_rows, rank, p_sorted[i])) break;
+  }
+  if (p_cut) *p_cut = i < n ? p_sorted[i] : std::numeric_limits<double>::infinity();
+  return i;
+}
+
+void kmd_lf_table_fill(double* table, uint64_t size) { lf_table_fill(table, size); }
+
+double kmd_chisqc(double v, double x)
+{
+  // only v == 1 (a = 0.5) is on the path; other v are outside this library's scope
+  if (v != 1.0) return std::numeric_limits<double>::quiet_NaN();
+  return host_igamc_half(x / 2.0);
+}
+
+void kmd_kmer_to_string(const uint64_t* words, uint32_t kmer_words, uint32_t k, char* out)
+{
+  static const char alphabet[4] = {'A', 'C', 'T', 'G'};
+  for (uint32_t i = 0; i < k; i++)
+  {
+    const uint32_t bit = 2 * (k - 1 - i);
+    const uint32_t w = bit / 64;
+    out[i] = alphabet[w < kmer_words ? (words[w] >> (bit % 64)) & 3u : 0];
+  }
+  out[k] = 0;
+}
+
+// fmt's default ("{}") double formatting: shortest digits that round-trip; fixed notation when the
+// decimal exponent is in [-4, 16), exponent notation otherwise.
+static int format_shortest(double x, char* out, size_t cap)
+{
+  if (std::isnan(x)) return snprintf(out, cap, "nan");
+  if (std::isinf(x)) return snprintf(out, cap, x < 0 ? "-inf" : "inf");
+  if (x == 0) return snprintf(out, cap, std::signbit(x) ? "-0" : "0");
+  char buf[40];
+  int prec = 0;
+  for (; prec < 17; prec++)
+  {
+    snprintf(buf, sizeof buf, "%.*e", prec, x);
+    if (strtod(buf, nullptr) == x) break;
+  }
+  // buf = [-]d[.ddd]e[+-]XX
+  std::string digits;
+  const char* q = buf;
+  bool neg = *q == '-';
+  if (neg) q++;
+  for (; *q && *q != 'e'; q++)
+    if (*q != '.') digits.push_back(*q);
+  const int exp10 = atoi(q + 1);
+  while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+  std::string s = neg ? "-" : "";
+  if (exp10 >= -4 && exp10 < 16)
+  {
+    if (exp10 < 0)
+    {
+      s += "0.";
+      s.append(static_cast<size_t>(-exp10 - 1), '0');
+      s += digits;
+    }
+    else
+    {
+      const size_t int_len = static_cast<size_t>(exp10) + 1;
+      if (digits.size() <= int_len)
+      {
+        s += digits;
+        s.append(int_len - digits.size(), '0');
+      }
+      else
+      {
+        s += digits.substr(0, int_len);
+        s += ".";
+        s += digits.substr(int_len);
+      }
+    }
+  }
+  else
+  {
+    s += digits.substr(0, 1);
+    if (digits.size() > 1) { s += "."; s += digits.substr(1); }
+    char e[16];
+    snprintf(e, sizeof e, "e%c%02d", exp10 < 0 ? '-' : '+', std::abs(exp10));
+    s += e;
+  }
+  return snprintf(out, cap, "%s", s.c_str());
+}
+
+size_t kmd_format_fasta(uint64_t index, const kmd_survivor* s, uint32_t kmer_words, uint32_t k, char* out, size_t cap)
+{
+  char mean_case[48];
+  format_shortest(s->mean_case, mean_case, sizeof mean_case);
+  const double mc = s->mean_control;
+  const unsigned long long mc_int = !(mc >= 0) ? 0ull : (mc >= 18446744073709551615.0 ? ~0ull : static_cast<unsigned long long>(mc));
+  char head[192];
+  const int hl = snprintf(head, sizeof head, ">%llu_pval=%g_control=%llu_case=%s\n", static_cast<unsigned long long>(index),
+                          s->p_value, mc_int, mean_case);
+  std::vector<char> seq(k + 1);
+  kmd_kmer_to_string(s->kmer, kmer_words, k, seq.data());
+  const size_t lines = (k + 59) / 60;
+  const size_t need = static_cast<size_t>(hl) + k + lines;
+  if (need + 1 > cap || !out) return need;
+  char* w = out;
+  memcpy(w, head, hl); w += hl;
+  for (uint32_t i = 0; i < k; i += 60)
+  {
+    const uint32_t n = std::min<uint32_t>(60, k - i);
+    memcpy(w, seq.data() + i, n); w += n;
+    *w++ = '\n';
+  }
+  *w = 0;
+  return need;
+}
+
+void* kmd_host_alloc(size_t bytes)
+{
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void kmd_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+void kmd_synth_totals(const kmd_synth* s, uint64_t* totals)
+{
+  const uint32_t n = s->nb_controls + s->nb_cases;
+  // every sample is drawn from the same abundance classes, so the declared per-sample totals are
+  // equal up to +-1 % (a sequencing-depth jitter), seeded like the rows
+  for (uint32_t j = 0; j < n; j++)
+    totals[j] = 990000000ull + synth::mix64(s->seed * 0x9E3779B97F4A7C15ull + j) % 20000001ull;
+}
+
+int kmd_synth_fill_host(const kmd_synth* s, void* h_rows, uint64_t n_rows, uint64_t row_base, int threads)
+{
+  synth::Params p;
+  if (synth_params(s, &p) || !h_rows) return KMD_ERR_ARG;
+  const synth::Tables* t = build_synth_tables();
+  uint8_t* dst = static_cast<uint8_t*>(h_rows);
+  auto work = [&](uint64_t lo, uint64_t hi) {
+    for (uint64_t i = lo; i < hi; i++) synth::make_row(p, *t, row_base + i, dst + i * p.row_bytes);
+  };
+  if (threads <= 1 || n_rows < 4096) { work(0, n_rows); return KMD_OK; }
+  std::vector<std::thread> pool;
+  const uint64_t chunk = (n_rows + threads - 1) / threads;
+  for (int i = 0; i < threads; i++)
+  {
+    const uint64_t lo = std::min(n_rows, i * chunk), hi = std::min(n_rows, lo + chunk);
+    pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
+  return KMD_OK;
+}
+
+int kmd_synth_fill_device(const kmd_synth* s, int device, void* d_rows, uint64_t n_rows, uint64_t row_base, void* cuda_stream)
+{
+  synth::Params p;
+  if (synth_params(s, &p) || !d_rows) return KMD_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return KMD_ERR_CUDA;
+  static synth::Tables* d_tables[64] = {nullptr};
+  if (device < 0 || device >= 64) return KMD_ERR_ARG;
+  if (!d_tables[device])
+  {
+    if (cudaMalloc(&d_tables[device], sizeof(synth::Tables)) != cudaSuccess) return KMD_ERR_NOMEM;
+    if (cudaMemcpy(d_tables[device], build_synth_tables(), sizeof(synth::Tables), cudaMemcpyHostToDevice) != cudaSuccess) return KMD_ERR_CUDA;
+  }
+  if (n_rows == 0) return KMD_OK;
+  const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>((n_rows + 127) / 128, 148 * 16));
+  synth_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(p, d_tables[device], static_cast<uint8_t*>(d_rows), n_rows, row_base);
+  return cudaGetLastError() == cudaSuccess ? KMD_OK : KMD_ERR_CUDA;
+}
+
+}  // extern "C"

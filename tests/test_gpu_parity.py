@@ -1,0 +1,329 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the oracle on the same
+seeded inputs.  Integer/byte/index results (rows, k-mers, signs, counts, sums) must be bit-exact;
+p-values and the two "means" are fp64 and must agree within 1e-9 relative (BASELINE.json
+north_star), in practice ~1e-13 (CUDA vs glibc log/exp).
+"""
+import numpy as np
+import pytest
+
+import kmdiff_b200 as K
+import oracle
+from conftest import SHAPES, make_cohort, rel_err
+
+pytestmark = pytest.mark.gpu
+
+P_RTOL = 1e-9   # stated tolerance on fp64 p-values (north_star)
+THR = 0.05 / 100000
+
+
+def ctx_for(spec, totals, thr=THR, **kw):
+    nc, nk = spec.nb_controls, spec.nb_cases
+    return K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), kmer_size=spec.kmer_size,
+                         count_bytes=spec.count_bytes, threshold=thr, **kw)
+
+
+def oracle_for(spec, totals):
+    return oracle.Model(spec.nb_controls, spec.nb_cases, totals)
+
+
+def check_survivors(got, want):
+    assert len(got) == len(want)
+    assert np.array_equal(got["row"], want["row"])
+    assert np.array_equal(got["kmer"], want["kmer"])
+    assert np.array_equal(got["sign"], want["sign"])
+    assert np.array_equal(got["mean_case"], want["mean_case"])
+    assert np.array_equal(got["mean_control"], want["mean_control"])
+    if len(want):
+        nz = want["p"] > 0
+        assert np.array_equal(got["p_value"][~nz], want["p"][~nz])
+        assert rel_err(got["p_value"][nz], want["p"][nz]).max() <= P_RTOL
+
+
+@pytest.mark.parametrize("shape", list(SHAPES))
+def test_scan_matches_oracle(shape):
+    # sizes chosen so the ring sees several full tiles per CTA *and* a ragged tail
+    n = 300_007 if SHAPES[shape][0] + SHAPES[shape][1] < 100 else 60_013
+    spec, rows, totals = make_cohort(shape, n, seed=11)
+    m = oracle_for(spec, totals)
+    want, w_ctl, w_case = m.diff(rows, spec.kmer_words, spec.count_bytes, THR)
+    with ctx_for(spec, totals) as ctx:
+        ctx.scan_host(rows)
+        c = ctx.counters()
+        got = ctx.survivors()
+    assert c.rows == n
+    assert (c.survivors, c.n_control, c.n_case) == (len(want), w_ctl, w_case)
+    assert len(want) > 0
+    check_survivors(got, want)
+
+
+@pytest.mark.parametrize("shape", ["c2", "c5", "b1", "odd", "straddle", "tiny"])
+def test_model_rows_every_row(shape):
+    """IModel::process on every row (no screen): p, sign, means."""
+    spec, rows, totals = make_cohort(shape, 20_000, seed=5)
+    p, sign, mc, kk = oracle_for(spec, totals).rows(rows, spec.kmer_words, spec.count_bytes)
+    with ctx_for(spec, totals) as ctx:
+        gp, gsign, gmc, gkk = ctx.model_rows(rows)
+    assert np.array_equal(gsign, sign)
+    assert np.array_equal(gkk, kk)
+    assert np.array_equal(gmc, mc)
+    nz = p > 0
+    assert np.array_equal(gp[~nz], p[~nz])
+    assert rel_err(gp[nz], p[nz]).max() <= P_RTOL
+
+
+def test_poisson_likelihood_signs():
+    """reference tests/model_test.cpp:45-81 — 30x200 vs 30x100 is CONTROL, swapped CASE, equal NO;
+    plus the two known answers measured on the reference."""
+    ones = [1] * 30
+    m = K.PoissonLikelihood(30, 30, ones, ones, 50)
+    p, s, mc, kk = m.process([200] * 30, [100] * 30)
+    assert s == K.Significance.CONTROL and (mc, kk) == (6000.0, 3000.0)
+    assert abs(p - 1.0932047323640264e-223) / 1.0932047323640264e-223 <= P_RTOL
+    assert m.process([100] * 30, [200] * 30)[1] == K.Significance.CASE
+    assert m.process([100] * 30, [100] * 30)[1] == K.Significance.NO
+    m2 = K.PoissonLikelihood(10, 10, [10**9] * 10, [12 * 10**8] * 10, 10000)
+    p, s, mc, kk = m2.process([5, 3, 0, 7, 2, 4, 6, 1, 0, 3], [30, 25, 41, 0, 33, 28, 19, 45, 22, 37])
+    assert s == K.Significance.CASE and mc == 37.200000000000003 and kk == 280.0
+    assert abs(p - 1.7928739662752438e-42) / 1.7928739662752438e-42 <= P_RTOL
+
+
+def test_empty_and_tiny_inputs():
+    spec, rows, totals = make_cohort("c2", 0)
+    with ctx_for(spec, totals) as ctx:
+        ctx.scan_host(rows, n_rows=0)
+        c = ctx.counters()
+        assert (c.rows, c.survivors) == (0, 0)
+        assert len(ctx.survivors()) == 0
+        assert ctx.correct(K.CorrectionType.BENJAMINI, 0.05, 0) == (0, 0)
+        assert len(ctx.significant()) == 0
+    # fewer rows than one ring tile: everything goes through the tail path
+    for n in (1, 15, 17, 511):
+        spec, rows, totals = make_cohort("c2", n, seed=n, enriched_ppm=300_000)
+        want, *_ = oracle_for(spec, totals).diff(rows, 1, 4, THR)
+        with ctx_for(spec, totals) as ctx:
+            ctx.scan_host(rows)
+            check_survivors(ctx.survivors(), want)
+
+
+def test_batches_accumulate_and_reset():
+    """partitions arrive as separate scan calls; survivors accumulate across them in row order"""
+    spec, rows, totals = make_cohort("c2", 200_000, seed=3)
+    want, w_ctl, w_case = oracle_for(spec, totals).diff(rows, 1, 4, THR)
+    R = spec.row_bytes
+    cuts = [0, 70_001, 70_002, 150_000, 200_000]
+    with ctx_for(spec, totals) as ctx:
+        for part, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])):
+            ctx.scan_host(rows[lo * R:hi * R], row_base=lo, partition=part)
+        got = ctx.survivors()
+        check_survivors(got, want)
+        part_of = np.searchsorted(cuts, got["row"], side="right") - 1
+        assert np.array_equal(got["partition"], part_of)
+        ctx.reset()
+        assert ctx.counters().rows == 0 and len(ctx.survivors()) == 0
+        ctx.scan_host(rows[:1000 * R])
+        assert ctx.counters().rows == 1000
+
+
+def test_device_resident_scan_equals_host_scan():
+    import torch
+    spec, rows, totals = make_cohort("c5", 123_457, seed=9)
+    want, *_ = oracle_for(spec, totals).diff(rows, 2, 2, THR)
+    d = torch.from_numpy(rows).cuda()
+    with ctx_for(spec, totals) as ctx:
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx.scan_device(d.data_ptr(), 123_457)
+        check_survivors(ctx.survivors(), want)
+        assert ctx.scan_kernel_ms() > 0
+        assert ctx.launch_count() >= 2
+
+
+def test_synthetic_rows_identical_on_host_and_device():
+    import torch
+    for shape in ("c2", "c5", "b1", "odd"):
+        nc, nk, k, b = SHAPES[shape]
+        spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=1 << 30, seed=99)
+        n, base = 50_003, 123_456_789
+        host = spec.rows_host(n, base)
+        d = torch.empty(n * spec.row_bytes, dtype=torch.uint8, device="cuda")
+        spec.rows_device(d.data_ptr(), n, base)
+        torch.cuda.synchronize()
+        assert np.array_equal(d.cpu().numpy(), host)
+
+
+@pytest.mark.parametrize("thr", [0.5, 1e-3, 5e-7, 1e-30, 1e-300, 0.0])
+def test_prefilter_threshold_sweep(thr):
+    """the fp32 screen must never drop a row whatever the prefilter threshold is"""
+    spec, rows, totals = make_cohort("c2", 100_000, seed=21, enriched_ppm=20_000)
+    want, *_ = oracle_for(spec, totals).diff(rows, 1, 4, thr)
+    with ctx_for(spec, totals, thr=thr, max_survivors=1 << 18) as ctx:
+        ctx.scan_host(rows)
+        check_survivors(ctx.survivors(), want)
+
+
+def test_threshold_one_keeps_every_row():
+    spec, rows, totals = make_cohort("c2", 5_000, seed=2)
+    want, *_ = oracle_for(spec, totals).diff(rows, 1, 4, 1.0)
+    assert len(want) == 5_000
+    with ctx_for(spec, totals, thr=1.0) as ctx:
+        ctx.scan_host(rows)
+        check_survivors(ctx.survivors(), want)
+
+
+def adversarial_rows(nc, nk, count_bytes, rng, n):
+    """rows built to sit on the decision boundary and at the extremes of the count range"""
+    dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[count_bytes]
+    # cohort sums stay below 2^31: beyond that the reference narrows the sum to `int` (model.hpp:133),
+    # which is undefined behaviour, so there is nothing to be at parity with
+    cmax = min(int(np.iinfo(dt).max), (2**31 - 1) // max(nc, nk))
+    N = nc + nk
+    counts = np.zeros((n, N), dtype=np.uint64)
+    kind = rng.integers(0, 6, size=n)
+    for i in range(n):
+        k = kind[i]
+        if k == 0:      # one cohort all zero
+            counts[i, nc:] = rng.integers(0, 40, size=nk)
+        elif k == 1:
+            counts[i, :nc] = rng.integers(0, 40, size=nc)
+        elif k == 2:    # huge counts
+            counts[i] = rng.integers(cmax // 2, cmax, size=N, endpoint=True)
+        elif k == 3:    # near the boundary: base b vs b+delta with LR around 12..14
+            b = int(rng.integers(1, 2000))
+            counts[i, :nc] = b
+            d = int(np.sqrt(2 * 13.0 * 2 * b * nc / (nc * nk)) * rng.uniform(0.8, 1.2)) + 1
+            counts[i, nc:] = b + d
+        elif k == 4:    # single non-zero
+            counts[i, rng.integers(0, N)] = rng.integers(1, min(cmax, 500))
+        else:           # sparse big
+            j = rng.integers(0, N, size=3)
+            counts[i, j] = rng.integers(1, cmax, size=3, endpoint=True)
+    counts = np.minimum(counts, cmax).astype(dt)
+    counts[counts.sum(axis=1) == 0, 0] = 1
+    kmers = np.arange(1, n + 1, dtype=np.uint64)
+    rows = np.zeros((n, 8 + N * count_bytes), dtype=np.uint8)
+    rows[:, :8] = kmers.view(np.uint8).reshape(n, 8)
+    rows[:, 8:] = counts.view(np.uint8).reshape(n, -1)
+    return rows.ravel()
+
+
+@pytest.mark.parametrize("nc,nk,b", [(10, 10, 4), (3, 17, 2), (8, 8, 1), (100, 100, 4)])
+def test_screen_has_no_false_negatives_on_adversarial_rows(nc, nk, b):
+    rng = np.random.default_rng(1234 + nc + b)
+    n = 40_000
+    rows = adversarial_rows(nc, nk, b, rng, n)
+    totals = np.full(nc + nk, 10**9, dtype=np.uint64)
+    totals[nc:] += 3 * 10**8
+    for thr in (5e-7, 1e-2):
+        m = oracle.Model(nc, nk, totals)
+        want, *_ = m.diff(rows, 1, b, thr)
+        with K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), kmer_size=31, count_bytes=b,
+                           threshold=thr, max_survivors=1 << 17) as ctx:
+            ctx.scan_host(rows)
+            got = ctx.survivors()
+        assert len(want) > 100
+        check_survivors(got, want)
+
+
+@pytest.mark.parametrize("corr", ["NOTHING", "BONFERRONI", "BENJAMINI", "SIDAK", "HOLM"])
+def test_corrections_match_oracle(corr):
+    kind = K.CorrectionType[corr]
+    spec, rows, totals = make_cohort("c2", 400_000, seed=17, enriched_ppm=3000)
+    m = oracle_for(spec, totals)
+    want, *_ = m.diff(rows, 1, 4, THR)
+    # m chosen so that the correction actually bites for every corrector
+    for total in (400_000, 10**9, 10**13):
+        sig_level = 0.05 if kind != K.CorrectionType.NOTHING else 1e-12
+        keep = oracle.aggregate(want["p"], int(kind), sig_level, total)
+        with ctx_for(spec, totals) as ctx:
+            ctx.scan_host(rows)
+            n_ctl, n_case = ctx.correct(kind, sig_level, total)
+            got = ctx.significant()
+        exp = want[keep]
+        assert len(got) == len(exp)
+        assert n_ctl == int((exp["sign"] == 0).sum()) and n_case == int((exp["sign"] != 0).sum())
+        # same records in the same order (row order, or ascending p with ties by row)
+        assert np.array_equal(got["row"], exp["row"])
+        if kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM):
+            assert np.all(np.diff(got["p_value"]) >= 0)
+
+
+def test_benjamini_breaks_at_first_failure():
+    """reference tests/corrector_test.cpp:20-27 semantics on the device path: sorted walk stops at
+    the first rejection even if later p-values would pass their own rank test."""
+    spec, rows, totals = make_cohort("c2", 300_000, seed=23, enriched_ppm=1000)
+    want, *_ = oracle_for(spec, totals).diff(rows, 1, 4, THR)
+    ps = np.sort(want["p"])
+    total = 300_000
+    with ctx_for(spec, totals) as ctx:
+        ctx.scan_host(rows)
+        sp = ctx.sorted_pvalues()
+        assert np.all(np.diff(sp) >= 0) and len(sp) == len(ps)
+        n_acc, cut = K.first_reject(sp, K.CorrectionType.BENJAMINI, 0.05, total)
+        keep = oracle.aggregate(want["p"], oracle.BENJAMINI, 0.05, total)
+        assert n_acc == len(keep)
+        a, b = ctx.keep_below(cut)
+        assert a + b == n_acc
+        assert np.array_equal(ctx.significant()["row"], want["row"][keep])
+
+
+def test_survivor_overflow_is_reported():
+    spec, rows, totals = make_cohort("c2", 50_000, seed=4, enriched_ppm=200_000)
+    with ctx_for(spec, totals, max_survivors=64) as ctx:
+        ctx.scan_host(rows)
+        with pytest.raises(K.KmdError) as e:
+            ctx.survivors()
+        assert e.value.code == 4
+
+
+def test_fasta_records_match_reference_format():
+    spec, rows, totals = make_cohort("c5", 60_000, seed=8)
+    want, *_ = oracle_for(spec, totals).diff(rows, 2, 2, THR)
+    with ctx_for(spec, totals) as ctx:
+        ctx.scan_host(rows)
+        got = ctx.survivors()
+    for i in range(min(50, len(got))):
+        seq = oracle.kmer_to_string(want["kmer"][i], 63)
+        exp = oracle.fasta_record(i, want["p"][i], want["mean_control"][i], want["mean_case"][i], seq)
+        rec = K.format_fasta(i, got[i], 63)
+        # header prints p with 6 significant digits: identical text unless p sits on a rounding edge
+        assert rec.split("\n", 1)[1] == exp.split("\n", 1)[1]
+        assert rec.split("_pval=")[0] == exp.split("_pval=")[0]
+        assert rec.split("_control=")[1] == exp.split("_control=")[1]
+
+
+@pytest.mark.parametrize("shape,n", [("c2", 30_000_000), ("c3", 3_000_000)])
+def test_large_batch_properties(shape, n):
+    """size-independent properties at sizes the oracle would take minutes for: device-generated rows,
+    survivors sorted & unique, counters consistent, re-scan idempotent, two half scans == one full."""
+    import torch
+    nc, nk, k, b = SHAPES[shape]
+    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=n, seed=1234)
+    totals = spec.totals()
+    d = torch.empty(n * spec.row_bytes, dtype=torch.uint8, device="cuda")
+    spec.rows_device(d.data_ptr(), n)
+    torch.cuda.synchronize()
+    with ctx_for(spec, totals) as ctx:
+        ctx.scan_device(d.data_ptr(), n)
+        c = ctx.counters()
+        s1 = ctx.survivors()
+        assert c.rows == n and c.survivors == len(s1) == c.n_control + c.n_case
+        assert c.candidates >= c.survivors
+        assert np.all(np.diff(s1["row"].astype(np.int64)) > 0)
+        assert np.all(s1["p_value"] <= THR)
+        # expected enrichment rate ~ enriched_ppm
+        assert 0.5e-3 * n < len(s1) < 2e-3 * n
+        # false-positive rate of the screen stays negligible
+        assert c.candidates <= 1.05 * c.survivors + 100
+        ctx.reset()
+        half = (n // 2) // 16 * 16
+        ctx.scan_device(d.data_ptr(), half, 0, 0)
+        ctx.scan_device(d.data_ptr() + half * spec.row_bytes, n - half, half, 1)
+        s2 = ctx.survivors()
+        assert np.array_equal(s1["row"], s2["row"]) and np.array_equal(s1["p_value"], s2["p_value"])
+        # spot-check 2000 survivors + 2000 random rows against the oracle
+        m = oracle_for(spec, totals)
+        pick = np.unique(np.concatenate([s1["row"][:: max(1, len(s1) // 2000)],
+                                         np.random.default_rng(0).integers(0, n, 2000).astype(np.uint64)]))
+        sub = np.concatenate([spec.rows_host(1, int(r)) for r in pick])
+        want, *_ = m.diff(sub, spec.kmer_words, spec.count_bytes, THR)
+        got_rows = set(s1["row"].tolist())
+        assert {int(pick[i]) for i in want["row"]} == {int(r) for r in pick if int(r) in got_rows}
