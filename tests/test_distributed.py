@@ -1,0 +1,104 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: partition sharding, the global row count
+and the cross-rank BENJAMINI / HOLM walk.  Each rank plays one GPU: its "survivors" come from the
+oracle on its own partitions; the merged decision must equal the single-process oracle's.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+THR = 0.05 / 100000
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _cohort():
+    import kmdiff_b200 as K
+    spec = K.SynthSpec(10, 10, kmer_size=31, count_bytes=4, total_rows=240_000, seed=77, enriched_ppm=3000)
+    return spec, spec.rows_host(spec.total_rows), spec.totals()
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import kmdiff_b200 as K
+        import oracle
+        from kmdiff_b200 import distributed as D
+
+        spec, rows, totals = _cohort()
+        R = spec.row_bytes
+        # 7 ragged partitions, sharded by size
+        cuts = [0, 10_000, 90_000, 90_001, 130_000, 200_000, 215_000, 240_000]
+        sizes = [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+        mine = D.assign_partitions(sizes, world)[rank]
+        m = oracle.Model(10, 10, totals)
+        surv, n_rows, n_ctl, n_case = [], 0, 0, 0
+        for p in mine:
+            s, a, b = m.diff(rows[cuts[p] * R:cuts[p + 1] * R], 1, 4, THR, row_base=cuts[p])
+            surv.append(s)
+            n_rows += sizes[p]
+            n_ctl += a
+            n_case += b
+        surv = np.concatenate(surv)
+        dev = torch.device("cpu")
+        total, g_ctl, g_case = D.global_counters(n_rows, n_ctl, n_case, dev)
+        res = {"total": total, "ctl": g_ctl, "case": g_case}
+        for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM):
+            for m_total in (total, 10**12):
+                n_acc, cut = D.global_cut(np.sort(surv["p"]), kind, 0.05, m_total, dev)
+                kept = surv["row"][surv["p"] < cut]
+                res[f"{int(kind)}_{m_total}"] = (n_acc, cut, kept)
+        np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.array([res], dtype=object), allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_assign_partitions_is_a_balanced_disjoint_cover():
+    from kmdiff_b200 import distributed as D
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 4, 8):
+        sizes = rng.integers(1, 10**6, size=64).tolist()
+        a = D.assign_partitions(sizes, world)
+        flat = sorted(i for r in a for i in r)
+        assert flat == list(range(64))
+        loads = [sum(sizes[i] for i in r) for r in a]
+        assert max(loads) - min(loads) <= max(sizes)
+        assert a == D.assign_partitions(sizes, world)
+    assert D.assign_partitions([5, 5, 5], 8)[3:] == [[] for _ in range(5)]
+
+
+def test_two_ranks_reach_the_single_process_decision(tmp_path):
+    import kmdiff_b200 as K
+    import oracle
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"rank{r}.npy", allow_pickle=True)[0] for r in range(world)]
+
+    spec, rows, totals = _cohort()
+    want, w_ctl, w_case = oracle.Model(10, 10, totals).diff(rows, 1, 4, THR)
+    for r in res:
+        assert (r["total"], r["ctl"], r["case"]) == (spec.total_rows, w_ctl, w_case)
+    for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM):
+        for m_total in (spec.total_rows, 10**12):
+            keep = oracle.aggregate(want["p"], int(kind), 0.05, m_total)
+            key = f"{int(kind)}_{m_total}"
+            assert res[0][key][0] == res[1][key][0] == len(keep)
+            assert res[0][key][1] == res[1][key][1]
+            got = np.sort(np.concatenate([res[0][key][2], res[1][key][2]]))
+            assert np.array_equal(got, np.sort(want["row"][keep]))
+    assert 0 < len(oracle.aggregate(want["p"], oracle.BENJAMINI, 0.05, 10**12)) < len(want)

@@ -1,0 +1,173 @@
+"""Pins the oracle (oracle/kmd_oracle.c, the CPU restatement used as the parity checker) against
+(1) the golden values of the reference's own unit tests, (2) committed vectors produced by the
+unmodified reference library (tests/golden/make_golden.py), and (3) — only where oracle/_ref was
+built, i.e. where /root/reference exists — the reference library itself on fresh seeded inputs.
+
+CPU only.  Same libm on both sides (x86-64 glibc), no FMA contraction on either: bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def unhex(a):
+    return np.array([float.fromhex(x) for x in a], dtype=np.float64)
+
+
+@pytest.fixture(scope="module")
+def ref_tests():
+    with open(os.path.join(GOLDEN, "reference_tests.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def vectors():
+    with open(os.path.join(GOLDEN, "ref_vectors.json")) as f:
+        return json.load(f)
+
+
+# ---- (1) the reference's own unit-test goldens --------------------------------------------------
+
+def test_log_factorial_table_goldens(ref_tests):
+    """reference tests/factorial_test.cpp:7-16 — EXPECT_EQ on doubles, i.e. bit-exact"""
+    g = ref_tests["lf_table"]
+    t = oracle.lf_table(g["size"])
+    for k, v in g["values"].items():
+        assert oracle.lf_lookup(t, int(k)) == v
+
+
+def test_model_sign_goldens(ref_tests):
+    """reference tests/model_test.cpp:45-81"""
+    g = ref_tests["model_signs"]
+    nb = g["nb"]
+    m = oracle.Model(nb, nb, np.full(2 * nb, g["totals"], np.uint64), lf_size=g["preload"])
+    for case in g["cases"]:
+        row = np.zeros(8 + 8 * nb, np.uint8)
+        row[8:] = np.array([case["controls"]] * nb + [case["cases"]] * nb, np.uint32).view(np.uint8)
+        _, sign, _, _ = m.rows(row, 1, 4)
+        assert sign[0] == {"CONTROL": oracle.CONTROL, "CASE": oracle.CASE, "NO": oracle.NO}[case["sign"]]
+
+
+def test_known_answers(ref_tests):
+    """p-values measured on the reference binary — the reference's tests pin no p-value"""
+    for ka in ref_tests["known_answers"]:
+        m = oracle.Model(ka["nc"], ka["nk"], np.array(ka["totals_c"] + ka["totals_k"], np.uint64), lf_size=ka["preload"])
+        row = np.zeros(8 + 4 * (ka["nc"] + ka["nk"]), np.uint8)
+        row[8:] = np.array(ka["controls"] + ka["cases"], np.uint32).view(np.uint8)
+        p, s, mc, kk = m.rows(row, 1, 4)
+        assert (p[0], s[0], mc[0], kk[0]) == (ka["p"], ka["sign"], ka["mean_control"], ka["mean_case"])
+
+
+def test_corrector_goldens(ref_tests):
+    """reference tests/corrector_test.cpp:9-45"""
+    for c in ref_tests["correctors"]:
+        oc = oracle.Corrector(oracle.CORRECTIONS[c["type"].lower()], c["threshold"], c["total"])
+        for _ in range(c["prime"]):
+            oc.apply(0.0)
+        assert oc.apply(c["accept"]) and not oc.apply(c["reject"]), c
+
+
+# ---- (2) committed vectors from the reference library -------------------------------------------
+
+def test_lf_vectors(vectors):
+    v = vectors["lf"]
+    t = oracle.lf_table(v["size"])
+    got = np.array([oracle.lf_lookup(t, i) for i in v["idx"]])
+    assert np.array_equal(got, unhex(v["values"]))
+
+
+def test_chisqc_vectors(vectors):
+    v = vectors["chisqc"]
+    got = np.array([oracle.chisqc(v["v"], x) for x in unhex(v["x"])])
+    assert np.array_equal(got, unhex(v["p"]))
+
+
+def test_cohort_vectors(vectors):
+    for c in vectors["cohorts"]:
+        rows = np.frombuffer(bytes.fromhex(c["rows_hex"]), dtype=np.uint8)
+        m = oracle.Model(c["nc"], c["nk"], np.array(c["totals"], np.uint64), lf_size=c["lf_size"])
+        p, s, mc, kk = m.rows(rows, (c["k"] + 31) // 32, c["count_bytes"])
+        assert np.array_equal(p, unhex(c["p"])), c["name"]
+        assert s.tolist() == c["sign"], c["name"]
+        assert np.array_equal(mc, unhex(c["mean_control"])), c["name"]
+        assert np.array_equal(kk, unhex(c["mean_case"])), c["name"]
+
+
+def test_corrector_vectors(vectors):
+    for c in vectors["correctors"]:
+        oc = oracle.Corrector(oracle.CORRECTIONS[c["type"]], c["threshold"], c["total"])
+        assert [int(oc.apply(float(x))) for x in unhex(c["p"])] == c["apply_in_order"], (c["type"], c["total"])
+
+
+def test_aggregate_matches_stateful_walk(vectors):
+    """kmo_aggregate == the reference's (sorted_)aggregator::run built from the stateful predicates"""
+    rng = np.random.default_rng(5)
+    p = np.exp(rng.uniform(np.log(1e-14), np.log(1e-4), 500))
+    for kind in (oracle.NOTHING, oracle.BONFERRONI, oracle.SIDAK):
+        keep = oracle.aggregate(p, kind, 0.05 if kind else 1e-8, 10**6)
+        oc = oracle.Corrector(kind, 0.05 if kind else 1e-8, 10**6)
+        assert keep.tolist() == [i for i, x in enumerate(p) if oc.apply(float(x))]
+    for kind in (oracle.BENJAMINI, oracle.HOLM):
+        keep = oracle.aggregate(p, kind, 0.05, 10**6)
+        order = np.argsort(p, kind="stable")
+        oc = oracle.Corrector(kind, 0.05, 10**6)
+        exp = []
+        for i in order:
+            if not oc.apply(float(p[i])):
+                break
+            exp.append(int(i))
+        assert keep.tolist() == exp and 0 < len(exp) < len(p)
+
+
+def test_kmer_to_string():
+    # A0 C1 T2 G3, first base most significant (kmtricks kmer.hpp:38, 797-810)
+    assert oracle.kmer_to_string([0b00011011], 4) == "ACTG"
+    assert oracle.kmer_to_string([0], 31) == "A" * 31
+    w = [3, 1]  # 128-bit: low word ...G, high word ...C at base index k-1-32
+    s = oracle.kmer_to_string(w, 63)
+    assert s[-1] == "G" and s[62 - 32] == "C" and s.count("A") == 61
+
+
+def test_fasta_record_format():
+    """aggregator.hpp:55-62: >{n}_pval={:g}_control={size_t}_case={} + 60-column wrap (kseq++)"""
+    r = oracle.fasta_record(0, 1.11209e-10, 0.0, 30.0, "A" * 31)
+    assert r == ">0_pval=1.11209e-10_control=0_case=30\n" + "A" * 31 + "\n"
+    r = oracle.fasta_record(7, 1.0429e-17, 52.9, 37.2, "C" * 63)
+    assert r == ">7_pval=1.0429e-17_control=52_case=37.2\n" + "C" * 60 + "\n" + "CCC\n"
+
+
+# ---- (3) the live reference library, where it was built ------------------------------------------
+
+needs_ref = pytest.mark.skipif(not oracle.ref_available(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+@needs_ref
+@pytest.mark.parametrize("nc,nk,b,kw", [(10, 10, 4, 1), (100, 100, 4, 1), (50, 50, 2, 2), (7, 6, 1, 1)])
+def test_oracle_equals_reference_on_seeded_rows(nc, nk, b, kw):
+    rng = np.random.default_rng(nc * 1000 + b)
+    n = 20_000
+    dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[b]
+    lam = rng.gamma(2.0, 3.0, size=(n, 1))
+    counts = rng.poisson(lam, size=(n, nc + nk))
+    boost = rng.random(n) < 0.05
+    counts[boost, nc:] += rng.poisson(30.0, size=(int(boost.sum()), nk))
+    counts = np.minimum(counts, np.iinfo(dt).max).astype(dt)
+    rows = np.zeros((n, 8 * kw + (nc + nk) * b), np.uint8)
+    rows[:, 8 * kw:] = counts.view(np.uint8).reshape(n, -1)
+    totals = rng.integers(9 * 10**8, 11 * 10**8, nc + nk).astype(np.uint64)
+    want = oracle.ref_model_rows(nc, nk, totals, 10000, rows, kw, b, threads=4)
+    got = oracle.Model(nc, nk, totals).rows(rows, kw, b)
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w)
+
+
+@needs_ref
+def test_oracle_chisqc_equals_reference_on_dense_grid():
+    xs = np.exp(np.linspace(np.log(1e-8), np.log(1500.0), 4000))
+    assert all(oracle.chisqc(1.0, float(x)) == oracle.ref_chisqc(1.0, float(x)) for x in xs)
