@@ -128,6 +128,12 @@ int kmd_scan_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_
 int kmd_counters_get(kmd_context* ctx, kmd_counters* out);
 /* prefilter survivors ordered by row (what the FileAccumulators hold, accumulator.hpp:156-285) */
 int kmd_survivors(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n);
+/* Append n host-side survivor records (FileAccumulator::push, accumulator.hpp:176-188) and count
+ * rows_tested more rows as tested: the entry for survivors that were not produced by kmd_scan_* —
+ * rows judged on the host by a user IModel plugin (--cmodel), or spill files of an earlier run being
+ * re-corrected.  Sign counters are updated like merge.hpp:95-98.  The correction, sorting and
+ * output stages then treat them exactly like scanned survivors. */
+int kmd_push_survivors(kmd_context* ctx, const kmd_survivor* records, uint64_t n, uint64_t rows_tested);
 
 /* diagnostics for bench.py: kernels launched on behalf of ctx so far, and the device time of the
  * most recent lrt_scan kernel launch (CUDA events on the context's stream) */

@@ -230,6 +230,11 @@ class DiffContext:
             self._ck(self._L.kmd_survivors(self._h, out.ctypes.data, n.value, C.byref(n)))
         return out
 
+    def push_survivors(self, records: np.ndarray, rows_tested: int = 0) -> None:
+        """append host-side survivor records (plugin models, resumed spill files)"""
+        rec = np.ascontiguousarray(records, dtype=SURVIVOR_DTYPE)
+        self._ck(self._L.kmd_push_survivors(self._h, rec.ctypes.data, rec.size, int(rows_tested)))
+
     # -- IModel::process, batched --
     def model_rows(self, rows):
         a = _as_u8(rows)

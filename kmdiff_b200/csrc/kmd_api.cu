@@ -495,6 +495,25 @@ __global__ void gather_records_kernel(uint32_t n, const uint32_t* order, Survivo
   out[i] = r;
 }
 
+// FileAccumulator::push for records that arrive from the host (plugin models, resumed spill files)
+__global__ void push_records_kernel(uint32_t n, const kmd_survivor* in, SurvivorArrays s, DeviceCounters* cnt, uint32_t cap)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const kmd_survivor r = in[i];
+  const uint32_t pos = atomicAdd(&cnt->surv_count, 1u);
+  if (r.sign == KMD_SIGN_CONTROL) atomicAdd(&cnt->n_control, 1u); else atomicAdd(&cnt->n_case, 1u);
+  if (pos >= cap) { atomicOr(&cnt->overflow, 2u); return; }
+  s.kmer0[pos] = r.kmer[0];
+  s.kmer1[pos] = r.kmer[1];
+  s.p[pos] = r.p_value;
+  s.sign[pos] = r.sign;
+  s.part[pos] = r.partition;
+  s.mc[pos] = r.mean_control;
+  s.kk[pos] = r.mean_case;
+  s.row[pos] = r.row;
+}
+
 __global__ void synth_kernel(synth::Params p, const synth::Tables* t, uint8_t* dst, uint64_t n_rows, uint64_t row_base)
 {
   for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n_rows;
@@ -1013,6 +1032,29 @@ int kmd_survivors(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n
   int rc = ensure_order(ctx, 1);
   if (rc) return rc;
   return download_records(ctx, ctx->d_vals[0], ctx->h_cnt->surv_count, out, cap, n);
+}
+
+int kmd_push_survivors(kmd_context* ctx, const kmd_survivor* records, uint64_t n, uint64_t rows_tested)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (n && !records) return fail(ctx, KMD_ERR_ARG, "null records");
+  if (n >= (1ull << 31)) return fail(ctx, KMD_ERR_ARG, "too many records in one call");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (n)
+  {
+    int rc = ensure_out(ctx, n);
+    if (rc) return rc;
+    KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_out, records, n * sizeof(kmd_survivor), cudaMemcpyHostToDevice, ctx->stream));
+    push_records_kernel<<<blocks_for(static_cast<uint32_t>(n)), 256, 0, ctx->stream>>>(static_cast<uint32_t>(n), ctx->d_out, ctx->surv,
+                                                                                       ctx->d_cnt, static_cast<uint32_t>(ctx->cap));
+    ctx->launches++;
+    KMD_CUDA(ctx, cudaGetLastError());
+    KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `records` may be pageable and reused by the caller
+  }
+  ctx->rows_tested += rows_tested;
+  ctx->order_state = 0;
+  ctx->final_valid = false;
+  return KMD_OK;
 }
 
 static int model_rows_launch(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, double* p, int32_t* sign, double* mc, double* kk)

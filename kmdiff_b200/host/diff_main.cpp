@@ -1,0 +1,837 @@
+// kmdiff-b200 — the `kmdiff diff` command line over the B200 hot path.
+//
+// Host-side counterpart of (reference file:line):
+//   main / CLI                      src/main.cc:52-103, src/cli.cpp:148-362
+//   main_diff / do_diff / do_correction   include/kmdiff/cmd/diff.hpp:66-164, 227-260, 262-377
+//   global_merge::merge(paths) + matrix_proxy   include/kmdiff/merge.hpp:194-203, 341-397
+//   plugin_manager                  include/kmdiff/model_manager.hpp:33-94
+//   FileAccumulator / KmerSign::dump   include/kmdiff/accumulator.hpp:156-285, kmer.hpp:113-127
+//   aggregator::writer              include/kmdiff/aggregator.hpp:27-71, 197-199
+//
+// What runs where: this program only frames bytes (run-dir parsing, matrix files -> pinned buffers,
+// spill files, FASTA text).  Every row is tested on the GPU through the C-ABI (include/kmdiff_b200.h);
+// there is no CPU implementation of the built-in model here.  Only a user `--cmodel` plugin — by
+// contract a host C++ object called once per row — is evaluated on the host, and its survivors are
+// pushed into the same device-side accumulators for correction and output.
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <functional>
+#include <limits>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <dlfcn.h>
+#include <sys/resource.h>
+#include <sys/time.h>
+
+#include <kmdiff/imodel.hpp>
+#include <kmdiff_b200.h>
+
+#include "km_formats.hpp"
+
+using namespace kmd_host;
+
+// ---- logging: spdlog pattern "[%Y-%m-%d %H:%M:%S.%e] [%^%l%$] %v" on stderr (main.cc:62-64) ----------
+
+namespace {
+
+enum Level { L_DEBUG = 0, L_INFO = 1, L_WARN = 2, L_ERROR = 3 };
+Level g_level = L_INFO;
+std::mutex g_log_mutex;
+
+void logf(Level lv, const char* fmt, ...)
+{
+  if (lv < g_level) return;
+  static const char* names[] = {"debug", "info", "warning", "error"};
+  char msg[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(msg, sizeof msg, fmt, ap);
+  va_end(ap);
+  timeval tv;
+  gettimeofday(&tv, nullptr);
+  tm t;
+  localtime_r(&tv.tv_sec, &t);
+  char ts[32];
+  strftime(ts, sizeof ts, "%Y-%m-%d %H:%M:%S", &t);
+  std::lock_guard<std::mutex> lock(g_log_mutex);
+  fprintf(stderr, "[%s.%03d] [%s] %s\n", ts, static_cast<int>(tv.tv_usec / 1000), names[lv], msg);
+}
+
+struct Timer  // include/kmdiff/time.hpp, src/time.cpp:29-47
+{
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double seconds() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+  std::string formatted() const
+  {
+    long s = static_cast<long>(seconds());
+    const long d = s / 86400; s %= 86400;
+    const long h = s / 3600; s %= 3600;
+    const long m = s / 60; s %= 60;
+    char buf[64]; int n = 0;
+    if (d) n += snprintf(buf + n, sizeof buf - n, "%02ldd", d);
+    if (h) n += snprintf(buf + n, sizeof buf - n, "%02ldh", h);
+    if (m) n += snprintf(buf + n, sizeof buf - n, "%02ldm", m);
+    snprintf(buf + n, sizeof buf - n, "%02lds", s);
+    return buf;
+  }
+};
+
+// ---- options (cmd/diff_opt.hpp, cli.cpp:148-362) ------------------------------------------------------
+
+struct DiffOptions
+{
+  std::string kmtricks_dir, output_directory = "./kmdiff_output", verbosity = "info";
+  size_t nb_controls = 0, nb_cases = 0, nb_threads = std::max(1u, std::thread::hardware_concurrency());
+  double threshold = 0.05;
+  size_t cutoff = 100000;
+  int correction = KMD_CORR_BONFERRONI;
+  bool kff = false, in_memory = false, cpr = false, keep_tmp = false, save_sk = false;
+  std::string model_lib_path, model_config;
+  bool pop_correction = false;
+  std::string gender, covariates;
+  double kmer_pca = 0.001;
+  size_t ploidy = 2, npc = 2, seed = 0, log_size = 10000;
+  // extensions of this implementation
+  int gpus = 0;               // 0 = every visible device
+  size_t count_bytes = 4;     // the reference fixes this at compile time (MAX_C); here a runtime option
+  size_t max_survivors = 0;
+  size_t total_kmers = 0;
+};
+
+[[noreturn]] void usage(int code)
+{
+  fputs(
+    "kmdiff-b200 diff — differential k-mers analysis (B200-native `kmdiff diff`)\n\n"
+    "  -d/--km-run DIR         kmtricks run directory.\n"
+    "  -o/--output-dir DIR     output directory. {./kmdiff_output}\n"
+    "  -1/--nb-controls INT    number of controls.\n"
+    "  -2/--nb-cases INT       number of cases.\n"
+    "  -s/--significance FLOAT significance threshold in [0, 0.5]. {0.05}\n"
+    "  -u/--cutoff INT         divide the significance threshold by N for the prefilter. {100000}\n"
+    "  -c/--correction STR     bonferroni|benjamini|sidak|holm|disabled {bonferroni}\n"
+    "  -f/--kff-output         (not supported by this build)\n"
+    "  -m/--in-memory  -r/--cpr   accepted and ignored, as in the reference\n"
+    "  --keep-tmp              keep partitions/p{i}_uncorrected spill files.\n"
+    "  --save-sk               build the matrix of significant k-mers.\n"
+    " [custom model]\n"
+    "  --cmodel STR            path to model shared library (IModel plugin).\n"
+    "  --config STR            model config.\n"
+    " [dev]\n"
+    "  --log-factorial INT     size of precomputed table. {10000}\n"
+    " [common]\n"
+    "  -t/--threads INT        host threads (matrix readers / plugin model). {hw}\n"
+    "  -v/--verbose STR        debug|info|warning|error {info}\n"
+    "  -h/--help  --version\n"
+    " [this implementation]\n"
+    "  --gpus INT              GPUs to shard the partitions over. {all visible}\n"
+    "  --count-bytes INT       count width of the matrices: 1, 2 or 4 (the reference's compile-time MAX_C). {4}\n"
+    "  --max-survivors INT     capacity of the per-GPU survivor buffers. {4194304}\n",
+    code ? stderr : stdout);
+  exit(code);
+}
+
+[[noreturn]] void cli_error(const std::string& msg)
+{
+  fprintf(stderr, "[Error] %s\n", msg.c_str());
+  exit(1);
+}
+
+bool is_number(const std::string& s) { return !s.empty() && s.find_first_not_of("0123456789") == std::string::npos; }
+
+DiffOptions parse_cli(int argc, char** argv)
+{
+  if (argc < 2) usage(1);
+  const std::string cmd = argv[1];
+  if (cmd == "-h" || cmd == "--help") usage(0);
+  if (cmd == "--version") { puts("kmdiff-b200 0.1.0 (kmdiff 1.1.0 `diff` interface)"); exit(0); }
+  if (cmd == "infos") { puts("kmdiff-b200 0.1.0: sm_100a CUDA hot path, C-ABI v1; commands: diff"); exit(0); }
+  if (cmd != "diff") cli_error("unknown command '" + cmd + "' (this build implements `diff`; `count` is kmtricks' job)");
+  DiffOptions o;
+  bool have_d = false, have_1 = false, have_2 = false;
+  for (int i = 2; i < argc; i++)
+  {
+    const std::string a = argv[i];
+    auto value = [&]() -> std::string {
+      if (i + 1 >= argc) cli_error(a + ": missing value");
+      return argv[++i];
+    };
+    auto number = [&]() -> size_t {
+      const std::string v = value();
+      if (!is_number(v)) cli_error(a + " " + v + " : Not a number!");
+      return std::stoull(v);
+    };
+    if (a == "-d" || a == "--km-run")
+    {
+      o.kmtricks_dir = value(); have_d = true;
+      if (!fs::is_directory(o.kmtricks_dir)) cli_error(a + " " + o.kmtricks_dir + " : Directory doesn't exist.");
+      if (!fs::exists(o.kmtricks_dir + "/kmtricks.fof")) cli_error(a + " " + o.kmtricks_dir + " : Not a kmtricks runtime directory.");
+    }
+    else if (a == "-o" || a == "--output-dir") o.output_directory = value();
+    else if (a == "-1" || a == "--nb-controls") { o.nb_controls = number(); have_1 = true; }
+    else if (a == "-2" || a == "--nb-cases") { o.nb_cases = number(); have_2 = true; }
+    else if (a == "-s" || a == "--significance")
+    {
+      const std::string v = value();
+      char* end = nullptr;
+      o.threshold = strtod(v.c_str(), &end);
+      if (end == v.c_str()) cli_error(a + " " + v + ": Not a number!");
+      if (o.threshold < 0.0 || o.threshold > 0.5) cli_error("Not in range [0.0, 0.5]");
+    }
+    else if (a == "-u" || a == "--cutoff") o.cutoff = number();
+    else if (a == "-c" || a == "--correction")
+    {
+      const std::string v = value();
+      if (v == "bonferroni") o.correction = KMD_CORR_BONFERRONI;
+      else if (v == "benjamini") o.correction = KMD_CORR_BENJAMINI;
+      else if (v == "sidak") o.correction = KMD_CORR_SIDAK;
+      else if (v == "holm") o.correction = KMD_CORR_HOLM;
+      else if (v == "disabled") o.correction = KMD_CORR_NOTHING;
+      else cli_error(a + " " + v + " : Not in bonferroni|benjamini|sidak|holm|disabled");
+    }
+    else if (a == "-f" || a == "--kff-output") o.kff = true;
+    else if (a == "-m" || a == "--in-memory") o.in_memory = true;
+    else if (a == "-r" || a == "--cpr") o.cpr = true;
+    else if (a == "--keep-tmp") o.keep_tmp = true;
+    else if (a == "--save-sk") o.save_sk = true;
+    else if (a == "--cmodel")
+    {
+      o.model_lib_path = value();
+      const std::string ext = fs::path(o.model_lib_path).extension().string();
+      if (ext != ".so" && ext != ".dylib") cli_error(a + " " + o.model_lib_path + " : extension must be so|dylib");
+    }
+    else if (a == "--config") o.model_config = value();
+    else if (a == "--pop-correction") o.pop_correction = true;
+    else if (a == "--gender") o.gender = value();
+    else if (a == "--covariates") o.covariates = value();
+    else if (a == "--kmer-pca") o.kmer_pca = atof(value().c_str());
+    else if (a == "--ploidy") o.ploidy = number();
+    else if (a == "--n-pc") o.npc = number();
+    else if (a == "--learning-rate" || a == "--max-iteration" || a == "--epsilon") value();  // inert in the reference too
+    else if (a == "--stand" || a == "--irls") {}
+    else if (a == "--random-seed") o.seed = number();
+    else if (a == "--log-factorial") o.log_size = number();
+    else if (a == "-t" || a == "--threads") o.nb_threads = std::max<size_t>(1, number());
+    else if (a == "-v" || a == "--verbose")
+    {
+      o.verbosity = value();
+      if (o.verbosity != "debug" && o.verbosity != "info" && o.verbosity != "warning" && o.verbosity != "error")
+        cli_error(a + " " + o.verbosity + " : Not in debug|info|warning|error");
+    }
+    else if (a == "-h" || a == "--help") usage(0);
+    else if (a == "--version") { puts("kmdiff-b200 0.1.0"); exit(0); }
+    else if (a == "--gpus") o.gpus = static_cast<int>(number());
+    else if (a == "--count-bytes") o.count_bytes = number();
+    else if (a == "--max-survivors") o.max_survivors = number();
+    else cli_error("unknown parameter " + a);
+  }
+  if (!have_d) cli_error("-d/--km-run is required");
+  if (!have_1 || !have_2) cli_error("-1/--nb-controls and -2/--nb-cases are required");
+  if (o.count_bytes != 1 && o.count_bytes != 2 && o.count_bytes != 4) cli_error("--count-bytes must be 1, 2 or 4");
+  return o;
+}
+
+// options.bin: 37 bytes (cmd/diff_opt.hpp:78-88) + total_kmers appended — the reference forgets it and a
+// resumed run then corrects with m = 0; the extra 8 bytes are ignored by the reference's loader.
+void dump_opt(const DiffOptions& o, const std::string& path)
+{
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) return;
+  const double thr = o.threshold, cutoff = static_cast<double>(o.cutoff), pca = o.kmer_pca;
+  const int32_t corr = o.correction;
+  const uint8_t pop = o.pop_correction;
+  const uint64_t npc = o.npc, total = o.total_kmers;
+  fwrite(&thr, 8, 1, f); fwrite(&cutoff, 8, 1, f); fwrite(&corr, 4, 1, f); fwrite(&pop, 1, 1, f);
+  fwrite(&pca, 8, 1, f); fwrite(&npc, 8, 1, f); fwrite(&total, 8, 1, f);
+  fclose(f);
+}
+
+// ---- device contexts ------------------------------------------------------------------------------------
+
+struct CtxDeleter { void operator()(kmd_context* c) const { kmd_destroy(c); } };
+using ctx_ptr = std::unique_ptr<kmd_context, CtxDeleter>;
+
+void ck(kmd_context* ctx, int rc, const char* what)
+{
+  if (rc != KMD_OK) throw KmdError("GpuError", std::string(what) + ": " + kmd_last_error(ctx));
+}
+
+// Partition tag and row index of a survivor: rows are numbered inside their partition; the partition
+// index sits above bit 40 so that device-side row order == (partition, row) order.
+constexpr int kPartShift = 40;
+
+struct Partition { std::string path; uint32_t index; uint64_t bytes; };
+
+// One GPU's share: a reader thread decodes its partitions into pinned buffers, this thread feeds the GPU.
+class GpuWorker
+{
+ public:
+  GpuWorker(int device, const DiffOptions& o, const RunConfig& cfg, uint64_t sum_controls, uint64_t sum_cases)
+    : m_device(device), m_opt(o)
+  {
+    kmd_config c{};
+    c.abi_version = KMD_ABI_VERSION;
+    c.device = device;
+    c.nb_controls = static_cast<uint32_t>(o.nb_controls);
+    c.nb_cases = static_cast<uint32_t>(o.nb_cases);
+    c.kmer_size = cfg.kmer_size;
+    c.kmer_words = (cfg.kmer_size + 31) / 32;
+    c.count_bytes = static_cast<uint32_t>(o.count_bytes);
+    c.sum_controls = sum_controls;
+    c.sum_cases = sum_cases;
+    c.threshold = o.threshold / static_cast<double>(o.cutoff);   // cmd/diff.hpp:146
+    c.lf_table = nullptr;
+    c.lf_size = o.log_size;
+    c.max_survivors = o.max_survivors;
+    kmd_context* raw = nullptr;
+    const int rc = kmd_create(&c, &raw);
+    if (rc != KMD_OK) throw KmdError("GpuError", std::string("kmd_create: ") + kmd_last_error(nullptr));
+    m_ctx.reset(raw);
+    m_row_bytes = 8ull * c.kmer_words + (o.nb_controls + o.nb_cases) * o.count_bytes;
+    m_buf_rows = std::max<uint64_t>(1, (64ull << 20) / m_row_bytes);
+    for (auto& b : m_bufs)
+    {
+      b.data = static_cast<uint8_t*>(kmd_host_alloc(m_buf_rows * m_row_bytes));
+      if (!b.data) throw KmdError("GpuError", "kmd_host_alloc failed");
+    }
+  }
+  ~GpuWorker()
+  {
+    for (auto& b : m_bufs) kmd_host_free(b.data);
+  }
+
+  kmd_context* ctx() { return m_ctx.get(); }
+  int device() const { return m_device; }
+  std::vector<Partition> partitions;
+  std::exception_ptr error;
+
+  void run()
+  {
+    try
+    {
+      std::thread reader([this] { read_loop(); });
+      feed_loop();
+      reader.join();
+      if (m_reader_error) std::rethrow_exception(m_reader_error);
+      ck(m_ctx.get(), kmd_sync(m_ctx.get()), "kmd_sync");
+    }
+    catch (...) { error = std::current_exception(); }
+  }
+
+ private:
+  struct Buf { uint8_t* data = nullptr; uint64_t rows = 0; uint64_t row_base = 0; uint32_t partition = 0; bool last = false; };
+
+  void read_loop()
+  {
+    try
+    {
+      for (const Partition& p : partitions)
+      {
+        MatrixFile mf(p.path, m_row_bytes);
+        const uint32_t slots = (mf.hdr.kmer_size + 31) / 32;
+        if (mf.hdr.nb_counts != m_opt.nb_controls + m_opt.nb_cases)
+          throw KmdError("InputError", p.path + ": " + std::to_string(mf.hdr.nb_counts) + " counts per row, expected " +
+                                         std::to_string(m_opt.nb_controls + m_opt.nb_cases));
+        if (mf.hdr.kmer_slots != slots) throw KmdError("InputError", p.path + ": unexpected kmer_slots");
+        uint64_t local = 0;
+        for (;;)
+        {
+          Buf* b = acquire_free();
+          const size_t got = mf.payload->read(b->data, m_buf_rows * m_row_bytes);
+          if (got % m_row_bytes) throw KmdError("InputError", p.path + ": truncated row");
+          b->rows = got / m_row_bytes;
+          b->row_base = (static_cast<uint64_t>(p.index) << kPartShift) + local;
+          b->partition = p.index;
+          local += b->rows;
+          const bool eof = b->rows < m_buf_rows;
+          publish(b);
+          if (eof) break;
+        }
+        logf(L_DEBUG, "partition %u: %llu rows (gpu %d)", p.index, static_cast<unsigned long long>(local), m_device);
+      }
+    }
+    catch (...) { m_reader_error = std::current_exception(); }
+    Buf* b = acquire_free();
+    b->rows = 0; b->last = true;
+    publish(b);
+  }
+
+  void feed_loop()
+  {
+    for (;;)
+    {
+      Buf* b;
+      {
+        std::unique_lock<std::mutex> lk(m_mu);
+        m_cv.wait(lk, [this] { return !m_ready.empty(); });
+        b = m_ready.front(); m_ready.pop();
+      }
+      const bool last = b->last;
+      if (b->rows) ck(m_ctx.get(), kmd_scan_host(m_ctx.get(), b->data, b->rows, b->row_base, b->partition), "kmd_scan_host");
+      {
+        std::lock_guard<std::mutex> lk(m_mu);
+        b->last = false;
+        m_free.push(b);
+      }
+      m_cv.notify_all();
+      if (last) break;
+    }
+  }
+
+  Buf* acquire_free()
+  {
+    std::unique_lock<std::mutex> lk(m_mu);
+    if (!m_init) { for (auto& b : m_bufs) m_free.push(&b); m_init = true; }
+    m_cv.wait(lk, [this] { return !m_free.empty(); });
+    Buf* b = m_free.front(); m_free.pop();
+    return b;
+  }
+  void publish(Buf* b)
+  {
+    { std::lock_guard<std::mutex> lk(m_mu); m_ready.push(b); }
+    m_cv.notify_all();
+  }
+
+  int m_device;
+  const DiffOptions& m_opt;
+  ctx_ptr m_ctx;
+  uint64_t m_row_bytes = 0, m_buf_rows = 0;
+  Buf m_bufs[3];
+  std::queue<Buf*> m_free, m_ready;
+  std::mutex m_mu;
+  std::condition_variable m_cv;
+  bool m_init = false;
+  std::exception_ptr m_reader_error;
+};
+
+// ---- user model plugins (model_manager.hpp:33-94) --------------------------------------------------------
+
+template <size_t MAX_C>
+struct PluginModel
+{
+  using model_t = kmdiff::IModel<MAX_C>;
+  using count_t = typename model_t::count_type;
+  void* handle = nullptr;
+  std::string name;
+  std::shared_ptr<model_t> model;
+
+  void init(const std::string& path, const std::string& config)
+  {
+    handle = dlopen(path.c_str(), RTLD_LAZY);
+    if (!handle) throw KmdError("PluginError", std::string("dlerror: ") + dlerror());
+    dlerror();
+    auto name_fn = reinterpret_cast<std::string (*)()>(dlsym(handle, "plugin_name"));
+    if (const char* e = dlerror()) throw KmdError("PluginError", std::string("dlerror: ") + e);
+    name = name_fn();
+    const std::string sym = "create" + std::to_string(sizeof(count_t) * 8);
+    auto create = reinterpret_cast<model_t* (*)()>(dlsym(handle, sym.c_str()));
+    if (const char* e = dlerror()) throw KmdError("PluginError", std::string("dlerror: ") + e);
+    model_t* m = create();
+    m->configure(config);
+    model.reset(m);   // deleted through the virtual destructor; the handle stays open, as in the reference
+    logf(L_INFO, "Plugin '%s' loaded.", name.c_str());
+  }
+};
+
+// The reference's diff_observer::process (merge.hpp:68-103) with a user model: per row on the host, one
+// shared model instance, `threads` reader threads over the partitions.  Survivors go to the device-side
+// accumulators of `ctx` through kmd_push_survivors.
+template <size_t MAX_C>
+void run_plugin_model(PluginModel<MAX_C>& pm, const std::vector<Partition>& parts, const DiffOptions& o, const RunConfig& cfg,
+                      kmd_context* ctx)
+{
+  using count_t = typename PluginModel<MAX_C>::count_t;
+  const uint32_t kw = (cfg.kmer_size + 31) / 32;
+  const size_t n = o.nb_controls + o.nb_cases;
+  const size_t R = 8 * kw + n * sizeof(count_t);
+  const double thr = o.threshold / static_cast<double>(o.cutoff);
+  std::atomic<size_t> next{0};
+  std::mutex push_mu;
+  std::exception_ptr err;
+  auto work = [&] {
+    try
+    {
+      std::vector<uint8_t> buf(R * 4096);
+      std::vector<count_t> row(n);
+      std::vector<kmd_survivor> out;
+      for (size_t pi = next++; pi < parts.size(); pi = next++)
+      {
+        MatrixFile mf(parts[pi].path, R);
+        uint64_t local = 0;
+        out.clear();
+        for (;;)
+        {
+          const size_t got = mf.payload->read(buf.data(), buf.size());
+          const size_t rows = got / R;
+          for (size_t r = 0; r < rows; r++)
+          {
+            const uint8_t* src = buf.data() + r * R;
+            memcpy(row.data(), src + 8 * kw, n * sizeof(count_t));
+            kmdiff::Range<count_t> rc(row, 0, o.nb_controls), rk(row, o.nb_controls, o.nb_cases);
+            auto [p, sign, mc, mk] = pm.model->process(rc, rk);
+            if (p <= thr)
+            {
+              kmd_survivor s{};
+              memcpy(s.kmer, src, 8 * kw);
+              s.p_value = p; s.sign = static_cast<int32_t>(sign); s.partition = parts[pi].index;
+              s.mean_control = mc; s.mean_case = mk;
+              s.row = (static_cast<uint64_t>(parts[pi].index) << kPartShift) + local + r;
+              out.push_back(s);
+            }
+          }
+          local += rows;
+          if (got < buf.size()) break;
+        }
+        std::lock_guard<std::mutex> lk(push_mu);
+        ck(ctx, kmd_push_survivors(ctx, out.data(), out.size(), local), "kmd_push_survivors");
+      }
+    }
+    catch (...) { std::lock_guard<std::mutex> lk(push_mu); err = std::current_exception(); }
+  };
+  std::vector<std::thread> pool;
+  for (size_t t = 0; t < std::min(o.nb_threads, std::max<size_t>(1, parts.size())); t++) pool.emplace_back(work);
+  for (auto& t : pool) t.join();
+  if (err) std::rethrow_exception(err);
+}
+
+// ---- spill files: partitions/p{i}_uncorrected (accumulator.hpp:156-285, kmer.hpp:113-127) --------------
+
+void write_spill_files(const std::vector<kmd_survivor>& surv, uint32_t nb_partitions, uint32_t kmer_words, const std::string& dir)
+{
+  std::vector<std::unique_ptr<Lz4FrameWriter>> w(nb_partitions);
+  std::vector<FILE*> files(nb_partitions, nullptr);
+  for (uint32_t p = 0; p < nb_partitions; p++)
+  {
+    files[p] = fopen((dir + "/p" + std::to_string(p) + "_uncorrected").c_str(), "wb");
+    if (!files[p]) throw KmdError("IOError", "Unable to create spill file in " + dir);
+    w[p] = std::make_unique<Lz4FrameWriter>(files[p]);
+  }
+  for (const kmd_survivor& s : surv)
+  {
+    if (s.partition >= nb_partitions) continue;
+    Lz4FrameWriter& o = *w[s.partition];
+    o.write(s.kmer, 8 * kmer_words);   // all words: the reference drops the high word for k > 32 (SURVEY.md §8 hazard 1)
+    o.write(&s.p_value, 8);
+    o.write(&s.sign, 4);
+    o.write(&s.mean_control, 8);
+    o.write(&s.mean_case, 8);
+  }
+  for (uint32_t p = 0; p < nb_partitions; p++) { w[p]->close(); fclose(files[p]); }
+}
+
+// ---- FASTA output (aggregator.hpp:27-71, 197-199) -----------------------------------------------------------
+
+struct FastaPair
+{
+  FILE* control = nullptr;
+  FILE* cases = nullptr;
+  uint64_t n_control = 0, n_case = 0;
+  explicit FastaPair(const std::string& dir)
+  {
+    control = fopen((dir + "/control_kmers.fasta").c_str(), "w");
+    cases = fopen((dir + "/case_kmers.fasta").c_str(), "w");
+    if (!control || !cases) throw KmdError("IOError", "Unable to create output FASTA files in " + dir);
+  }
+  void write(const kmd_survivor& s, uint32_t kmer_words, uint32_t k)
+  {
+    char buf[1024];
+    const bool is_control = s.sign == KMD_SIGN_CONTROL;   // NO goes to the case file (aggregator.hpp:155-162)
+    const size_t n = kmd_format_fasta(is_control ? n_control : n_case, &s, kmer_words, k, buf, sizeof buf);
+    fwrite(buf, 1, n, is_control ? control : cases);
+    (is_control ? n_control : n_case)++;
+  }
+  ~FastaPair() { if (control) fclose(control); if (cases) fclose(cases); }
+};
+
+size_t peak_rss_mb()
+{
+  rusage ru;
+  getrusage(RUSAGE_SELF, &ru);
+  return static_cast<size_t>(ru.ru_maxrss * 0.0009765625);
+}
+
+std::vector<kmd_survivor> fetch(kmd_context* ctx, bool significant)
+{
+  uint64_t n = 0;
+  ck(ctx, significant ? kmd_significant(ctx, nullptr, 0, &n) : kmd_survivors(ctx, nullptr, 0, &n), "count records");
+  std::vector<kmd_survivor> out(n);
+  if (n) ck(ctx, significant ? kmd_significant(ctx, out.data(), n, &n) : kmd_survivors(ctx, out.data(), n, &n), "fetch records");
+  return out;
+}
+
+// ---- main_diff (cmd/diff.hpp:262-377) ---------------------------------------------------------------------
+
+void main_diff(DiffOptions& opt)
+{
+  Timer whole;
+  if (opt.kff) throw KmdError("OptionError", "-f/--kff-output is not supported by this build (FASTA only).");
+  if (opt.pop_correction && opt.model_lib_path.empty())
+    throw KmdError("OptionError", "--pop-correction is not available in this build yet (SURVEY.md §8 a17-a19).");
+
+  const RunConfig cfg = get_kmtricks_config(opt.kmtricks_dir);
+  if (cfg.kmer_size > 64) throw KmdError("OptionError", "k > 64 is not supported (the reference cannot write such k-mers either).");
+  const uint32_t kw = (cfg.kmer_size + 31) / 32;
+  const std::string part_dir = opt.output_directory + "/partitions";
+  fs::create_directories(part_dir);
+
+  // ---- do_diff ----
+  Timer merge_time;
+  logf(L_INFO, "Process partitions");
+  const std::vector<std::string> matrix_paths = list_matrices(opt.kmtricks_dir);
+  if (matrix_paths.empty())
+    throw KmdError("InputError", "no count matrices under " + opt.kmtricks_dir + "/matrices (per-sample count files are not "
+                                 "supported yet: build the matrices with `kmtricks pipeline --until merge --mode kmer:count:bin`).");
+  { std::ofstream touch(opt.kmtricks_dir + "/kmdiff-count.opt", std::ios::app); }   // the reference leaves this marker (cmd/diff.hpp:100)
+
+  std::vector<uint64_t> total_controls, total_cases;
+  get_total_kmer(opt.kmtricks_dir, opt.nb_controls, opt.nb_cases, cfg.abundance_min, total_controls, total_cases);
+  uint64_t sum_c = 0, sum_k = 0;
+  for (uint64_t t : total_controls) sum_c += t;
+  for (uint64_t t : total_cases) sum_k += t;
+
+  std::vector<Partition> parts;
+  for (const std::string& p : matrix_paths)
+  {
+    // partition index from the header (matrix_{p}.count[.lz4])
+    MatrixFile mf(p, 8ull * kw + (opt.nb_controls + opt.nb_cases) * opt.count_bytes);
+    parts.push_back({p, mf.hdr.partition, static_cast<uint64_t>(fs::file_size(p))});
+  }
+  uint32_t nb_partitions = cfg.nb_partitions;
+  for (const Partition& p : parts) nb_partitions = std::max(nb_partitions, p.index + 1);
+
+  int n_dev = kmd_device_count();
+  if (n_dev <= 0) throw KmdError("GpuError", "no CUDA device visible: kmdiff-b200 has no CPU fallback.");
+  if (opt.gpus > 0) n_dev = std::min(n_dev, opt.gpus);
+  const bool plugin = !opt.model_lib_path.empty();
+  if (plugin)
+  {
+    if (opt.pop_correction) logf(L_WARN, "population stratification correction disabled with custom models.");
+    opt.pop_correction = false;
+    n_dev = 1;
+  }
+  n_dev = std::max(1, std::min<int>(n_dev, static_cast<int>(parts.size())));
+
+  std::vector<std::unique_ptr<GpuWorker>> workers;
+  for (int d = 0; d < n_dev; d++) workers.push_back(std::make_unique<GpuWorker>(d, opt, cfg, sum_c, sum_k));
+
+  if (plugin)
+  {
+    switch (opt.count_bytes)
+    {
+      case 1: { PluginModel<kmdiff::maxc8> pm; pm.init(opt.model_lib_path, opt.model_config); run_plugin_model(pm, parts, opt, cfg, workers[0]->ctx()); break; }
+      case 2: { PluginModel<kmdiff::maxc16> pm; pm.init(opt.model_lib_path, opt.model_config); run_plugin_model(pm, parts, opt, cfg, workers[0]->ctx()); break; }
+      default: { PluginModel<kmdiff::maxc32> pm; pm.init(opt.model_lib_path, opt.model_config); run_plugin_model(pm, parts, opt, cfg, workers[0]->ctx()); break; }
+    }
+  }
+  else
+  {
+    // size-balanced partition -> GPU assignment (largest first onto the least loaded device)
+    std::vector<size_t> order(parts.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return parts[a].bytes != parts[b].bytes ? parts[a].bytes > parts[b].bytes : a < b; });
+    std::vector<uint64_t> load(n_dev, 0);
+    for (size_t i : order)
+    {
+      const int d = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+      workers[d]->partitions.push_back(parts[i]);
+      load[d] += parts[i].bytes;
+    }
+    std::vector<std::thread> pool;
+    for (auto& w : workers) pool.emplace_back([&w] { w->run(); });
+    for (auto& t : pool) t.join();
+    for (auto& w : workers) if (w->error) std::rethrow_exception(w->error);
+  }
+
+  uint64_t total_kmers = 0, nb_sign = 0, sign_controls = 0, sign_cases = 0;
+  for (auto& w : workers)
+  {
+    kmd_counters c;
+    ck(w->ctx(), kmd_counters_get(w->ctx(), &c), "kmd_counters_get");
+    total_kmers += c.rows; nb_sign += c.survivors; sign_controls += c.n_control; sign_cases += c.n_case;
+  }
+  opt.total_kmers = total_kmers;
+  logf(L_INFO, "Partitions processed (%s)", merge_time.formatted().c_str());
+  logf(L_INFO, "%llu/%llu significant k-mers.", static_cast<unsigned long long>(nb_sign), static_cast<unsigned long long>(total_kmers));
+  logf(L_INFO, "Before correction: %llu (control), %llu (case).", static_cast<unsigned long long>(sign_controls),
+       static_cast<unsigned long long>(sign_cases));
+
+  dump_opt(opt, opt.output_directory + "/options.bin");
+  if (opt.keep_tmp)
+  {
+    std::vector<kmd_survivor> all;
+    for (auto& w : workers) { auto s = fetch(w->ctx(), false); all.insert(all.end(), s.begin(), s.end()); }
+    write_spill_files(all, nb_partitions, kw, part_dir);
+  }
+
+  // ---- do_correction ----
+  Timer agg_time;
+  logf(L_INFO, opt.correction == KMD_CORR_NOTHING ? "Aggregate partitions..." : "Aggregate partitions and apply significance correction...");
+  const bool sorted = opt.correction == KMD_CORR_BENJAMINI || opt.correction == KMD_CORR_HOLM;
+  std::vector<std::vector<kmd_survivor>> kept(workers.size());
+  if (sorted && workers.size() > 1)
+  {
+    // one global ascending walk over all GPUs' survivors (aggregator.hpp:282-310)
+    std::vector<double> merged;
+    for (auto& w : workers)
+    {
+      uint64_t n = 0;
+      ck(w->ctx(), kmd_sorted_pvalues(w->ctx(), nullptr, 0, &n), "kmd_sorted_pvalues");
+      const size_t at = merged.size();
+      merged.resize(at + n);
+      if (n) ck(w->ctx(), kmd_sorted_pvalues(w->ctx(), merged.data() + at, n, &n), "kmd_sorted_pvalues");
+      std::inplace_merge(merged.begin(), merged.begin() + at, merged.end());
+    }
+    double cut = 0;
+    kmd_first_reject(merged.data(), merged.size(), opt.correction, opt.threshold, total_kmers, &cut);
+    for (size_t i = 0; i < workers.size(); i++)
+    {
+      ck(workers[i]->ctx(), kmd_keep_below(workers[i]->ctx(), cut, nullptr, nullptr), "kmd_keep_below");
+      kept[i] = fetch(workers[i]->ctx(), true);
+    }
+  }
+  else
+  {
+    for (size_t i = 0; i < workers.size(); i++)
+    {
+      ck(workers[i]->ctx(), kmd_correct(workers[i]->ctx(), opt.correction, opt.threshold, total_kmers, nullptr, nullptr), "kmd_correct");
+      kept[i] = fetch(workers[i]->ctx(), true);
+    }
+  }
+  // k-way merge of the per-GPU outputs: ascending p for BH/Holm, (partition, row) otherwise
+  std::vector<kmd_survivor> final_records;
+  for (auto& k : kept) final_records.insert(final_records.end(), k.begin(), k.end());
+  if (workers.size() > 1)
+  {
+    if (sorted)
+      std::stable_sort(final_records.begin(), final_records.end(), [](const kmd_survivor& a, const kmd_survivor& b) {
+        return a.p_value != b.p_value ? a.p_value < b.p_value : a.row < b.row; });
+    else
+      std::stable_sort(final_records.begin(), final_records.end(), [](const kmd_survivor& a, const kmd_survivor& b) { return a.row < b.row; });
+  }
+  {
+    FastaPair out(opt.output_directory);
+    for (const kmd_survivor& s : final_records) out.write(s, kw, cfg.kmer_size);
+    logf(L_INFO, "Partitions aggregated (%s)", agg_time.formatted().c_str());
+    logf(L_INFO, "Significant k-mers: %llu (control), %llu (case).", static_cast<unsigned long long>(out.n_control),
+         static_cast<unsigned long long>(out.n_case));
+  }
+  if (opt.save_sk)
+  {
+    // matrix of the significant k-mers: one pass over the inputs, rows picked by (partition, row)
+    const std::string dir = opt.output_directory + "/positive_kmer_matrix/matrices";
+    fs::create_directories(dir);
+    const size_t R = 8ull * kw + (opt.nb_controls + opt.nb_cases) * opt.count_bytes;
+    std::vector<std::vector<uint64_t>> want(nb_partitions);
+    for (const kmd_survivor& s : final_records) want[s.partition].push_back(s.row & ((1ull << kPartShift) - 1));
+    for (const Partition& p : parts)
+    {
+      auto& rows = want[p.index];
+      std::sort(rows.begin(), rows.end());
+      MatrixWriter w(dir + "/matrix_" + std::to_string(p.index) + ".count", cfg.kmer_size, kw, static_cast<uint32_t>(opt.count_bytes),
+                     static_cast<uint32_t>(opt.nb_controls + opt.nb_cases), p.index);
+      if (rows.empty()) continue;
+      MatrixFile mf(p.path, R);
+      std::vector<uint8_t> buf(R * 4096);
+      uint64_t base = 0; size_t next = 0;
+      for (;;)
+      {
+        const size_t got = mf.payload->read(buf.data(), buf.size());
+        const size_t n = got / R;
+        while (next < rows.size() && rows[next] < base + n) { w.write(buf.data() + (rows[next] - base) * R, R); next++; }
+        base += n;
+        if (got < buf.size() || next == rows.size()) break;
+      }
+    }
+  }
+  if (!opt.keep_tmp)
+  {
+    std::error_code ec;
+    for (uint32_t p = 0; p < nb_partitions; p++) fs::remove(part_dir + "/p" + std::to_string(p) + "_uncorrected", ec);
+  }
+  logf(L_INFO, "Done in %s, Peak RSS -> %zu MB.", whole.formatted().c_str(), peak_rss_mb());
+}
+
+// Hidden developer commands used by tests/test_host_cli.py to exercise the host-side format code without a GPU:
+//   dev-cat FILE SKIP [lz4]  decoded payload of a kmtricks file (SKIP header bytes; LZ4 frame iff its compressed flag is set or "lz4" is given)
+//   dev-pack IN OUT          IN wrapped into one LZ4 frame of stored blocks
+//   dev-config DIR NC NK     run-dir config and per-sample totals
+int dev_command(int argc, char** argv)
+{
+  const std::string cmd = argv[1];
+  if (cmd == "dev-cat" && (argc == 4 || argc == 5))
+  {
+    FILE* f = fopen(argv[2], "rb");
+    if (!f) return 2;
+    std::vector<uint8_t> head(static_cast<size_t>(atol(argv[3])));
+    if (!head.empty() && fread(head.data(), 1, head.size(), f) != head.size()) return 2;
+    const bool compressed = argc == 5 || (head.size() >= 13 && head[12] != 0);
+    PayloadReader pr(f, compressed);
+    std::vector<uint8_t> buf(1 << 20);
+    for (size_t n; (n = pr.read(buf.data(), buf.size())) > 0;) fwrite(buf.data(), 1, n, stdout);
+    fclose(f);
+    return 0;
+  }
+  if (cmd == "dev-pack" && argc == 4)
+  {
+    FILE* in = fopen(argv[2], "rb");
+    FILE* out = fopen(argv[3], "wb");
+    if (!in || !out) return 2;
+    Lz4FrameWriter w(out);
+    std::vector<uint8_t> buf(100000);
+    for (size_t n; (n = fread(buf.data(), 1, buf.size(), in)) > 0;) w.write(buf.data(), n);
+    w.close();
+    fclose(in); fclose(out);
+    return 0;
+  }
+  if (cmd == "dev-config" && argc == 5)
+  {
+    const RunConfig c = get_kmtricks_config(argv[2]);
+    std::vector<uint64_t> tc, tk;
+    get_total_kmer(argv[2], static_cast<size_t>(atol(argv[3])), static_cast<size_t>(atol(argv[4])), c.abundance_min, tc, tk);
+    printf("kmer_size=%u abundance_min=%u nb_partitions=%u\n", c.kmer_size, c.abundance_min, c.nb_partitions);
+    for (uint64_t t : tc) printf("control %llu\n", static_cast<unsigned long long>(t));
+    for (uint64_t t : tk) printf("case %llu\n", static_cast<unsigned long long>(t));
+    for (const std::string& m : list_matrices(argv[2])) printf("matrix %s\n", m.c_str());
+    return 0;
+  }
+  return 2;
+}
+
+}  // namespace
+
+int main(int argc, char** argv)
+{
+  if (argc >= 2 && !strncmp(argv[1], "dev-", 4))
+  {
+    try { return dev_command(argc, argv); }
+    catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 3; }
+  }
+  DiffOptions opt = parse_cli(argc, argv);
+  g_level = opt.verbosity == "debug" ? L_DEBUG : opt.verbosity == "info" ? L_INFO : opt.verbosity == "warning" ? L_WARN : L_ERROR;
+  if (opt.correction == KMD_CORR_BENJAMINI || opt.correction == KMD_CORR_HOLM)
+    logf(L_WARN, "-c/--correction %s: all significants k-mers will live in memory.", opt.correction == KMD_CORR_BENJAMINI ? "benjamini" : "holm");
+  if (opt.in_memory) logf(L_WARN, "-m/--in-memory: all significants k-mers will live in memory.");
+  try
+  {
+    main_diff(opt);
+  }
+  catch (const KmdError& e)
+  {
+    logf(L_ERROR, "%s - %s", e.name.c_str(), e.what());
+  }
+  catch (const std::exception& e)
+  {
+    logf(L_ERROR, "%s", e.what());
+  }
+  return 0;   // like the reference: errors are logged, the exit code stays 0 (main.cc:93-102)
+}

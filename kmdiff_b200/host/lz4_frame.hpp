@@ -1,0 +1,246 @@
+// LZ4 frame streams as kmtricks writes them (kmtricks/io/lz4_stream.hpp: LZ4F default preferences =
+// 64 KiB linked blocks, no checksums; every `.lz4` file of a run directory and every spill file
+// `partitions/p{i}_uncorrected` is one such frame after the kmtricks header).
+//
+// Written from the public LZ4 frame / block format descriptions (lz4_Frame_format.md,
+// lz4_Block_format.md); the reference links the vendored liblz4 1.9.3 instead, which is not available
+// to this build.  Reader: any conforming frame (linked or independent blocks, stored blocks, optional
+// checksums are skipped, concatenated frames).  Writer: a conforming frame of stored (uncompressed)
+// blocks — readable by liblz4, hence by the reference, at the cost of no compression; spill files
+// are small (<= 1e-3 of the rows).
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace kmd_host {
+
+// xxHash32 (public specification) — only needed for the one-byte frame-header checksum.
+inline uint32_t xxh32(const uint8_t* p, size_t len, uint32_t seed)
+{
+  const uint32_t P1 = 2654435761u, P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+  auto rotl = [](uint32_t x, int r) { return (x << r) | (x >> (32 - r)); };
+  auto rd32 = [](const uint8_t* q) { uint32_t v; memcpy(&v, q, 4); return v; };
+  const uint8_t* end = p + len;
+  uint32_t h;
+  if (len >= 16)
+  {
+    uint32_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+    for (; p + 16 <= end; p += 16)
+    {
+      v1 = rotl(v1 + rd32(p) * P2, 13) * P1;
+      v2 = rotl(v2 + rd32(p + 4) * P2, 13) * P1;
+      v3 = rotl(v3 + rd32(p + 8) * P2, 13) * P1;
+      v4 = rotl(v4 + rd32(p + 12) * P2, 13) * P1;
+    }
+    h = rotl(v1, 1) + rotl(v2, 7) + rotl(v3, 12) + rotl(v4, 18);
+  }
+  else
+    h = seed + P5;
+  h += static_cast<uint32_t>(len);
+  for (; p + 4 <= end; p += 4) h = rotl(h + rd32(p) * P3, 17) * P4;
+  for (; p < end; p++) h = rotl(h + *p * P5, 11) * P1;
+  h ^= h >> 15; h *= P2; h ^= h >> 13; h *= P3; h ^= h >> 16;
+  return h;
+}
+
+// Decodes one LZ4 block into dst[0, cap); matches may reach back before dst (linked blocks: the caller
+// guarantees `history` valid bytes precede dst).  Returns the decoded size.
+inline size_t lz4_block_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t history)
+{
+  const uint8_t* ip = src;
+  const uint8_t* const iend = src + n;
+  uint8_t* op = dst;
+  uint8_t* const oend = dst + cap;
+  while (ip < iend)
+  {
+    const unsigned token = *ip++;
+    size_t lit = token >> 4;
+    if (lit == 15)
+    {
+      unsigned b;
+      do { if (ip >= iend) throw std::runtime_error("lz4: truncated literal length"); b = *ip++; lit += b; } while (b == 255);
+    }
+    if (lit > static_cast<size_t>(iend - ip) || lit > static_cast<size_t>(oend - op)) throw std::runtime_error("lz4: literal run overflows");
+    memcpy(op, ip, lit);
+    op += lit; ip += lit;
+    if (ip >= iend) break;  // the last sequence has no match part
+    if (iend - ip < 2) throw std::runtime_error("lz4: truncated offset");
+    const size_t off = ip[0] | (static_cast<size_t>(ip[1]) << 8);
+    ip += 2;
+    size_t ml = token & 15;
+    if (ml == 15)
+    {
+      unsigned b;
+      do { if (ip >= iend) throw std::runtime_error("lz4: truncated match length"); b = *ip++; ml += b; } while (b == 255);
+    }
+    ml += 4;
+    if (off == 0 || off > static_cast<size_t>(op - dst) + history) throw std::runtime_error("lz4: offset out of window");
+    if (ml > static_cast<size_t>(oend - op)) throw std::runtime_error("lz4: match overflows");
+    const uint8_t* m = op - off;
+    if (off >= ml) { memcpy(op, m, ml); op += ml; }
+    else for (size_t i = 0; i < ml; i++) *op++ = m[i];  // overlapping run
+  }
+  return static_cast<size_t>(op - dst);
+}
+
+// Pull-style reader of a FILE* positioned at the start of an LZ4 frame.
+class Lz4FrameReader
+{
+ public:
+  explicit Lz4FrameReader(FILE* f) : m_f(f) {}
+
+  // up to n decoded bytes into dst; 0 at end of stream
+  size_t read(uint8_t* dst, size_t n)
+  {
+    size_t got = 0;
+    while (got < n)
+    {
+      if (m_pos == m_end && !next_block()) break;
+      const size_t take = std::min(n - got, m_end - m_pos);
+      memcpy(dst + got, m_win.data() + m_pos, take);
+      m_pos += take; got += take;
+    }
+    return got;
+  }
+
+ private:
+  static constexpr size_t kHistory = 64 * 1024;
+
+  bool fill(void* p, size_t n) { return fread(p, 1, n, m_f) == n; }
+
+  bool open_frame()
+  {
+    uint32_t magic;
+    for (;;)
+    {
+      if (!fill(&magic, 4)) return false;
+      if ((magic & 0xFFFFFFF0u) == 0x184D2A50u)  // skippable frame
+      {
+        uint32_t sz; if (!fill(&sz, 4)) return false;
+        if (fseek(m_f, sz, SEEK_CUR)) return false;
+        continue;
+      }
+      break;
+    }
+    if (magic != 0x184D2204u) throw std::runtime_error("lz4: bad frame magic");
+    uint8_t flg, bd;
+    if (!fill(&flg, 1) || !fill(&bd, 1)) throw std::runtime_error("lz4: truncated frame header");
+    if ((flg >> 6) != 1) throw std::runtime_error("lz4: unsupported frame version");
+    m_block_checksum = flg & 0x10;
+    m_content_checksum = flg & 0x04;
+    m_linked = !(flg & 0x20);
+    if (flg & 0x08) { uint64_t cs; fill(&cs, 8); }
+    if (flg & 0x01) { uint32_t id; fill(&id, 4); }
+    uint8_t hc; fill(&hc, 1);
+    const unsigned bs = (bd >> 4) & 7;
+    if (bs < 4) throw std::runtime_error("lz4: bad block size code");
+    m_block_max = static_cast<size_t>(1) << (8 + 2 * bs);
+    m_win.resize(kHistory + m_block_max);
+    m_hist = 0; m_pos = m_end = kHistory;
+    m_in_frame = true;
+    return true;
+  }
+
+  bool next_block()
+  {
+    for (;;)
+    {
+      if (!m_in_frame && !open_frame()) return false;
+      uint32_t hdr;
+      if (!fill(&hdr, 4)) throw std::runtime_error("lz4: truncated block header");
+      if (hdr == 0)  // EndMark
+      {
+        if (m_content_checksum) { uint32_t c; fill(&c, 4); }
+        m_in_frame = false;
+        continue;
+      }
+      const bool stored = hdr & 0x80000000u;
+      const size_t n = hdr & 0x7FFFFFFFu;
+      if (n > m_block_max) throw std::runtime_error("lz4: block larger than the frame's maximum");
+      // slide the last 64 KiB of output in front of the window
+      const size_t produced = m_end - kHistory;
+      if (m_linked && produced)
+      {
+        const size_t keep = std::min(kHistory, m_hist + produced);
+        memmove(m_win.data() + kHistory - keep, m_win.data() + m_end - keep, keep);
+        m_hist = keep;
+      }
+      size_t out;
+      if (stored)
+      {
+        if (!fill(m_win.data() + kHistory, n)) throw std::runtime_error("lz4: truncated block");
+        out = n;
+      }
+      else
+      {
+        m_src.resize(n);
+        if (!fill(m_src.data(), n)) throw std::runtime_error("lz4: truncated block");
+        out = lz4_block_decode(m_src.data(), n, m_win.data() + kHistory, m_block_max, m_linked ? m_hist : 0);
+      }
+      if (m_block_checksum) { uint32_t c; fill(&c, 4); }
+      m_pos = kHistory; m_end = kHistory + out;
+      if (out) return true;
+    }
+  }
+
+  FILE* m_f;
+  std::vector<uint8_t> m_win, m_src;
+  size_t m_block_max = 0, m_hist = 0, m_pos = 0, m_end = 0;
+  bool m_in_frame = false, m_linked = true, m_block_checksum = false, m_content_checksum = false;
+};
+
+// Push-style writer: one frame of stored 64 KiB blocks.
+class Lz4FrameWriter
+{
+ public:
+  explicit Lz4FrameWriter(FILE* f) : m_f(f)
+  {
+    const uint8_t desc[2] = {0x60 /* version 1, independent blocks */, 0x40 /* 64 KiB */};
+    const uint32_t magic = 0x184D2204u;
+    fwrite(&magic, 4, 1, m_f);
+    fwrite(desc, 1, 2, m_f);
+    const uint8_t hc = static_cast<uint8_t>(xxh32(desc, 2, 0) >> 8);
+    fwrite(&hc, 1, 1, m_f);
+    m_buf.reserve(kBlock);
+  }
+  void write(const void* p, size_t n)
+  {
+    const uint8_t* s = static_cast<const uint8_t*>(p);
+    while (n)
+    {
+      const size_t take = std::min(n, kBlock - m_buf.size());
+      m_buf.insert(m_buf.end(), s, s + take);
+      s += take; n -= take;
+      if (m_buf.size() == kBlock) flush();
+    }
+  }
+  void close()
+  {
+    if (!m_f) return;
+    flush();
+    const uint32_t end = 0;
+    fwrite(&end, 4, 1, m_f);
+    m_f = nullptr;
+  }
+  ~Lz4FrameWriter() { close(); }
+
+ private:
+  static constexpr size_t kBlock = 64 * 1024;
+  void flush()
+  {
+    if (m_buf.empty()) return;
+    const uint32_t hdr = static_cast<uint32_t>(m_buf.size()) | 0x80000000u;
+    fwrite(&hdr, 4, 1, m_f);
+    fwrite(m_buf.data(), 1, m_buf.size(), m_f);
+    m_buf.clear();
+  }
+  FILE* m_f;
+  std::vector<uint8_t> m_buf;
+};
+
+}  // namespace kmd_host

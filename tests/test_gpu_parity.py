@@ -170,12 +170,16 @@ def test_threshold_one_keeps_every_row():
 
 
 def adversarial_rows(nc, nk, count_bytes, rng, n):
-    """rows built to sit on the decision boundary and at the extremes of the count range"""
+    """rows built to sit on the decision boundary and at the extremes of the count range.
+
+    Cohort sums beyond the log-factorial table cost the oracle (like the reference,
+    log_factorial_table.hpp:14-18) an O(sum) loop of log() per look-up, so rows with large sums are
+    kept few: most rows stay below 60 000 per cohort, a dozen reach ~1e6.  Sums never reach 2^31,
+    where the reference narrows to `int` (model.hpp:133) and parity is undefined."""
     dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[count_bytes]
-    # cohort sums stay below 2^31: beyond that the reference narrows the sum to `int` (model.hpp:133),
-    # which is undefined behaviour, so there is nothing to be at parity with
-    cmax = min(int(np.iinfo(dt).max), (2**31 - 1) // max(nc, nk))
+    cmax = int(np.iinfo(dt).max)
     N = nc + nk
+    per_elem = max(1, min(cmax, 60_000 // max(nc, nk)))       # keeps a cohort sum <= 60 000
     counts = np.zeros((n, N), dtype=np.uint64)
     kind = rng.integers(0, 6, size=n)
     for i in range(n):
@@ -184,18 +188,24 @@ def adversarial_rows(nc, nk, count_bytes, rng, n):
             counts[i, nc:] = rng.integers(0, 40, size=nk)
         elif k == 1:
             counts[i, :nc] = rng.integers(0, 40, size=nc)
-        elif k == 2:    # huge counts
-            counts[i] = rng.integers(cmax // 2, cmax, size=N, endpoint=True)
+        elif k == 2:    # large counts, beyond the 10 000-entry table
+            counts[i] = rng.integers(per_elem // 2, per_elem, size=N, endpoint=True)
         elif k == 3:    # near the boundary: base b vs b+delta with LR around 12..14
-            b = int(rng.integers(1, 2000))
+            b = int(rng.integers(1, max(2, min(2000, per_elem - 200))))
             counts[i, :nc] = b
             d = int(np.sqrt(2 * 13.0 * 2 * b * nc / (nc * nk)) * rng.uniform(0.8, 1.2)) + 1
-            counts[i, nc:] = b + d
+            counts[i, nc:] = min(cmax, b + d)
         elif k == 4:    # single non-zero
             counts[i, rng.integers(0, N)] = rng.integers(1, min(cmax, 500))
-        else:           # sparse big
+        else:           # sparse, a few big values
             j = rng.integers(0, N, size=3)
-            counts[i, j] = rng.integers(1, cmax, size=3, endpoint=True)
+            counts[i, j] = rng.integers(1, min(cmax, 15_000), size=3, endpoint=True)
+    # a dozen rows with cohort sums ~1e6 (4-byte counts only), alternately balanced and one-sided
+    if count_bytes == 4:
+        for t, i in enumerate(rng.choice(n, size=12, replace=False)):
+            counts[i] = 0
+            counts[i, :nc] = 1_000_000 // nc
+            counts[i, nc:] = (1_000_000 // nk) if t % 2 == 0 else 3
     counts = np.minimum(counts, cmax).astype(dt)
     counts[counts.sum(axis=1) == 0, 0] = 1
     kmers = np.arange(1, n + 1, dtype=np.uint64)
@@ -208,7 +218,7 @@ def adversarial_rows(nc, nk, count_bytes, rng, n):
 @pytest.mark.parametrize("nc,nk,b", [(10, 10, 4), (3, 17, 2), (8, 8, 1), (100, 100, 4)])
 def test_screen_has_no_false_negatives_on_adversarial_rows(nc, nk, b):
     rng = np.random.default_rng(1234 + nc + b)
-    n = 40_000
+    n = 20_000
     rows = adversarial_rows(nc, nk, b, rng, n)
     totals = np.full(nc + nk, 10**9, dtype=np.uint64)
     totals[nc:] += 3 * 10**8

@@ -1,0 +1,265 @@
+"""The C++ host program `kmdiff-b200 diff` (kmdiff_b200/host): kmtricks format code on the CPU, and —
+on a GPU — whole runs compared with the oracle and, where oracle/_ref/kmdiff travelled along, with the
+unmodified reference binary on the same run directory (same FASTA records as sets; the reference's
+record order for the stateless correctors is thread-interleaving dependent).
+"""
+import os
+import re
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import kmdiff_b200 as K
+import oracle
+from kmdiff_b200 import build as kb
+from kmdiff_b200 import kmtricks_io as kio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+THR_ARGS = ["-s", "0.05", "-u", "100000"]
+
+
+@pytest.fixture(scope="module")
+def cli():
+    path = kb.build_cli()
+    assert path and os.path.exists(path)
+    return path
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, **kw)
+
+
+def make_run_dir(tmp_path, shape=(10, 10, 31, 4), n_rows=120_000, parts=5, lz4=False, seed=31, ppm=3000):
+    nc, nk, k, b = shape
+    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=n_rows, seed=seed, enriched_ppm=ppm)
+    d = str(tmp_path / "run")
+    kio.write_run_dir(d, spec, n_rows, parts, lz4=lz4)
+    return spec, d
+
+
+def read_fasta(path):
+    recs = []
+    with open(path) as f:
+        head, seq = None, []
+        for line in f:
+            line = line.rstrip("\n")
+            if line.startswith(">"):
+                if head is not None:
+                    recs.append((head, "".join(seq)))
+                head, seq = line, []
+            else:
+                seq.append(line)
+        if head is not None:
+            recs.append((head, "".join(seq)))
+    return recs
+
+
+def strip_index(head):
+    return head.split("_", 1)[1]
+
+
+# ---- CPU: format code ------------------------------------------------------------------------------
+
+def test_lz4_frame_reader_decodes_real_lz4_frames(cli, tmp_path):
+    """a matrix compressed by liblz4 (via pyarrow: LZ4F default preferences, linked 64 KiB blocks — what
+    kmtricks' lz4_stream writes) decodes to the original payload"""
+    spec = K.SynthSpec(10, 10, total_rows=60_000, seed=5)
+    rows = spec.rows_host(60_000)
+    path = str(tmp_path / "matrix_0.count.lz4")
+    kio.write_matrix(path, rows, 31, 4, 20, 0, lz4=True)
+    assert os.path.getsize(path) < rows.nbytes * 0.8          # it really is compressed
+    out = subprocess.run([cli, "dev-cat", path, "45"], capture_output=True, timeout=120)
+    assert out.returncode == 0
+    assert np.array_equal(np.frombuffer(out.stdout, np.uint8), rows)
+    # highly repetitive input: long overlapping matches
+    rep = np.tile(np.arange(7, dtype=np.uint8), 300_000)
+    kio.write_matrix(path, rep, 31, 4, 20, 0, lz4=True)
+    out = subprocess.run([cli, "dev-cat", path, "45"], capture_output=True, timeout=120)
+    assert np.array_equal(np.frombuffer(out.stdout, np.uint8), rep)
+
+
+def test_lz4_frame_writer_is_readable_by_liblz4(cli, tmp_path):
+    import pyarrow as pa
+    data = np.random.default_rng(0).integers(0, 256, 300_001, dtype=np.uint8)
+    src, dst = tmp_path / "in.bin", tmp_path / "out.lz4"
+    data.tofile(src)
+    assert run([cli, "dev-pack", str(src), str(dst)]).returncode == 0
+    with pa.CompressedInputStream(pa.OSFile(str(dst)), "lz4") as s:
+        back = s.read()
+    assert back == data.tobytes()
+    out = subprocess.run([cli, "dev-cat", str(dst), "0", "lz4"], capture_output=True, timeout=60)
+    assert out.stdout == data.tobytes()
+
+
+def test_run_dir_config_and_totals(cli, tmp_path):
+    spec, d = make_run_dir(tmp_path, n_rows=2000, parts=3)
+    r = run([cli, "dev-config", d, "10", "10"])
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().split("\n")
+    assert lines[0] == "kmer_size=31 abundance_min=1 nb_partitions=3"
+    totals = [int(x.split()[1]) for x in lines[1:21]]
+    assert totals == [int(t) for t in spec.totals()]
+    tc, tk = kio.get_total_kmer(d, 10, 10, 1)
+    assert totals == tc + tk
+    assert [x.split()[1] for x in lines[21:]] == kio.list_matrices(d)
+    # abundance-min correction of the totals (kmtricks_utils.cpp:93-107): fof "! 3" subtracts 1*h[0] + 2*h[1]
+    hu = np.arange(1, 256, dtype=np.uint64)
+    kio.write_hist(os.path.join(d, "histograms", "C0.hist"), 31, 0, 10**6, hist_u=hu)
+    with open(os.path.join(d, "kmtricks.fof")) as f:
+        fof = f.read().replace("C0 : /dev/null/C0.fa", "C0 : /dev/null/C0.fa ! 3")
+    with open(os.path.join(d, "kmtricks.fof"), "w") as f:
+        f.write(fof)
+    r = run([cli, "dev-config", d, "10", "10"])
+    assert int(r.stdout.split("\n")[1].split()[1]) == 10**6 - 1 * 1 - 2 * 2
+
+
+def test_cli_argument_checks(cli, tmp_path):
+    r = run([cli, "diff", "-d", str(tmp_path), "-1", "1", "-2", "1"])
+    assert r.returncode == 1 and "Not a kmtricks runtime directory" in r.stderr
+    spec, d = make_run_dir(tmp_path, n_rows=100, parts=1)
+    assert "Not in range [0.0, 0.5]" in run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-s", "0.7"]).stderr
+    assert run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-c", "fdr"]).returncode == 1
+    assert run([cli, "diff", "-d", d, "-1", "x", "-2", "10"]).returncode == 1
+    assert run([cli, "--version"]).stdout.startswith("kmdiff-b200")
+
+
+@pytest.mark.skipif(K._lib.load().kmd_device_count() > 0, reason="a GPU is present")
+def test_cli_without_gpu_fails_loudly_with_exit_code_zero(cli, tmp_path):
+    """like the reference, errors are logged and the exit code stays 0 (main.cc:93-102); and there is no CPU path"""
+    spec, d = make_run_dir(tmp_path, n_rows=100, parts=1)
+    r = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", str(tmp_path / "out")])
+    assert r.returncode == 0
+    assert re.search(r"\[error\] GpuError - .*no CPU fallback", r.stderr)
+    assert not os.path.exists(tmp_path / "out" / "case_kmers.fasta")
+
+
+def test_example_plugin_builds_against_public_header(tmp_path):
+    so = tmp_path / "libex_model.so"
+    r = run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+             os.path.join(ROOT, "plugins", "ex_model.cpp"), "-o", str(so)])
+    assert r.returncode == 0, r.stderr
+    syms = run(["nm", "-D", str(so)]).stdout
+    for s in ("plugin_name", "create8", "create16", "create32"):
+        assert re.search(rf"\bT {s}\b", syms)
+
+
+# ---- GPU: whole runs ---------------------------------------------------------------------------------
+
+def expected_records(spec, n_rows, parts, corr, sig=0.05, cutoff=100000):
+    """what `kmdiff diff` must write, from the oracle: (control set, case set) of 'header-without-index\\nseq'"""
+    rows = spec.rows_host(n_rows)
+    m = oracle.Model(spec.nb_controls, spec.nb_cases, spec.totals())
+    want, *_ = m.diff(rows, spec.kmer_words, spec.count_bytes, sig / cutoff)
+    keep = oracle.aggregate(want["p"], oracle.CORRECTIONS[corr], sig, n_rows)
+    ctl, case = [], []
+    for r in want[keep]:
+        seq = oracle.kmer_to_string(r["kmer"][:spec.kmer_words], spec.kmer_size)
+        rec = oracle.fasta_record(0, r["p"], r["mean_control"], r["mean_case"], seq)
+        head, body = rec.split("\n", 1)
+        (ctl if r["sign"] == oracle.CONTROL else case).append((strip_index(head), body.replace("\n", "")))
+    return ctl, case, len(want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("corr", ["bonferroni", "benjamini", "sidak", "holm", "disabled"])
+@pytest.mark.parametrize("lz4", [False, True])
+def test_cli_matches_oracle(cli, tmp_path, corr, lz4):
+    n, parts = 120_000, 5
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=parts, lz4=lz4)
+    out = str(tmp_path / "out")
+    sig = "1e-9" if corr == "disabled" else "0.05"
+    r = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "-c", corr, "-s", sig, "-u", "100000" if corr != "disabled" else "1"])
+    assert r.returncode == 0 and "[error]" not in r.stderr, r.stderr
+    ctl, case, n_pref = expected_records(spec, n, parts, corr, float(sig), 100000 if corr != "disabled" else 1)
+    got_ctl = [(strip_index(h), s) for h, s in read_fasta(os.path.join(out, "control_kmers.fasta"))]
+    got_case = [(strip_index(h), s) for h, s in read_fasta(os.path.join(out, "case_kmers.fasta"))]
+    assert len(ctl) + len(case) > 50
+    if corr in ("benjamini", "holm"):
+        assert got_ctl == ctl and got_case == case        # ascending p, ties by row: fully ordered
+    else:
+        assert sorted(got_ctl) == sorted(ctl) and sorted(got_case) == sorted(case)
+    assert f"{n_pref}/{n} significant k-mers." in r.stderr
+    assert f"Significant k-mers: {len(ctl)} (control), {len(case)} (case)." in r.stderr
+    # running index per file (aggregator.hpp:55-62)
+    heads = [h for h, _ in read_fasta(os.path.join(out, "case_kmers.fasta"))]
+    assert [int(h[1:].split("_")[0]) for h in heads] == list(range(len(heads)))
+    with open(os.path.join(out, "options.bin"), "rb") as f:
+        ob = f.read()
+    thr, cutoff, c, pop = struct.unpack("<ddiB", ob[:21])
+    assert (thr, c, pop) == (float(sig), oracle.CORRECTIONS[corr], 0) and struct.unpack("<Q", ob[37:45])[0] == n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,cb", [((50, 50, 63, 2), 2), ((12, 20, 21, 1), 1)])
+def test_cli_other_count_widths_and_wide_kmers(cli, tmp_path, shape, cb):
+    n, parts = 50_000, 3
+    spec, d = make_run_dir(tmp_path, shape=shape, n_rows=n, parts=parts)
+    out = str(tmp_path / "out")
+    r = run([cli, "diff", "-d", d, "-1", str(shape[0]), "-2", str(shape[1]), "-o", out, "--count-bytes", str(cb), "--keep-tmp"])
+    assert "[error]" not in r.stderr, r.stderr
+    ctl, case, n_pref = expected_records(spec, n, parts, "bonferroni")
+    got = [(strip_index(h), s) for f in ("control_kmers.fasta", "case_kmers.fasta") for h, s in read_fasta(os.path.join(out, f))]
+    assert sorted(got) == sorted(ctl + case) and len(got) > 10
+    if shape[2] > 60:
+        assert all(len(s) == 63 for _, s in got)
+        with open(os.path.join(out, "case_kmers.fasta")) as f:
+            lines = f.read().split("\n")
+        assert len(lines[1]) == 60 and len(lines[2]) == 3      # kseq++ wraps sequences at 60 columns
+    # --keep-tmp: spill files in the reference's record layout (kmer words | f64 p | i32 sign | f64 | f64)
+    rec = 8 * spec.kmer_words + 28
+    total = 0
+    for p in range(parts):
+        raw = subprocess.run([cli, "dev-cat", os.path.join(out, "partitions", f"p{p}_uncorrected"), "0", "lz4"],
+                             capture_output=True, timeout=60).stdout
+        assert len(raw) % rec == 0
+        total += len(raw) // rec
+    assert total == n_pref
+
+
+@pytest.mark.gpu
+def test_cli_matches_reference_binary(cli, tmp_path):
+    """the unmodified reference `kmdiff diff` and kmdiff-b200 on the same run directory"""
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("oracle/_ref/kmdiff not built")
+    n, parts = 200_000, 8
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=parts, seed=99)
+    for corr in ("bonferroni", "benjamini"):
+        out_ref, out_new = str(tmp_path / f"ref_{corr}"), str(tmp_path / f"new_{corr}")
+        opt = os.path.join(d, "kmdiff-count.opt")
+        if os.path.exists(opt):
+            os.remove(opt)
+        r = run([oracle.REF_BIN, "diff", "--km-run", d, "-1", "10", "-2", "10", "-o", out_ref, "-c", corr, "-t", "4"] + THR_ARGS)
+        assert "[error]" not in r.stderr, r.stderr
+        if os.path.exists(opt):
+            os.remove(opt)
+        r2 = run([cli, "diff", "--km-run", d, "-1", "10", "-2", "10", "-o", out_new, "-c", corr, "-t", "4"] + THR_ARGS)
+        assert "[error]" not in r2.stderr, r2.stderr
+        for f in ("control_kmers.fasta", "case_kmers.fasta"):
+            a = sorted((strip_index(h), s) for h, s in read_fasta(os.path.join(out_ref, f)))
+            b = sorted((strip_index(h), s) for h, s in read_fasta(os.path.join(out_new, f)))
+            assert len(a) > 5 and a == b, (corr, f, len(a), len(b))
+        # the summary lines the reference prints
+        for pat in (r"\d+/\d+ significant k-mers\.", r"Before correction: \d+ \(control\), \d+ \(case\)\.",
+                    r"Significant k-mers: \d+ \(control\), \d+ \(case\)\."):
+            assert re.search(pat, r.stderr).group(0) == re.search(pat, r2.stderr).group(0)
+
+
+@pytest.mark.gpu
+def test_cli_plugin_model(cli, tmp_path):
+    so = tmp_path / "libex_model.so"
+    assert run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+                os.path.join(ROOT, "plugins", "ex_model.cpp"), "-o", str(so)]).returncode == 0
+    n = 40_000
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=4, ppm=5000)
+    out = str(tmp_path / "out")
+    r = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "--cmodel", str(so), "--config", "3.0", "-t", "3"])
+    assert "[error]" not in r.stderr and "Plugin 'FoldChangeModel' loaded." in r.stderr, r.stderr
+    counts = spec.rows_host(n).reshape(n, -1)[:, 8:].copy().view(np.uint32).reshape(n, 20).astype(np.float64)
+    mc, mk = counts[:, :10].mean(axis=1), counts[:, 10:].mean(axis=1)
+    up, down = mk > 3.0 * (mc + 1), mc > 3.0 * (mk + 1)
+    got_case = read_fasta(os.path.join(out, "case_kmers.fasta"))
+    got_ctl = read_fasta(os.path.join(out, "control_kmers.fasta"))
+    assert len(got_case) == int(up.sum()) > 0 and len(got_ctl) == int((down & ~up).sum())
+    assert f"{int((up | down).sum())}/{n} significant k-mers." in r.stderr
