@@ -106,6 +106,8 @@ struct kmd_context
   uint32_t n_final = 0;
   int order_state = 0;           // 0 none, 1 row order over all survivors, 2 p order over all survivors
   bool final_valid = false;
+  bool final_sorted = false;     // d_order is in output order (row order, or ascending p); else sorted lazily at fetch
+  uint64_t max_row_key = 0;      // upper bound of every survivor's row index: bounds the radix passes of a row sort
 
   // host staging for kmd_scan_host / kmd_model_rows_host
   uint8_t* d_stage[2] = {nullptr, nullptr};
@@ -495,6 +497,42 @@ __global__ void gather_records_kernel(uint32_t n, const uint32_t* order, Survivo
   out[i] = r;
 }
 
+// Stateless correctors (aggregator::worker, aggregator.hpp:137-163): every survivor is tested on its own, so the
+// kept slots are appended in arrival order (warp-aggregated atomics) and only ordered when they are fetched.
+__global__ void __launch_bounds__(256) keep_unordered_kernel(DeviceCounters* cnt, uint32_t cap, const double* p, double cut,
+                                                             const int32_t* sign, uint32_t* out_order)
+{
+  const uint32_t n = min(cnt->surv_count, cap);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t rounds = (n + stride - 1) / stride;
+  uint32_t n_ctl = 0, n_case = 0;
+  for (uint32_t r = 0, i = blockIdx.x * blockDim.x + threadIdx.x; r < rounds; r++, i += stride)
+  {
+    const bool keep = i < n && p[i] < cut;
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, keep);
+    if (!ballot) continue;
+    uint32_t pos = 0;
+    if (lane == 0) pos = atomicAdd(&cnt->keep_total, __popc(ballot));
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0) + __popc(ballot & ((1u << lane) - 1));
+    if (keep)
+    {
+      out_order[pos] = i;
+      if (sign[i] == KMD_SIGN_CONTROL) n_ctl++; else n_case++;
+    }
+  }
+  for (uint32_t o = 16; o > 0; o >>= 1)
+  {
+    n_ctl += __shfl_xor_sync(0xFFFFFFFFu, n_ctl, o);
+    n_case += __shfl_xor_sync(0xFFFFFFFFu, n_case, o);
+  }
+  if (lane == 0)
+  {
+    if (n_ctl) atomicAdd(&cnt->keep_control, n_ctl);
+    if (n_case) atomicAdd(&cnt->keep_case, n_case);
+  }
+}
+
 // FileAccumulator::push for records that arrive from the host (plugin models, resumed spill files)
 __global__ void push_records_kernel(uint32_t n, const kmd_survivor* in, SurvivorArrays s, DeviceCounters* cnt, uint32_t cap)
 {
@@ -595,6 +633,7 @@ int scan_device_impl(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, u
     done += n;
   }
   ctx->rows_tested += n_rows;
+  ctx->max_row_key = std::max(ctx->max_row_key, row_base + n_rows);
   ctx->order_state = 0;
   ctx->final_valid = false;
   return KMD_OK;
@@ -626,22 +665,24 @@ int fetch_counters(kmd_context* ctx)
   return KMD_OK;
 }
 
-// stable radix sort of (key, slot) pairs currently in d_keys[0]/d_vals[0]; result back in [0]
-int radix_sort(kmd_context* ctx, uint32_t n)
+// stable LSD radix sort of the (key, slot) pairs in d_keys[0]/d_vals[0] over the low 8*n_passes key bits
+// (higher bits must be equal in all keys); the sorted slots end up in d_vals[0]
+int radix_sort(kmd_context* ctx, uint32_t n, int n_passes = 8)
 {
-  if (n < 2) return KMD_OK;
+  if (n < 2 || n_passes <= 0) return KMD_OK;
   const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
   const size_t need = static_cast<size_t>(n_tiles) * 256;
   if (need > ctx->hist_entries)
   {
     if (ctx->d_hist) cudaFree(ctx->d_hist);
     ctx->d_hist = nullptr;
+    ctx->hist_entries = 0;
     KMD_CUDA(ctx, cudaMalloc(&ctx->d_hist, need * sizeof(uint32_t)));
     ctx->hist_entries = need;
   }
   const uint32_t blocks = (n_tiles + kSortWarps - 1) / kSortWarps;
   int cur = 0;
-  for (int pass = 0; pass < 8; pass++)
+  for (int pass = 0; pass < n_passes; pass++)
   {
     const int shift = 8 * pass;
     sort_hist_kernel<<<blocks, kSortWarps * 32, 0, ctx->stream>>>(ctx->d_keys[cur], n, shift, n_tiles, ctx->d_hist);
@@ -652,8 +693,16 @@ int radix_sort(kmd_context* ctx, uint32_t n)
     cur ^= 1;
   }
   KMD_CUDA(ctx, cudaGetLastError());
-  // 8 passes: the result is back in buffer 0
+  if (cur == 1)
+    KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_vals[0], ctx->d_vals[1], n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   return KMD_OK;
+}
+
+int row_key_passes(const kmd_context* ctx)
+{
+  int bits = 0;
+  for (uint64_t v = ctx->max_row_key; v; v >>= 1) bits++;
+  return std::max(1, (bits + 7) / 8);
 }
 
 inline uint32_t blocks_for(uint32_t n) { return std::max<uint32_t>(1, (n + 255) / 256); }
@@ -669,7 +718,7 @@ int ensure_order(kmd_context* ctx, int want)
   {
     iota_keys_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->surv.row, ctx->surv.p, 0, nullptr, ctx->d_keys[0], ctx->d_vals[0]);
     ctx->launches++;
-    if ((rc = radix_sort(ctx, n))) return rc;
+    if ((rc = radix_sort(ctx, n, row_key_passes(ctx)))) return rc;
     ctx->order_state = 1;
   }
   if (want == 2 && ctx->order_state == 1)
@@ -685,7 +734,7 @@ int ensure_order(kmd_context* ctx, int want)
   {
     iota_keys_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->surv.row, ctx->surv.p, 0, nullptr, ctx->d_keys[0], ctx->d_vals[0]);
     ctx->launches++;
-    if ((rc = radix_sort(ctx, n))) return rc;
+    if ((rc = radix_sort(ctx, n, row_key_passes(ctx)))) return rc;
     ctx->order_state = 1;
   }
   KMD_CUDA(ctx, cudaGetLastError());
@@ -736,6 +785,7 @@ int keep_below_impl(kmd_context* ctx, double cut, uint64_t* n_control, uint64_t*
   if (rc) return rc;
   ctx->n_final = n ? ctx->h_cnt->keep_total : 0;
   ctx->final_valid = true;
+  ctx->final_sorted = true;
   if (n_control) *n_control = ctx->h_cnt->keep_control;
   if (n_case) *n_case = ctx->h_cnt->keep_case;
   return KMD_OK;
@@ -955,8 +1005,10 @@ int kmd_reset(kmd_context* ctx)
   KMD_CUDA(ctx, cudaSetDevice(ctx->device));
   KMD_CUDA(ctx, cudaMemsetAsync(ctx->d_cnt, 0, sizeof(DeviceCounters), ctx->stream));
   ctx->rows_tested = 0;
+  ctx->max_row_key = 0;
   ctx->order_state = 0;
   ctx->final_valid = false;
+  ctx->final_sorted = false;
   ctx->n_final = 0;
   return KMD_OK;
 }
@@ -987,7 +1039,9 @@ int kmd_scan_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_
   {
     const int b = static_cast<int>(c & 1);
     const uint64_t n = std::min(chunk_rows, n_rows - done);
-    if (c >= 2) KMD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_scan[b], 0));
+    // the scan that last read this staging buffer (possibly enqueued by an earlier call) must be done;
+    // waiting on a never-recorded event is a no-op
+    KMD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_scan[b], 0));
     KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage[b], src + done * R, n * R, cudaMemcpyHostToDevice, ctx->copy_stream));
     KMD_CUDA(ctx, cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream));
     KMD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0));
@@ -1051,6 +1105,7 @@ int kmd_push_survivors(kmd_context* ctx, const kmd_survivor* records, uint64_t n
     KMD_CUDA(ctx, cudaGetLastError());
     KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `records` may be pageable and reused by the caller
   }
+  for (uint64_t i = 0; i < n; i++) ctx->max_row_key = std::max(ctx->max_row_key, records[i].row);
   ctx->rows_tested += rows_tested;
   ctx->order_state = 0;
   ctx->final_valid = false;
@@ -1127,9 +1182,6 @@ int kmd_correct(kmd_context* ctx, int correction, double significance, uint64_t 
   if (correction < KMD_CORR_NOTHING || correction > KMD_CORR_HOLM) return fail(ctx, KMD_ERR_ARG, "unknown correction %d", correction);
   KMD_CUDA(ctx, cudaSetDevice(ctx->device));
   const bool sorted = correction == KMD_CORR_BENJAMINI || correction == KMD_CORR_HOLM;
-  int rc = ensure_order(ctx, sorted ? 2 : 1);
-  if (rc) return rc;
-  const uint32_t n = ctx->h_cnt->surv_count;
   if (!sorted)
   {
     double cut;
@@ -1139,8 +1191,23 @@ int kmd_correct(kmd_context* ctx, int correction, double significance, uint64_t 
       case KMD_CORR_SIDAK: cut = 1 - std::pow(1 - significance, 1.0 / static_cast<double>(total_rows)); break;   // corrector.cpp:52
       default: cut = significance; break;                                                                        // corrector.cpp:88
     }
-    return keep_below_impl(ctx, cut, n_control, n_case);
+    KMD_CUDA(ctx, cudaMemsetAsync(&ctx->d_cnt->keep_control, 0, 3 * sizeof(uint32_t), ctx->stream));
+    keep_unordered_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_cnt, static_cast<uint32_t>(ctx->cap), ctx->surv.p, cut,
+                                                                       ctx->surv.sign, ctx->d_order);
+    ctx->launches++;
+    KMD_CUDA(ctx, cudaGetLastError());
+    int rc0 = fetch_counters(ctx);
+    if (rc0) return rc0;
+    ctx->n_final = ctx->h_cnt->keep_total;
+    ctx->final_valid = true;
+    ctx->final_sorted = false;
+    if (n_control) *n_control = ctx->h_cnt->keep_control;
+    if (n_case) *n_case = ctx->h_cnt->keep_case;
+    return KMD_OK;
   }
+  int rc = ensure_order(ctx, 2);
+  if (rc) return rc;
+  const uint32_t n = ctx->h_cnt->surv_count;
   // BENJAMINI / HOLM: ascending walk, stop at the first rejection (aggregator.hpp:282-310)
   KMD_CUDA(ctx, cudaMemsetAsync(&ctx->d_cnt->keep_control, 0, 3 * sizeof(uint32_t), ctx->stream));
   uint32_t n_keep = 0;
@@ -1165,6 +1232,7 @@ int kmd_correct(kmd_context* ctx, int correction, double significance, uint64_t 
   if ((rc = fetch_counters(ctx))) return rc;
   ctx->n_final = n_keep;
   ctx->final_valid = true;
+  ctx->final_sorted = true;
   if (n_control) *n_control = ctx->h_cnt->keep_control;
   if (n_case) *n_case = ctx->h_cnt->keep_case;
   return KMD_OK;
@@ -1175,6 +1243,18 @@ int kmd_significant(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t*
   if (!ctx) return KMD_ERR_ARG;
   if (!ctx->final_valid) return fail(ctx, KMD_ERR_STATE, "kmd_significant called before kmd_correct / kmd_keep_below");
   KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->final_sorted && ctx->n_final > 1)
+  {
+    // stateless correctors leave the kept slots in arrival order: put them in row order now
+    iota_keys_kernel<<<blocks_for(ctx->n_final), 256, 0, ctx->stream>>>(ctx->n_final, ctx->surv.row, ctx->surv.p, 0, ctx->d_order,
+                                                                         ctx->d_keys[0], ctx->d_vals[0]);
+    ctx->launches++;
+    int rc = radix_sort(ctx, ctx->n_final, row_key_passes(ctx));
+    if (rc) return rc;
+    KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, ctx->d_vals[0], ctx->n_final * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->order_state = 0;   // the full-survivor ordering in d_vals[0] was overwritten
+  }
+  ctx->final_sorted = true;
   return download_records(ctx, ctx->d_order, ctx->n_final, out, cap, n);
 }
 

@@ -13,8 +13,8 @@
 
 namespace kmd {
 
-constexpr int kSortTile = 2048;  // keys per warp
-constexpr int kSortWarps = 4;    // warps per CTA
+constexpr int kSortTile = 512;   // keys per warp
+constexpr int kSortWarps = 8;    // warps per CTA
 
 __global__ void __launch_bounds__(kSortWarps * 32)
 sort_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t n_tiles,
