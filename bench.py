@@ -333,13 +333,17 @@ def bench_b200(args) -> None:
     scan_avg_ms = sum(scan_ms) / len(scan_ms)
     achieved = rows * R / (scan_avg_ms * 1e-3) / 1e9
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "r01_lrt_scan_ncu.json")
-    if os.path.exists(prof):
+    traffic_src = None
+    import glob
+    for prof in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_lrt_scan_ncu.json")), reverse=True):
         try:
             with open(prof) as f:
                 pj = json.load(f)
             if pj.get("config") == cfg_name and pj.get("rows"):
+                # ncu --set full capture of the same kernel at pj["rows"] rows; DRAM bytes scale with rows
                 traffic = pj["dram_bytes_per_launch"] * (rows / pj["rows"])
+                traffic_src = os.path.relpath(prof, ROOT)
+                break
         except Exception:
             pass
 
@@ -391,7 +395,7 @@ def bench_b200(args) -> None:
             "screen_candidates": int(c.candidates),
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "lrt_scan_kernel", "ms_per_launch": scan_avg_ms,
+                     "traffic": traffic, "traffic_source": traffic_src, "kernel": "lrt_scan_kernel", "ms_per_launch": scan_avg_ms,
                      "algorithmic_bytes_per_launch": rows * R, "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": e2e_rows * R,
                 "d2h_bytes_per_step": int(d2h), "rows_per_step": e2e_rows, "steps": args.e2e_steps,
