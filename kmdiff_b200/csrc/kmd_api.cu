@@ -78,7 +78,7 @@ struct kmd_context
   double lr_cut = 0;            // LR*(threshold) on the host
   // scan plan
   kmd::ScanParams plan{};
-  uint32_t consumer_warps = kmd::kConsumerWarps;
+  uint32_t consumer_warps = 16;
   size_t scan_smem = 0;
   bool direct = false;          // stream rows with plain global loads instead of the TMA ring
 
@@ -258,11 +258,18 @@ int make_plan(kmd_context* ctx)
   P.words_ctrl = P.fast ? c.nb_controls * B / 8 : 0;
   P.straddle_elems = P.fast ? (c.nb_controls * B % 8) / B : 0;
 
-  const uint32_t warps = std::min<uint32_t>(kConsumerWarps, std::max<uint32_t>(1, env_u32("KMD_SCAN_WARPS", kConsumerWarps)));
+  // consumer geometry: `groups` groups of `gw` warps; a group sums one tile at a time
+  uint32_t groups = std::max<uint32_t>(1, env_u32("KMD_SCAN_GROUPS", 3));
+  uint32_t gw = std::max<uint32_t>(1, env_u32("KMD_SCAN_WARPS", 8));
+  if (groups * gw > kMaxConsumerWarps) return fail(ctx, KMD_ERR_ARG, "KMD_SCAN_GROUPS x KMD_SCAN_WARPS exceeds 31 consumer warps");
+  const uint32_t warps = groups * gw;
   ctx->consumer_warps = warps;
+  P.consumer_warps = warps;
+  P.groups = groups;
+  P.group_warps = gw;
 
   const uint32_t ring_budget = 200 * 1024;
-  const uint32_t target_tile = env_u32("KMD_SCAN_TILE_BYTES", 40 * 1024);
+  const uint32_t target_tile = env_u32("KMD_SCAN_TILE_BYTES", 24 * 1024);
   const uint32_t units = P.fast ? P.words_total : N;
 
   // lanes per row: cheapest estimated issue cost among the choices whose full pass fits the ring
@@ -270,8 +277,8 @@ int make_plan(kmd_context* ctx)
   double best_cost = 1e30;
   for (uint32_t g = 1; g <= 32; g *= 2)
   {
-    const uint64_t pass_rows = static_cast<uint64_t>(warps) * (32 / g);
-    if (pass_rows * P.row_bytes > ring_budget / 3 && g < 32) continue;
+    const uint64_t pass_rows = static_cast<uint64_t>(gw) * (32 / g);
+    if (pass_rows * P.row_bytes * std::max<uint32_t>(2, groups) > ring_budget && g < 32) continue;
     const uint32_t conf = conflict_degree(P.row_bytes, P.kmer_bytes, g, P.fast, B);
     uint32_t lg = 0;
     while ((1u << lg) < g) lg++;
@@ -283,9 +290,9 @@ int make_plan(kmd_context* ctx)
   if (P.lanes_per_row == 0 || (P.lanes_per_row & (P.lanes_per_row - 1)) || P.lanes_per_row > 32)
     return fail(ctx, KMD_ERR_ARG, "KMD_SCAN_G must be a power of two in [1,32]");
 
-  // rows per tile: whole passes of all consumer warps, rounded to 16 rows so that tile bytes are a
+  // rows per tile: whole passes of one consumer group, rounded to 16 rows so that tile bytes are a
   // multiple of 16 for any R
-  uint32_t pass_rows = warps * (32 / P.lanes_per_row);
+  uint32_t pass_rows = gw * (32 / P.lanes_per_row);
   pass_rows = (pass_rows + 15) / 16 * 16;
   uint32_t passes = std::max<uint32_t>(1, target_tile / (pass_rows * P.row_bytes));
   P.tile_rows = env_u32("KMD_SCAN_TILE_ROWS", pass_rows * passes);
@@ -324,7 +331,7 @@ int make_plan(kmd_context* ctx)
 // Same work as lrt_scan_kernel without the shared-memory ring: rows are read with plain global
 // loads.  Used for rows too large for the ring, and as the A/B baseline (KMD_SCAN_MODE=direct).
 template <int B>
-__global__ void __launch_bounds__(kScanThreads) lrt_scan_direct_kernel(const ScanParams P, uint32_t warps)
+__global__ void __launch_bounds__(kMaxScanThreads) lrt_scan_direct_kernel(const ScanParams P, uint32_t warps)
 {
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= warps) return;
@@ -579,7 +586,7 @@ int launch_scan(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, uint64
     const uint64_t chunks = (n_rows + P.tile_rows - 1) / P.tile_rows;
     const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(chunks, static_cast<uint64_t>(ctx->sm_count) * 2));
     cudaEventRecord(ctx->ev_k0, ctx->stream);
-    lrt_scan_direct_kernel<B><<<grid, kScanThreads, 0, ctx->stream>>>(P, ctx->consumer_warps);
+    lrt_scan_direct_kernel<B><<<grid, ctx->consumer_warps * 32, 0, ctx->stream>>>(P, ctx->consumer_warps);
     cudaEventRecord(ctx->ev_k1, ctx->stream);
   }
   else
@@ -587,7 +594,7 @@ int launch_scan(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, uint64
     P.n_tiles = static_cast<uint32_t>(n_rows / P.tile_rows);
     const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(P.n_tiles, ctx->sm_count));
     cudaEventRecord(ctx->ev_k0, ctx->stream);
-    lrt_scan_kernel<B><<<grid, kScanThreads, ctx->scan_smem, ctx->stream>>>(P);
+    lrt_scan_kernel<B><<<grid, (ctx->consumer_warps + 1) * 32, ctx->scan_smem, ctx->stream>>>(P);
     cudaEventRecord(ctx->ev_k1, ctx->stream);
   }
   ctx->scan_timed = true;

@@ -30,10 +30,10 @@
 
 namespace kmd {
 
-constexpr int kConsumerWarps = 16;
-constexpr int kScanThreads = (kConsumerWarps + 1) * 32;  // + 1 producer warp
-constexpr int kMaxStages = 8;
-constexpr int kBarrierBytes = 128;                       // full[8] + empty[8] mbarriers
+constexpr int kMaxConsumerWarps = 31;                    // + 1 producer warp = 1024 threads
+constexpr int kMaxScanThreads = (kMaxConsumerWarps + 1) * 32;
+constexpr int kMaxStages = 16;
+constexpr int kBarrierBytes = 16 * kMaxStages;           // full[] + empty[] mbarriers
 
 struct ScanParams
 {
@@ -48,6 +48,9 @@ struct ScanParams
   uint32_t stages;
   uint32_t stage_bytes;    // >= tile_rows*R, multiple of 128
   uint32_t lanes_per_row;  // g: power of two, 1..32
+  uint32_t consumer_warps; // warps 0..consumer_warps-1 consume, warp consumer_warps produces
+  uint32_t groups;         // consumer groups; group j consumes the CTA's tiles t = j, j+groups, ...
+  uint32_t group_warps;    // consumer_warps / groups; stages % groups == 0
   uint32_t fast;           // 1: (N*B) % 8 == 0 -> 8-byte word path
   uint32_t words_ctrl;     // words made of control counts only
   uint32_t straddle_elems; // control counts in the word that straddles the cohorts (0: none)
@@ -156,21 +159,27 @@ template <>
 struct Acc<4>
 {
   uint64_t v = 0;
-  __device__ __forceinline__ void word(uint64_t x) { v += (x & 0xFFFFFFFFull) + (x >> 32); }
-  __device__ __forceinline__ void elem(uint32_t e) { v += e; }
+  // one IMAD.WIDE.U32 per count: 64-bit accumulate of a 32-bit value on the FMA pipe
+  __device__ __forceinline__ void elem(uint32_t e) { asm("mad.wide.u32 %0, %1, 1, %0;" : "+l"(v) : "r"(e)); }
+  __device__ __forceinline__ void word(uint64_t x)
+  {
+    elem(static_cast<uint32_t>(x));
+    elem(static_cast<uint32_t>(x >> 32));
+  }
   __device__ __forceinline__ uint64_t total() const { return v; }
 };
 template <>
 struct Acc<2>
 {
-  uint64_t packed = 0;  // two independent 32-bit lanes; N*65535 < 2^32 for any N <= 65536
+  uint32_t v = 0;  // N*65535 < 2^32 for any N <= 65536 samples
+  // dp2a: v += lo16(x)*1 + hi16(x)*1 — one instruction per two counts
   __device__ __forceinline__ void word(uint64_t x)
   {
-    const uint64_t m = 0x0000FFFF0000FFFFull;
-    packed += (x & m) + ((x >> 16) & m);
+    v = __dp2a_lo(static_cast<uint32_t>(x), 0x00000101u, v);
+    v = __dp2a_lo(static_cast<uint32_t>(x >> 32), 0x00000101u, v);
   }
-  __device__ __forceinline__ void elem(uint32_t e) { packed += e; }
-  __device__ __forceinline__ uint64_t total() const { return (packed & 0xFFFFFFFFull) + (packed >> 32); }
+  __device__ __forceinline__ void elem(uint32_t e) { v += e; }
+  __device__ __forceinline__ uint64_t total() const { return v; }
 };
 template <>
 struct Acc<1>
@@ -290,10 +299,10 @@ __device__ __forceinline__ void scan_rows(const ScanParams& P, const Loader& ld,
 }
 
 template <int B>
-__global__ void __launch_bounds__(kScanThreads, 1) lrt_scan_kernel(const ScanParams P)
+__global__ void __launch_bounds__(kMaxScanThreads, 1) lrt_scan_kernel(const ScanParams P)
 {
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t bars = smem_u32(smem);              // full[s] at +8s, empty[s] at +64+8s
+  const uint32_t bars = smem_u32(smem);              // full[s] at +8s, empty[s] at +8*kMaxStages+8s
   const uint32_t ring = bars + kBarrierBytes;
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -303,7 +312,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) lrt_scan_kernel(const ScanPar
     for (uint32_t s = 0; s < P.stages; s++)
     {
       mbar_init(bars + 8 * s, 1);
-      mbar_init(bars + 64 + 8 * s, kConsumerWarps);
+      mbar_init(bars + 8 * kMaxStages + 8 * s, P.group_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -311,7 +320,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) lrt_scan_kernel(const ScanPar
 
   const uint32_t tile_bytes = P.tile_rows * P.row_bytes;
 
-  if (warp == kConsumerWarps)
+  if (warp == P.consumer_warps)
   {
     // ---- producer: one thread keeps `stages` tiles in flight ----
     if (lane == 0)
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) lrt_scan_kernel(const ScanPar
       {
         const uint32_t s = i % P.stages;
         const uint32_t phase = (i / P.stages) & 1;
-        mbar_wait(bars + 64 + 8 * s, phase ^ 1);  // consumers released this slot
+        mbar_wait(bars + 8 * kMaxStages + 8 * s, phase ^ 1);  // consumers released this slot
         mbar_expect_tx(bars + 8 * s, tile_bytes);
         bulk_g2s(ring + s * P.stage_bytes, P.rows + static_cast<uint64_t>(tile) * tile_bytes,
                  tile_bytes, bars + 8 * s);
@@ -330,17 +339,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) lrt_scan_kernel(const ScanPar
   }
   else
   {
-    // ---- consumers ----
-    uint32_t i = 0;
-    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x, i++)
+    // ---- consumers: group j of group_warps warps owns the CTA's tiles t = j, j+groups, ... so that
+    //      several tiles are being summed at once while each stays small enough for a deep ring ----
+    const uint32_t group = warp / P.group_warps;
+    const uint32_t gwarp = warp - group * P.group_warps;
+    for (uint32_t t = group;; t += P.groups)
     {
-      const uint32_t s = i % P.stages;
-      const uint32_t phase = (i / P.stages) & 1;
+      const uint64_t tile = blockIdx.x + static_cast<uint64_t>(t) * gridDim.x;
+      if (tile >= P.n_tiles) break;
+      const uint32_t s = t % P.stages;
+      const uint32_t phase = (t / P.stages) & 1;
       mbar_wait(bars + 8 * s, phase);
       SmemLoader ld{ring + s * P.stage_bytes};
-      scan_rows<B>(P, ld, P.tile_rows, tile * P.tile_rows, warp, kConsumerWarps, lane);
+      scan_rows<B>(P, ld, P.tile_rows, static_cast<uint32_t>(tile) * P.tile_rows, gwarp, P.group_warps, lane);
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + 64 + 8 * s);
+      if (lane == 0) mbar_arrive(bars + 8 * kMaxStages + 8 * s);
     }
     // ---- tail: rows after the last full tile, straight from global memory, by the last CTA ----
     const uint64_t done = static_cast<uint64_t>(P.n_tiles) * P.tile_rows;
@@ -348,7 +361,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) lrt_scan_kernel(const ScanPar
     {
       GmemLoader ld{P.rows + done * P.row_bytes};
       scan_rows<B>(P, ld, static_cast<uint32_t>(P.n_rows - done), static_cast<uint32_t>(done), warp,
-                   kConsumerWarps, lane);
+                   P.consumer_warps, lane);
     }
   }
 }

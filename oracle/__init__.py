@@ -55,6 +55,14 @@ class _Corrector(C.Structure):
                 ("rank", C.c_uint64)]
 
 
+class _PopStrat(C.Structure):
+    _fields_ = [("n", C.c_int), ("nb_controls", C.c_int), ("nb_cases", C.c_int), ("npc", C.c_int),
+                ("null_p", C.c_int), ("alt_p", C.c_int), ("max_iter", C.c_int), ("epsilon", C.c_double),
+                ("null_features", C.POINTER(C.c_double)), ("alt_features", C.POINTER(C.c_double)),
+                ("Y", C.POINTER(C.c_double)), ("totals", C.POINTER(C.c_double)),
+                ("null_model", C.POINTER(C.c_double))]
+
+
 SURVIVOR_DTYPE = np.dtype([("kmer", "<u8", (2,)), ("p", "<f8"), ("sign", "<i4"), ("pad_", "<i4"),
                            ("mean_control", "<f8"), ("mean_case", "<f8"), ("row", "<u8")])
 
@@ -89,6 +97,24 @@ def lib() -> C.CDLL:
         L.kmo_aggregate.restype = u64
         L.kmo_aggregate.argtypes = [vp, u64, C.c_int, d, u64, vp]
         L.kmo_kmer_to_string.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+        # population stratification (kmd_popstrat_oracle.h)
+        i32 = C.c_int
+        L.kmo_sampler_rows.restype = u64
+        L.kmo_sampler_rows.argtypes = [u64, d, u64, u64, vp]
+        L.kmo_sigmoid.restype = d
+        L.kmo_sigmoid.argtypes = [d]
+        L.kmo_inverse.argtypes = [vp, i32, vp, C.POINTER(i32), C.POINTER(i32)]
+        L.kmo_glm_irls.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(i32), C.POINTER(i32),
+                                   C.POINTER(d), C.POINTER(i32)]
+        L.kmo_popstrat_init.restype = i32
+        L.kmo_popstrat_init.argtypes = [C.POINTER(_PopStrat), i32, i32, vp, vp, i32]
+        L.kmo_popstrat_free.argtypes = [C.POINTER(_PopStrat)]
+        L.kmo_popstrat_apply.restype = d
+        L.kmo_popstrat_apply.argtypes = [C.POINTER(_PopStrat), vp, vp, C.POINTER(i32), C.POINTER(d)]
+        L.kmo_smartpca_xtx.restype = u64
+        L.kmo_smartpca_xtx.argtypes = [vp, u64, i32, i32, vp]
+        L.kmo_sym_eig.argtypes = [vp, i32, vp, vp]
+        L.kmo_smartpca_pcs.argtypes = [vp, u64, i32, i32, vp, i32, vp]
         _lib = L
     return _lib
 
@@ -118,6 +144,21 @@ def ref() -> C.CDLL:
         L.ref_corrector_apply.restype = C.c_int
         L.ref_corrector_apply.argtypes = [vp, d]
         L.ref_corrector_destroy.argtypes = [vp]
+        if hasattr(L, "ref_glm_irls"):
+            i32 = C.c_int
+            L.ref_sampler_rows.restype = sz
+            L.ref_sampler_rows.argtypes = [sz, d, sz, vp]
+            L.ref_sigmoid.restype = d
+            L.ref_sigmoid.argtypes = [d]
+            L.ref_inverse.argtypes = [vp, i32, vp, C.POINTER(i32), C.POINTER(i32)]
+            L.ref_glm_irls.argtypes = [vp, vp, i32, i32, i32, vp, C.POINTER(i32), C.POINTER(i32),
+                                       C.POINTER(d), C.POINTER(i32)]
+            L.ref_popstrat_create.restype = vp
+            L.ref_popstrat_create.argtypes = [sz, sz, vp, sz, C.c_char_p, C.c_char_p]
+            L.ref_popstrat_destroy.argtypes = [vp]
+            L.ref_popstrat_state.argtypes = [vp, vp, vp, vp]
+            L.ref_popstrat_apply.restype = d
+            L.ref_popstrat_apply.argtypes = [vp, vp, sz]
         _ref = L
     return _ref
 
@@ -265,6 +306,143 @@ class RefCorrector:
             ref().ref_corrector_destroy(self._h)
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------
+# Population stratification (kmd_popstrat_oracle.c; reference popstrat.hpp / linear_model.cpp / smartpca)
+# ------------------------------------------------------------------------------------------------
+
+def sampler_rows(seed: int, kmer_pca: float, n: int, first_row: int = 0) -> np.ndarray:
+    """Sampler::sample() decisions for rows first_row..first_row+n-1 (popstrat.hpp:107-146)."""
+    out = np.zeros(n, dtype=np.uint8)
+    lib().kmo_sampler_rows(seed, kmer_pca, first_row, n, out.ctypes.data)
+    return out.astype(bool)
+
+
+def glm_irls(x: np.ndarray, y: np.ndarray, max_iters: int = 100, impl: str = "oracle"):
+    """glm_irls (linear_model.cpp:297-410) -> (weights, singular, nan, error, iterations)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n, p = x.shape
+    w = np.empty(p, np.float64)
+    s, q, it = C.c_int(), C.c_int(), C.c_int()
+    e = C.c_double()
+    f = lib().kmo_glm_irls if impl == "oracle" else ref().ref_glm_irls
+    f(x.ctypes.data, y.ctypes.data, n, p, max_iters, w.ctypes.data, C.byref(s), C.byref(q), C.byref(e),
+      C.byref(it))
+    return w, bool(s.value), bool(q.value), e.value, it.value
+
+
+def inverse(a: np.ndarray, impl: str = "oracle"):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    inv = np.empty((n, n), np.float64)
+    s, q = C.c_int(), C.c_int()
+    f = lib().kmo_inverse if impl == "oracle" else ref().ref_inverse
+    f(a.ctypes.data, n, inv.ctypes.data, C.byref(s), C.byref(q))
+    return inv, bool(s.value), bool(q.value)
+
+
+class PopStrat:
+    """pop_strat_corrector (popstrat.hpp:148-372): features, standardize, null model, apply."""
+
+    def __init__(self, nb_controls: int, nb_cases: int, totals, Z: np.ndarray, npc: int):
+        self.totals = np.ascontiguousarray(totals, dtype=np.uint64)
+        Z10 = np.zeros((nb_controls + nb_cases, 10), np.float64)
+        Z = np.asarray(Z, dtype=np.float64)
+        Z10[:, :Z.shape[1]] = Z
+        self.Z = Z10
+        self._c = _PopStrat()
+        rc = lib().kmo_popstrat_init(C.byref(self._c), nb_controls, nb_cases, self.totals.ctypes.data,
+                                     Z10.ctypes.data, npc)
+        if rc:
+            raise ValueError("kmo_popstrat_init failed")
+        n, pc, pa = self._c.n, self._c.null_p, self._c.alt_p
+        self.n, self.null_p, self.alt_p = n, pc, pa
+        self.null_features = np.ctypeslib.as_array(self._c.null_features, shape=(n, pc)).copy()
+        self.alt_features = np.ctypeslib.as_array(self._c.alt_features, shape=(n, pa)).copy()
+        self.null_model = np.ctypeslib.as_array(self._c.null_model, shape=(pc,)).copy()
+        self.Y = np.ctypeslib.as_array(self._c.Y, shape=(n,)).copy()
+
+    def apply(self, counts, full: bool = False):
+        counts = np.ascontiguousarray(counts, dtype=np.float64)
+        model = np.empty(self.alt_p, np.float64)
+        it = C.c_int()
+        llr = C.c_double()
+        p = lib().kmo_popstrat_apply(C.byref(self._c), counts.ctypes.data, model.ctypes.data,
+                                     C.byref(it), C.byref(llr))
+        return (p, model, it.value, llr.value) if full else p
+
+    def __del__(self):
+        try:
+            lib().kmo_popstrat_free(C.byref(self._c))
+        except Exception:
+            pass
+
+
+class RefPopStrat:
+    """The unmodified pop_strat_corrector behind ref_shim.cpp, fed through the files do_pop reads."""
+
+    def __init__(self, nb_controls: int, nb_cases: int, totals, Z: np.ndarray, npc: int, workdir: str):
+        totals = np.ascontiguousarray(totals, dtype=np.uint64)
+        n = nb_controls + nb_cases
+        Z10 = np.zeros((n, 10), np.float64)
+        Z = np.asarray(Z, dtype=np.float64)
+        Z10[:, :Z.shape[1]] = Z
+        pcs = os.path.join(workdir, "pcs.evec")
+        ind = os.path.join(workdir, "gwas_eigenstratX.ind")
+        with open(pcs, "w") as f:
+            for row in Z10:     # evec2pca.perl layout: " %.04f" per component
+                f.write("".join((" " if v <= 0 else "  ") + "%.04f" % v for v in row) + "\n")
+        with open(ind, "w") as f:
+            for i in range(n):
+                f.write(f"S{i}\tU\t{'Control' if i < nb_controls else 'Case'}\n")
+        self.n, self.null_p, self.alt_p = n, npc + 2, npc + 3
+        self._h = ref().ref_popstrat_create(nb_controls, nb_cases, totals.ctypes.data, npc,
+                                            pcs.encode(), ind.encode())
+        self.null_features = np.empty((n, self.null_p), np.float64)
+        self.alt_features = np.empty((n, self.alt_p), np.float64)
+        self.null_model = np.empty(self.null_p, np.float64)
+        ref().ref_popstrat_state(self._h, self.null_features.ctypes.data, self.alt_features.ctypes.data,
+                                 self.null_model.ctypes.data)
+
+    def apply(self, counts) -> float:
+        counts = np.ascontiguousarray(counts, dtype=np.float64)
+        return ref().ref_popstrat_apply(self._h, counts.ctypes.data, counts.size)
+
+    def __del__(self):
+        try:
+            ref().ref_popstrat_destroy(self._h)
+        except Exception:
+            pass
+
+
+def smartpca_xtx(geno: np.ndarray, is_diploid: bool = True):
+    """(XTX normalised like smartpca.c:1011-1023, SNPs used).  geno: m x n of 0/1."""
+    geno = np.ascontiguousarray(geno, dtype=np.uint8)
+    m, n = geno.shape
+    xtx = np.empty((n, n), np.float64)
+    used = lib().kmo_smartpca_xtx(geno.ctypes.data, m, n, int(is_diploid), xtx.ctypes.data)
+    return xtx, used
+
+
+def sym_eig(a: np.ndarray):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    evals = np.empty(n, np.float64)
+    evecs = np.empty((n, n), np.float64)
+    lib().kmo_sym_eig(a.ctypes.data, n, evals.ctypes.data, evecs.ctypes.data)
+    return evals, evecs
+
+
+def smartpca_pcs(geno: np.ndarray, evecs: np.ndarray, numeigs: int = 10, is_diploid: bool = True):
+    geno = np.ascontiguousarray(geno, dtype=np.uint8)
+    evecs = np.ascontiguousarray(evecs, dtype=np.float64)
+    m, n = geno.shape
+    pcs = np.empty((n, numeigs), np.float64)
+    lib().kmo_smartpca_pcs(geno.ctypes.data, m, n, int(is_diploid), evecs.ctypes.data, numeigs,
+                           pcs.ctypes.data)
+    return pcs
 
 
 # ------------------------------------------------------------------------------------------------

@@ -14,6 +14,9 @@
 //   alglib::chisquarecdistribution            thirdparty/alglib/src/specialfunctions.cpp:2750
 //   kmdiff::make_corrector / ICorrector       src/corrector.cpp:101-117
 //   the per-row loop of diff_observer::process include/kmdiff/merge.hpp:68-103
+//   kmdiff::Sampler<MAX_C>::sample()          include/kmdiff/popstrat.hpp:107-146
+//   kmdiff::glm_irls / inverse / sigmoid      src/linear_model.cpp:297-410, 139-189, 191-195
+//   kmdiff::pop_strat_corrector               include/kmdiff/popstrat.hpp:148-372, src/popstrat.cpp
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -21,10 +24,26 @@
 #include <thread>
 #include <vector>
 
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <random>
+#include <sstream>
+#include <string>
+#include <tuple>
+
 #include <kmdiff/model.hpp>
 #include <kmdiff/corrector.hpp>
 #include <kmdiff/log_factorial_table.hpp>
+#include <kmdiff/linear_model.hpp>
 #include <specialfunctions.h>
+
+// pop_strat_corrector::apply(KmerSign&) and its feature matrices are private; the shim reads them
+// to pin the oracle, so the class is opened up for this translation unit only (every standard
+// header it uses is already included above).
+#define private public
+#include <kmdiff/popstrat.hpp>
+#undef private
 
 namespace {
 
@@ -141,6 +160,81 @@ int ref_corrector_apply(void* h, double p)
 void ref_corrector_destroy(void* h)
 {
   delete static_cast<std::shared_ptr<kmdiff::ICorrector>*>(h);
+}
+
+
+// ---- population stratification ------------------------------------------------------------------
+
+// Sampler::sample() n times: out[i] = (draw i < v).  geno/snp sinks are not touched by sample().
+std::size_t ref_sampler_rows(std::size_t seed, double v, std::size_t n, std::uint8_t* out)
+{
+  kmdiff::Sampler<4294967295> s(nullptr, nullptr, v, seed);
+  std::size_t taken = 0;
+  for (std::size_t i = 0; i < n; i++) { out[i] = s.sample() ? 1 : 0; taken += out[i]; }
+  return taken;
+}
+
+double ref_sigmoid(double x) { return kmdiff::sigmoid(x); }
+
+void ref_inverse(const double* a, int n, double* inv, int* singular, int* is_nan)
+{
+  kmdiff::matrix_t m(n, kmdiff::vector_t(n));
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) m[i][j] = a[i * n + j];
+  auto [r, s, q] = kmdiff::inverse(m, n);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) inv[i * n + j] = r[i][j];
+  *singular = s; *is_nan = q;
+}
+
+void ref_glm_irls(const double* x, const double* y, int n, int p, int max_iters, double* weight,
+                  int* singular, int* is_nan, double* err, int* iters)
+{
+  kmdiff::matrix_t X(n, kmdiff::vector_t(p));
+  kmdiff::vector_t Y(y, y + n);
+  for (int i = 0; i < n; i++) for (int j = 0; j < p; j++) X[i][j] = x[i * p + j];
+  auto [w, s, q, e, it] = kmdiff::glm_irls(X, Y, max_iters);
+  for (int j = 0; j < p; j++) weight[j] = w[j];
+  *singular = s; *is_nan = q; *err = e; *iters = it;
+}
+
+// pop_strat_corrector built the way do_pop builds it (cmd/diff.hpp:203-211): load_Z / load_Y read
+// the files the caller wrote (pcs.evec: 10 numbers per line; .ind: "id\tU\tControl|Case").
+void* ref_popstrat_create(std::size_t nc, std::size_t nk, const std::uint64_t* totals, std::size_t npc,
+                          const char* pcs_evec, const char* ind_file)
+{
+  std::vector<std::size_t> tc(totals, totals + nc), tk(totals + nc, totals + nc + nk);
+  auto* c = new kmdiff::pop_strat_corrector(nc, nk, tc, tk, npc);
+  c->load_Z(pcs_evec);
+  c->load_Y(ind_file);
+  c->load_C("");
+  c->load_ginfo("");
+  c->init_global_features();
+  return c;
+}
+
+void ref_popstrat_destroy(void* h) { delete static_cast<kmdiff::pop_strat_corrector*>(h); }
+
+// null / alt global feature matrices after standardize() and the null model
+void ref_popstrat_state(void* h, double* null_features, double* alt_features, double* null_model)
+{
+  auto* c = static_cast<kmdiff::pop_strat_corrector*>(h);
+  const std::size_t n = c->m_size, pc = c->m_null_feature_count, pa = c->m_alt_feature_count;
+  for (std::size_t i = 0; i < n; i++)
+  {
+    for (std::size_t j = 0; j < pc; j++) null_features[i * pc + j] = c->m_null_global_features[i][j];
+    for (std::size_t j = 0; j < pa; j++) alt_features[i * pa + j] = c->m_alt_global_features[i][j];
+  }
+  for (std::size_t j = 0; j < pc; j++) null_model[j] = c->m_null_model[j];
+}
+
+// pop_strat_corrector::apply(KmerSign&) on one survivor's counts -> corrected p-value
+double ref_popstrat_apply(void* h, const double* counts, std::size_t n)
+{
+  auto* c = static_cast<kmdiff::pop_strat_corrector*>(h);
+  std::vector<double> v(counts, counts + n);
+  km::Kmer<32> k;
+  kmdiff::KmerSign<32> ks(std::move(k), 0.5, kmdiff::Significance::CASE, v, 0.0, 0.0);
+  c->apply(ks);
+  return ks.m_pvalue;
 }
 
 } // extern "C"

@@ -3,6 +3,7 @@
 direct loads) on device-resident synthetic rows.  Prints one line per setting: GB/s of the scan kernel
 (CUDA events around the launch, best of 5 after 2 warm-ups).  Usage: python profiles/sweep_scan.py [c2 c3 c5]"""
 import itertools
+import time
 import json
 import os
 import sys
@@ -19,7 +20,7 @@ SHAPES = {"c2": (10, 10, 31, 4, 100_000_000), "c3": (100, 100, 31, 4, 10_000_000
 
 
 def measure(spec, totals, data, rows, env):
-    for k in ("KMD_SCAN_TILE_BYTES", "KMD_SCAN_STAGES", "KMD_SCAN_WARPS", "KMD_SCAN_G", "KMD_SCAN_MODE"):
+    for k in ("KMD_SCAN_TILE_BYTES", "KMD_SCAN_STAGES", "KMD_SCAN_WARPS", "KMD_SCAN_G", "KMD_SCAN_MODE", "KMD_SCAN_GROUPS"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     nc, nk = spec.nb_controls, spec.nb_cases
@@ -42,6 +43,9 @@ def measure(spec, totals, data, rows, env):
     return rows * spec.row_bytes / (best * 1e-3) / 1e9, n_surv
 
 
+T0 = time.time()
+
+
 def main():
     names = sys.argv[1:] or ["c2", "c3", "c5"]
     out = []
@@ -55,20 +59,23 @@ def main():
         base, ns = measure(spec, totals, data, rows, {})
         print(f"{name} R={spec.row_bytes} default: {base:.0f} GB/s survivors={ns}", flush=True)
         out.append({"config": name, "env": {}, "gbps": base})
-        settings = [{"KMD_SCAN_MODE": "direct"}]
-        for tile, stages in itertools.product((8192, 16384, 24576, 32768, 49152, 65536), (2, 3, 4, 6, 8)):
-            settings.append({"KMD_SCAN_TILE_BYTES": tile, "KMD_SCAN_STAGES": stages})
-        for warps in (4, 8, 12):
-            settings.append({"KMD_SCAN_WARPS": warps})
-        for g in (1, 2, 4, 8, 16, 32):
-            settings.append({"KMD_SCAN_G": g})
+        settings = []
+        if os.environ.get("SWEEP_FULL"):
+            settings.append({"KMD_SCAN_MODE": "direct"})
+            for tile, stages in itertools.product((8192, 16384, 24576, 32768, 49152, 65536), (2, 3, 4, 6, 8)):
+                settings.append({"KMD_SCAN_TILE_BYTES": tile, "KMD_SCAN_STAGES": stages})
+            for g in (1, 2, 4, 8, 16, 32):
+                settings.append({"KMD_SCAN_G": g})
+        for (groups, warps), tile in itertools.product(((1, 24), (2, 12), (2, 15), (3, 8), (3, 10), (4, 7), (5, 6)),
+                                                       (16384, 32768)):
+            settings.append({"KMD_SCAN_GROUPS": groups, "KMD_SCAN_WARPS": warps, "KMD_SCAN_TILE_BYTES": tile})
         for env in settings:
             gbps, ns2 = measure(spec, totals, data, rows, env)
             if gbps is None:
                 print(f"{name} {env}: rejected ({ns2})", flush=True)
                 continue
             assert ns2 == ns, (ns2, ns)
-            print(f"{name} {env}: {gbps:.0f} GB/s", flush=True)
+            print(f"{name} {env}: {gbps:.0f} GB/s  [t={time.time() - T0:.1f}s]", flush=True)
             out.append({"config": name, "env": env, "gbps": gbps})
         del data
         torch.cuda.empty_cache()
