@@ -302,6 +302,16 @@ int make_plan(kmd_context* ctx)
   uint32_t stages = tile_bytes ? static_cast<uint32_t>(ring_budget / P.stage_bytes) : 0;
   stages = std::min<uint32_t>(stages, kMaxStages);
   stages = std::min<uint32_t>(stages, std::max<uint32_t>(1, env_u32("KMD_SCAN_STAGES", kMaxStages)));
+  // A consumer group must be the only reader of a ring slot in consecutive phases (a group that ran a
+  // whole ring ahead of another would alias the mbarrier parity), so the ring holds a multiple of
+  // `groups` stages; with fewer stages than groups the rows are streamed with plain loads instead.
+  if (stages < groups)
+  {
+    P.groups = 1;  // one group of all consumer warps
+    P.group_warps = warps;
+  }
+  else
+    stages -= stages % groups;
   P.stages = stages;
   const char* mode = getenv("KMD_SCAN_MODE");
   ctx->direct = stages < 2 || tile_bytes >= (1u << 20) || (mode && !strcmp(mode, "direct"));
