@@ -171,6 +171,64 @@ int kmd_keep_below(kmd_context* ctx, double p_cut, uint64_t* n_control, uint64_t
 uint64_t kmd_first_reject(const double* p_sorted, uint64_t n, int correction, double significance,
                           uint64_t total_rows, double* p_cut);
 
+/* ---- --pop-correction: Sampler -> smartpca Gram matrix -> PCs -> per-k-mer logistic GLM
+ *      (cmd/diff.hpp:168-224, 307-362; include/kmdiff/popstrat.hpp; src/popstrat.cpp;
+ *       src/linear_model.cpp; thirdparty/hawk/EIG6.0.1-Hawk/src/eigensrc/smartpca.c) ------------ */
+
+/* Sampler<MAX_C> constructor arguments (popstrat.hpp:107-118) + smartpca's `-p` and capacity */
+typedef struct kmd_popstrat_config
+{
+  double kmer_pca;      /* --kmer-pca: probability that a row is sampled                   */
+  uint64_t seed;        /* --random-seed; 0 = default-constructed engine (popstrat.hpp:116) */
+  uint32_t is_diploid;  /* --ploidy 2 (run_eigenstrat_smartpca's is_diploid)               */
+  uint32_t n_pc;        /* --n-pc: principal components used as covariates (<= 10)          */
+  uint64_t max_sampled; /* capacity of the presence matrix; 0 = 1<<21 sampled k-mers        */
+} kmd_popstrat_config;
+
+/* Turn the context into diff_observer_strat (merge.hpp:129-177): from now on every kmd_scan_* also
+ * runs the Sampler on its rows (draw index = row_base + row, i.e. the reference's `-t 1` visiting
+ * order when row_base is the number of rows of the partitions visited before) and keeps the N counts
+ * of every prefilter survivor.  Must be called before the first scan. */
+int kmd_popstrat_enable(kmd_context* ctx, const kmd_popstrat_config* cfg);
+int kmd_popstrat_sampled(kmd_context* ctx, uint64_t* n);
+/* gwas_eigenstratX.geno (popstrat.hpp:56-80) as bytes: geno[s*N + i] = sample i carries sampled
+ * k-mer s, rows[s] = its global row index; ordered by row like the file the reference writes. */
+int kmd_popstrat_geno(kmd_context* ctx, uint8_t* geno, uint64_t* rows, uint64_t cap, uint64_t* n);
+/* smartpca's XTX (smartpca.c:907-1025) of the sampled k-mers: int8 tensor-core Gram matrices per
+ * carrier-count bucket, combined in fp64.  xtx: N*N row-major.  normalize != 0 divides by
+ * trace/(N-1) (smartpca.c:1019-1023); multi-GPU callers sum the un-normalised matrices of all ranks
+ * first and call kmd_smartpca_normalize.  n_used = SNPs with at least one carrier. */
+int kmd_popstrat_gram(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used);
+/* device time (ms) of the tensor-core kernel of the last kmd_popstrat_gram */
+int kmd_popstrat_gram_ms(kmd_context* ctx, float* ms);
+/* pop_strat_corrector: load_Z/load_Y + init_global_features (src/popstrat.cpp:153-171, 270-370),
+ * including standardize() and the null-model IRLS.  Z: N x 10 row-major (what load_Z parses from
+ * pcs.evec); totals: per-sample k-mer totals, controls first.  null_model: null_p = n_pc + 2
+ * weights, may be NULL. */
+int kmd_popstrat_init(kmd_context* ctx, const double* Z, const uint64_t* totals, double* null_model);
+/* pop_strat_corrector::apply over all accumulators (popstrat.hpp:186-246): every prefilter
+ * survivor's p-value is replaced by the GLM likelihood-ratio p-value (one warp per k-mer). */
+int kmd_popstrat_apply(kmd_context* ctx);
+/* pop_strat_corrector::apply(KmerSign&) (popstrat.hpp:249-333) on caller-supplied count vectors:
+ * counts = n_kmers x N host counts of count_bytes each.  Outputs may be NULL: p (corrected
+ * p-value), model (n_kmers x alt_p weights, alt_p = n_pc + 3), llr, iters. */
+int kmd_popstrat_fit(kmd_context* ctx, const void* counts, uint64_t n_kmers, double* p, double* model,
+                     double* llr, int32_t* iters);
+/* counts of the prefilter survivors, row order like kmd_survivors: n x N values of count_bytes */
+int kmd_survivor_counts(kmd_context* ctx, void* out, uint64_t cap, uint64_t* n);
+
+/* host-side (no device needed) */
+void kmd_smartpca_normalize(double* xtx, uint32_t n);
+/* all eigenvalues (descending) and unit eigenvectors (evecs[j*n+i]; largest component positive) of
+ * a symmetric matrix: smartpca's eigvecs (eigsubs.c:35-51).  Returns 0 on success. */
+int kmd_sym_eig(const double* a, uint32_t n, double* evals, double* evecs);
+/* the numeigs leading principal components as the reference reads them back: eigenvectors of the
+ * normalised XTX, projected and rescaled to unit length (smartpca.c:1140-1329), printed "%10.4f"
+ * (pcs.evec) and parsed (load_Z).  evals: n (may be NULL); pcs: n x numeigs row-major. */
+int kmd_smartpca_pcs(const double* xtx, uint32_t n, uint32_t numeigs, double* evals, double* pcs);
+/* Sampler decisions of rows [first_row, first_row+n) on the host (same arithmetic as the kernel) */
+uint64_t kmd_sampler_rows(uint64_t seed, double kmer_pca, uint64_t first_row, uint64_t n, uint8_t* out);
+
 /* ---- host-side pieces of the path that stay on the CPU -------------------------------------- */
 
 /* LogFactorialTable (src/log_factorial_table.cpp:5-22): table[i] = log(i)+log(i-1)+...+log(2) */

@@ -8,7 +8,8 @@ fails loudly if it is missing.
 """
 from .api import (CorrectionType, DiffContext, KmdError, LogFactorialTable, PoissonLikelihood,  # noqa: F401
                   Significance, basic_threshold, benjamini, bonferroni, correction_from_str,
-                  first_reject, format_fasta, holm, kmer_to_string, make_corrector, sidak)
+                  first_reject, format_fasta, holm, kmer_to_string, make_corrector, sampler_rows, sidak,
+                  smartpca_pcs, sym_eig)
 from .kmtricks_io import SynthSpec  # noqa: F401
 
 __version__ = "0.1.0"

@@ -24,6 +24,10 @@ SYMBOLS = [
     "kmd_lf_table_fill", "kmd_chisqc", "kmd_corrector_apply", "kmd_kmer_to_string",
     "kmd_format_fasta", "kmd_host_alloc", "kmd_host_free", "kmd_synth_fill_host",
     "kmd_synth_fill_device", "kmd_synth_totals",
+    "kmd_popstrat_enable", "kmd_popstrat_sampled", "kmd_popstrat_geno", "kmd_popstrat_gram",
+    "kmd_popstrat_gram_ms", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
+    "kmd_survivor_counts", "kmd_smartpca_normalize", "kmd_sym_eig", "kmd_smartpca_pcs",
+    "kmd_sampler_rows",
 ]
 
 
@@ -39,6 +43,11 @@ class Config(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("candidates", C.c_uint64), ("survivors", C.c_uint64),
                 ("n_control", C.c_uint64), ("n_case", C.c_uint64)]
+
+
+class PopstratConfig(C.Structure):
+    _fields_ = [("kmer_pca", C.c_double), ("seed", C.c_uint64), ("is_diploid", C.c_uint32),
+                ("n_pc", C.c_uint32), ("max_sampled", C.c_uint64)]
 
 
 class Synth(C.Structure):
@@ -115,5 +124,20 @@ def load() -> C.CDLL:
     L.kmd_synth_fill_device.argtypes = [C.POINTER(Synth), C.c_int, vp, u64, u64, vp]
     L.kmd_synth_totals.argtypes = [C.POINTER(Synth), vp]
     L.kmd_synth_totals.restype = None
+    L.kmd_popstrat_enable.argtypes = [vp, C.POINTER(PopstratConfig)]
+    L.kmd_popstrat_sampled.argtypes = [vp, pu64]
+    L.kmd_popstrat_geno.argtypes = [vp, vp, vp, u64, pu64]
+    L.kmd_popstrat_gram.argtypes = [vp, vp, C.c_int, pu64]
+    L.kmd_popstrat_gram_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.kmd_popstrat_init.argtypes = [vp, vp, vp, vp]
+    L.kmd_popstrat_apply.argtypes = [vp]
+    L.kmd_popstrat_fit.argtypes = [vp, vp, u64, vp, vp, vp, vp]
+    L.kmd_survivor_counts.argtypes = [vp, vp, u64, pu64]
+    L.kmd_smartpca_normalize.argtypes = [vp, u32]
+    L.kmd_smartpca_normalize.restype = None
+    L.kmd_sym_eig.argtypes = [vp, u32, vp, vp]
+    L.kmd_smartpca_pcs.argtypes = [vp, u32, u32, vp, vp]
+    L.kmd_sampler_rows.argtypes = [u64, d, u64, u64, vp]
+    L.kmd_sampler_rows.restype = u64
     _lib = L
     return L

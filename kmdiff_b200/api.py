@@ -22,7 +22,7 @@ from typing import Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import SURVIVOR_DTYPE, Config, Counters
+from ._lib import SURVIVOR_DTYPE, Config, Counters, PopstratConfig
 
 
 class KmdError(RuntimeError):
@@ -274,6 +274,114 @@ class DiffContext:
         nc, nk = C.c_uint64(), C.c_uint64()
         self._ck(self._L.kmd_keep_below(self._h, p_cut, C.byref(nc), C.byref(nk)))
         return nc.value, nk.value
+
+
+    # -- population stratification (--pop-correction) --
+    @property
+    def nb_samples(self) -> int:
+        return self.nb_controls + self.nb_cases
+
+    def popstrat_enable(self, kmer_pca: float, seed: int = 0, is_diploid: bool = True, n_pc: int = 2,
+                        max_sampled: int = 0) -> None:
+        """Sampler(geno, snp, kmer_pca, seed) (popstrat.hpp:107-118): every later scan also samples."""
+        cfg = PopstratConfig(float(kmer_pca), int(seed), int(bool(is_diploid)), int(n_pc), int(max_sampled))
+        self._ck(self._L.kmd_popstrat_enable(self._h, C.byref(cfg)))
+        self.n_pc = int(n_pc)
+
+    def popstrat_sampled(self) -> int:
+        n = C.c_uint64()
+        self._ck(self._L.kmd_popstrat_sampled(self._h, C.byref(n)))
+        return n.value
+
+    def popstrat_geno(self) -> tuple[np.ndarray, np.ndarray]:
+        """(geno [m, N] 0/1, global row index of each sampled k-mer), in row order (the .geno file)."""
+        m = self.popstrat_sampled()
+        geno = np.zeros((m, self.nb_samples), dtype=np.uint8)
+        rows = np.zeros(m, dtype=np.uint64)
+        n = C.c_uint64()
+        if m:
+            self._ck(self._L.kmd_popstrat_geno(self._h, geno.ctypes.data, rows.ctypes.data, m, C.byref(n)))
+        return geno, rows
+
+    def popstrat_gram(self, normalize: bool = True) -> tuple[np.ndarray, int]:
+        """smartpca's XTX of the sampled k-mers (int8 tensor-core Gram + fp64 fix-up); -> (xtx, n_used)."""
+        xtx = np.zeros((self.nb_samples, self.nb_samples), dtype=np.float64)
+        used = C.c_uint64()
+        self._ck(self._L.kmd_popstrat_gram(self._h, xtx.ctypes.data, int(normalize), C.byref(used)))
+        return xtx, used.value
+
+    def popstrat_gram_ms(self) -> float:
+        ms = C.c_float()
+        self._ck(self._L.kmd_popstrat_gram_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def popstrat_init(self, Z: np.ndarray, totals: np.ndarray) -> np.ndarray:
+        """pop_strat_corrector::init_global_features; Z: [N, 10]; returns the null model weights."""
+        Z = np.ascontiguousarray(Z, dtype=np.float64)
+        assert Z.shape == (self.nb_samples, 10)
+        t = np.ascontiguousarray(totals, dtype=np.uint64)
+        assert t.size == self.nb_samples
+        null_model = np.zeros(self.n_pc + 2, dtype=np.float64)
+        self._ck(self._L.kmd_popstrat_init(self._h, Z.ctypes.data, t.ctypes.data, null_model.ctypes.data))
+        return null_model
+
+    def popstrat_apply(self) -> None:
+        """pop_strat_corrector::apply over the accumulators: survivors' p-values become GLM p-values."""
+        self._ck(self._L.kmd_popstrat_apply(self._h))
+
+    def popstrat_fit(self, counts: np.ndarray):
+        """pop_strat_corrector::apply(KmerSign&) on [n_kmers, N] counts -> (p, model, llr, iters)."""
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[self.count_bytes]
+        c = np.ascontiguousarray(counts, dtype=dt).reshape(-1, self.nb_samples)
+        m = c.shape[0]
+        p = np.zeros(m, np.float64)
+        model = np.zeros((m, self.n_pc + 3), np.float64)
+        llr = np.zeros(m, np.float64)
+        iters = np.zeros(m, np.int32)
+        self._ck(self._L.kmd_popstrat_fit(self._h, c.ctypes.data, m, p.ctypes.data, model.ctypes.data,
+                                          llr.ctypes.data, iters.ctypes.data))
+        return p, model, llr, iters
+
+    def survivor_counts(self) -> np.ndarray:
+        """[n_survivors, N] counts of the prefilter survivors, row order like survivors()."""
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[self.count_bytes]
+        n = C.c_uint64()
+        self._ck(self._L.kmd_survivor_counts(self._h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, self.nb_samples), dtype=dt)
+        if n.value:
+            self._ck(self._L.kmd_survivor_counts(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+
+def sym_eig(a: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """eigenvalues (descending) and eigenvectors (rows) of a symmetric matrix (host helper)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    n = a.shape[0]
+    ev = np.zeros(n)
+    vec = np.zeros((n, n))
+    rc = _lib.load().kmd_sym_eig(a.ctypes.data, n, ev.ctypes.data, vec.ctypes.data)
+    if rc:
+        raise KmdError(rc, "eigensolver did not converge")
+    return ev, vec
+
+
+def smartpca_pcs(xtx: np.ndarray, numeigs: int = 10) -> tuple[np.ndarray, np.ndarray]:
+    """(eigenvalues, pcs [N, numeigs]) as pcs.evec holds them after "%10.4f" (host helper)."""
+    x = np.ascontiguousarray(xtx, dtype=np.float64)
+    n = x.shape[0]
+    ev = np.zeros(n)
+    pcs = np.zeros((n, numeigs))
+    rc = _lib.load().kmd_smartpca_pcs(x.ctypes.data, n, numeigs, ev.ctypes.data, pcs.ctypes.data)
+    if rc:
+        raise KmdError(rc, "smartpca_pcs failed")
+    return ev, pcs
+
+
+def sampler_rows(seed: int, kmer_pca: float, first_row: int, n: int) -> np.ndarray:
+    """Sampler decisions of rows [first_row, first_row + n) (host helper, jump-ahead LCG)."""
+    out = np.zeros(n, dtype=np.uint8)
+    _lib.load().kmd_sampler_rows(int(seed), float(kmer_pca), int(first_row), int(n), out.ctypes.data)
+    return out
 
 
 def first_reject(p_sorted: np.ndarray, correction: int, significance: float, total_rows: int):

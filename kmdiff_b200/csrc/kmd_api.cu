@@ -18,7 +18,10 @@
 
 #include <cuda_runtime.h>
 
+#include "kmd_eig.hpp"
+#include "kmd_grm.cuh"
 #include "kmd_math.cuh"
+#include "kmd_popstrat.cuh"
 #include "kmd_scan.cuh"
 #include "kmd_sort.cuh"
 #include "kmd_synth.cuh"
@@ -58,6 +61,33 @@ struct DeviceCounters
   uint32_t keep_case;
   uint32_t keep_total;
   uint32_t pad_;
+};
+
+// --pop-correction state: the Sampler's output (presence vectors of the sampled k-mers), the counts of
+// the prefilter survivors (KmerSign::m_counts_ratio under WITH_POPSTRAT) and the GLM features.
+struct PopState
+{
+  bool enabled = false;
+  kmd_popstrat_config cfg{};
+  uint32_t state0 = 1;
+  uint64_t cap = 0;                        // max sampled k-mers
+  unsigned long long* d_total = nullptr;   // sampled so far
+  unsigned long long* d_done = nullptr;    // slots with a presence vector
+  uint32_t* d_overflow = nullptr;
+  uint64_t* d_slot_rows = nullptr;
+  uint8_t* d_geno = nullptr;               // [cap][N] 0/1
+  uint32_t* d_carriers = nullptr;          // [cap]
+  uint8_t* d_surv_counts = nullptr;        // [max_survivors][N * count_bytes]
+  // GLM
+  bool glm_ready = false;
+  uint32_t null_p = 0, alt_p = 0;
+  double* d_null_feat = nullptr;           // [N][null_p]
+  double* d_alt_feat = nullptr;            // [N][alt_p]
+  double* d_y = nullptr;
+  double* d_totals = nullptr;
+  double null_likelihood = 0;
+  std::vector<double> null_model;
+  float gram_ms = 0;                       // device time of the last grm_umma_kernel launch
 };
 
 }  // namespace
@@ -114,9 +144,14 @@ struct kmd_context
   size_t stage_bytes = 0;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_scan[2] = {nullptr, nullptr};
+
+  PopState pop;
 };
 
 namespace {
+
+void pop_free(kmd_context* ctx);   // kmd_popstrat_api.inl
+int pop_reset(kmd_context* ctx);
 
 int fail(kmd_context* ctx, int code, const char* fmt, ...)
 {
@@ -368,6 +403,8 @@ struct ExactArgs
   SurvivorArrays out;
   uint32_t cap;
   uint32_t kmer_words;
+  uint8_t* counts_out;    // --pop-correction: the survivor's N counts (merge.hpp:161-163), else null
+  uint32_t counts_bytes;  // N * count_bytes
 };
 
 // diff_observer::process on the candidate rows: exact fp64 LRT in reference order, the `<=`
@@ -416,6 +453,11 @@ __global__ void __launch_bounds__(256) lrt_exact_kernel(const ExactArgs A)
         A.out.mc[pos] = st.mean_control;
         A.out.kk[pos] = st.mean_case;
         A.out.row[pos] = A.row_base + r;
+        if (A.counts_out)
+        {
+          uint8_t* dst = A.counts_out + static_cast<size_t>(pos) * A.counts_bytes;
+          for (uint32_t b = 0; b < A.counts_bytes; b++) dst[b] = ld.ld8(A.geom.kmer_bytes + b);
+        }
       }
       else
         atomicOr(&A.cnt->overflow, 2u);
@@ -624,8 +666,44 @@ int launch_scan(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, uint64
   A.out = ctx->surv;
   A.cap = static_cast<uint32_t>(ctx->cap);
   A.kmer_words = ctx->cfg.kmer_words;
+  A.counts_out = ctx->pop.enabled ? ctx->pop.d_surv_counts : nullptr;
+  A.counts_bytes = (ctx->cfg.nb_controls + ctx->cfg.nb_cases) * ctx->cfg.count_bytes;
   lrt_exact_kernel<B><<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(A);
   KMD_CUDA(ctx, cudaGetLastError());
+  if (ctx->pop.enabled)
+  {
+    // diff_observer_strat::process (merge.hpp:143-174): the Sampler sees every row, draw index = global row index
+    PopState& ps = ctx->pop;
+    pop::SamplerArgs S;
+    S.state0 = ps.state0;
+    S.v = ps.cfg.kmer_pca;
+    S.v_scaled = ps.cfg.kmer_pca * 2147483646.0;
+    S.first_row = row_base;
+    S.n_rows = n_rows;
+    S.rows_per_thread = 64;
+    S.total = ps.d_total;
+    S.out_rows = ps.d_slot_rows;
+    S.cap = ps.cap;
+    const uint64_t threads = (n_rows + S.rows_per_thread - 1) / S.rows_per_thread;
+    pop::sampler_kernel<<<static_cast<uint32_t>((threads + 255) / 256), 256, 0, ctx->stream>>>(S);
+    pop::PresenceArgs Q;
+    Q.rows = d_rows;
+    Q.row_base = row_base;
+    Q.row_bytes = P.row_bytes;
+    Q.kmer_bytes = P.kmer_bytes;
+    Q.n = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
+    Q.count_bytes = ctx->cfg.count_bytes;
+    Q.total = ps.d_total;
+    Q.done = ps.d_done;
+    Q.slot_rows = ps.d_slot_rows;
+    Q.geno = ps.d_geno;
+    Q.carriers = ps.d_carriers;
+    Q.cap = ps.cap;
+    pop::presence_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(Q);
+    pop::presence_done_kernel<<<1, 1, 0, ctx->stream>>>(ps.d_total, ps.d_done, ps.cap, ps.d_overflow);
+    ctx->launches += 3;
+    KMD_CUDA(ctx, cudaGetLastError());
+  }
   return KMD_OK;
 }
 
@@ -887,6 +965,7 @@ void kmd_destroy(kmd_context* ctx)
     if (ctx->ev_scan[b]) cudaEventDestroy(ctx->ev_scan[b]);
   }
   cudaFree(ctx->d_hist); cudaFree(ctx->d_p_sorted); cudaFree(ctx->d_out); cudaFree(ctx->d_order);
+  pop_free(ctx);
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1027,7 +1106,7 @@ int kmd_reset(kmd_context* ctx)
   ctx->final_valid = false;
   ctx->final_sorted = false;
   ctx->n_final = 0;
-  return KMD_OK;
+  return pop_reset(ctx);
 }
 
 int kmd_scan_device(kmd_context* ctx, const void* d_rows, uint64_t n_rows, uint64_t row_base, uint32_t partition)
@@ -1490,3 +1569,5 @@ int kmd_synth_fill_device(const kmd_synth* s, int device, void* d_rows, uint64_t
 }
 
 }  // extern "C"
+
+#include "kmd_popstrat_api.inl"

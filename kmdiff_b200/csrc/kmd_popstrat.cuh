@@ -171,7 +171,7 @@ __global__ void presence_done_kernel(const unsigned long long* total, unsigned l
 // ---- logistic GLM by IRLS, one warp per k-mer ---------------------------------------------------
 
 constexpr int kMaxP = 16;       // features per model (1 + n_pc + total + ratio <= 13 in the reference)
-constexpr int kIrlsWarps = 8;
+constexpr int kIrlsWarps = 8;    // at most; fewer when the per-warp state of a large cohort fills shared memory
 
 struct IrlsArgs
 {
@@ -254,7 +254,8 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
   IrlsWarp X{F, A.own_last ? xl : nullptr, A.ldf, p, n};
   const uint32_t pp = p * p;
 
-  for (uint32_t item = blockIdx.x * kIrlsWarps + warp; item < n_items; item += gridDim.x * kIrlsWarps)
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  for (uint32_t item = blockIdx.x * warps_per_block + warp; item < n_items; item += gridDim.x * warps_per_block)
   {
     // ---- local_features[i][p-1] = counts[i] / totals[i]  (popstrat.hpp:254-257) ----
     if (A.own_last)
