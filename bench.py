@@ -41,7 +41,11 @@ CONFIGS = {
     "c2": (10, 10, 31, 4, 1_000_000_000, "bonferroni"),
     "c3": (100, 100, 31, 4, 150_000_000, "benjamini"),   # 2e9 rows = 1.6 TB do not fit one GPU
     "c5": (50, 50, 63, 2, 500_000_000, "bonferroni"),    # per-GPU share of 4e9 rows over 8 GPUs
+    # BASELINE.json configs[3]: population stratification, 10 PCs, 1e6 sampled k-mers, logistic GLM
+    "c4": (200, 200, 31, 4, 60_000_000, "bonferroni"),
 }
+C4_NPC = 10
+C4_SAMPLED = 1_000_000
 SIGNIFICANCE = 0.05
 CUTOFF = 100000
 
@@ -229,6 +233,12 @@ def bench_b200(args) -> None:
     ctx = K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), kmer_size=k, count_bytes=b,
                         threshold=thr, device=local_rank, max_survivors=max(1 << 22, rows // 200))
     ctx.set_stream(stream.cuda_stream)
+    popstrat = cfg_name == "c4"
+    pop_ms = {"gram_kernel": [], "gram_call": [], "pca_host": [], "glm": [], "sampled": 0, "used": 0}
+    if popstrat:
+        if world > 1:
+            raise SystemExit("bench.py: c4 is a single-GPU bench line (the multi-GPU Gram sum is covered by tests)")
+        ctx.popstrat_enable(C4_SAMPLED / rows, seed=42, is_diploid=True, n_pc=C4_NPC, max_sampled=2 * C4_SAMPLED)
 
     # ---- resident workload: this rank's rows, generated on the device (seeded, counter-based) ----
     data = torch.empty(rows * R, dtype=torch.uint8, device=dev)
@@ -237,11 +247,33 @@ def bench_b200(args) -> None:
 
     counts_dev = torch.zeros(3, dtype=torch.int64, device=dev)
 
+    def pop_stage(timed: bool):
+        # do_pop (cmd/diff.hpp:168-224): Gram matrix of the sampled k-mers -> PCs -> null model -> GLM per survivor
+        t0 = time.perf_counter()
+        xtx, used = ctx.popstrat_gram()
+        t1 = time.perf_counter()
+        _, Z = K.smartpca_pcs(xtx, 10)
+        t2 = time.perf_counter()
+        ctx.popstrat_init(Z, totals)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        ctx.popstrat_apply()
+        g1.record(stream)
+        if timed:
+            g1.synchronize()
+            pop_ms["gram_kernel"].append(ctx.popstrat_gram_ms())
+            pop_ms["gram_call"].append(1e3 * (t1 - t0))
+            pop_ms["pca_host"].append(1e3 * (t2 - t1))
+            pop_ms["glm"].append(g0.elapsed_time(g1))
+            pop_ms["used"] = int(used)
+
     def step():
         ctx.reset()
         ctx.scan_device(data.data_ptr(), rows, row_base=rank * rows, partition=rank)
         c = ctx.counters()
         total_rows = c.rows
+        if popstrat:
+            pop_stage(True)
         if world > 1:
             counts_dev.copy_(torch.tensor([c.rows, c.n_control, c.n_case], dtype=torch.int64), non_blocking=True)
             dist.all_reduce(counts_dev)
@@ -292,7 +324,7 @@ def bench_b200(args) -> None:
     value = rows * world * args.steps / (elapsed_ms * 1e-3)
 
     # ---- end to end through the C-ABI with host buffers ----
-    e2e_rows = min(rows, args.e2e_rows)
+    e2e_rows = min(rows, args.e2e_rows, (8 << 30) // R)      # at most 8 GiB of pinned host rows
     L = _lib.load()
     hptr = L.kmd_host_alloc(e2e_rows * R)
     if not hptr:
@@ -309,6 +341,8 @@ def bench_b200(args) -> None:
         ctx.scan_host(hptr, e2e_rows, row_base=rank * rows, partition=rank)
         cc = ctx.counters()
         total = cc.rows * world
+        if popstrat:
+            pop_stage(False)
         r = ctx.correct(corr_kind, SIGNIFICANCE, total)
         sig = ctx.significant()
         d2h = sig.nbytes + 48 * 3
@@ -354,7 +388,7 @@ def bench_b200(args) -> None:
 
     # ---- CPU baseline: the reference binary on a bounded prefix of the same matrix (N=1 only) ----
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not popstrat:
         cores = os.cpu_count() or 1
         try:
             if reference_available():
@@ -399,10 +433,37 @@ def bench_b200(args) -> None:
                      "algorithmic_bytes_per_launch": rows * R, "peak_source": peak_src},
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": e2e_rows * R,
                 "d2h_bytes_per_step": int(d2h), "rows_per_step": e2e_rows, "steps": args.e2e_steps,
-                "api": "kmd_scan_host + kmd_correct + kmd_significant (pinned host buffer)"},
+                "api": ("kmd_scan_host + kmd_popstrat_{gram,init,apply} + kmd_correct + kmd_significant" if popstrat else
+                        "kmd_scan_host + kmd_correct + kmd_significant") + " (pinned host buffer)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if popstrat:
+        n = nc + nk
+        k = args.steps
+        avg = lambda v: sum(v[-k:]) / max(1, len(v[-k:]))
+        gram_ms = avg(pop_ms["gram_kernel"])
+        used = pop_ms["used"]
+        ops = 2.0 * n * n * used                       # algorithmic int8 multiply-adds x2 of X X^T
+        bf16 = None
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                bf16 = float(json.load(f)["bf16_tflops"])
+        except Exception:
+            pass
+        int8_peak = 2.0 * bf16 if bf16 else 4500.0
+        line["popstrat"] = {
+            "n_pc": C4_NPC, "sampled_kmers_used": used, "survivors_fitted": int(c.survivors),
+            "gram": {"bound": "tensor", "kernel": "grm_umma_kernel", "ms_per_launch": gram_ms,
+                     "achieved": ops / (gram_ms * 1e-3) / 1e12 if gram_ms else None, "peak": int8_peak, "unit": "TOP/s",
+                     "frac": (ops / (gram_ms * 1e-3) / 1e12) / int8_peak if gram_ms else None,
+                     "peak_source": "2 x measured dense bf16 (MEASURED_PEAKS.json): int8 tensor rate" if bf16 else "nominal 4.5 POP/s",
+                     "call_ms": avg(pop_ms["gram_call"]),
+                     "note": "2*N^2*m ops; N=400 occupies 4 of 4 M tiles x 512 TMEM columns after padding to 512"},
+            "pca_host_ms": avg(pop_ms["pca_host"]),
+            "glm": {"kernel": "irls_kernel", "ms": avg(pop_ms["glm"]),
+                    "kmers_per_s": int(c.survivors) / (avg(pop_ms["glm"]) * 1e-3) if pop_ms["glm"] else None},
+        }
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))

@@ -190,6 +190,11 @@ typedef struct kmd_popstrat_config
  * order when row_base is the number of rows of the partitions visited before) and keeps the N counts
  * of every prefilter survivor.  Must be called before the first scan. */
 int kmd_popstrat_enable(kmd_context* ctx, const kmd_popstrat_config* cfg);
+/* Decouple the Sampler's draw index from row_base: the next scanned row takes draw `next_draw`, every
+ * further row the following one, whatever row_base the scans are given.  The host program numbers
+ * survivor rows (partition << 40 | row) but draws in the reference's `-t 1` visiting order, i.e. with
+ * next_draw = number of rows in the partitions visited before (merge.hpp:341-397). */
+int kmd_popstrat_set_draw_index(kmd_context* ctx, uint64_t next_draw);
 int kmd_popstrat_sampled(kmd_context* ctx, uint64_t* n);
 /* gwas_eigenstratX.geno (popstrat.hpp:56-80) as bytes: geno[s*N + i] = sample i carries sampled
  * k-mer s, rows[s] = its global row index; ordered by row like the file the reference writes. */

@@ -24,7 +24,7 @@ SYMBOLS = [
     "kmd_lf_table_fill", "kmd_chisqc", "kmd_corrector_apply", "kmd_kmer_to_string",
     "kmd_format_fasta", "kmd_host_alloc", "kmd_host_free", "kmd_synth_fill_host",
     "kmd_synth_fill_device", "kmd_synth_totals",
-    "kmd_popstrat_enable", "kmd_popstrat_sampled", "kmd_popstrat_geno", "kmd_popstrat_gram",
+    "kmd_popstrat_enable", "kmd_popstrat_set_draw_index", "kmd_popstrat_sampled", "kmd_popstrat_geno", "kmd_popstrat_gram",
     "kmd_popstrat_gram_ms", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
     "kmd_survivor_counts", "kmd_smartpca_normalize", "kmd_sym_eig", "kmd_smartpca_pcs",
     "kmd_sampler_rows",
@@ -125,6 +125,7 @@ def load() -> C.CDLL:
     L.kmd_synth_totals.argtypes = [C.POINTER(Synth), vp]
     L.kmd_synth_totals.restype = None
     L.kmd_popstrat_enable.argtypes = [vp, C.POINTER(PopstratConfig)]
+    L.kmd_popstrat_set_draw_index.argtypes = [vp, u64]
     L.kmd_popstrat_sampled.argtypes = [vp, pu64]
     L.kmd_popstrat_geno.argtypes = [vp, vp, vp, u64, pu64]
     L.kmd_popstrat_gram.argtypes = [vp, vp, C.c_int, pu64]

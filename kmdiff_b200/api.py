@@ -288,6 +288,10 @@ class DiffContext:
         self._ck(self._L.kmd_popstrat_enable(self._h, C.byref(cfg)))
         self.n_pc = int(n_pc)
 
+    def popstrat_set_draw_index(self, next_draw: int) -> None:
+        """The next scanned row takes Sampler draw `next_draw`, whatever row_base the scans are given."""
+        self._ck(self._L.kmd_popstrat_set_draw_index(self._h, int(next_draw)))
+
     def popstrat_sampled(self) -> int:
         n = C.c_uint64()
         self._ck(self._L.kmd_popstrat_sampled(self._h, C.byref(n)))

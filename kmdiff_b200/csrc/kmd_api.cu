@@ -70,6 +70,8 @@ struct PopState
   bool enabled = false;
   kmd_popstrat_config cfg{};
   uint32_t state0 = 1;
+  bool draw_override = false;              // kmd_popstrat_set_draw_index: draws follow their own counter
+  uint64_t draw_next = 0;
   uint64_t cap = 0;                        // max sampled k-mers
   unsigned long long* d_total = nullptr;   // sampled so far
   unsigned long long* d_done = nullptr;    // slots with a presence vector
@@ -679,6 +681,8 @@ int launch_scan(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, uint64
     S.v = ps.cfg.kmer_pca;
     S.v_scaled = ps.cfg.kmer_pca * 2147483646.0;
     S.first_row = row_base;
+    S.first_draw = ps.draw_override ? ps.draw_next : row_base;
+    ps.draw_next += n_rows;
     S.n_rows = n_rows;
     S.rows_per_thread = 64;
     S.total = ps.d_total;

@@ -78,7 +78,8 @@ struct SamplerArgs
   uint32_t state0;        // engine state before the draw of global row 0
   double v;               // --kmer-pca
   double v_scaled;        // v * R
-  uint64_t first_row;     // global index of row 0 of this batch == index of its draw
+  uint64_t first_row;     // global index (survivor/geno row tag) of row 0 of this batch
+  uint64_t first_draw;    // index of the draw of row 0 of this batch (== first_row unless overridden)
   uint64_t n_rows;
   uint32_t rows_per_thread;
   unsigned long long* total;  // number of sampled rows so far (all batches)
@@ -94,8 +95,8 @@ __global__ void __launch_bounds__(256) sampler_kernel(const SamplerArgs A)
   const uint64_t r0 = t * A.rows_per_thread;
   if (r0 >= A.n_rows) return;
   const uint64_t r1 = min(r0 + A.rows_per_thread, A.n_rows);
-  // state before the draw of row first_row + r0: two engine calls per earlier row
-  uint32_t x = lcg_mul(A.state0, lcg_pow(kLcgA, 2ull * ((A.first_row + r0) % (kLcgM - 1u))));
+  // state before draw first_draw + r0: two engine calls per earlier row
+  uint32_t x = lcg_mul(A.state0, lcg_pow(kLcgA, 2ull * ((A.first_draw + r0) % (kLcgM - 1u))));
   for (uint64_t r = r0; r < r1; r++)
   {
     const uint32_t x1 = lcg_mul(x, kLcgA);

@@ -275,6 +275,15 @@ int kmd_popstrat_enable(kmd_context* ctx, const kmd_popstrat_config* cfg)
   return pop_reset(ctx);
 }
 
+int kmd_popstrat_set_draw_index(kmd_context* ctx, uint64_t next_draw)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (!ctx->pop.enabled) return fail(ctx, KMD_ERR_STATE, "population stratification is not enabled on this context");
+  ctx->pop.draw_override = true;
+  ctx->pop.draw_next = next_draw;
+  return KMD_OK;
+}
+
 int kmd_popstrat_sampled(kmd_context* ctx, uint64_t* n)
 {
   if (!ctx || !n) return KMD_ERR_ARG;

@@ -106,6 +106,7 @@ struct DiffOptions
   int gpus = 0;               // 0 = every visible device
   size_t count_bytes = 4;     // the reference fixes this at compile time (MAX_C); here a runtime option
   size_t max_survivors = 0;
+  size_t max_sampled = 0;     // capacity of the per-GPU presence matrix (--pop-correction); 0 = 2097152
   size_t total_kmers = 0;
 };
 
@@ -124,6 +125,13 @@ struct DiffOptions
     "  -m/--in-memory  -r/--cpr   accepted and ignored, as in the reference\n"
     "  --keep-tmp              keep partitions/p{i}_uncorrected spill files.\n"
     "  --save-sk               build the matrix of significant k-mers.\n"
+    " [population stratification]\n"
+    "  --pop-correction        apply correction of population stratification.\n"
+    "  --kmer-pca FLOAT        proportion of k-mers used for PCA (in [0.0, 0.05]). {0.001}\n"
+    "  --ploidy INT            ploidy level. {2}\n"
+    "  --n-pc INT              number of principal components (in [2, 10]). {2}\n"
+    "  --random-seed INT       seed of the k-mer sampler. {0}\n"
+    "  --gender/--covariates   accepted; both fail in the reference too (see DESIGN.md).\n"
     " [custom model]\n"
     "  --cmodel STR            path to model shared library (IModel plugin).\n"
     "  --config STR            model config.\n"
@@ -136,7 +144,8 @@ struct DiffOptions
     " [this implementation]\n"
     "  --gpus INT              GPUs to shard the partitions over. {all visible}\n"
     "  --count-bytes INT       count width of the matrices: 1, 2 or 4 (the reference's compile-time MAX_C). {4}\n"
-    "  --max-survivors INT     capacity of the per-GPU survivor buffers. {4194304}\n",
+    "  --max-survivors INT     capacity of the per-GPU survivor buffers. {4194304}\n"
+    "  --max-sampled INT       capacity of the per-GPU sampled k-mer buffer (--pop-correction). {2097152}\n",
     code ? stderr : stdout);
   exit(code);
 }
@@ -233,6 +242,7 @@ DiffOptions parse_cli(int argc, char** argv)
     else if (a == "--gpus") o.gpus = static_cast<int>(number());
     else if (a == "--count-bytes") o.count_bytes = number();
     else if (a == "--max-survivors") o.max_survivors = number();
+    else if (a == "--max-sampled") o.max_sampled = number();
     else cli_error("unknown parameter " + a);
   }
   if (!have_d) cli_error("-d/--km-run is required");
@@ -270,7 +280,7 @@ void ck(kmd_context* ctx, int rc, const char* what)
 // index sits above bit 40 so that device-side row order == (partition, row) order.
 constexpr int kPartShift = 40;
 
-struct Partition { std::string path; uint32_t index; uint64_t bytes; };
+struct Partition { std::string path; uint32_t index; uint64_t bytes; uint64_t draw_base = 0; };
 
 // One GPU's share: a reader thread decodes its partitions into pinned buffers, this thread feeds the GPU.
 class GpuWorker
@@ -297,6 +307,17 @@ class GpuWorker
     const int rc = kmd_create(&c, &raw);
     if (rc != KMD_OK) throw KmdError("GpuError", std::string("kmd_create: ") + kmd_last_error(nullptr));
     m_ctx.reset(raw);
+    if (o.pop_correction)
+    {
+      // Sampler(geno, snp, opt->kmer_pca, opt->seed) (cmd/diff.hpp:325-329)
+      kmd_popstrat_config pc{};
+      pc.kmer_pca = o.kmer_pca;
+      pc.seed = o.seed;
+      pc.is_diploid = o.ploidy == 2;
+      pc.n_pc = static_cast<uint32_t>(o.npc);
+      pc.max_sampled = o.max_sampled;
+      ck(raw, kmd_popstrat_enable(raw, &pc), "kmd_popstrat_enable");
+    }
     m_row_bytes = 8ull * c.kmer_words + (o.nb_controls + o.nb_cases) * o.count_bytes;
     m_buf_rows = std::max<uint64_t>(1, (64ull << 20) / m_row_bytes);
     for (auto& b : m_bufs)
@@ -329,7 +350,7 @@ class GpuWorker
   }
 
  private:
-  struct Buf { uint8_t* data = nullptr; uint64_t rows = 0; uint64_t row_base = 0; uint32_t partition = 0; bool last = false; };
+  struct Buf { uint8_t* data = nullptr; uint64_t rows = 0; uint64_t row_base = 0; uint64_t draw_base = 0; uint32_t partition = 0; bool last = false; };
 
   void read_loop()
   {
@@ -351,6 +372,7 @@ class GpuWorker
           if (got % m_row_bytes) throw KmdError("InputError", p.path + ": truncated row");
           b->rows = got / m_row_bytes;
           b->row_base = (static_cast<uint64_t>(p.index) << kPartShift) + local;
+          b->draw_base = p.draw_base + local;
           b->partition = p.index;
           local += b->rows;
           const bool eof = b->rows < m_buf_rows;
@@ -377,7 +399,12 @@ class GpuWorker
         b = m_ready.front(); m_ready.pop();
       }
       const bool last = b->last;
-      if (b->rows) ck(m_ctx.get(), kmd_scan_host(m_ctx.get(), b->data, b->rows, b->row_base, b->partition), "kmd_scan_host");
+      if (b->rows)
+      {
+        // Sampler draws follow the reference's `-t 1` visiting order, not the (partition, row) tag
+        if (m_opt.pop_correction) ck(m_ctx.get(), kmd_popstrat_set_draw_index(m_ctx.get(), b->draw_base), "kmd_popstrat_set_draw_index");
+        ck(m_ctx.get(), kmd_scan_host(m_ctx.get(), b->data, b->rows, b->row_base, b->partition), "kmd_scan_host");
+      }
       {
         std::lock_guard<std::mutex> lk(m_mu);
         b->last = false;
@@ -506,18 +533,21 @@ void run_plugin_model(PluginModel<MAX_C>& pm, const std::vector<Partition>& part
 
 // ---- spill files: partitions/p{i}_uncorrected (accumulator.hpp:156-285, kmer.hpp:113-127) --------------
 
-void write_spill_files(const std::vector<kmd_survivor>& surv, uint32_t nb_partitions, uint32_t kmer_words, const std::string& dir)
+// counts != nullptr: the WITH_POPSTRAT tail `u16 N | N x f64 counts` (kmer.hpp:118-123); surv and counts are parallel.
+void write_spill_files(const std::vector<kmd_survivor>& surv, uint32_t nb_partitions, uint32_t kmer_words, const std::string& dir,
+                       const char* suffix = "_uncorrected", const std::vector<double>* counts = nullptr, uint16_t n_counts = 0)
 {
   std::vector<std::unique_ptr<Lz4FrameWriter>> w(nb_partitions);
   std::vector<FILE*> files(nb_partitions, nullptr);
   for (uint32_t p = 0; p < nb_partitions; p++)
   {
-    files[p] = fopen((dir + "/p" + std::to_string(p) + "_uncorrected").c_str(), "wb");
+    files[p] = fopen((dir + "/p" + std::to_string(p) + suffix).c_str(), "wb");
     if (!files[p]) throw KmdError("IOError", "Unable to create spill file in " + dir);
     w[p] = std::make_unique<Lz4FrameWriter>(files[p]);
   }
-  for (const kmd_survivor& s : surv)
+  for (size_t i = 0; i < surv.size(); i++)
   {
+    const kmd_survivor& s = surv[i];
     if (s.partition >= nb_partitions) continue;
     Lz4FrameWriter& o = *w[s.partition];
     o.write(s.kmer, 8 * kmer_words);   // all words: the reference drops the high word for k > 32 (SURVEY.md §8 hazard 1)
@@ -525,6 +555,11 @@ void write_spill_files(const std::vector<kmd_survivor>& surv, uint32_t nb_partit
     o.write(&s.sign, 4);
     o.write(&s.mean_control, 8);
     o.write(&s.mean_case, 8);
+    if (counts)
+    {
+      o.write(&n_counts, 2);
+      o.write(counts->data() + i * n_counts, 8ull * n_counts);
+    }
   }
   for (uint32_t p = 0; p < nb_partitions; p++) { w[p]->close(); fclose(files[p]); }
 }
@@ -569,14 +604,152 @@ std::vector<kmd_survivor> fetch(kmd_context* ctx, bool significant)
   return out;
 }
 
+
+// ---- do_pop (cmd/diff.hpp:168-224): eigenstrat inputs, PCA, per-k-mer GLM ------------------------------------
+
+std::vector<double> fetch_counts_as_double(kmd_context* ctx, size_t n_samples, size_t count_bytes, uint64_t expect)
+{
+  uint64_t n = 0;
+  ck(ctx, kmd_survivor_counts(ctx, nullptr, 0, &n), "kmd_survivor_counts");
+  if (n != expect) throw KmdError("GpuError", "survivor counts out of step with the survivor records");
+  std::vector<uint8_t> raw(n * n_samples * count_bytes);
+  if (n) ck(ctx, kmd_survivor_counts(ctx, raw.data(), n, &n), "kmd_survivor_counts");
+  std::vector<double> out(n * n_samples);
+  for (size_t i = 0; i < out.size(); i++)
+  {
+    uint32_t v = 0;
+    memcpy(&v, raw.data() + i * count_bytes, count_bytes);   // little-endian counts
+    out[i] = static_cast<double>(v);
+  }
+  return out;
+}
+
+void do_pop(std::vector<std::unique_ptr<GpuWorker>>& workers, const DiffOptions& opt, const std::string& pop_dir,
+            const std::vector<uint64_t>& total_controls, const std::vector<uint64_t>& total_cases)
+{
+  Timer pca_time;
+  const uint32_t n = static_cast<uint32_t>(opt.nb_controls + opt.nb_cases);
+
+  // write_gwas_info x2 + control.ind / case.ind, write_gwas_eigenstrat_total, write_parfile (src/popstrat.cpp:9-96)
+  const std::vector<FofEntry> fof = parse_fof(opt.kmtricks_dir + "/kmtricks.fof");
+  {
+    std::ofstream par(pop_dir + "/parfile.txt");
+    // std::map order of parfile_map (popstrat.hpp:28-37)
+    par << "evaloutname: gwas_eigenstrat.eval\n" << "evecoutname: gwas_eigenstrat.evec\n" << "genotypename: gwas_eigenstratX.geno\n"
+        << "indivname: gwas_eigenstratX.ind\n" << "numoutevec: 10\n" << "numoutlieriter: 0\n" << "snpname: gwas_eigenstratX.snp\n"
+        << "usenorm: YES\n";
+    for (const char* name : {"/gwas_infos.txt", "/gwas_eigenstratX.ind"})
+    {
+      std::ofstream out(pop_dir + name), coind(pop_dir + "/control.ind"), caind(pop_dir + "/case.ind");
+      for (size_t i = 0; i < fof.size(); i++)
+      {
+        const bool control = i < opt.nb_controls;
+        out << fof[i].id << "\tU\t" << (control ? "Control" : "Case") << "\n";
+        (control ? coind : caind) << fof[i].id << "\tU\t" << (control ? "Control" : "Case") << "\n";
+      }
+    }
+    std::ofstream tot(pop_dir + "/gwas_eigenstratX.total");
+    for (uint64_t t : total_controls) tot << t << "\n";
+    for (uint64_t t : total_cases) tot << t << "\n";
+  }
+
+  // gwas_eigenstratX.geno / .snp: the sampled k-mers of all GPUs in (partition, row) order
+  // (EigGenoFile::push / EigSnpFile::push, popstrat.hpp:65-72, 92-96)
+  struct Sampled { uint64_t row; size_t worker; uint64_t slot; };
+  std::vector<Sampled> sampled;
+  std::vector<std::vector<uint8_t>> geno(workers.size());
+  for (size_t w = 0; w < workers.size(); w++)
+  {
+    kmd_context* ctx = workers[w]->ctx();
+    uint64_t m = 0;
+    ck(ctx, kmd_popstrat_sampled(ctx, &m), "kmd_popstrat_sampled");
+    geno[w].resize(m * n);
+    std::vector<uint64_t> rows(m);
+    if (m) ck(ctx, kmd_popstrat_geno(ctx, geno[w].data(), rows.data(), m, &m), "kmd_popstrat_geno");
+    for (uint64_t s = 0; s < m; s++) sampled.push_back({rows[s], w, s});
+  }
+  std::sort(sampled.begin(), sampled.end(), [](const Sampled& a, const Sampled& b) { return a.row < b.row; });
+  {
+    FILE* g = fopen((pop_dir + "/gwas_eigenstratX.geno").c_str(), "w");
+    FILE* snp = fopen((pop_dir + "/gwas_eigenstratX.snp").c_str(), "w");
+    if (!g || !snp) throw KmdError("IOError", "Unable to create eigenstrat inputs in " + pop_dir);
+    std::string line(2ull * n + 1, '\t');
+    line[2ull * n] = '\n';
+    for (size_t i = 0; i < sampled.size(); i++)
+    {
+      const uint8_t* v = geno[sampled[i].worker].data() + sampled[i].slot * n;
+      for (uint32_t j = 0; j < n; j++) line[2ull * j] = v[j] ? '1' : '0';
+      fwrite(line.data(), 1, line.size(), g);
+      fprintf(snp, "%zu\t1\t0.0\t0\n", i);
+    }
+    fclose(g); fclose(snp);
+  }
+  logf(L_DEBUG, "%zu k-mers sampled for the PCA", sampled.size());
+
+  // smartpca (run_eigenstrat_smartpca, src/popstrat.cpp:98-137): XTX summed over the GPUs, one host eigensolve
+  std::vector<double> xtx(static_cast<size_t>(n) * n, 0.0), part(static_cast<size_t>(n) * n);
+  uint64_t used = 0;
+  for (auto& w : workers)
+  {
+    uint64_t u = 0;
+    ck(w->ctx(), kmd_popstrat_gram(w->ctx(), part.data(), 0, &u), "kmd_popstrat_gram");
+    for (size_t i = 0; i < xtx.size(); i++) xtx[i] += part[i];
+    used += u;
+  }
+  if (used == 0 || n < 2) throw KmdError("EigenStratError", "eigenstrat/smartpca failed.");
+  kmd_smartpca_normalize(xtx.data(), n);
+  const uint32_t numeigs = std::min<uint32_t>(n, 10);
+  std::vector<double> evals(n), pcs(static_cast<size_t>(n) * numeigs);
+  if (kmd_smartpca_pcs(xtx.data(), n, numeigs, evals.data(), pcs.data()) != KMD_OK)
+    throw KmdError("EigenStratError", "eigenstrat/smartpca failed.");
+  {
+    // gwas_eigenstrat.eval ("%12.6f" per eigenvalue) and pcs.evec as evec2pca.perl prints it
+    // (" " + " " for positive values + "%.04f" per component, one line per individual)
+    FILE* ev = fopen((pop_dir + "/gwas_eigenstrat.eval").c_str(), "w");
+    FILE* pc = fopen((pop_dir + "/pcs.evec").c_str(), "w");
+    if (!ev || !pc) throw KmdError("IOError", "Unable to create PCA outputs in " + pop_dir);
+    for (uint32_t i = 0; i < n; i++) fprintf(ev, "%12.6f\n", evals[i]);
+    for (uint32_t i = 0; i < n; i++)
+    {
+      for (uint32_t j = 0; j < numeigs; j++)
+      {
+        const double v = pcs[static_cast<size_t>(i) * numeigs + j];
+        fprintf(pc, v > 0 ? "  %.04f" : " %.04f", v);
+      }
+      fputc('\n', pc);
+    }
+    fclose(ev); fclose(pc);
+  }
+  logf(L_INFO, "PCA done. (%s).", pca_time.formatted().c_str());
+
+  Timer pop_time;
+  logf(L_INFO, "Apply population stratification correction...");
+  // load_Z: 10 numbers per individual (src/popstrat.cpp:153-162); fewer than 10 samples leave the rest 0
+  std::vector<double> Z(static_cast<size_t>(n) * 10, 0.0);
+  for (uint32_t i = 0; i < n; i++)
+    for (uint32_t j = 0; j < numeigs; j++) Z[static_cast<size_t>(i) * 10 + j] = pcs[static_cast<size_t>(i) * numeigs + j];
+  std::vector<uint64_t> totals(total_controls);
+  totals.insert(totals.end(), total_cases.begin(), total_cases.end());
+  for (auto& w : workers)
+  {
+    ck(w->ctx(), kmd_popstrat_init(w->ctx(), Z.data(), totals.data(), nullptr), "kmd_popstrat_init");
+    ck(w->ctx(), kmd_popstrat_apply(w->ctx()), "kmd_popstrat_apply");
+    ck(w->ctx(), kmd_sync(w->ctx()), "kmd_sync");
+  }
+  logf(L_INFO, "Population correction done. (%s).", pop_time.formatted().c_str());
+}
+
 // ---- main_diff (cmd/diff.hpp:262-377) ---------------------------------------------------------------------
 
 void main_diff(DiffOptions& opt)
 {
   Timer whole;
   if (opt.kff) throw KmdError("OptionError", "-f/--kff-output is not supported by this build (FASTA only).");
-  if (opt.pop_correction && opt.model_lib_path.empty())
-    throw KmdError("OptionError", "--pop-correction is not available in this build yet (SURVEY.md §8 a17-a19).");
+  if (opt.pop_correction && !opt.covariates.empty())
+    throw KmdError("OptionError", "--covariates is not supported: the reference's load_C never terminates on a non-empty file (src/popstrat.cpp:205-213).");
+  if (opt.pop_correction && !opt.gender.empty())
+    throw KmdError("IOError", "Unknown gender: the reference rejects every --gender file (src/popstrat.cpp:26-41).");
+  if (opt.pop_correction && opt.npc > 10) throw KmdError("OptionError", "--n-pc must be <= 10 (pcs.evec holds 10 components).");
 
   const RunConfig cfg = get_kmtricks_config(opt.kmtricks_dir);
   if (cfg.kmer_size > 64) throw KmdError("OptionError", "k > 64 is not supported (the reference cannot write such k-mers either).");
@@ -608,6 +781,7 @@ void main_diff(DiffOptions& opt)
   }
   uint32_t nb_partitions = cfg.nb_partitions;
   for (const Partition& p : parts) nb_partitions = std::max(nb_partitions, p.index + 1);
+  std::sort(parts.begin(), parts.end(), [](const Partition& a, const Partition& b) { return a.index < b.index; });
 
   int n_dev = kmd_device_count();
   if (n_dev <= 0) throw KmdError("GpuError", "no CUDA device visible: kmdiff-b200 has no CPU fallback.");
@@ -620,6 +794,42 @@ void main_diff(DiffOptions& opt)
     n_dev = 1;
   }
   n_dev = std::max(1, std::min<int>(n_dev, static_cast<int>(parts.size())));
+
+  std::string pop_dir;
+  if (opt.pop_correction)
+  {
+    pop_dir = opt.output_directory + "/popstrat";
+    fs::create_directories(pop_dir);
+    // The Sampler draws once per row in visiting order (popstrat.hpp:121-135).  With `-t 1` the reference visits the
+    // partitions one after the other, so the draw index of a row = rows of the partitions before it + its own index;
+    // partitions are taken in index order here (the reference follows directory order, which is unspecified).
+    const size_t R = 8ull * kw + (opt.nb_controls + opt.nb_cases) * opt.count_bytes;
+    std::vector<uint64_t> rows(parts.size(), 0);
+    std::atomic<size_t> next{0};
+    std::exception_ptr err;
+    std::mutex err_mu;
+    auto count = [&] {
+      for (size_t i; (i = next.fetch_add(1)) < parts.size();)
+      {
+        try
+        {
+          MatrixFile mf(parts[i].path, R);
+          if (!mf.hdr.compressed) { rows[i] = mf.rows_if_raw; continue; }
+          std::vector<uint8_t> buf(R * 16384);
+          uint64_t bytes = 0;
+          for (size_t got; (got = mf.payload->read(buf.data(), buf.size())) > 0;) bytes += got;
+          rows[i] = bytes / R;
+        }
+        catch (...) { std::lock_guard<std::mutex> lk(err_mu); err = std::current_exception(); }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < std::min(opt.nb_threads, parts.size()); t++) pool.emplace_back(count);
+    for (auto& t : pool) t.join();
+    if (err) std::rethrow_exception(err);
+    uint64_t base = 0;
+    for (size_t i = 0; i < parts.size(); i++) { parts[i].draw_base = base; base += rows[i]; }
+  }
 
   std::vector<std::unique_ptr<GpuWorker>> workers;
   for (int d = 0; d < n_dev; d++) workers.push_back(std::make_unique<GpuWorker>(d, opt, cfg, sum_c, sum_k));
@@ -666,11 +876,29 @@ void main_diff(DiffOptions& opt)
        static_cast<unsigned long long>(sign_cases));
 
   dump_opt(opt, opt.output_directory + "/options.bin");
-  if (opt.keep_tmp)
-  {
+  const uint16_t n_samples = static_cast<uint16_t>(opt.nb_controls + opt.nb_cases);
+  // spill files of the prefilter survivors; with --pop-correction they carry the counts (the WITH_POPSTRAT tail)
+  auto spill = [&](const char* suffix) {
     std::vector<kmd_survivor> all;
-    for (auto& w : workers) { auto s = fetch(w->ctx(), false); all.insert(all.end(), s.begin(), s.end()); }
-    write_spill_files(all, nb_partitions, kw, part_dir);
+    std::vector<double> counts;
+    for (auto& w : workers)
+    {
+      auto s = fetch(w->ctx(), false);
+      if (opt.pop_correction)
+      {
+        auto c = fetch_counts_as_double(w->ctx(), n_samples, opt.count_bytes, s.size());
+        counts.insert(counts.end(), c.begin(), c.end());
+      }
+      all.insert(all.end(), s.begin(), s.end());
+    }
+    write_spill_files(all, nb_partitions, kw, part_dir, suffix, opt.pop_correction ? &counts : nullptr, n_samples);
+  };
+  if (opt.keep_tmp) spill("_uncorrected");
+
+  if (opt.pop_correction)
+  {
+    do_pop(workers, opt, pop_dir, total_controls, total_cases);
+    if (opt.keep_tmp) spill("_popstrat_uncorrected");
   }
 
   // ---- do_correction ----
@@ -756,7 +984,11 @@ void main_diff(DiffOptions& opt)
   if (!opt.keep_tmp)
   {
     std::error_code ec;
-    for (uint32_t p = 0; p < nb_partitions; p++) fs::remove(part_dir + "/p" + std::to_string(p) + "_uncorrected", ec);
+    for (uint32_t p = 0; p < nb_partitions; p++)
+    {
+      fs::remove(part_dir + "/p" + std::to_string(p) + "_uncorrected", ec);
+      fs::remove(part_dir + "/p" + std::to_string(p) + "_popstrat_uncorrected", ec);
+    }
   }
   logf(L_INFO, "Done in %s, Peak RSS -> %zu MB.", whole.formatted().c_str(), peak_rss_mb());
 }

@@ -221,7 +221,7 @@ class SynthSpec:
 
 
 def write_run_dir(run_dir: str, spec: SynthSpec, n_rows: int, nb_partitions: int, lz4: bool = False,
-                  payload: np.ndarray | None = None) -> list[str]:
+                  payload: np.ndarray | None = None, totals: np.ndarray | None = None) -> list[str]:
     """A kmtricks run directory `kmdiff diff` (reference and ours) accepts in matrix mode, holding
     rows [0, n_rows) of the synthetic matrix split into nb_partitions contiguous partitions."""
     os.makedirs(os.path.join(run_dir, "matrices"), exist_ok=True)
@@ -233,7 +233,8 @@ def write_run_dir(run_dir: str, spec: SynthSpec, n_rows: int, nb_partitions: int
             f.write(f"{ident} : /dev/null/{ident}.fa\n")
     with open(os.path.join(run_dir, "options.txt"), "w") as f:
         f.write(f"kmer_size={spec.kmer_size}, c_ab_min=1,\n")
-    totals = spec.totals()
+    if totals is None:
+        totals = spec.totals()
     for j, ident in enumerate(ids):
         write_hist(os.path.join(run_dir, "histograms", f"{ident}.hist"), spec.kmer_size, j, int(totals[j]))
     stale = os.path.join(run_dir, "kmdiff-count.opt")

@@ -220,3 +220,89 @@ def test_pop_correction_end_to_end():
     if not edge.any():
         assert np.array_equal(sig["row"], want["row"][keep])
         assert n_ctl + n_case == len(keep)
+
+
+@pytest.mark.parametrize("lz4", [False, True])
+def test_cli_pop_correction(tmp_path, lz4):
+    """`kmdiff-b200 diff --pop-correction` on a run directory == the same pipeline driven through the
+    C-ABI in process (which the tests above hold against the oracle): popstrat/ files, corrected
+    spill files and the FASTA output."""
+    import os
+    import subprocess
+
+    from kmdiff_b200 import build as kb
+    from kmdiff_b200 import kmtricks_io as kio
+    from test_host_cli import read_fasta, strip_index
+
+    cli = kb.build_cli()
+    nc, nk, npc, m, parts = 40, 40, 4, 60_000, 4
+    n = nc + nk
+    counts, _ = _cohort_with_structure(nc, nk, m, seed=78)
+    counts[:, 0] = np.maximum(counts[:, 0], 1)
+    rows = np.zeros((m, 8 + 4 * n), dtype=np.uint8)
+    rows[:, :8] = (np.arange(m, dtype=np.uint64) * np.uint64(977) + np.uint64(5)).view(np.uint8).reshape(m, 8)
+    rows[:, 8:] = counts.view(np.uint8).reshape(m, 4 * n)
+    totals = counts.sum(0).astype(np.uint64) * np.uint64(1000)
+    v, seed = 0.2, 31
+    spec = K.SynthSpec(nc, nk, kmer_size=31, count_bytes=4, total_rows=m, seed=1)
+    d, out = str(tmp_path / "run"), str(tmp_path / "out")
+    kio.write_run_dir(d, spec, m, parts, lz4=lz4, payload=rows.ravel(), totals=totals)
+    r = subprocess.run([cli, "diff", "-d", d, "-1", str(nc), "-2", str(nk), "-o", out, "--pop-correction", "--kmer-pca", str(v),
+                        "--random-seed", str(seed), "--n-pc", str(npc), "--keep-tmp", "-c", "bonferroni", "-s", "0.05",
+                        "-u", "100000"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "[error]" not in r.stderr, r.stderr
+    assert "PCA done." in r.stderr and "Population correction done." in r.stderr
+
+    with K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), count_bytes=4, threshold=THR) as ctx:
+        ctx.popstrat_enable(v, seed=seed, n_pc=npc)
+        ctx.scan_host(rows.ravel())
+        before = ctx.survivors()
+        geno, grow = ctx.popstrat_geno()
+        xtx, used = ctx.popstrat_gram()
+        evals, Z = K.smartpca_pcs(xtx, 10)
+        ctx.popstrat_init(Z, totals)
+        ctx.popstrat_apply()
+        after = ctx.survivors()
+        ctx.correct(K.CorrectionType.BONFERRONI, 0.05, m)
+        sig = ctx.significant()
+    assert len(before) > 20 and len(sig) > 0
+
+    pop = os.path.join(out, "popstrat")
+    with open(os.path.join(pop, "gwas_eigenstratX.geno")) as f:
+        lines = f.read().split("\n")[:-1]
+    assert len(lines) == len(geno)
+    want_lines = ["".join("1\t" if x else "0\t" for x in g) for g in geno]
+    assert lines == want_lines
+    with open(os.path.join(pop, "gwas_eigenstratX.snp")) as f:
+        snp = f.read().split("\n")[:-1]
+    assert snp[0] == "0\t1\t0.0\t0" and snp[-1] == f"{len(geno) - 1}\t1\t0.0\t0" and len(snp) == len(geno)
+    Zf = np.loadtxt(os.path.join(pop, "pcs.evec"))
+    assert Zf.shape == (n, 10) and np.abs(Zf - Z).max() < 1e-12
+    with open(os.path.join(pop, "gwas_eigenstratX.ind")) as f:
+        ind = f.read().split("\n")[:-1]
+    assert ind[0] == "C0\tU\tControl" and ind[-1] == f"K{nk - 1}\tU\tCase" and len(ind) == n
+    with open(os.path.join(pop, "gwas_eigenstratX.total")) as f:
+        assert [int(x) for x in f.read().split()] == [int(t) for t in totals]
+
+    # spill files: records | u16 N | N x f64 counts; p{i}_uncorrected holds the LRT p, p{i}_popstrat_uncorrected the GLM p
+    rec = 8 + 28 + 2 + 8 * n
+    for suffix, want in (("_uncorrected", before), ("_popstrat_uncorrected", after)):
+        got_p, got_counts = [], []
+        for p in range(parts):
+            raw = subprocess.run([cli, "dev-cat", os.path.join(out, "partitions", f"p{p}{suffix}"), "0", "lz4"],
+                                 capture_output=True, timeout=60).stdout
+            assert len(raw) % rec == 0
+            for i in range(len(raw) // rec):
+                b = raw[i * rec:(i + 1) * rec]
+                got_p.append(np.frombuffer(b[8:16], dtype=np.float64)[0])
+                assert np.frombuffer(b[36:38], dtype=np.uint16)[0] == n
+                got_counts.append(np.frombuffer(b[38:], dtype=np.float64))
+        assert len(got_p) == len(want)
+        assert np.array_equal(np.array(got_p), want["p_value"], equal_nan=True)
+        assert np.array_equal(np.array(got_counts), counts[want["row"].astype(np.int64)].astype(np.float64))
+
+    want_recs = sorted((strip_index(K.format_fasta(0, s, 31).split("\n", 1)[0]),
+                        K.format_fasta(0, s, 31).split("\n", 1)[1].replace("\n", "")) for s in sig)
+    got = sorted((strip_index(h), s) for f in ("control_kmers.fasta", "case_kmers.fasta")
+                 for h, s in read_fasta(os.path.join(out, f)))
+    assert got == want_recs
