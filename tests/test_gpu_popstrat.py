@@ -243,17 +243,18 @@ def test_cli_pop_correction(tmp_path, lz4):
     rows[:, :8] = (np.arange(m, dtype=np.uint64) * np.uint64(977) + np.uint64(5)).view(np.uint8).reshape(m, 8)
     rows[:, 8:] = counts.view(np.uint8).reshape(m, 4 * n)
     totals = counts.sum(0).astype(np.uint64) * np.uint64(1000)
+    # -s 0.5: with 80 samples the GLM p-values saturate near 2e-6 (perfect separation), above 0.05/m
     v, seed = 0.2, 31
     spec = K.SynthSpec(nc, nk, kmer_size=31, count_bytes=4, total_rows=m, seed=1)
     d, out = str(tmp_path / "run"), str(tmp_path / "out")
     kio.write_run_dir(d, spec, m, parts, lz4=lz4, payload=rows.ravel(), totals=totals)
     r = subprocess.run([cli, "diff", "-d", d, "-1", str(nc), "-2", str(nk), "-o", out, "--pop-correction", "--kmer-pca", str(v),
-                        "--random-seed", str(seed), "--n-pc", str(npc), "--keep-tmp", "-c", "bonferroni", "-s", "0.05",
+                        "--random-seed", str(seed), "--n-pc", str(npc), "--keep-tmp", "-c", "bonferroni", "-s", "0.5",
                         "-u", "100000"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "[error]" not in r.stderr, r.stderr
     assert "PCA done." in r.stderr and "Population correction done." in r.stderr
 
-    with K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), count_bytes=4, threshold=THR) as ctx:
+    with K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), count_bytes=4, threshold=0.5 / 100000) as ctx:
         ctx.popstrat_enable(v, seed=seed, n_pc=npc)
         ctx.scan_host(rows.ravel())
         before = ctx.survivors()
@@ -263,7 +264,7 @@ def test_cli_pop_correction(tmp_path, lz4):
         ctx.popstrat_init(Z, totals)
         ctx.popstrat_apply()
         after = ctx.survivors()
-        ctx.correct(K.CorrectionType.BONFERRONI, 0.05, m)
+        ctx.correct(K.CorrectionType.BONFERRONI, 0.5, m)
         sig = ctx.significant()
     assert len(before) > 20 and len(sig) > 0
 
