@@ -135,6 +135,25 @@ int kmd_survivors(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n
  * output stages then treat them exactly like scanned survivors. */
 int kmd_push_survivors(kmd_context* ctx, const kmd_survivor* records, uint64_t n, uint64_t rows_tested);
 
+/* ---- per-sample count files instead of matrices: global_merge::merge() -> km::KmerMerger
+ *      (merge.hpp:237-309; kmtricks/merge.hpp:102-361; record layout kmtricks/io/kmer_file.hpp:127-137) ---- */
+
+/* N-way merge of the samples' sorted (k-mer, count) streams into dense matrix rows on the device,
+ * then the same test as kmd_scan_device on those rows (they never leave HBM).  streams[s] points to
+ * n_records[s] HOST records of sample s (controls first, nb_controls + nb_cases streams): kmer_words*8
+ * bytes of k-mer then count_bytes of count, ascending and unique within a stream.  A count below
+ * ab_min[s] is reported as 0 and a row is kept when at least one sample is solid (KmerMerger with
+ * recurrence_min = 1, save_if = 0, as merge.hpp:266-267 constructs it).  The streams of one call must
+ * cover one k-mer range completely (a whole partition, or the records <= a common bound of every
+ * stream) and hold fewer than 2^31 records in total.  n_rows (may be NULL) = rows produced; they are
+ * numbered row_base, row_base+1, ... in ascending k-mer order.  Synchronous for the host buffers. */
+int kmd_merge_scan_host(kmd_context* ctx, const void* const* streams, const uint64_t* n_records,
+                        const uint32_t* ab_min, uint64_t row_base, uint32_t partition, uint64_t* n_rows);
+/* The merged rows themselves (what KmerMerger::write_as_bin would put in a matrix file,
+ * kmtricks/merge.hpp:262-272), copied back to the host: tests, tools.  No test is run. */
+int kmd_merge_rows_host(kmd_context* ctx, const void* const* streams, const uint64_t* n_records,
+                        const uint32_t* ab_min, void* rows_out, uint64_t cap_rows, uint64_t* n_rows);
+
 /* diagnostics for bench.py: kernels launched on behalf of ctx so far, and the device time of the
  * most recent lrt_scan kernel launch (CUDA events on the context's stream) */
 uint64_t kmd_launch_count(const kmd_context* ctx);

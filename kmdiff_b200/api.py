@@ -209,6 +209,36 @@ class DiffContext:
             ptr = a.ctypes.data
         self._ck(self._L.kmd_scan_host(self._h, C.c_void_p(ptr), n_rows, row_base, partition))
 
+    # -- per-sample count files: km::KmerMerger (kmtricks/merge.hpp:102-361) --
+    def _merge_args(self, streams, ab_min):
+        n = self.nb_samples
+        assert len(streams) == n, f"{n} streams expected (controls first)"
+        rec = 8 * self.kmer_words + self.count_bytes
+        arrs = [_as_u8(s) for s in streams]
+        for a in arrs:
+            assert a.size % rec == 0, "stream is not a whole number of records"
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data if a.size else None for a in arrs])
+        cnt = (C.c_uint64 * n)(*[a.size // rec for a in arrs])
+        ab = np.ascontiguousarray(np.broadcast_to(np.asarray(ab_min, dtype=np.uint32), (n,)))
+        return arrs, ptrs, cnt, ab
+
+    def merge_scan_host(self, streams, ab_min=1, row_base: int = 0, partition: int = 0) -> int:
+        """global_merge::merge() for one partition (merge.hpp:259-301): N-way merge of the samples'
+        sorted (k-mer, count) records on the device + the LRT scan of the merged rows; -> rows."""
+        arrs, ptrs, cnt, ab = self._merge_args(streams, ab_min)
+        n = C.c_uint64()
+        self._ck(self._L.kmd_merge_scan_host(self._h, ptrs, cnt, ab.ctypes.data, row_base, partition, C.byref(n)))
+        return n.value
+
+    def merge_rows_host(self, streams, ab_min=1) -> np.ndarray:
+        """the merged dense rows (KmerMerger::write_as_bin payload), [n_rows, row_bytes] uint8"""
+        arrs, ptrs, cnt, ab = self._merge_args(streams, ab_min)
+        cap = int(sum(cnt))
+        out = np.zeros((max(cap, 1), self.row_bytes), dtype=np.uint8)
+        n = C.c_uint64()
+        self._ck(self._L.kmd_merge_rows_host(self._h, ptrs, cnt, ab.ctypes.data, out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value]
+
     def counters(self) -> Counters:
         c = Counters()
         self._ck(self._L.kmd_counters_get(self._h, C.byref(c)))

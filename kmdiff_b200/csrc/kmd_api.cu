@@ -21,6 +21,7 @@
 #include "kmd_eig.hpp"
 #include "kmd_grm.cuh"
 #include "kmd_math.cuh"
+#include "kmd_merge.cuh"
 #include "kmd_popstrat.cuh"
 #include "kmd_scan.cuh"
 #include "kmd_sort.cuh"
@@ -92,6 +93,23 @@ struct PopState
   float gram_ms = 0;                       // device time of the last grm_umma_kernel launch
 };
 
+// per-sample count-file input (kmd_merge_*): grow-only device buffers of the merge tree
+struct MergeState
+{
+  uint8_t* raw = nullptr; size_t raw_cap = 0;
+  uint64_t* klo[2] = {nullptr, nullptr}; size_t klo_cap[2] = {0, 0};
+  uint64_t* khi[2] = {nullptr, nullptr}; size_t khi_cap[2] = {0, 0};
+  uint64_t* pay[2] = {nullptr, nullptr}; size_t pay_cap[2] = {0, 0};
+  uint32_t* flag = nullptr; size_t flag_cap = 0;
+  uint32_t* tile = nullptr; size_t tile_cap = 0;
+  uint32_t* head_pos = nullptr; size_t head_cap = 0;
+  uint8_t* rows = nullptr; size_t rows_cap = 0;
+  uint64_t* stream_off = nullptr; size_t off_cap = 0;
+  uint32_t* ab_min = nullptr; size_t ab_cap = 0;
+  uint32_t* plan = nullptr; size_t plan_cap = 0;
+  uint32_t* total = nullptr;
+};
+
 }  // namespace
 
 struct kmd_context
@@ -148,11 +166,13 @@ struct kmd_context
   cudaEvent_t ev_scan[2] = {nullptr, nullptr};
 
   PopState pop;
+  MergeState mrg;
 };
 
 namespace {
 
 void pop_free(kmd_context* ctx);   // kmd_popstrat_api.inl
+void merge_free(kmd_context* ctx); // kmd_merge_api.inl
 int pop_reset(kmd_context* ctx);
 
 int fail(kmd_context* ctx, int code, const char* fmt, ...)
@@ -970,6 +990,7 @@ void kmd_destroy(kmd_context* ctx)
   }
   cudaFree(ctx->d_hist); cudaFree(ctx->d_p_sorted); cudaFree(ctx->d_out); cudaFree(ctx->d_order);
   pop_free(ctx);
+  merge_free(ctx);
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1575,3 +1596,4 @@ int kmd_synth_fill_device(const kmd_synth* s, int device, void* d_rows, uint64_t
 }  // extern "C"
 
 #include "kmd_popstrat_api.inl"
+#include "kmd_merge_api.inl"

@@ -1,0 +1,220 @@
+// C-ABI entry points of the per-sample count-file input path (included at the end of kmd_api.cu).
+// Kernels: kmd_merge.cuh.  Reference: km::KmerMerger (kmtricks/merge.hpp:102-361) driven by
+// global_merge::merge() (include/kmdiff/merge.hpp:237-309).
+
+namespace {
+
+template <class T>
+int grow(kmd_context* ctx, T*& p, size_t& cap, size_t want)
+{
+  if (want <= cap) return KMD_OK;
+  if (p) { KMD_CUDA(ctx, cudaFree(p)); p = nullptr; cap = 0; }
+  want += want / 8;   // head room: the chunks of one partition have similar sizes
+  void* q = nullptr;
+  KMD_CUDA(ctx, cudaMalloc(&q, want * sizeof(T)));
+  p = static_cast<T*>(q);
+  cap = want;
+  return KMD_OK;
+}
+
+void merge_free(kmd_context* ctx)
+{
+  MergeState& m = ctx->mrg;
+  cudaFree(m.raw);
+  for (int b = 0; b < 2; b++) { cudaFree(m.klo[b]); cudaFree(m.khi[b]); cudaFree(m.pay[b]); }
+  cudaFree(m.flag); cudaFree(m.tile); cudaFree(m.head_pos); cudaFree(m.rows); cudaFree(m.stream_off);
+  cudaFree(m.ab_min); cudaFree(m.plan); cudaFree(m.total);
+  m = MergeState{};
+}
+
+struct MergePass { size_t run_off, pair_tile; uint32_t n_runs, n_pairs, tiles; };
+
+template <int W>
+int merge_passes(kmd_context* ctx, const std::vector<MergePass>& passes, int* final_buf)
+{
+  MergeState& m = ctx->mrg;
+  int cur = 0;
+  for (const MergePass& ps : passes)
+  {
+    mrg::MergeArgs<W> A{};
+    A.in = {m.klo[cur], m.khi[cur]};
+    A.out = {m.klo[cur ^ 1], m.khi[cur ^ 1]};
+    A.pay_in = m.pay[cur];
+    A.pay_out = m.pay[cur ^ 1];
+    A.run_off = m.plan + ps.run_off;
+    A.pair_tile = m.plan + ps.pair_tile;
+    A.n_runs = ps.n_runs;
+    A.n_pairs = ps.n_pairs;
+    if (ps.tiles)
+    {
+      mrg::merge_pass_kernel<W><<<ps.tiles, mrg::kThreads, 0, ctx->stream>>>(A);
+      ctx->launches++;
+    }
+    cur ^= 1;
+  }
+  KMD_CUDA(ctx, cudaGetLastError());
+  *final_buf = cur;
+  return KMD_OK;
+}
+
+template <int W>
+int merge_rows(kmd_context* ctx, int buf, uint32_t n, uint32_t* n_rows_out)
+{
+  MergeState& m = ctx->mrg;
+  const uint32_t n_samples = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
+  const uint32_t tiles = (n + mrg::kScanTile - 1) / mrg::kScanTile;
+  int rc;
+  if ((rc = grow(ctx, m.flag, m.flag_cap, n))) return rc;
+  if ((rc = grow(ctx, m.tile, m.tile_cap, tiles))) return rc;
+  mrg::KeyArrays<W> keys{m.klo[buf], m.khi[buf]};
+  mrg::heads_kernel<W><<<tiles, 256, 0, ctx->stream>>>(keys, m.pay[buf], n, m.flag, m.tile);
+  scan_exclusive_kernel<<<1, 1024, 0, ctx->stream>>>(m.tile, tiles, m.total);
+  ctx->launches += 2;
+  uint32_t n_rows = 0;
+  KMD_CUDA(ctx, cudaMemcpyAsync(&n_rows, m.total, sizeof n_rows, cudaMemcpyDeviceToHost, ctx->stream));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // also: every H2D copy of the caller's streams is done
+  *n_rows_out = n_rows;
+  if (n_rows == 0) return KMD_OK;
+  if ((rc = grow(ctx, m.head_pos, m.head_cap, n_rows))) return rc;
+  if ((rc = grow(ctx, m.rows, m.rows_cap, static_cast<size_t>(n_rows) * ctx->plan.row_bytes + 16))) return rc;
+  mrg::head_positions_kernel<<<tiles, 256, 0, ctx->stream>>>(m.flag, n, m.tile, m.head_pos);
+  const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>((n_rows + 7) / 8, ctx->sm_count * 8));
+  switch (ctx->cfg.count_bytes)
+  {
+    case 1: mrg::rows_kernel<W, 1><<<blocks, 256, 0, ctx->stream>>>(keys, m.pay[buf], n, m.head_pos, n_rows, n_samples, m.rows); break;
+    case 2: mrg::rows_kernel<W, 2><<<blocks, 256, 0, ctx->stream>>>(keys, m.pay[buf], n, m.head_pos, n_rows, n_samples, m.rows); break;
+    default: mrg::rows_kernel<W, 4><<<blocks, 256, 0, ctx->stream>>>(keys, m.pay[buf], n, m.head_pos, n_rows, n_samples, m.rows); break;
+  }
+  ctx->launches += 2;
+  KMD_CUDA(ctx, cudaGetLastError());
+  return KMD_OK;
+}
+
+// streams[s] = n_records[s] records of sample s (kmer_words*8 bytes of k-mer, count_bytes of count), ascending
+// and unique per stream.  Leaves the dense rows in ctx->mrg.rows.
+int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min, uint32_t* n_rows)
+{
+  MergeState& m = ctx->mrg;
+  const uint32_t N = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
+  const uint32_t W = ctx->cfg.kmer_words, B = ctx->cfg.count_bytes;
+  const size_t rec = 8ull * W + B;
+  if (N > 0xFFFFu) return fail(ctx, KMD_ERR_ARG, "more than 65535 samples");
+  std::vector<uint64_t> off(N + 1, 0);
+  for (uint32_t s = 0; s < N; s++)
+  {
+    if (n_records[s] && !streams[s]) return fail(ctx, KMD_ERR_ARG, "null stream pointer (sample %u)", s);
+    off[s + 1] = off[s] + n_records[s];
+  }
+  const uint64_t n64 = off[N];
+  *n_rows = 0;
+  if (n64 == 0) return KMD_OK;
+  if (n64 >= (1ull << 31)) return fail(ctx, KMD_ERR_ARG, "more than 2^31 records in one merge call: split the partition into k-mer ranges");
+  const uint32_t n = static_cast<uint32_t>(n64);
+
+  int rc;
+  if ((rc = grow(ctx, m.raw, m.raw_cap, n * rec))) return rc;
+  for (int b = 0; b < 2; b++)
+  {
+    if ((rc = grow(ctx, m.klo[b], m.klo_cap[b], n))) return rc;
+    if (W == 2 && (rc = grow(ctx, m.khi[b], m.khi_cap[b], n))) return rc;
+    if ((rc = grow(ctx, m.pay[b], m.pay_cap[b], n))) return rc;
+  }
+  if ((rc = grow(ctx, m.stream_off, m.off_cap, N + 1))) return rc;
+  if ((rc = grow(ctx, m.ab_min, m.ab_cap, N))) return rc;
+  if (!m.total) KMD_CUDA(ctx, cudaMalloc(&m.total, sizeof(uint32_t)));
+
+  // the merge tree: leaves = streams, every pass halves the number of runs
+  std::vector<uint32_t> plan;
+  std::vector<MergePass> passes;
+  {
+    std::vector<uint32_t> runs(off.begin(), off.end());   // n_runs + 1 offsets
+    while (runs.size() - 1 > 1)
+    {
+      const uint32_t n_runs = static_cast<uint32_t>(runs.size() - 1), n_pairs = (n_runs + 1) / 2;
+      MergePass ps{};
+      ps.n_runs = n_runs; ps.n_pairs = n_pairs;
+      ps.run_off = plan.size();
+      plan.insert(plan.end(), runs.begin(), runs.end());
+      ps.pair_tile = plan.size();
+      std::vector<uint32_t> next(1, 0);
+      uint32_t tiles = 0;
+      for (uint32_t q = 0; q < n_pairs; q++)
+      {
+        const uint32_t end = runs[std::min<uint32_t>(2 * q + 2, n_runs)];
+        plan.push_back(tiles);
+        tiles += (end - runs[2 * q] + mrg::kTile - 1) / mrg::kTile;
+        next.push_back(end);
+      }
+      plan.push_back(tiles);
+      ps.tiles = tiles;
+      passes.push_back(ps);
+      runs.swap(next);
+    }
+  }
+  if ((rc = grow(ctx, m.plan, m.plan_cap, std::max<size_t>(1, plan.size())))) return rc;
+
+  KMD_CUDA(ctx, cudaMemcpyAsync(m.stream_off, off.data(), (N + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  KMD_CUDA(ctx, cudaMemcpyAsync(m.ab_min, ab_min, N * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (!plan.empty())
+    KMD_CUDA(ctx, cudaMemcpyAsync(m.plan, plan.data(), plan.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  for (uint32_t s = 0; s < N; s++)
+    if (n_records[s])
+      KMD_CUDA(ctx, cudaMemcpyAsync(m.raw + off[s] * rec, streams[s], n_records[s] * rec, cudaMemcpyHostToDevice, ctx->stream));
+
+  mrg::UnpackArgs U{};
+  U.raw = m.raw; U.stream_off = m.stream_off; U.ab_min = m.ab_min; U.n_streams = N; U.n = n;
+  U.kmer_words = W; U.count_bytes = B;
+  U.klo = m.klo[0]; U.khi = m.khi[0]; U.pay = m.pay[0];
+  const uint32_t ublocks = std::max<uint32_t>(1, std::min<uint32_t>((n + 255) / 256, ctx->sm_count * 8));
+  mrg::unpack_kernel<<<ublocks, 256, 0, ctx->stream>>>(U);
+  ctx->launches++;
+  KMD_CUDA(ctx, cudaGetLastError());
+
+  int buf = 0;
+  rc = W == 2 ? merge_passes<2>(ctx, passes, &buf) : merge_passes<1>(ctx, passes, &buf);
+  if (rc) return rc;
+  // plan/off/ab_min are host temporaries: merge_rows synchronises the stream before we return
+  return W == 2 ? merge_rows<2>(ctx, buf, n, n_rows) : merge_rows<1>(ctx, buf, n, n_rows);
+}
+
+int merge_check(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (!streams || !n_records || !ab_min) return fail(ctx, KMD_ERR_ARG, "null argument");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return KMD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kmd_merge_scan_host(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min,
+                        uint64_t row_base, uint32_t partition, uint64_t* n_rows)
+{
+  int rc = merge_check(ctx, streams, n_records, ab_min);
+  if (rc) return rc;
+  uint32_t rows = 0;
+  if ((rc = merge_impl(ctx, streams, n_records, ab_min, &rows))) return rc;
+  if (n_rows) *n_rows = rows;
+  if (rows == 0) return KMD_OK;
+  return scan_device_impl(ctx, ctx->mrg.rows, rows, row_base, partition);
+}
+
+int kmd_merge_rows_host(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min,
+                        void* rows_out, uint64_t cap_rows, uint64_t* n_rows)
+{
+  int rc = merge_check(ctx, streams, n_records, ab_min);
+  if (rc) return rc;
+  uint32_t rows = 0;
+  if ((rc = merge_impl(ctx, streams, n_records, ab_min, &rows))) return rc;
+  if (n_rows) *n_rows = rows;
+  if (rows == 0) return KMD_OK;
+  if (!rows_out || rows > cap_rows) return fail(ctx, KMD_ERR_ARG, "output holds %llu rows, the merge produced %u",
+                                                static_cast<unsigned long long>(cap_rows), rows);
+  KMD_CUDA(ctx, cudaMemcpyAsync(rows_out, ctx->mrg.rows, static_cast<size_t>(rows) * ctx->plan.row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KMD_OK;
+}
+
+}  // extern "C"

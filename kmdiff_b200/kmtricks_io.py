@@ -78,6 +78,84 @@ def read_matrix(path: str) -> tuple[MatrixHeader, np.ndarray]:
     return hdr, np.frombuffer(body, dtype=np.uint8)
 
 
+# ---- per-sample count files: counts/partition_{p}/<sample>.kmer[.lz4] (km/io/kmer_file.hpp) --------------
+
+KMER_MAGIC = 0x72656D6B
+KMER_HEADER_BYTES = 41
+
+
+@dataclass
+class KmerFileHeader:
+    """km/io/kmer_file.hpp:26-67 (13-byte base header + 28 bytes)"""
+    compressed: int
+    kmer_size: int
+    kmer_slots: int
+    count_slots: int
+    id: int
+    partition: int
+
+    def pack(self) -> bytes:
+        return struct.pack("<QIBQIIIII", KM_MAGIC, 0, self.compressed, KMER_MAGIC, self.kmer_size,
+                           self.kmer_slots, self.count_slots, self.id, self.partition)
+
+    @staticmethod
+    def unpack(b: bytes) -> "KmerFileHeader":
+        km, _ver, comp, mm, k, ks, cs, i, p = struct.unpack("<QIBQIIIII", b[:KMER_HEADER_BYTES])
+        if km != KM_MAGIC or mm != KMER_MAGIC:
+            raise IOError("Invalid file format.")
+        return KmerFileHeader(comp, k, ks, cs, i, p)
+
+
+def write_kmer_file(path: str, records, kmer_size: int, count_bytes: int, sample_id: int = 0,
+                    partition: int = 0, lz4: bool = False) -> None:
+    """records: bytes of (kmer_slots*8 + count_bytes)-byte records, ascending k-mers (KmerWriter::write,
+    km/io/kmer_file.hpp:94-101)."""
+    payload = np.ascontiguousarray(records).view(np.uint8).ravel()
+    hdr = KmerFileHeader(int(lz4), kmer_size, (kmer_size + 31) // 32, count_bytes, sample_id, partition)
+    with open(path, "wb") as f:
+        f.write(hdr.pack())
+        if lz4:
+            import pyarrow as pa
+            f.write(pa.compress(payload.tobytes(), codec="lz4", asbytes=True))
+        else:
+            payload.tofile(f)
+
+
+def read_kmer_file(path: str) -> tuple[KmerFileHeader, np.ndarray]:
+    """-> (header, record bytes); the record's count width is the header's count_slots
+    (KmerReader::read, km/io/kmer_file.hpp:127-137)."""
+    with open(path, "rb") as f:
+        hdr = KmerFileHeader.unpack(f.read(KMER_HEADER_BYTES))
+        body = f.read()
+    if hdr.compressed:
+        import pyarrow as pa
+        with pa.CompressedInputStream(pa.BufferReader(body), "lz4") as s:
+            body = s.read()
+    return hdr, np.frombuffer(body, dtype=np.uint8)
+
+
+def get_partition_paths(run_dir: str, partition: int) -> list[str]:
+    """KmDir::get_files_to_merge(p, true, KMER) (km/kmdir.hpp:48-73): one `.kmer.lz4` per fof sample, fof order."""
+    fof = parse_fof(os.path.join(run_dir, "kmtricks.fof"))
+    return [os.path.join(run_dir, "counts", f"partition_{partition}", f"{ident}.kmer.lz4") for ident, _ in fof]
+
+
+def rows_to_streams(payload, nb_samples: int, kmer_words: int, count_bytes: int) -> list[np.ndarray]:
+    """Split dense matrix rows into per-sample (k-mer, count) record streams, zero counts dropped —
+    the inverse of the merge (what `kmtricks count` leaves per sample for these rows)."""
+    R = 8 * kmer_words + nb_samples * count_bytes
+    rows = np.ascontiguousarray(payload).view(np.uint8).reshape(-1, R)
+    dt = {1: np.uint8, 2: "<u2", 4: "<u4"}[count_bytes]
+    counts = np.ascontiguousarray(rows[:, 8 * kmer_words:]).view(dt).reshape(rows.shape[0], nb_samples)
+    out = []
+    for s in range(nb_samples):
+        sel = counts[:, s] != 0
+        rec = np.concatenate([rows[sel, :8 * kmer_words],
+                              np.ascontiguousarray(counts[sel, s:s + 1]).view(np.uint8).reshape(-1, count_bytes)], axis=1)
+        out.append(np.ascontiguousarray(rec).ravel())
+    return out
+
+
 def write_hist(path: str, kmer_size: int, sample_id: int, total: int, lower: int = 1, upper: int = 255,
                hist_u: np.ndarray | None = None) -> None:
     n = upper - lower + 1
@@ -221,7 +299,8 @@ class SynthSpec:
 
 
 def write_run_dir(run_dir: str, spec: SynthSpec, n_rows: int, nb_partitions: int, lz4: bool = False,
-                  payload: np.ndarray | None = None, totals: np.ndarray | None = None) -> list[str]:
+                  payload: np.ndarray | None = None, totals: np.ndarray | None = None,
+                  count_files: bool = False) -> list[str]:
     """A kmtricks run directory `kmdiff diff` (reference and ours) accepts in matrix mode, holding
     rows [0, n_rows) of the synthetic matrix split into nb_partitions contiguous partitions."""
     os.makedirs(os.path.join(run_dir, "matrices"), exist_ok=True)
@@ -249,6 +328,15 @@ def write_run_dir(run_dir: str, spec: SynthSpec, n_rows: int, nb_partitions: int
             rows = spec.rows_host(hi - lo, lo)
         else:
             rows = payload[lo * spec.row_bytes:hi * spec.row_bytes]
+        if count_files:
+            # what `kmtricks pipeline --until count` leaves: one sorted (k-mer, count) file per sample
+            # and partition, no matrices (the reference then merges them itself, cmd/diff.hpp:88-95)
+            streams = rows_to_streams(rows, n, spec.kmer_words, spec.count_bytes)
+            for j, ident in enumerate(ids):
+                path = os.path.join(run_dir, "counts", f"partition_{p}", f"{ident}.kmer.lz4")
+                write_kmer_file(path, streams[j], spec.kmer_size, spec.count_bytes, j, p, lz4)
+                paths.append(path)
+            continue
         path = os.path.join(run_dir, "matrices", f"matrix_{p}.count" + (".lz4" if lz4 else ""))
         write_matrix(path, rows, spec.kmer_size, spec.count_bytes, n, p, lz4)
         paths.append(path)

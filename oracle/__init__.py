@@ -115,6 +115,9 @@ def lib() -> C.CDLL:
         L.kmo_smartpca_xtx.argtypes = [vp, u64, i32, i32, vp]
         L.kmo_sym_eig.argtypes = [vp, i32, vp, vp]
         L.kmo_smartpca_pcs.argtypes = [vp, u64, i32, i32, vp, i32, vp]
+        # per-sample count files (kmd_merge_oracle.h)
+        L.kmo_kmer_merge.restype = u64
+        L.kmo_kmer_merge.argtypes = [vp, vp, C.c_uint32, i32, i32, vp, C.c_uint32, C.c_uint32, vp, u64]
         _lib = L
     return _lib
 
@@ -159,6 +162,9 @@ def ref() -> C.CDLL:
             L.ref_popstrat_state.argtypes = [vp, vp, vp, vp]
             L.ref_popstrat_apply.restype = d
             L.ref_popstrat_apply.argtypes = [vp, vp, sz]
+        if hasattr(L, "ref_kmer_merge"):
+            L.ref_kmer_merge.restype = sz
+            L.ref_kmer_merge.argtypes = [vp, sz, C.c_uint32, C.c_int, vp, vp, sz]
         _ref = L
     return _ref
 
@@ -249,6 +255,35 @@ def aggregate(p: np.ndarray, kind: int, threshold: float, total: int) -> np.ndar
     keep = np.empty(max(1, p.size), dtype=np.uint64)
     n = lib().kmo_aggregate(p.ctypes.data, p.size, kind, threshold, total, keep.ctypes.data)
     return keep[:n].astype(np.int64)
+
+
+def kmer_merge(streams, kmer_words: int, count_bytes: int, ab_min=1, recurrence_min: int = 1,
+               save_if: int = 0) -> np.ndarray:
+    """km::KmerMerger over in-memory record streams (kmd_merge_oracle.c) -> dense rows [n, R] uint8."""
+    n = len(streams)
+    arrs = [np.ascontiguousarray(np.asarray(s).view(np.uint8)).ravel() for s in streams]
+    rec = 8 * kmer_words + count_bytes
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data if a.size else None for a in arrs])
+    cnt = (C.c_uint64 * n)(*[a.size // rec for a in arrs])
+    ab = np.ascontiguousarray(np.broadcast_to(np.asarray(ab_min, dtype=np.uint32), (n,)))
+    cap = int(sum(cnt))
+    R = 8 * kmer_words + n * count_bytes
+    out = np.zeros((max(cap, 1), R), dtype=np.uint8)
+    kept = lib().kmo_kmer_merge(ptrs, cnt, n, kmer_words, count_bytes, ab.ctypes.data, recurrence_min, save_if,
+                                out.ctypes.data, cap)
+    return out[:kept]
+
+
+def ref_kmer_merge(paths, kmer_size: int, count_bytes: int, ab_min=1, cap_rows: int = 1 << 20) -> np.ndarray:
+    """The real km::KmerMerger (oracle/_ref) over .kmer[.lz4] files -> dense rows [n, R] uint8."""
+    n = len(paths)
+    arr = (C.c_char_p * n)(*[p.encode() for p in paths])
+    ab = np.ascontiguousarray(np.broadcast_to(np.asarray(ab_min, dtype=np.uint32), (n,)))
+    R = 8 * ((kmer_size + 31) // 32) + n * count_bytes
+    out = np.zeros((cap_rows, R), dtype=np.uint8)
+    kept = ref().ref_kmer_merge(arr, n, kmer_size, count_bytes, ab.ctypes.data, out.ctypes.data, cap_rows)
+    assert kept <= cap_rows
+    return out[:kept]
 
 
 def kmer_to_string(words, k: int) -> str:

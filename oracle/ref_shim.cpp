@@ -17,6 +17,7 @@
 //   kmdiff::Sampler<MAX_C>::sample()          include/kmdiff/popstrat.hpp:107-146
 //   kmdiff::glm_irls / inverse / sigmoid      src/linear_model.cpp:297-410, 139-189, 191-195
 //   kmdiff::pop_strat_corrector               include/kmdiff/popstrat.hpp:148-372, src/popstrat.cpp
+//   km::KmerMerger / km::KmerReader           thirdparty/kmtricks/include/kmtricks/merge.hpp:102-361, io/kmer_file.hpp
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
@@ -37,6 +38,7 @@
 #include <kmdiff/log_factorial_table.hpp>
 #include <kmdiff/linear_model.hpp>
 #include <specialfunctions.h>
+#include <kmtricks/merge.hpp>
 
 // pop_strat_corrector::apply(KmerSign&) and its feature matrices are private; the shim reads them
 // to pin the oracle, so the class is opened up for this translation unit only (every standard
@@ -99,6 +101,43 @@ struct RefModel
 };
 
 } // namespace
+
+// km::KmerMerger over per-sample .kmer[.lz4] files exactly as global_merge::merge() builds it
+// (include/kmdiff/merge.hpp:266-267: recurrence_min 1, save_if 0) with a row-collecting observer in place
+// of diff_observer.  Rows: kmer_slots*8 bytes + n_paths counts of count_bytes.  Returns kept rows
+// (rows beyond cap_rows are counted, not stored).
+namespace {
+template <std::size_t K, std::size_t MAX_C>
+struct RowCollector : km::IMergeObserver<K, MAX_C>
+{
+  using count_t = typename km::selectC<MAX_C>::type;
+  std::uint8_t* out; std::size_t cap, n = 0, kw;
+  RowCollector(std::uint8_t* o, std::size_t c, std::size_t w) : out(o), cap(c), kw(w) {}
+  void process(km::Kmer<K>& kmer, std::vector<count_t>& counts) override
+  {
+    const std::size_t R = 8 * kw + counts.size() * sizeof(count_t);
+    if (out && n < cap)
+    {
+      std::memcpy(out + n * R, kmer.get_data64(), 8 * kw);
+      std::memcpy(out + n * R + 8 * kw, counts.data(), counts.size() * sizeof(count_t));
+    }
+    n++;
+  }
+};
+
+template <std::size_t K, std::size_t MAX_C>
+std::size_t kmer_merge(const char* const* paths, std::size_t n_paths, std::uint32_t kmer_size, const std::uint32_t* ab_min,
+                       std::uint8_t* rows_out, std::size_t cap_rows)
+{
+  std::vector<std::string> p(paths, paths + n_paths);
+  std::vector<std::uint32_t> a(ab_min, ab_min + n_paths);
+  km::KmerMerger<K, MAX_C> merger(p, a, kmer_size, 1, 0);
+  auto obs = std::make_shared<RowCollector<K, MAX_C>>(rows_out, cap_rows, (kmer_size + 31) / 32);
+  merger.merge(obs);
+  return obs->n;
+}
+}
+
 
 extern "C" {
 
@@ -235,6 +274,20 @@ double ref_popstrat_apply(void* h, const double* counts, std::size_t n)
   kmdiff::KmerSign<32> ks(std::move(k), 0.5, kmdiff::Significance::CASE, v, 0.0, 0.0);
   c->apply(ks);
   return ks.m_pvalue;
+}
+
+std::size_t ref_kmer_merge(const char* const* paths, std::size_t n_paths, std::uint32_t kmer_size, int count_bytes,
+                           const std::uint32_t* ab_min, std::uint8_t* rows_out, std::size_t cap_rows)
+{
+  // main.cc:74-75 dispatches on k < 32 / < 64; count width is the compile-time MAX_C of the build
+  if (count_bytes == 4)
+    return kmer_size < 32 ? kmer_merge<32, 4294967295>(paths, n_paths, kmer_size, ab_min, rows_out, cap_rows)
+                          : kmer_merge<64, 4294967295>(paths, n_paths, kmer_size, ab_min, rows_out, cap_rows);
+  if (count_bytes == 2)
+    return kmer_size < 32 ? kmer_merge<32, 65535>(paths, n_paths, kmer_size, ab_min, rows_out, cap_rows)
+                          : kmer_merge<64, 65535>(paths, n_paths, kmer_size, ab_min, rows_out, cap_rows);
+  return kmer_size < 32 ? kmer_merge<32, 255>(paths, n_paths, kmer_size, ab_min, rows_out, cap_rows)
+                        : kmer_merge<64, 255>(paths, n_paths, kmer_size, ab_min, rows_out, cap_rows);
 }
 
 } // extern "C"
