@@ -1,0 +1,146 @@
+"""GPU parity of the per-sample count-file input: the device merge tree behind
+kmd_merge_rows_host / kmd_merge_scan_host against the oracle's km::KmerMerger restatement, the
+reference's golden vectors and its merge_test.cpp fixture.  Everything here is integer work: bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import kmdiff_b200 as K
+import oracle
+from kmdiff_b200 import kmtricks_io as kio
+from conftest import SHAPES, make_cohort, rel_err
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIXTURE = os.path.join(GOLDEN, "km_out_dir")
+THR = 0.05 / 100000
+
+
+def ctx_for(nc, nk, k, b, totals=None, thr=THR, **kw):
+    if totals is None:
+        totals = np.full(nc + nk, 10**9, dtype=np.uint64)
+    return K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), kmer_size=k, count_bytes=b,
+                         threshold=thr, **kw)
+
+
+def test_reference_fixture_merge_test_cpp():
+    """tests/merge_test.cpp through the CUDA path: 320 rows, 0 control / 0 case survivors"""
+    cfg = kio.get_kmtricks_config(FIXTURE)
+    tc, tk = kio.get_total_kmer(FIXTURE, 1, 1, cfg.abundance_min)
+    with K.DiffContext(1, 1, tc[0], tk[0], kmer_size=cfg.kmer_size, count_bytes=4, threshold=0.05 / 10000, lf_size=100) as ctx:
+        base = 0
+        for p in range(cfg.nb_partitions):
+            streams = [kio.read_kmer_file(q)[1] for q in kio.get_partition_paths(FIXTURE, p)]
+            want = oracle.kmer_merge(streams, 1, 4)
+            assert np.array_equal(ctx.merge_rows_host(streams), want)
+            base += ctx.merge_scan_host(streams, row_base=base, partition=p)
+        c = ctx.counters()
+    assert (c.rows, c.n_control, c.n_case) == (320, 0, 0)
+
+
+@pytest.mark.parametrize("ci", range(8))
+def test_merge_matches_reference_vectors(ci):
+    with open(os.path.join(GOLDEN, "merge_vectors.json")) as f:
+        c = json.load(f)["cases"][ci]
+    streams = [np.frombuffer(bytes.fromhex(s), dtype=np.uint8) for s in c["streams"]]
+    want = np.frombuffer(bytes.fromhex(c["rows"]), dtype=np.uint8).reshape(c["n_rows"], -1)
+    n = c["n_samples"]
+    with ctx_for(n // 2, n - n // 2, c["kmer_size"], c["count_bytes"]) as ctx:
+        got = ctx.merge_rows_host(streams, c["ab_min"])
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("shape,n_rows", [("c2", 200_003), ("c5", 50_021), ("b1", 120_000), ("odd", 70_001),
+                                          ("tiny", 9_000), ("b2odd", 33_333), ("c3", 6_007), ("c4", 3_001)])
+def test_merge_inverts_rows_to_streams(shape, n_rows):
+    """dense synthetic rows -> per-sample streams -> device merge == the rows; then the merged rows are scanned
+    on the device and the survivors equal the oracle's on the original matrix"""
+    spec, rows, totals = make_cohort(shape, n_rows, seed=23)
+    n = spec.nb_controls + spec.nb_cases
+    streams = kio.rows_to_streams(rows, n, spec.kmer_words, spec.count_bytes)
+    dense = rows.reshape(-1, spec.row_bytes)
+    with ctx_for(spec.nb_controls, spec.nb_cases, spec.kmer_size, spec.count_bytes, totals) as ctx:
+        got = ctx.merge_rows_host(streams)
+        assert np.array_equal(got, dense)
+        assert np.array_equal(got, oracle.kmer_merge(streams, spec.kmer_words, spec.count_bytes))
+        assert ctx.merge_scan_host(streams, row_base=5, partition=3) == n_rows
+        c = ctx.counters()
+        surv = ctx.survivors()
+    want, w_ctl, w_case = oracle.Model(spec.nb_controls, spec.nb_cases, totals).diff(rows, spec.kmer_words, spec.count_bytes, THR)
+    assert (c.rows, c.survivors, c.n_control, c.n_case) == (n_rows, len(want), w_ctl, w_case)
+    assert np.array_equal(surv["row"], want["row"] + 5)
+    assert np.array_equal(surv["kmer"], want["kmer"])
+    assert np.array_equal(surv["sign"], want["sign"])
+    assert np.all(surv["partition"] == 3)
+    assert rel_err(surv["p_value"], want["p"]).max() <= 1e-9
+
+
+@pytest.mark.parametrize("n,k,b", [(2, 31, 4), (3, 20, 1), (37, 31, 2), (64, 63, 4), (129, 31, 4), (400, 31, 1)])
+def test_merge_ab_min_and_ragged_streams(n, k, b):
+    """abundance thresholds per sample, empty streams, streams of very different lengths, sample counts that are
+    not powers of two (lone runs in the merge tree)"""
+    rng = np.random.default_rng(n * 7 + k)
+    kw = (k + 31) // 32
+    m = 20_000
+    lo = np.unique(rng.integers(0, 2**min(62, 2 * k), size=m, dtype=np.uint64))
+    if kw == 2:
+        hi = np.sort(rng.integers(0, 4, size=len(lo), dtype=np.uint64))   # many equal high words
+        order = np.lexsort((lo, hi))
+        lo, hi = lo[order], hi[order]
+    streams = []
+    for s in range(n):
+        dens = [0.0, 0.9, 0.02, 0.3][s % 4] if n > 3 else 0.5
+        sel = rng.random(len(lo)) < dens
+        rec = np.zeros((int(sel.sum()), 8 * kw + b), dtype=np.uint8)
+        rec[:, :8] = lo[sel].view(np.uint8).reshape(-1, 8)
+        if kw == 2:
+            rec[:, 8:16] = hi[sel].view(np.uint8).reshape(-1, 8)
+        cnt = rng.integers(1, min(2**(8 * b) - 1, 12), size=int(sel.sum()), dtype=np.uint64)
+        rec[:, 8 * kw:] = cnt.view(np.uint8).reshape(-1, 8)[:, :b]
+        streams.append(rec.ravel())
+    ab = rng.integers(1, 6, size=n).astype(np.uint32)
+    want = oracle.kmer_merge(streams, kw, b, ab)
+    with ctx_for(n // 2, n - n // 2, k, b) as ctx:
+        got = ctx.merge_rows_host(streams, ab)
+        assert got.shape == want.shape and np.array_equal(got, want)
+        # a second call on the same context reuses the device buffers
+        got1 = ctx.merge_rows_host(streams[::-1], ab[::-1].copy())
+        assert np.array_equal(got1, oracle.kmer_merge(streams[::-1], kw, b, ab[::-1].copy()))
+
+
+def test_merge_empty_inputs():
+    with ctx_for(2, 2, 31, 4) as ctx:
+        empty = [np.empty(0, np.uint8)] * 4
+        assert ctx.merge_rows_host(empty).shape[0] == 0
+        assert ctx.merge_scan_host(empty) == 0
+        assert ctx.counters().rows == 0
+        one = [np.empty(0, np.uint8)] * 3 + [np.frombuffer((7).to_bytes(8, "little") + (9).to_bytes(4, "little"), dtype=np.uint8)]
+        rows = ctx.merge_rows_host(one)
+        assert rows.shape == (1, 24) and rows[0, :8].view("<u8")[0] == 7 and list(rows[0, 8:].view("<u4")) == [0, 0, 0, 9]
+        # every count below the threshold: the k-mer has no solid sample and is dropped (recurrence_min = 1)
+        assert ctx.merge_rows_host(one, ab_min=10).shape[0] == 0
+
+
+def test_chunked_merge_equals_whole_partition():
+    """the host program feeds a partition in k-mer ranges: merging [.., bound] and (bound, ..] separately gives
+    the same rows as one call"""
+    spec, rows, totals = make_cohort("c2", 100_000, seed=4)
+    n = 20
+    streams = kio.rows_to_streams(rows, n, 1, 4)
+    dense = rows.reshape(-1, spec.row_bytes)
+    bound = np.ascontiguousarray(dense[41_234, :8]).view("<u8")[0]
+    first, second = [], []
+    for s in streams:
+        rec = s.reshape(-1, 12)
+        km = np.ascontiguousarray(rec[:, :8]).view("<u8").ravel()
+        cut = int(np.searchsorted(km, bound, side="right"))
+        first.append(rec[:cut].ravel())
+        second.append(rec[cut:].ravel())
+    with ctx_for(10, 10, 31, 4, totals) as ctx:
+        a = ctx.merge_rows_host(first)
+        b = ctx.merge_rows_host(second)
+    assert len(a) == 41_235
+    assert np.array_equal(np.concatenate([a, b]), dense)
