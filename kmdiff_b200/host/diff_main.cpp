@@ -107,6 +107,7 @@ struct DiffOptions
   size_t count_bytes = 4;     // the reference fixes this at compile time (MAX_C); here a runtime option
   size_t max_survivors = 0;
   size_t max_sampled = 0;     // capacity of the per-GPU presence matrix (--pop-correction); 0 = 2097152
+  size_t merge_records = 32u << 20;   // count-file input: records merged on the device per call (all samples together)
   size_t total_kmers = 0;
 };
 
@@ -243,6 +244,7 @@ DiffOptions parse_cli(int argc, char** argv)
     else if (a == "--count-bytes") o.count_bytes = number();
     else if (a == "--max-survivors") o.max_survivors = number();
     else if (a == "--max-sampled") o.max_sampled = number();
+    else if (a == "--merge-records") o.merge_records = number();
     else cli_error("unknown parameter " + a);
   }
   if (!have_d) cli_error("-d/--km-run is required");
@@ -280,7 +282,14 @@ void ck(kmd_context* ctx, int rc, const char* what)
 // index sits above bit 40 so that device-side row order == (partition, row) order.
 constexpr int kPartShift = 40;
 
-struct Partition { std::string path; uint32_t index; uint64_t bytes; uint64_t draw_base = 0; };
+struct Partition
+{
+  std::string path;                        // matrix_{p}.count[.lz4]; empty in count-file mode
+  uint32_t index;
+  uint64_t bytes;
+  uint64_t draw_base = 0;
+  std::vector<std::string> sample_paths;   // count-file mode: counts/partition_{p}/<sample>.kmer.lz4, fof order
+};
 
 // One GPU's share: a reader thread decodes its partitions into pinned buffers, this thread feeds the GPU.
 class GpuWorker
@@ -340,6 +349,12 @@ class GpuWorker
   {
     try
     {
+      if (!partitions.empty() && !partitions.front().sample_paths.empty())
+      {
+        merge_loop();
+        ck(m_ctx.get(), kmd_sync(m_ctx.get()), "kmd_sync");
+        return;
+      }
       std::thread reader([this] { read_loop(); });
       feed_loop();
       reader.join();
@@ -351,6 +366,145 @@ class GpuWorker
 
  private:
   struct Buf { uint8_t* data = nullptr; uint64_t rows = 0; uint64_t row_base = 0; uint64_t draw_base = 0; uint32_t partition = 0; bool last = false; };
+
+  // Run directories without matrices (cmd/diff.hpp:88-95 -> global_merge::merge(), merge.hpp:237-309): every
+  // partition is N per-sample files of sorted (k-mer, count) records.  The reference walks them with
+  // km::KmerMerger, one row at a time; here each stream is buffered, the records up to the smallest "last
+  // buffered k-mer" of the streams still open form a complete k-mer range, and that range is merged and tested
+  // on the device (kmd_merge_scan_host).  ab_min is 1 for every sample, as cmd/diff.hpp:109 passes it.
+  void merge_loop()
+  {
+    const uint32_t N = static_cast<uint32_t>(m_opt.nb_controls + m_opt.nb_cases);
+    const uint32_t kw = static_cast<uint32_t>((m_row_bytes - static_cast<uint64_t>(N) * m_opt.count_bytes) / 8);
+    const uint32_t B = static_cast<uint32_t>(m_opt.count_bytes);
+    const size_t rec = 8ull * kw + B;
+    const uint64_t budget = std::max<uint64_t>(1ull << 12, m_opt.merge_records);
+    const size_t per = static_cast<size_t>(std::max<uint64_t>(1024, budget / N));
+    const std::vector<uint32_t> ab_min(N, 1);
+    struct Stream { std::unique_ptr<KmerFile> file; std::vector<uint8_t> buf, disk; size_t n = 0; bool eof = false; };
+    auto key_less = [kw](const uint8_t* a, const uint8_t* b) {
+      for (int w = static_cast<int>(kw) - 1; w >= 0; w--)
+      {
+        uint64_t x, y;
+        memcpy(&x, a + 8 * w, 8); memcpy(&y, b + 8 * w, 8);
+        if (x != y) return x < y;
+      }
+      return false;
+    };
+    for (const Partition& p : partitions)
+    {
+      if (p.sample_paths.size() != N) throw KmdError("ConfigError", "kmtricks.fof does not list --nb-controls + --nb-cases samples.");
+      std::vector<Stream> st(N);
+      for (uint32_t s = 0; s < N; s++)
+      {
+        st[s].file = std::make_unique<KmerFile>(p.sample_paths[s]);
+        const KmerHeader& h = st[s].file->hdr;
+        if (h.kmer_slots != kw) throw KmdError("InputError", p.sample_paths[s] + ": unexpected kmer_slots");
+        if (h.count_slots == 0 || h.count_slots > 4) throw KmdError("InputError", p.sample_paths[s] + ": unexpected count_slots");
+        st[s].buf.resize(per * rec);
+      }
+      uint64_t local = 0;
+      for (;;)
+      {
+        // refill every open stream up to `per` buffered records, the samples spread over the reader threads
+        std::atomic<uint32_t> next{0};
+        std::exception_ptr err;
+        std::mutex err_mu;
+        auto fill = [&] {
+          for (uint32_t s; (s = next.fetch_add(1)) < N;)
+          {
+            Stream& t = st[s];
+            if (t.eof || t.n >= per) continue;
+            try
+            {
+              const size_t want = per - t.n;
+              const uint32_t cs = t.file->hdr.count_slots;
+              size_t got_rec;
+              if (cs == B)
+              {
+                const size_t got = t.file->payload->read(t.buf.data() + t.n * rec, want * rec);
+                if (got % rec) throw KmdError("InputError", p.sample_paths[s] + ": truncated record");
+                got_rec = got / rec;
+              }
+              else
+              {
+                // count stored narrower or wider than this run's count type: KmerReader::read copies count_slots
+                // bytes into a count_type (kmer_file.hpp:132); widen with zeros / keep the low bytes
+                const size_t drec = 8ull * kw + cs;
+                t.disk.resize(want * drec);
+                const size_t got = t.file->payload->read(t.disk.data(), want * drec);
+                if (got % drec) throw KmdError("InputError", p.sample_paths[s] + ": truncated record");
+                got_rec = got / drec;
+                for (size_t i = 0; i < got_rec; i++)
+                {
+                  uint8_t* dst = t.buf.data() + (t.n + i) * rec;
+                  memset(dst, 0, rec);
+                  memcpy(dst, t.disk.data() + i * drec, 8ull * kw + std::min<uint32_t>(cs, B));
+                }
+              }
+              t.n += got_rec;
+              if (got_rec < want) t.eof = true;
+            }
+            catch (...) { std::lock_guard<std::mutex> lk(err_mu); err = std::current_exception(); }
+          }
+        };
+        const size_t n_thr = std::max<size_t>(1, std::min<size_t>(m_opt.nb_threads, N));
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < n_thr; t++) pool.emplace_back(fill);
+        fill();
+        for (auto& t : pool) t.join();
+        if (err) std::rethrow_exception(err);
+
+        // every stream still open may later deliver k-mers above its last buffered one only
+        const uint8_t* bound = nullptr;
+        for (const Stream& t : st)
+          if (!t.eof && t.n)
+          {
+            const uint8_t* last = t.buf.data() + (t.n - 1) * rec;
+            if (!bound || key_less(last, bound)) bound = last;
+          }
+        std::vector<uint8_t> bound_key;
+        if (bound) bound_key.assign(bound, bound + 8 * kw);
+        std::vector<const void*> ptrs(N);
+        std::vector<uint64_t> cnt(N);
+        uint64_t total = 0;
+        for (uint32_t s = 0; s < N; s++)
+        {
+          size_t cut = st[s].n;
+          if (bound)
+          {
+            // first record whose k-mer is > bound
+            size_t lo = 0, hi = st[s].n;
+            while (lo < hi)
+            {
+              const size_t mid = (lo + hi) / 2;
+              if (key_less(bound_key.data(), st[s].buf.data() + mid * rec)) hi = mid; else lo = mid + 1;
+            }
+            cut = lo;
+          }
+          ptrs[s] = st[s].buf.data();
+          cnt[s] = cut;
+          total += cut;
+        }
+        if (total == 0) break;   // every stream is exhausted
+        if (m_opt.pop_correction)
+          ck(m_ctx.get(), kmd_popstrat_set_draw_index(m_ctx.get(), m_draw_next), "kmd_popstrat_set_draw_index");
+        uint64_t n_rows = 0;
+        ck(m_ctx.get(), kmd_merge_scan_host(m_ctx.get(), ptrs.data(), cnt.data(), ab_min.data(),
+                                            (static_cast<uint64_t>(p.index) << kPartShift) + local, p.index, &n_rows),
+           "kmd_merge_scan_host");
+        local += n_rows;
+        m_draw_next += n_rows;
+        for (uint32_t s = 0; s < N; s++)
+        {
+          Stream& t = st[s];
+          if (cnt[s] && cnt[s] < t.n) memmove(t.buf.data(), t.buf.data() + cnt[s] * rec, (t.n - cnt[s]) * rec);
+          t.n -= cnt[s];
+        }
+      }
+      logf(L_DEBUG, "partition %u: %llu rows merged from %u count files (gpu %d)", p.index, static_cast<unsigned long long>(local), N, m_device);
+    }
+  }
 
   void read_loop()
   {
@@ -433,6 +587,7 @@ class GpuWorker
   const DiffOptions& m_opt;
   ctx_ptr m_ctx;
   uint64_t m_row_bytes = 0, m_buf_rows = 0;
+  uint64_t m_draw_next = 0;   // count-file mode: Sampler draw index = rows merged so far (one worker, partition order)
   Buf m_bufs[3];
   std::queue<Buf*> m_free, m_ready;
   std::mutex m_mu;
@@ -761,10 +916,9 @@ void main_diff(DiffOptions& opt)
   Timer merge_time;
   logf(L_INFO, "Process partitions");
   const std::vector<std::string> matrix_paths = list_matrices(opt.kmtricks_dir);
-  if (matrix_paths.empty())
-    throw KmdError("InputError", "no count matrices under " + opt.kmtricks_dir + "/matrices (per-sample count files are not "
-                                 "supported yet: build the matrices with `kmtricks pipeline --until merge --mode kmer:count:bin`).");
-  { std::ofstream touch(opt.kmtricks_dir + "/kmdiff-count.opt", std::ios::app); }   // the reference leaves this marker (cmd/diff.hpp:100)
+  // no matrices: the per-sample count files of every partition are merged on the fly (cmd/diff.hpp:88-95)
+  const bool from_matrix = !matrix_paths.empty();
+  if (from_matrix) { std::ofstream touch(opt.kmtricks_dir + "/kmdiff-count.opt", std::ios::app); }   // the reference leaves this marker (cmd/diff.hpp:100)
 
   std::vector<uint64_t> total_controls, total_cases;
   get_total_kmer(opt.kmtricks_dir, opt.nb_controls, opt.nb_cases, cfg.abundance_min, total_controls, total_cases);
@@ -777,7 +931,27 @@ void main_diff(DiffOptions& opt)
   {
     // partition index from the header (matrix_{p}.count[.lz4])
     MatrixFile mf(p, 8ull * kw + (opt.nb_controls + opt.nb_cases) * opt.count_bytes);
-    parts.push_back({p, mf.hdr.partition, static_cast<uint64_t>(fs::file_size(p))});
+    Partition part{};
+    part.path = p; part.index = mf.hdr.partition; part.bytes = static_cast<uint64_t>(fs::file_size(p));
+    parts.push_back(part);
+  }
+  if (!from_matrix)
+  {
+    if (!opt.model_lib_path.empty())
+      throw KmdError("OptionError", "--cmodel needs count matrices (`kmtricks pipeline --until merge --mode kmer:count:bin`): "
+                                    "per-sample count files are merged on the GPU, user models run on the host.");
+    if (opt.save_sk) throw KmdError("OptionError", "--save-sk needs count matrices as input.");
+    for (uint32_t p = 0; p < cfg.nb_partitions; p++)
+    {
+      Partition part{};
+      part.index = p;
+      part.sample_paths = get_files_to_merge(opt.kmtricks_dir, p);
+      if (part.sample_paths.size() != opt.nb_controls + opt.nb_cases)
+        throw KmdError("ConfigError", "kmtricks.fof does not list --nb-controls + --nb-cases samples.");
+      std::error_code ec;
+      for (const std::string& sp : part.sample_paths) { const auto sz = fs::file_size(sp, ec); if (!ec) part.bytes += sz; }
+      parts.push_back(part);
+    }
   }
   uint32_t nb_partitions = cfg.nb_partitions;
   for (const Partition& p : parts) nb_partitions = std::max(nb_partitions, p.index + 1);
@@ -793,6 +967,7 @@ void main_diff(DiffOptions& opt)
     opt.pop_correction = false;
     n_dev = 1;
   }
+  if (!from_matrix && opt.pop_correction) n_dev = 1;   // Sampler draws follow the rows merged so far: one ordered stream
   n_dev = std::max(1, std::min<int>(n_dev, static_cast<int>(parts.size())));
 
   std::string pop_dir;
@@ -800,6 +975,9 @@ void main_diff(DiffOptions& opt)
   {
     pop_dir = opt.output_directory + "/popstrat";
     fs::create_directories(pop_dir);
+  }
+  if (opt.pop_correction && from_matrix)
+  {
     // The Sampler draws once per row in visiting order (popstrat.hpp:121-135).  With `-t 1` the reference visits the
     // partitions one after the other, so the draw index of a row = rows of the partitions before it + its own index;
     // partitions are taken in index order here (the reference follows directory order, which is unspecified).
@@ -856,6 +1034,9 @@ void main_diff(DiffOptions& opt)
       workers[d]->partitions.push_back(parts[i]);
       load[d] += parts[i].bytes;
     }
+    if (!from_matrix)   // index order per device: the running Sampler draw index follows it
+      for (auto& w : workers)
+        std::sort(w->partitions.begin(), w->partitions.end(), [](const Partition& a, const Partition& b) { return a.index < b.index; });
     std::vector<std::thread> pool;
     for (auto& w : workers) pool.emplace_back([&w] { w->run(); });
     for (auto& t : pool) t.join();

@@ -5,6 +5,8 @@
 //   km::KmHeader + MatrixFileHeader           km/io/io_common.hpp:125-158, km/io/matrix_file.hpp:26-91
 //   km::MatrixReader / MatrixWriter           km/io/matrix_file.hpp:93-154
 //   km::HistFileHeader / HistReader           km/io/hist_file.hpp:25-144
+//   km::KmerFileHeader / KmerReader           km/io/kmer_file.hpp:26-67, 112-137
+//   km::KmDir::get_files_to_merge             km/kmdir.hpp:48-73
 #pragma once
 
 #include <algorithm>
@@ -213,6 +215,61 @@ struct MatrixFile
   MatrixFile(const MatrixFile&) = delete;
   MatrixFile& operator=(const MatrixFile&) = delete;
 };
+
+// counts/partition_{p}/<sample>.kmer[.lz4]: 41-byte header, then records of kmer_slots*8 + count_slots bytes
+constexpr uint64_t kKmerMagic = 0x72656d6bull;
+constexpr size_t kKmerHeaderBytes = 41;
+
+#pragma pack(push, 1)
+struct KmerHeader
+{
+  uint64_t km_magic;
+  uint32_t km_version;
+  uint8_t compressed;
+  uint64_t kmer_magic;
+  uint32_t kmer_size;
+  uint32_t kmer_slots;
+  uint32_t count_slots;   // width of the count on disk (KmerReader::read, kmer_file.hpp:132)
+  uint32_t id;
+  uint32_t partition;
+};
+#pragma pack(pop)
+static_assert(sizeof(KmerHeader) == kKmerHeaderBytes, "kmer file header is 41 packed bytes");
+
+struct KmerFile
+{
+  FILE* f = nullptr;
+  KmerHeader hdr{};
+  std::unique_ptr<PayloadReader> payload;
+
+  explicit KmerFile(const std::string& path)
+  {
+    f = fopen(path.c_str(), "rb");
+    if (!f) throw KmdError("IOError", "Unable to open " + path);
+    if (fread(&hdr, sizeof hdr, 1, f) != 1 || hdr.km_magic != kKmMagic || hdr.kmer_magic != kKmerMagic)
+    {
+      fclose(f); f = nullptr;
+      throw KmdError("IOError", "Invalid file format: " + path);
+    }
+    payload = std::make_unique<PayloadReader>(f, hdr.compressed != 0);
+  }
+  ~KmerFile() { if (f) fclose(f); }
+  KmerFile(const KmerFile&) = delete;
+  KmerFile& operator=(const KmerFile&) = delete;
+};
+
+// KmDir::get_files_to_merge(p, true, KMER): one file per fof line, in fof order, named `.kmer.lz4` whatever
+// the header's compressed flag says; like the reference, only the first path is checked for existence.
+inline std::vector<std::string> get_files_to_merge(const std::string& run_dir, uint32_t partition)
+{
+  std::vector<std::string> paths;
+  for (const FofEntry& e : parse_fof(run_dir + "/kmtricks.fof"))
+  {
+    paths.push_back(run_dir + "/counts/partition_" + std::to_string(partition) + "/" + e.id + ".kmer.lz4");
+    if (!fs::exists(paths.front())) throw KmdError("FileNotFoundError", paths.front() + " is missing.");
+  }
+  return paths;
+}
 
 // --save-sk: matrix of the significant k-mers, same container (matrix_file.hpp:93-128), uncompressed payload
 class MatrixWriter

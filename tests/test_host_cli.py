@@ -263,3 +263,72 @@ def test_cli_plugin_model(cli, tmp_path):
     got_ctl = read_fasta(os.path.join(out, "control_kmers.fasta"))
     assert len(got_case) == int(up.sum()) > 0 and len(got_ctl) == int((down & ~up).sum())
     assert f"{int((up | down).sum())}/{n} significant k-mers." in r.stderr
+
+
+# ---- run directories without matrices: per-sample count files merged on the device (row a3) ---------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("merge_records", [0, 20_000])
+def test_cli_count_files_match_matrix_mode_and_reference(cli, tmp_path, merge_records):
+    """`kmtricks pipeline --until count` layout (counts/partition_p/<sample>.kmer.lz4, no matrices): the k-mers,
+    FASTA records and summary lines equal those of matrix mode on the same cohort and of the reference binary;
+    a small --merge-records forces many k-mer-range chunks per partition."""
+    n, parts = 150_000, 6
+    spec = K.SynthSpec(10, 10, kmer_size=31, count_bytes=4, total_rows=n, seed=77, enriched_ppm=3000)
+    d = str(tmp_path / "run_cf")
+    kio.write_run_dir(d, spec, n, parts, lz4=True, count_files=True)
+    out = str(tmp_path / "out_cf")
+    extra = ["--merge-records", str(merge_records)] if merge_records else []
+    for corr in ("bonferroni", "benjamini"):
+        r = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "-c", corr, "-t", "4"] + THR_ARGS + extra)
+        assert r.returncode == 0 and "[error]" not in r.stderr, r.stderr
+        ctl, case, n_pref = expected_records(spec, n, parts, corr)
+        got_ctl = [(strip_index(h), s) for h, s in read_fasta(os.path.join(out, "control_kmers.fasta"))]
+        got_case = [(strip_index(h), s) for h, s in read_fasta(os.path.join(out, "case_kmers.fasta"))]
+        assert len(ctl) + len(case) > 50
+        assert sorted(got_ctl) == sorted(ctl) and sorted(got_case) == sorted(case)
+        assert f"{n_pref}/{n} significant k-mers." in r.stderr
+        if os.path.exists(oracle.REF_BIN) and not merge_records:
+            out_ref = str(tmp_path / f"ref_{corr}")
+            rr = run([oracle.REF_BIN, "diff", "--km-run", d, "-1", "10", "-2", "10", "-o", out_ref, "-c", corr, "-t", "4"] + THR_ARGS)
+            assert "[error]" not in rr.stderr, rr.stderr
+            for f in ("control_kmers.fasta", "case_kmers.fasta"):
+                a = sorted((strip_index(h), s) for h, s in read_fasta(os.path.join(out_ref, f)))
+                b = sorted((strip_index(h), s) for h, s in read_fasta(os.path.join(out, f)))
+                assert a == b, (corr, f, len(a), len(b))
+            for pat in (r"\d+/\d+ significant k-mers\.", r"Before correction: \d+ \(control\), \d+ \(case\)\.",
+                        r"Significant k-mers: \d+ \(control\), \d+ \(case\)\."):
+                assert re.search(pat, rr.stderr).group(0) == re.search(pat, r.stderr).group(0)
+    assert not os.path.exists(os.path.join(d, "kmdiff-count.opt"))     # only matrix mode leaves the marker
+
+
+@pytest.mark.gpu
+def test_cli_reference_fixture_km_out_dir(cli, tmp_path):
+    """the reference's tests/data_test/km_out_dir (merge_test.cpp): 1 control + 1 case, k = 20, 4 partitions"""
+    import shutil
+    d = str(tmp_path / "km_out_dir")
+    shutil.copytree(os.path.join(ROOT, "tests", "golden", "km_out_dir"), d)
+    os.makedirs(os.path.join(d, "matrices"), exist_ok=True)
+    out = str(tmp_path / "out")
+    r = run([cli, "diff", "-d", d, "-1", "1", "-2", "1", "-o", out, "-u", "10000", "--log-factorial", "100"])
+    assert r.returncode == 0 and "[error]" not in r.stderr, r.stderr
+    assert "0/320 significant k-mers." in r.stderr
+    assert "Before correction: 0 (control), 0 (case)." in r.stderr
+    if os.path.exists(oracle.REF_BIN):
+        rr = run([oracle.REF_BIN, "diff", "--km-run", d, "-1", "1", "-2", "1", "-o", str(tmp_path / "ref"), "-u", "10000"])
+        assert "0/320 significant k-mers." in rr.stderr, rr.stderr
+
+
+@pytest.mark.gpu
+def test_cli_count_files_wide_kmers_two_byte_counts(cli, tmp_path):
+    n, parts = 40_000, 3
+    spec = K.SynthSpec(6, 7, kmer_size=63, count_bytes=2, total_rows=n, seed=5, enriched_ppm=4000)
+    d = str(tmp_path / "run_cf")
+    kio.write_run_dir(d, spec, n, parts, lz4=False, count_files=True)
+    out = str(tmp_path / "out")
+    r = run([cli, "diff", "-d", d, "-1", "6", "-2", "7", "-o", out, "--count-bytes", "2", "--merge-records", "50000"])
+    assert "[error]" not in r.stderr, r.stderr
+    ctl, case, n_pref = expected_records(spec, n, parts, "bonferroni")
+    got = [(strip_index(h), s) for f in ("control_kmers.fasta", "case_kmers.fasta") for h, s in read_fasta(os.path.join(out, f))]
+    assert sorted(got) == sorted(ctl + case) and len(got) > 10
+    assert f"{n_pref}/{n} significant k-mers." in r.stderr
