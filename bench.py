@@ -43,6 +43,9 @@ CONFIGS = {
     "c5": (50, 50, 63, 2, 500_000_000, "bonferroni"),    # per-GPU share of 4e9 rows over 8 GPUs
     # BASELINE.json configs[3]: population stratification, 10 PCs, 1e6 sampled k-mers, logistic GLM
     "c4": (200, 200, 31, 4, 60_000_000, "bonferroni"),
+    # the c2 cohort as `kmdiff count` leaves it: per-sample sorted (k-mer, count) files, no matrices
+    # (BASELINE.json configs[0]'s input layout; km::KmerMerger row of SURVEY.md §8a) — host streams in
+    "c2m": (10, 10, 31, 4, 8_000_000, "bonferroni"),
 }
 C4_NPC = 10
 C4_SAMPLED = 1_000_000
@@ -125,7 +128,7 @@ def make_reference_run_dir(cfg_name: str, sample_rows: int, partitions: int) -> 
     nc, nk, k, b, rows, _ = CONFIGS[cfg_name]
     spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=rows, seed=42)
     d = tempfile.mkdtemp(prefix="kmdiff_ref_run_", dir=os.environ.get("KMD_TMP", "/tmp"))
-    kio.write_run_dir(d, spec, sample_rows, partitions)
+    kio.write_run_dir(d, spec, sample_rows, partitions, count_files=cfg_name.endswith("m"))
     return d, spec.row_bytes
 
 
@@ -194,6 +197,143 @@ def bench_reference(args) -> None:
         "gpu_launches": 0,
     })
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm, per-sample count-file input (km::KmerMerger row): host streams -> device merge -> scan -> correction
+# ------------------------------------------------------------------------------------------------------
+
+def bench_merge(args) -> None:
+    import numpy as np
+    import torch
+
+    import kmdiff_b200 as K
+    from kmdiff_b200 import kmtricks_io as kio
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py: c2m is a single-GPU bench line")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — kmdiff_b200 has no CPU fallback")
+    cfg_name = args.config
+    nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
+    if args.rows:
+        rows = args.rows
+    n = nc + nk
+    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=rows, seed=42)
+    totals = spec.totals()
+    kw, rec = spec.kmer_words, 8 * spec.kmer_words + b
+    # the host program's reader state, prepared once: every sample's records of a k-mer range per merge call
+    # The streams live in pinned host memory, like the reader buffers of `kmdiff-b200 diff`.
+    import ctypes
+    from kmdiff_b200 import _lib
+    L = _lib.load()
+    chunk_rows = max(1, min(rows, (24 << 20) // n))
+    chunks, n_records, pinned = [], 0, []
+    for lo in range(0, rows, chunk_rows):
+        dense = spec.rows_host(min(chunk_rows, rows - lo), lo)
+        streams = kio.rows_to_streams(dense, n, kw, b)
+        n_records += sum(s.size for s in streams) // rec
+        total = sum(s.size for s in streams)
+        hptr = L.kmd_host_alloc(max(total, 1))
+        if not hptr:
+            raise SystemExit("kmd_host_alloc failed")
+        pinned.append(hptr)
+        hbuf = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint8)), shape=(max(total, 1),))
+        views, at = [], 0
+        for s_ in streams:
+            hbuf[at:at + s_.size] = s_
+            views.append(hbuf[at:at + s_.size])
+            at += s_.size
+        chunks.append(views)
+    thr = SIGNIFICANCE / CUTOFF
+    ctx = K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), kmer_size=k, count_bytes=b, threshold=thr)
+    corr_kind = K.correction_from_str(corr)
+    stage_ms = {"unpack": 0.0, "passes": 0.0, "rows": 0.0, "scan": 0.0}
+    n_passes = [0]
+
+    def step(timed=False):
+        ctx.reset()
+        base = 0
+        for streams in chunks:
+            base += ctx.merge_scan_host(streams, row_base=base)
+            if timed:
+                m = ctx.merge_ms()
+                for key in ("unpack", "passes", "rows"):
+                    stage_ms[key] += m[key]
+                n_passes[0] = m["n_passes"]
+                ctx.sync()
+                stage_ms["scan"] += ctx.scan_kernel_ms()
+        c = ctx.counters()
+        res = ctx.correct(corr_kind, SIGNIFICANCE, c.rows)
+        sig = ctx.significant()
+        return res, c, sig
+
+    for _ in range(max(3, args.warmup)):
+        res, c, sig = step()
+    assert c.rows == rows, (c.rows, rows)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res, c, sig = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = (ctx.launch_count() - launches0) // args.steps
+    step(timed=True)                      # per-stage device times, outside the timed region (adds syncs)
+    value = rows * args.steps / dt
+    peak, peak_src = load_peaks()
+    pass_bytes = n_passes[0] * n_records * 2 * (8 * kw + 8)     # every pass reads and writes (key, payload)
+    achieved = pass_bytes / (stage_ms["passes"] * 1e-3) / 1e9 if stage_ms["passes"] else None
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        try:
+            if reference_available():
+                sample = min(rows, reference_sample_rows("c2", cores) // 4)
+                parts = max(cores, 8)
+                run_dir, _ = make_reference_run_dir(cfg_name, sample, parts)
+                try:
+                    run_reference_once(run_dir, cfg_name, cores)
+                    dtc = run_reference_once(run_dir, cfg_name, cores)
+                finally:
+                    shutil.rmtree(run_dir, ignore_errors=True)
+                cpu = {"value": sample / dtc, "unit": "rows/s", "cores": cores, "kind": "reference",
+                       "sample": f"`kmdiff diff -t {cores}` (oracle/_ref/kmdiff, km::KmerMerger path) on the first {sample} "
+                                 f"rows as {parts} partitions x {n} uncompressed .kmer files, {dtc:.2f} s"}
+        except Exception as e:
+            cpu = {"value": None, "unit": "rows/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+
+    line = {
+        "metric": "kmer_rows_tested_per_sec", "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{cfg_name}: synthetic {nc}+{nk} samples, k={k}, {b}-byte counts as per-sample sorted count "
+                               f"streams (no matrices), device N-way merge + Poisson LRT + {corr}",
+                   "rows_per_gpu": rows, "records_per_gpu": n_records, "record_bytes": rec, "row_bytes": spec.row_bytes,
+                   "merge_calls_per_step": len(chunks), "merge_passes": n_passes[0],
+                   "l2": f"every merge call works on {n_records // max(1, len(chunks)) * 32 >> 20} MiB of (key, payload) arrays, above the 126 MB L2",
+                   "survivors_per_gpu": int(c.survivors), "significant": [int(res[0]), int(res[1])]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if achieved else None, "traffic": None, "kernel": "mrg::merge_pass_kernel",
+                     "ms_per_launch": stage_ms["passes"] / max(1, n_passes[0] * len(chunks)),
+                     "algorithmic_bytes_per_launch": pass_bytes // max(1, n_passes[0] * len(chunks)), "peak_source": peak_src,
+                     "stage_ms_per_step": stage_ms},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": n_records * rec, "d2h_bytes_per_step": int(sig.nbytes + 48),
+                "rows_per_step": rows, "steps": args.steps,
+                "api": "kmd_merge_scan_host (host record streams) + kmd_correct + kmd_significant; this path has no "
+                       "device-resident variant, value == e2e"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    ctx.close()
+    for hptr in pinned:
+        L.kmd_host_free(hptr)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -489,6 +629,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)
+    elif args.config.endswith("m"):
+        bench_merge(args)
     else:
         bench_b200(args)
 

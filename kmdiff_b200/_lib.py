@@ -27,7 +27,7 @@ SYMBOLS = [
     "kmd_popstrat_enable", "kmd_popstrat_set_draw_index", "kmd_popstrat_sampled", "kmd_popstrat_geno", "kmd_popstrat_gram",
     "kmd_popstrat_gram_ms", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
     "kmd_survivor_counts", "kmd_smartpca_normalize", "kmd_sym_eig", "kmd_smartpca_pcs",
-    "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_rows_host",
+    "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_rows_host", "kmd_merge_ms",
 ]
 
 
@@ -95,6 +95,7 @@ def load() -> C.CDLL:
     L.kmd_scan_host.argtypes = [vp, vp, u64, u64, u32]
     L.kmd_merge_scan_host.argtypes = [vp, vp, vp, vp, u64, u32, pu64]
     L.kmd_merge_rows_host.argtypes = [vp, vp, vp, vp, vp, u64, pu64]
+    L.kmd_merge_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u32), pu64]
     L.kmd_counters_get.argtypes = [vp, C.POINTER(Counters)]
     L.kmd_survivors.argtypes = [vp, vp, u64, pu64]
     L.kmd_push_survivors.argtypes = [vp, vp, u64, u64]

@@ -230,6 +230,13 @@ class DiffContext:
         self._ck(self._L.kmd_merge_scan_host(self._h, ptrs, cnt, ab.ctypes.data, row_base, partition, C.byref(n)))
         return n.value
 
+    def merge_ms(self) -> dict:
+        """device times of the last merge call: {'unpack', 'passes', 'rows'} in ms, 'n_passes', 'n_records'"""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        npass, nrec = C.c_uint32(), C.c_uint64()
+        self._ck(self._L.kmd_merge_ms(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(npass), C.byref(nrec)))
+        return {"unpack": a.value, "passes": b.value, "rows": c.value, "n_passes": npass.value, "n_records": nrec.value}
+
     def merge_rows_host(self, streams, ab_min=1) -> np.ndarray:
         """the merged dense rows (KmerMerger::write_as_bin payload), [n_rows, row_bytes] uint8"""
         arrs, ptrs, cnt, ab = self._merge_args(streams, ab_min)

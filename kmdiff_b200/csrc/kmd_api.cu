@@ -108,6 +108,10 @@ struct MergeState
   uint32_t* ab_min = nullptr; size_t ab_cap = 0;
   uint32_t* plan = nullptr; size_t plan_cap = 0;
   uint32_t* total = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // unpack | merge passes | row numbering + dense rows
+  bool timed = false;
+  uint32_t last_passes = 0;
+  uint64_t last_records = 0;
 };
 
 }  // namespace

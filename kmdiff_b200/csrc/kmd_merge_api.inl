@@ -24,6 +24,7 @@ void merge_free(kmd_context* ctx)
   for (int b = 0; b < 2; b++) { cudaFree(m.klo[b]); cudaFree(m.khi[b]); cudaFree(m.pay[b]); }
   cudaFree(m.flag); cudaFree(m.tile); cudaFree(m.head_pos); cudaFree(m.rows); cudaFree(m.stream_off);
   cudaFree(m.ab_min); cudaFree(m.plan); cudaFree(m.total);
+  for (cudaEvent_t e : m.ev) if (e) cudaEventDestroy(e);
   m = MergeState{};
 }
 
@@ -122,6 +123,8 @@ int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_r
   if ((rc = grow(ctx, m.stream_off, m.off_cap, N + 1))) return rc;
   if ((rc = grow(ctx, m.ab_min, m.ab_cap, N))) return rc;
   if (!m.total) KMD_CUDA(ctx, cudaMalloc(&m.total, sizeof(uint32_t)));
+  for (cudaEvent_t& e : m.ev) if (!e) KMD_CUDA(ctx, cudaEventCreate(&e));
+  m.timed = false;
 
   // the merge tree: leaves = streams, every pass halves the number of runs
   std::vector<uint32_t> plan;
@@ -161,6 +164,7 @@ int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_r
     if (n_records[s])
       KMD_CUDA(ctx, cudaMemcpyAsync(m.raw + off[s] * rec, streams[s], n_records[s] * rec, cudaMemcpyHostToDevice, ctx->stream));
 
+  KMD_CUDA(ctx, cudaEventRecord(m.ev[0], ctx->stream));
   mrg::UnpackArgs U{};
   U.raw = m.raw; U.stream_off = m.stream_off; U.ab_min = m.ab_min; U.n_streams = N; U.n = n;
   U.kmer_words = W; U.count_bytes = B;
@@ -171,10 +175,18 @@ int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_r
   KMD_CUDA(ctx, cudaGetLastError());
 
   int buf = 0;
+  KMD_CUDA(ctx, cudaEventRecord(m.ev[1], ctx->stream));
   rc = W == 2 ? merge_passes<2>(ctx, passes, &buf) : merge_passes<1>(ctx, passes, &buf);
   if (rc) return rc;
+  KMD_CUDA(ctx, cudaEventRecord(m.ev[2], ctx->stream));
   // plan/off/ab_min are host temporaries: merge_rows synchronises the stream before we return
-  return W == 2 ? merge_rows<2>(ctx, buf, n, n_rows) : merge_rows<1>(ctx, buf, n, n_rows);
+  rc = W == 2 ? merge_rows<2>(ctx, buf, n, n_rows) : merge_rows<1>(ctx, buf, n, n_rows);
+  if (rc) return rc;
+  KMD_CUDA(ctx, cudaEventRecord(m.ev[3], ctx->stream));
+  m.timed = true;
+  m.last_passes = static_cast<uint32_t>(passes.size());
+  m.last_records = n;
+  return KMD_OK;
 }
 
 int merge_check(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min)
@@ -199,6 +211,25 @@ int kmd_merge_scan_host(kmd_context* ctx, const void* const* streams, const uint
   if (n_rows) *n_rows = rows;
   if (rows == 0) return KMD_OK;
   return scan_device_impl(ctx, ctx->mrg.rows, rows, row_base, partition);
+}
+
+int kmd_merge_ms(kmd_context* ctx, float* unpack_ms, float* passes_ms, float* rows_ms, uint32_t* n_passes, uint64_t* n_records)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  MergeState& m = ctx->mrg;
+  if (!m.timed) return fail(ctx, KMD_ERR_STATE, "no merge call has completed on this context");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  KMD_CUDA(ctx, cudaEventSynchronize(m.ev[3]));
+  float a = 0, b = 0, c = 0;
+  KMD_CUDA(ctx, cudaEventElapsedTime(&a, m.ev[0], m.ev[1]));
+  KMD_CUDA(ctx, cudaEventElapsedTime(&b, m.ev[1], m.ev[2]));
+  KMD_CUDA(ctx, cudaEventElapsedTime(&c, m.ev[2], m.ev[3]));
+  if (unpack_ms) *unpack_ms = a;
+  if (passes_ms) *passes_ms = b;
+  if (rows_ms) *rows_ms = c;
+  if (n_passes) *n_passes = m.last_passes;
+  if (n_records) *n_records = m.last_records;
+  return KMD_OK;
 }
 
 int kmd_merge_rows_host(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min,

@@ -268,6 +268,41 @@ void dump_opt(const DiffOptions& o, const std::string& path)
   fclose(f);
 }
 
+// load_opt (cmd/diff_opt.hpp:90-104) + our total_kmers extension (0 when the file was written by the reference)
+struct PrevOptions { bool valid = false; double threshold = 0, cutoff = 0, kmer_pca = 0; int32_t correction = 0; uint8_t pop = 0; uint64_t npc = 0, total_kmers = 0; };
+
+PrevOptions load_opt(const std::string& path)
+{
+  PrevOptions o;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return o;
+  uint8_t b[45] = {0};
+  const size_t got = fread(b, 1, sizeof b, f);
+  fclose(f);
+  if (got < 37) return o;
+  memcpy(&o.threshold, b, 8); memcpy(&o.cutoff, b + 8, 8); memcpy(&o.correction, b + 16, 4); o.pop = b[20];
+  memcpy(&o.kmer_pca, b + 21, 8); memcpy(&o.npc, b + 29, 8);
+  if (got >= 45) memcpy(&o.total_kmers, b + 37, 8);
+  o.valid = true;
+  return o;
+}
+
+// compare_opt (cmd/diff_opt.hpp:106-133): bit 0 redo the scan, bit 1 redo the stratification, bit 2 redo the correction
+unsigned compare_opt(const DiffOptions& o, const PrevOptions& prev)
+{
+  unsigned r = 0;
+  if (o.threshold != prev.threshold || static_cast<double>(o.cutoff) != prev.cutoff) r |= 0b1;
+  if (prev.pop && o.pop_correction)
+  {
+    if (o.kmer_pca != prev.kmer_pca) r |= 0b11;
+    if (o.npc != prev.npc) r |= 0b10;
+  }
+  if (!prev.pop && o.pop_correction) r |= 0b11;
+  if (o.correction != prev.correction) r |= 0b100;
+  if (prev.pop && !o.pop_correction) r |= 0b100;
+  return r;
+}
+
 // ---- device contexts ------------------------------------------------------------------------------------
 
 struct CtxDeleter { void operator()(kmd_context* c) const { kmd_destroy(c); } };
@@ -381,7 +416,19 @@ class GpuWorker
     const uint64_t budget = std::max<uint64_t>(1ull << 12, m_opt.merge_records);
     const size_t per = static_cast<size_t>(std::max<uint64_t>(1024, budget / N));
     const std::vector<uint32_t> ab_min(N, 1);
-    struct Stream { std::unique_ptr<KmerFile> file; std::vector<uint8_t> buf, disk; size_t n = 0; bool eof = false; };
+    // record buffers in pinned memory: the H2D copies of kmd_merge_scan_host then run at PCIe rate
+    struct PinnedBuf
+    {
+      uint8_t* p = nullptr;
+      explicit PinnedBuf(size_t bytes) : p(static_cast<uint8_t*>(kmd_host_alloc(bytes))) { if (!p) throw KmdError("GpuError", "kmd_host_alloc failed"); }
+      ~PinnedBuf() { kmd_host_free(p); }
+      PinnedBuf(const PinnedBuf&) = delete;
+      PinnedBuf& operator=(const PinnedBuf&) = delete;
+      uint8_t* data() const { return p; }
+    };
+    struct Stream { std::unique_ptr<KmerFile> file; std::unique_ptr<PinnedBuf> pin; std::vector<uint8_t> disk; size_t n = 0; bool eof = false; };
+    std::vector<std::unique_ptr<PinnedBuf>> pins(N);
+    for (auto& pb : pins) pb = std::make_unique<PinnedBuf>(per * rec);
     auto key_less = [kw](const uint8_t* a, const uint8_t* b) {
       for (int w = static_cast<int>(kw) - 1; w >= 0; w--)
       {
@@ -395,13 +442,15 @@ class GpuWorker
     {
       if (p.sample_paths.size() != N) throw KmdError("ConfigError", "kmtricks.fof does not list --nb-controls + --nb-cases samples.");
       std::vector<Stream> st(N);
+      struct Returner { std::vector<Stream>& st; std::vector<std::unique_ptr<PinnedBuf>>& pins;
+                        ~Returner() { for (size_t s = 0; s < st.size(); s++) if (st[s].pin) pins[s] = std::move(st[s].pin); } } returner{st, pins};
       for (uint32_t s = 0; s < N; s++)
       {
+        st[s].pin = std::move(pins[s]);
         st[s].file = std::make_unique<KmerFile>(p.sample_paths[s]);
         const KmerHeader& h = st[s].file->hdr;
         if (h.kmer_slots != kw) throw KmdError("InputError", p.sample_paths[s] + ": unexpected kmer_slots");
         if (h.count_slots == 0 || h.count_slots > 4) throw KmdError("InputError", p.sample_paths[s] + ": unexpected count_slots");
-        st[s].buf.resize(per * rec);
       }
       uint64_t local = 0;
       for (;;)
@@ -422,7 +471,7 @@ class GpuWorker
               size_t got_rec;
               if (cs == B)
               {
-                const size_t got = t.file->payload->read(t.buf.data() + t.n * rec, want * rec);
+                const size_t got = t.file->payload->read(t.pin->data() + t.n * rec, want * rec);
                 if (got % rec) throw KmdError("InputError", p.sample_paths[s] + ": truncated record");
                 got_rec = got / rec;
               }
@@ -437,7 +486,7 @@ class GpuWorker
                 got_rec = got / drec;
                 for (size_t i = 0; i < got_rec; i++)
                 {
-                  uint8_t* dst = t.buf.data() + (t.n + i) * rec;
+                  uint8_t* dst = t.pin->data() + (t.n + i) * rec;
                   memset(dst, 0, rec);
                   memcpy(dst, t.disk.data() + i * drec, 8ull * kw + std::min<uint32_t>(cs, B));
                 }
@@ -460,7 +509,7 @@ class GpuWorker
         for (const Stream& t : st)
           if (!t.eof && t.n)
           {
-            const uint8_t* last = t.buf.data() + (t.n - 1) * rec;
+            const uint8_t* last = t.pin->data() + (t.n - 1) * rec;
             if (!bound || key_less(last, bound)) bound = last;
           }
         std::vector<uint8_t> bound_key;
@@ -478,11 +527,11 @@ class GpuWorker
             while (lo < hi)
             {
               const size_t mid = (lo + hi) / 2;
-              if (key_less(bound_key.data(), st[s].buf.data() + mid * rec)) hi = mid; else lo = mid + 1;
+              if (key_less(bound_key.data(), st[s].pin->data() + mid * rec)) hi = mid; else lo = mid + 1;
             }
             cut = lo;
           }
-          ptrs[s] = st[s].buf.data();
+          ptrs[s] = st[s].pin->data();
           cnt[s] = cut;
           total += cut;
         }
@@ -498,7 +547,7 @@ class GpuWorker
         for (uint32_t s = 0; s < N; s++)
         {
           Stream& t = st[s];
-          if (cnt[s] && cnt[s] < t.n) memmove(t.buf.data(), t.buf.data() + cnt[s] * rec, (t.n - cnt[s]) * rec);
+          if (cnt[s] && cnt[s] < t.n) memmove(t.pin->data(), t.pin->data() + cnt[s] * rec, (t.n - cnt[s]) * rec);
           t.n -= cnt[s];
         }
       }
@@ -719,6 +768,40 @@ void write_spill_files(const std::vector<kmd_survivor>& surv, uint32_t nb_partit
   for (uint32_t p = 0; p < nb_partitions; p++) { w[p]->close(); fclose(files[p]); }
 }
 
+// FileAccumulator::get over a spill file of an earlier run of this program (accumulator.hpp:190-226,
+// KmerSign::load kmer.hpp:101-111): records without the WITH_POPSTRAT tail.  Rows are renumbered in file order.
+std::vector<kmd_survivor> read_spill_file(const std::string& path, uint32_t partition, uint32_t kmer_words)
+{
+  std::vector<kmd_survivor> out;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw KmdError("IOError", "Unable to open " + path);
+  struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+  Lz4FrameReader in(f);
+  const size_t rec = 8ull * kmer_words + 28;
+  std::vector<uint8_t> buf(rec * 4096);
+  uint64_t local = 0;
+  for (;;)
+  {
+    const size_t got = in.read(buf.data(), buf.size());
+    if (got % rec) throw KmdError("IOError", path + ": truncated record");
+    for (size_t i = 0; i < got / rec; i++)
+    {
+      const uint8_t* r = buf.data() + i * rec;
+      kmd_survivor s{};
+      memcpy(s.kmer, r, 8ull * kmer_words);
+      memcpy(&s.p_value, r + 8 * kmer_words, 8);
+      memcpy(&s.sign, r + 8 * kmer_words + 8, 4);
+      memcpy(&s.mean_control, r + 8 * kmer_words + 12, 8);
+      memcpy(&s.mean_case, r + 8 * kmer_words + 20, 8);
+      s.partition = partition;
+      s.row = (static_cast<uint64_t>(partition) << kPartShift) + local++;
+      out.push_back(s);
+    }
+    if (got < buf.size()) break;
+  }
+  return out;
+}
+
 // ---- FASTA output (aggregator.hpp:27-71, 197-199) -----------------------------------------------------------
 
 struct FastaPair
@@ -912,13 +995,36 @@ void main_diff(DiffOptions& opt)
   const std::string part_dir = opt.output_directory + "/partitions";
   fs::create_directories(part_dir);
 
+  // ---- an earlier run in the same output directory (cmd/diff.hpp:277-303) ----
+  // With its spill files kept (--keep-tmp) and the same prefilter, the scan is skipped and only the correction
+  // is redone (cmd/diff.hpp:340-349); when nothing changed and the FASTA files exist, nothing is redone.
+  // The reference forgets total_kmers in options.bin and would correct with m = 0; ours stores it.  Spill files
+  // of a --pop-correction run carry per-sample counts and are not resumed from: such a run is redone in full.
+  const PrevOptions prev = load_opt(opt.output_directory + "/options.bin");
+  bool resumed = false;
+  unsigned action = 0;
+  if (prev.valid)
+  {
+    action = compare_opt(opt, prev);
+    bool prev_1 = true;
+    for (uint32_t p = 0; p < cfg.nb_partitions && prev_1; p++) prev_1 = fs::exists(part_dir + "/p" + std::to_string(p) + "_uncorrected");
+    const bool prev_f = fs::exists(opt.output_directory + "/control_kmers.fasta") && fs::exists(opt.output_directory + "/case_kmers.fasta");
+    logf(L_DEBUG, "prev1 -> %d, prevf -> %d, action -> %u", prev_1, prev_f, action);
+    resumed = prev_1 && !(action & 0b1) && !opt.pop_correction && !prev.pop && prev.total_kmers > 0 && opt.model_lib_path.empty() && !opt.save_sk;
+    if (resumed && prev_f && action == 0)
+    {
+      logf(L_INFO, "Done in %s, Peak RSS -> %zu MB.", whole.formatted().c_str(), peak_rss_mb());
+      return;
+    }
+  }
+
   // ---- do_diff ----
   Timer merge_time;
-  logf(L_INFO, "Process partitions");
-  const std::vector<std::string> matrix_paths = list_matrices(opt.kmtricks_dir);
+  if (!resumed) logf(L_INFO, "Process partitions");
+  const std::vector<std::string> matrix_paths = resumed ? std::vector<std::string>{"<spill files>"} : list_matrices(opt.kmtricks_dir);
   // no matrices: the per-sample count files of every partition are merged on the fly (cmd/diff.hpp:88-95)
   const bool from_matrix = !matrix_paths.empty();
-  if (from_matrix) { std::ofstream touch(opt.kmtricks_dir + "/kmdiff-count.opt", std::ios::app); }   // the reference leaves this marker (cmd/diff.hpp:100)
+  if (from_matrix && !resumed) { std::ofstream touch(opt.kmtricks_dir + "/kmdiff-count.opt", std::ios::app); }   // the reference leaves this marker (cmd/diff.hpp:100)
 
   std::vector<uint64_t> total_controls, total_cases;
   get_total_kmer(opt.kmtricks_dir, opt.nb_controls, opt.nb_cases, cfg.abundance_min, total_controls, total_cases);
@@ -927,7 +1033,7 @@ void main_diff(DiffOptions& opt)
   for (uint64_t t : total_cases) sum_k += t;
 
   std::vector<Partition> parts;
-  for (const std::string& p : matrix_paths)
+  for (const std::string& p : resumed ? std::vector<std::string>{} : matrix_paths)
   {
     // partition index from the header (matrix_{p}.count[.lz4])
     MatrixFile mf(p, 8ull * kw + (opt.nb_controls + opt.nb_cases) * opt.count_bytes);
@@ -969,6 +1075,7 @@ void main_diff(DiffOptions& opt)
   }
   if (!from_matrix && opt.pop_correction) n_dev = 1;   // Sampler draws follow the rows merged so far: one ordered stream
   n_dev = std::max(1, std::min<int>(n_dev, static_cast<int>(parts.size())));
+  if (resumed) n_dev = 1;
 
   std::string pop_dir;
   if (opt.pop_correction)
@@ -1012,7 +1119,19 @@ void main_diff(DiffOptions& opt)
   std::vector<std::unique_ptr<GpuWorker>> workers;
   for (int d = 0; d < n_dev; d++) workers.push_back(std::make_unique<GpuWorker>(d, opt, cfg, sum_c, sum_k));
 
-  if (plugin)
+  if (resumed)
+  {
+    // accumulators re-opened on the kept spill files (cmd/diff.hpp:342-348)
+    uint64_t tested = prev.total_kmers;
+    for (uint32_t p = 0; p < cfg.nb_partitions; p++)
+    {
+      const std::vector<kmd_survivor> recs = read_spill_file(part_dir + "/p" + std::to_string(p) + "_uncorrected", p, kw);
+      ck(workers[0]->ctx(), kmd_push_survivors(workers[0]->ctx(), recs.data(), recs.size(), tested), "kmd_push_survivors");
+      tested = 0;
+    }
+    if (tested) ck(workers[0]->ctx(), kmd_push_survivors(workers[0]->ctx(), nullptr, 0, tested), "kmd_push_survivors");
+  }
+  else if (plugin)
   {
     switch (opt.count_bytes)
     {
@@ -1051,10 +1170,13 @@ void main_diff(DiffOptions& opt)
     total_kmers += c.rows; nb_sign += c.survivors; sign_controls += c.n_control; sign_cases += c.n_case;
   }
   opt.total_kmers = total_kmers;
-  logf(L_INFO, "Partitions processed (%s)", merge_time.formatted().c_str());
-  logf(L_INFO, "%llu/%llu significant k-mers.", static_cast<unsigned long long>(nb_sign), static_cast<unsigned long long>(total_kmers));
-  logf(L_INFO, "Before correction: %llu (control), %llu (case).", static_cast<unsigned long long>(sign_controls),
-       static_cast<unsigned long long>(sign_cases));
+  if (!resumed)
+  {
+    logf(L_INFO, "Partitions processed (%s)", merge_time.formatted().c_str());
+    logf(L_INFO, "%llu/%llu significant k-mers.", static_cast<unsigned long long>(nb_sign), static_cast<unsigned long long>(total_kmers));
+    logf(L_INFO, "Before correction: %llu (control), %llu (case).", static_cast<unsigned long long>(sign_controls),
+         static_cast<unsigned long long>(sign_cases));
+  }
 
   dump_opt(opt, opt.output_directory + "/options.bin");
   const uint16_t n_samples = static_cast<uint16_t>(opt.nb_controls + opt.nb_cases);
@@ -1074,7 +1196,7 @@ void main_diff(DiffOptions& opt)
     }
     write_spill_files(all, nb_partitions, kw, part_dir, suffix, opt.pop_correction ? &counts : nullptr, n_samples);
   };
-  if (opt.keep_tmp) spill("_uncorrected");
+  if (opt.keep_tmp && !resumed) spill("_uncorrected");
 
   if (opt.pop_correction)
   {

@@ -332,3 +332,35 @@ def test_cli_count_files_wide_kmers_two_byte_counts(cli, tmp_path):
     got = [(strip_index(h), s) for f in ("control_kmers.fasta", "case_kmers.fasta") for h, s in read_fasta(os.path.join(out, f))]
     assert sorted(got) == sorted(ctl + case) and len(got) > 10
     assert f"{n_pref}/{n} significant k-mers." in r.stderr
+
+
+# ---- resume from an earlier run's spill files (cmd/diff.hpp:277-303, 340-349) ---------------------------
+
+@pytest.mark.gpu
+def test_cli_resume_recorrects_from_spill_files(cli, tmp_path):
+    n, parts = 120_000, 5
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=parts)
+    out = str(tmp_path / "out")
+    base = [cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "--keep-tmp"] + THR_ARGS
+    r = run(base + ["-c", "bonferroni"])
+    assert "[error]" not in r.stderr and "Process partitions" in r.stderr, r.stderr
+    # same prefilter, other correction: the scan is skipped, the kept spill files are re-corrected with m = n
+    r2 = run(base + ["-c", "benjamini"])
+    assert "[error]" not in r2.stderr and "Process partitions" not in r2.stderr, r2.stderr
+    ctl, case, _ = expected_records(spec, n, parts, "benjamini")
+    got_ctl = [(strip_index(h), s) for h, s in read_fasta(os.path.join(out, "control_kmers.fasta"))]
+    got_case = [(strip_index(h), s) for h, s in read_fasta(os.path.join(out, "case_kmers.fasta"))]
+    assert len(ctl) + len(case) > 50
+    assert sorted(got_ctl) == sorted(ctl) and sorted(got_case) == sorted(case)
+    assert f"Significant k-mers: {len(ctl)} (control), {len(case)} (case)." in r2.stderr
+    with open(os.path.join(out, "options.bin"), "rb") as f:
+        ob = f.read()
+    assert struct.unpack("<i", ob[16:20])[0] == oracle.CORRECTIONS["benjamini"] and struct.unpack("<Q", ob[37:45])[0] == n
+    # nothing changed and the FASTA files exist: nothing is redone
+    before = os.path.getmtime(os.path.join(out, "case_kmers.fasta"))
+    r3 = run(base + ["-c", "benjamini"])
+    assert "Aggregate" not in r3.stderr and "Done in" in r3.stderr, r3.stderr
+    assert os.path.getmtime(os.path.join(out, "case_kmers.fasta")) == before
+    # another cutoff: the prefilter changed, everything is redone
+    r4 = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "--keep-tmp", "-s", "0.05", "-u", "1000", "-c", "benjamini"])
+    assert "Process partitions" in r4.stderr and "[error]" not in r4.stderr, r4.stderr
