@@ -91,6 +91,10 @@ struct PopState
   double null_likelihood = 0;
   std::vector<double> null_model;
   float gram_ms = 0;                       // device time of the last grm_umma_kernel launch
+  // grow-only scratch of kmd_popstrat_gram (bucketing, transposed presence matrix, integer Gram matrices):
+  // the presence matrix alone is ~0.5 GB at 1e6 sampled k-mers, too much to allocate and free per call
+  void* gram_scratch[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t gram_scratch_cap[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 // per-sample count-file input (kmd_merge_*): grow-only device buffers of the merge tree

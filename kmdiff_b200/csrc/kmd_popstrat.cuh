@@ -172,7 +172,8 @@ __global__ void presence_done_kernel(const unsigned long long* total, unsigned l
 // ---- logistic GLM by IRLS, one warp per k-mer ---------------------------------------------------
 
 constexpr int kMaxP = 16;       // features per model (1 + n_pc + total + ratio <= 13 in the reference)
-constexpr int kIrlsWarps = 8;    // at most; fewer when the per-warp state of a large cohort fills shared memory
+constexpr int kIrlsQ = (kMaxP * kMaxP + kMaxP + 31) / 32;   // [hessian | X^T S z] elements per lane, at most
+constexpr int kIrlsWarps = 10;    // at most; fewer when the per-warp state of a large cohort fills shared memory
 
 struct IrlsArgs
 {
@@ -220,8 +221,8 @@ struct IrlsWarp
 };
 
 // Shared memory layout (doubles): [features n*ldf (optional)] [y n] then per warp:
-//   xl[n] mu[n] eta[n] H[p*p] LU[p*p] INV[p*p] v[p] w[p] weight[p]
-__host__ __device__ inline size_t irls_warp_doubles(uint32_t n, uint32_t p) { return 3ull * n + 3ull * p * p + 3ull * p; }
+//   xl[n] mu[n] eta[n] d2[n] H[p*p] LU[p*p] INV[p*p] v[p] w[p] weight[p]
+__host__ __device__ inline size_t irls_warp_doubles(uint32_t n, uint32_t p) { return 4ull * n + 3ull * p * p + 3ull * p; }
 
 __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArgs A)
 {
@@ -243,7 +244,8 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
   double* xl = mine;
   double* mu = xl + n;
   double* eta = mu + n;
-  double* H = eta + n;       // hessian, later the forward-substitution results y[row][invc]
+  double* d2 = eta + n;      // (y - mu)^2 of the current iteration
+  double* H = d2 + n;        // hessian, later the forward-substitution results y[row][invc]
   double* LU = H + p * p;    // L strictly below the diagonal (unit diagonal implied), U on and above
   double* INV = LU + p * p;
   double* v = INV + p * p;   // X^T S z
@@ -254,6 +256,28 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
   const uint32_t n_items = A.n_items_dev ? min(*A.n_items_dev, A.n_items) : A.n_items;
   IrlsWarp X{F, A.own_last ? xl : nullptr, A.ldf, p, n};
   const uint32_t pp = p * p;
+
+  // elements of [hessian | X^T S z] owned by this lane: e = lane + 32 q; where column p-1 is the k-mer's own
+  // (alt model) it is read from xl with stride 1, every other column from the feature matrix with stride ldf
+  const uint32_t nq = (pp + p + 31) / 32;
+  const double* el_a[kIrlsQ];
+  const double* el_b[kIrlsQ];
+  uint32_t el_sa[kIrlsQ], el_sb[kIrlsQ];
+  bool el_v[kIrlsQ];
+#pragma unroll
+  for (int q = 0; q < kIrlsQ; q++)
+  {
+    const uint32_t e = lane + 32 * q;
+    const bool is_v = e >= pp;
+    uint32_t a = is_v ? e - pp : e / p, b = is_v ? 0 : e - (e / p) * p;
+    if (a >= p) a = 0;   // unused slot: any valid address
+    const bool own_a = A.own_last && a == p - 1, own_b = A.own_last && b == p - 1;
+    el_a[q] = own_a ? xl : F + a;
+    el_sa[q] = own_a ? 1 : A.ldf;
+    el_b[q] = own_b ? xl : F + b;
+    el_sb[q] = own_b ? 1 : A.ldf;
+    el_v[q] = is_v;
+  }
 
   const uint32_t warps_per_block = blockDim.x >> 5;
   for (uint32_t item = blockIdx.x * warps_per_block + warp; item < n_items; item += gridDim.x * warps_per_block)
@@ -285,63 +309,62 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
     int iter = 0, ise = 0, ine = 0;
     while (true)
     {
-      // error = sum (y - mu)^2 in row order; every lane carries the same sum
-      double error = 0.0;
-      uint32_t n_good = 0;
-      for (uint32_t i = 0; i < n; i++)
+      // Per-row terms, rows spread over the lanes (each is a function of its own row only):
+      //   d2 = (y - mu)^2, g = S[k] = mu (1 - mu), gz = S[k] * z[k] with z = eta + (y - mu) / (g + 1e-305).
+      // mu[] and eta[] are dead until the new weights rebuild them below, so they take g and gz.
+      for (uint32_t i = lane; i < n; i += 32)
       {
         const double m = mu[i];
         const double d = sub(ys[i], m);
-        error = add(error, mul(d, d));
-        n_good += mul(m, sub(1.0, m)) > 1e-305;
+        const double g = mul(m, sub(1.0, m));
+        d2[i] = mul(d, d);
+        const double z = add(eta[i], div(d, add(g, 1e-305)));
+        mu[i] = g;
+        eta[i] = mul(g, z);
+      }
+      __syncwarp();
+
+      // One walk over the rows, in row order, carries every sum of the iteration in the reference's order:
+      //   error         = sum_k d2[k]                               (every lane, same value)
+      //   hessian[a][b] = sum_{good k} X[k][a] * (S[k] * X[k][b])   (element e = a*p + b owned by lane e % 32)
+      //   (X^T S z)[j]  = sum_{good k} X[k][j] * (S[k] * z[k])      (element p*p + j)
+      double error = 0.0;
+      uint32_t n_good = 0;
+      {
+        double acc[kIrlsQ];
+#pragma unroll
+        for (int q = 0; q < kIrlsQ; q++) acc[q] = 0.0;
+        for (uint32_t k = 0; k < n; k++)
+        {
+          error = add(error, d2[k]);
+          const double g = mu[k];
+          if (!(g > 1e-305)) continue;   // warp-uniform
+          n_good++;
+          const double gz = eta[k];
+#pragma unroll
+          for (int q = 0; q < kIrlsQ; q++)
+          {
+            if (q < nq)                  // warp-uniform
+            {
+              const double xa = el_a[q][k * el_sa[q]];
+              const double xb = el_b[q][k * el_sb[q]];
+              const double other = el_v[q] ? gz : mul(g, xb);
+              acc[q] = add(acc[q], mul(xa, other));
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kIrlsQ; q++)
+        {
+          const uint32_t e = lane + 32 * q;
+          if (e < pp) H[e] = acc[q];
+          else if (e < pp + p) v[e - pp] = acc[q];
+        }
       }
       if (n_good == 0) break;
       error = div(error, static_cast<double>(n));
       if (fabs(sub(error, prev_error)) < 1e-6) break;
       prev_error = error;
-
-      // hessian[a][b] = sum_k X[k][a] * (S[k] * X[k][b]) over the good rows in order; a lane owns whole elements
-      {
-        double acc[(kMaxP * kMaxP + 31) / 32];
-#pragma unroll
-        for (int q = 0; q < (kMaxP * kMaxP + 31) / 32; q++) acc[q] = 0.0;
-        for (uint32_t k = 0; k < n; k++)
-        {
-          const double m = mu[k];
-          const double g = mul(m, sub(1.0, m));
-          if (!(g > 1e-305)) continue;
-#pragma unroll
-          for (int q = 0; q < (kMaxP * kMaxP + 31) / 32; q++)
-          {
-            const uint32_t e = lane + 32 * q;
-            if (e < pp)
-            {
-              const uint32_t a = e / p, b = e - a * p;
-              acc[q] = add(acc[q], mul(X.x(k, a), mul(g, X.x(k, b))));
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < (kMaxP * kMaxP + 31) / 32; q++)
-        {
-          const uint32_t e = lane + 32 * q;
-          if (e < pp) H[e] = acc[q];
-        }
-      }
-      // X^T (S z): z = eta + (y - mu) / (g + 1e-305)
-      if (lane < p)
-      {
-        double r = 0.0;
-        for (uint32_t k = 0; k < n; k++)
-        {
-          const double m = mu[k];
-          const double g = mul(m, sub(1.0, m));
-          if (!(g > 1e-305)) continue;
-          const double z = add(eta[k], div(sub(ys[k], m), add(g, 1e-305)));
-          r = add(r, mul(X.x(k, lane), mul(g, z)));
-        }
-        v[lane] = r;
-      }
       __syncwarp();
 
       // ---- inverse(hessian): Doolittle LU without pivoting (linear_model.cpp:94-137) ----

@@ -10,6 +10,7 @@ void pop_free(kmd_context* ctx)
   cudaFree(ps.d_total); cudaFree(ps.d_done); cudaFree(ps.d_overflow); cudaFree(ps.d_slot_rows);
   cudaFree(ps.d_geno); cudaFree(ps.d_carriers); cudaFree(ps.d_surv_counts);
   cudaFree(ps.d_null_feat); cudaFree(ps.d_alt_feat); cudaFree(ps.d_y); cudaFree(ps.d_totals);
+  for (void* q : ps.gram_scratch) cudaFree(q);
   ps = PopState{};
 }
 
@@ -88,6 +89,27 @@ struct DeviceBuf
   template <class T> T* as() { return static_cast<T*>(p); }
 };
 
+// non-owning view of one slot of PopState::gram_scratch
+struct ScratchBuf
+{
+  void* p = nullptr;
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+int gram_scratch(kmd_context* ctx, int slot, size_t bytes, ScratchBuf* out)
+{
+  PopState& ps = ctx->pop;
+  if (bytes > ps.gram_scratch_cap[slot])
+  {
+    if (ps.gram_scratch[slot]) { KMD_CUDA(ctx, cudaFree(ps.gram_scratch[slot])); ps.gram_scratch[slot] = nullptr; ps.gram_scratch_cap[slot] = 0; }
+    const size_t want = bytes + bytes / 8;
+    KMD_CUDA(ctx, cudaMalloc(&ps.gram_scratch[slot], want));
+    ps.gram_scratch_cap[slot] = want;
+  }
+  out->p = ps.gram_scratch[slot];
+  return KMD_OK;
+}
+
 int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used)
 {
   PopState& ps = ctx->pop;
@@ -102,8 +124,8 @@ int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used)
   if (m >= (1ull << 32)) return fail(ctx, KMD_ERR_ARG, "more than 2^32 sampled k-mers");
 
   // ---- bucket the SNPs by carrier count ----
-  DeviceBuf d_hist, d_koff, d_cursor, d_perm, d_pt, d_G, d_info, d_items, d_xtx;
-  KMD_CUDA(ctx, cudaMalloc(&d_hist.p, (n + 1) * sizeof(uint32_t)));
+  ScratchBuf d_hist, d_koff, d_cursor, d_perm, d_pt, d_G, d_info, d_items, d_xtx;
+  if ((rc = gram_scratch(ctx, 0, (n + 1) * sizeof(uint32_t), &d_hist))) return rc;
   KMD_CUDA(ctx, cudaMemsetAsync(d_hist.p, 0, (n + 1) * sizeof(uint32_t), ctx->stream));
   grm::carriers_hist_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ps.d_carriers, m, d_hist.as<uint32_t>());
   std::vector<uint32_t> hist(n + 1);
@@ -147,14 +169,14 @@ int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used)
   std::stable_sort(items.begin(), items.end(), [](const grm::WorkItem& a, const grm::WorkItem& b) { return a.kb_cnt > b.kb_cnt; });
 
   const size_t g_bytes = info.size() * static_cast<size_t>(n) * n * sizeof(int32_t);
-  KMD_CUDA(ctx, cudaMalloc(&d_koff.p, (n + 1) * sizeof(uint64_t)));
-  KMD_CUDA(ctx, cudaMalloc(&d_cursor.p, (n + 1) * sizeof(uint32_t)));
-  KMD_CUDA(ctx, cudaMalloc(&d_perm.p, k_pad * sizeof(uint32_t)));
-  KMD_CUDA(ctx, cudaMalloc(&d_pt.p, static_cast<size_t>(rows_alloc) * k_pad));
-  KMD_CUDA(ctx, cudaMalloc(&d_G.p, g_bytes));
-  KMD_CUDA(ctx, cudaMalloc(&d_info.p, info.size() * sizeof(grm::BucketInfo)));
-  KMD_CUDA(ctx, cudaMalloc(&d_items.p, items.size() * sizeof(grm::WorkItem)));
-  KMD_CUDA(ctx, cudaMalloc(&d_xtx.p, static_cast<size_t>(n) * n * sizeof(double)));
+  if ((rc = gram_scratch(ctx, 1, (n + 1) * sizeof(uint64_t), &d_koff))) return rc;
+  if ((rc = gram_scratch(ctx, 2, (n + 1) * sizeof(uint32_t), &d_cursor))) return rc;
+  if ((rc = gram_scratch(ctx, 3, k_pad * sizeof(uint32_t), &d_perm))) return rc;
+  if ((rc = gram_scratch(ctx, 4, static_cast<size_t>(rows_alloc) * k_pad, &d_pt))) return rc;
+  if ((rc = gram_scratch(ctx, 5, g_bytes, &d_G))) return rc;
+  if ((rc = gram_scratch(ctx, 6, info.size() * sizeof(grm::BucketInfo), &d_info))) return rc;
+  if ((rc = gram_scratch(ctx, 7, items.size() * sizeof(grm::WorkItem), &d_items))) return rc;
+  if ((rc = gram_scratch(ctx, 8, static_cast<size_t>(n) * n * sizeof(double), &d_xtx))) return rc;
   KMD_CUDA(ctx, cudaMemcpyAsync(d_koff.p, koff.data(), (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   KMD_CUDA(ctx, cudaMemcpyAsync(d_info.p, info.data(), info.size() * sizeof(grm::BucketInfo), cudaMemcpyHostToDevice, ctx->stream));
   KMD_CUDA(ctx, cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(grm::WorkItem), cudaMemcpyHostToDevice, ctx->stream));
@@ -207,7 +229,7 @@ size_t irls_smem(uint32_t n, uint32_t p, uint32_t ldf, bool feat_in_smem, uint32
 
 int launch_irls(kmd_context* ctx, pop::IrlsArgs A, uint32_t n_items_host)
 {
-  const size_t budget = 200 * 1024;
+  const size_t budget = 226 * 1024;   // of the 227 KB a CTA may take
   uint32_t warps = pop::kIrlsWarps;
   bool in_smem = true;
   while (warps > 1 && irls_smem(A.n, A.p, A.ldf, in_smem, warps) > budget) warps--;
