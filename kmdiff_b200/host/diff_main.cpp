@@ -122,7 +122,7 @@ struct DiffOptions
     "  -s/--significance FLOAT significance threshold in [0, 0.5]. {0.05}\n"
     "  -u/--cutoff INT         divide the significance threshold by N for the prefilter. {100000}\n"
     "  -c/--correction STR     bonferroni|benjamini|sidak|holm|disabled {bonferroni}\n"
-    "  -f/--kff-output         (not supported by this build)\n"
+    "  -f/--kff-output         output significant k-mers in kff format (no p-values, no counts).\n"
     "  -m/--in-memory  -r/--cpr   accepted and ignored, as in the reference\n"
     "  --keep-tmp              keep partitions/p{i}_uncorrected spill files.\n"
     "  --save-sk               build the matrix of significant k-mers.\n"
@@ -804,23 +804,113 @@ std::vector<kmd_survivor> read_spill_file(const std::string& path, uint32_t part
 
 // ---- FASTA output (aggregator.hpp:27-71, 197-199) -----------------------------------------------------------
 
+// ---- KFF output (-f/--kff-output): KffWriter (include/kmdiff/kff_utils.hpp:32-107) over kff-cpp-api 1.0 ----
+// (thirdparty/kff-cpp-api/kff_io.cpp: Kff_file::open :67-114, complete_header :241-257, Section_GV :709-800,
+// Section_Raw :891-953, 1018-1032, Section_Index :849-871, write_footer :549-566, close :167-206).
+// The file the reference leaves: 8-byte header ("KFF", version 1.0, encoding byte A0 C1 G3 T2 = 0x1e, not unique,
+// not canonical), empty metadata, one 'v' section {data_size = 0, k, max = 1} (names in std::map order), one 'r'
+// section with one block per k-mer (max = 1 -> no k-mer-count field; ceil(k/4) bytes, first byte holds the k % 4
+// leading bases; no data), an 'i' index of the two sections (offsets relative to the end of the index), a footer
+// 'v' section {first_index, footer_size = 49} and the "KFF" signature.  All integers big-endian.
+class KffWriter
+{
+ public:
+  KffWriter(const std::string& path, uint32_t k) : m_k(k)
+  {
+    m_f = fopen(path.c_str(), "wb");
+    if (!m_f) throw KmdError("IOError", "Unable to create " + path);
+    const uint8_t head[8] = {'K', 'F', 'F', 1, 0, 0x1e, 0, 0};
+    put(head, 8);
+    be(0, 4);                       // metadata size
+    m_pos_v = m_pos;
+    put("v", 1); be(3, 8);
+    var("data_size", 0); var("k", k); var("max", 1);
+    m_pos_r = m_pos;
+    put("r", 1); be(0, 8);          // block count, patched by close()
+  }
+  // 2 bits per base, first base most significant.  kmtricks words hold A0 C1 T2 G3 (kmer.hpp:38) and the
+  // reference packs (char >> 1) & 3 (kff_utils.hpp:72-82), the same code — hence the header's encoding byte 0x1e
+  void write(const uint64_t* words, uint32_t kmer_words)
+  {
+    uint8_t enc[64];
+    const uint32_t nbytes = (m_k + 3) / 4, rem = m_k % 4;
+    memset(enc, 0, nbytes);
+    for (uint32_t i = 0; i < m_k; i++)
+    {
+      const uint32_t bit = 2 * (m_k - 1 - i);                 // base i (0 = first) sits at bits [bit, bit+1]
+      const uint32_t v = bit / 64 < kmer_words ? static_cast<uint32_t>(words[bit / 64] >> (bit % 64)) & 3u : 0u;
+      // byte 0 holds the `rem` leading bases (if any), then 4 bases per byte
+      const uint32_t slot = rem ? (i < rem ? 0 : 1 + (i - rem) / 4) : i / 4;
+      const uint32_t in_byte = rem ? (i < rem ? rem - 1 - i : 3 - (i - rem) % 4) : 3 - i % 4;
+      enc[slot] |= static_cast<uint8_t>(v << (2 * in_byte));
+    }
+    put(enc, nbytes);
+    m_blocks++;
+  }
+  void close()
+  {
+    if (!m_f) return;
+    // footer: index section, then the variables that locate it
+    const uint64_t index_pos = m_pos;
+    const int64_t end_of_index = static_cast<int64_t>(index_pos) + 17 + 9 * 2;
+    put("i", 1); be(2, 8);
+    put("v", 1); be(static_cast<uint64_t>(static_cast<int64_t>(m_pos_v) - end_of_index), 8);
+    put("r", 1); be(static_cast<uint64_t>(static_cast<int64_t>(m_pos_r) - end_of_index), 8);
+    be(0, 8);                       // next index
+    put("v", 1); be(2, 8);
+    var("first_index", index_pos); var("footer_size", 9 + 2 * (12 + 8));
+    put("KFF", 3);
+    fseek(m_f, static_cast<long>(m_pos_r + 1), SEEK_SET);
+    m_pos = m_pos_r + 1;
+    be(m_blocks, 8);
+    fclose(m_f);
+    m_f = nullptr;
+  }
+  ~KffWriter() { close(); }
+
+ private:
+  void put(const void* p, size_t n) { fwrite(p, 1, n, m_f); m_pos += n; }
+  void be(uint64_t v, int bytes)
+  {
+    uint8_t b[8];
+    for (int i = 0; i < bytes; i++) b[i] = static_cast<uint8_t>(v >> (8 * (bytes - 1 - i)));
+    put(b, bytes);
+  }
+  void var(const char* name, uint64_t v) { put(name, strlen(name) + 1); be(v, 8); }
+  FILE* m_f = nullptr;
+  uint32_t m_k;
+  uint64_t m_pos = 0, m_pos_v = 0, m_pos_r = 0, m_blocks = 0;
+};
+
 struct FastaPair
 {
   FILE* control = nullptr;
   FILE* cases = nullptr;
+  std::unique_ptr<KffWriter> kff_control, kff_cases;    // -f/--kff-output: {control,case}_kmers.kff instead (aggregator.hpp:197-199)
   uint64_t n_control = 0, n_case = 0;
-  explicit FastaPair(const std::string& dir)
+  FastaPair(const std::string& dir, bool kff, uint32_t k)
   {
+    if (kff)
+    {
+      kff_control = std::make_unique<KffWriter>(dir + "/control_kmers.kff", k);
+      kff_cases = std::make_unique<KffWriter>(dir + "/case_kmers.kff", k);
+      return;
+    }
     control = fopen((dir + "/control_kmers.fasta").c_str(), "w");
     cases = fopen((dir + "/case_kmers.fasta").c_str(), "w");
     if (!control || !cases) throw KmdError("IOError", "Unable to create output FASTA files in " + dir);
   }
   void write(const kmd_survivor& s, uint32_t kmer_words, uint32_t k)
   {
-    char buf[1024];
     const bool is_control = s.sign == KMD_SIGN_CONTROL;   // NO goes to the case file (aggregator.hpp:155-162)
-    const size_t n = kmd_format_fasta(is_control ? n_control : n_case, &s, kmer_words, k, buf, sizeof buf);
-    fwrite(buf, 1, n, is_control ? control : cases);
+    if (kff_control)
+      (is_control ? kff_control : kff_cases)->write(s.kmer, kmer_words);
+    else
+    {
+      char buf[1024];
+      const size_t n = kmd_format_fasta(is_control ? n_control : n_case, &s, kmer_words, k, buf, sizeof buf);
+      fwrite(buf, 1, n, is_control ? control : cases);
+    }
     (is_control ? n_control : n_case)++;
   }
   ~FastaPair() { if (control) fclose(control); if (cases) fclose(cases); }
@@ -982,7 +1072,6 @@ void do_pop(std::vector<std::unique_ptr<GpuWorker>>& workers, const DiffOptions&
 void main_diff(DiffOptions& opt)
 {
   Timer whole;
-  if (opt.kff) throw KmdError("OptionError", "-f/--kff-output is not supported by this build (FASTA only).");
   if (opt.pop_correction && !opt.covariates.empty())
     throw KmdError("OptionError", "--covariates is not supported: the reference's load_C never terminates on a non-empty file (src/popstrat.cpp:205-213).");
   if (opt.pop_correction && !opt.gender.empty())
@@ -1250,7 +1339,7 @@ void main_diff(DiffOptions& opt)
       std::stable_sort(final_records.begin(), final_records.end(), [](const kmd_survivor& a, const kmd_survivor& b) { return a.row < b.row; });
   }
   {
-    FastaPair out(opt.output_directory);
+    FastaPair out(opt.output_directory, opt.kff, cfg.kmer_size);
     for (const kmd_survivor& s : final_records) out.write(s, kw, cfg.kmer_size);
     logf(L_INFO, "Partitions aggregated (%s)", agg_time.formatted().c_str());
     logf(L_INFO, "Significant k-mers: %llu (control), %llu (case).", static_cast<unsigned long long>(out.n_control),
@@ -1326,6 +1415,26 @@ int dev_command(int argc, char** argv)
     for (size_t n; (n = fread(buf.data(), 1, buf.size(), in)) > 0;) w.write(buf.data(), n);
     w.close();
     fclose(in); fclose(out);
+    return 0;
+  }
+  if (cmd == "dev-kff" && argc >= 4)
+  {
+    // dev-kff OUT K KMER...: the given k-mers (ACGT strings) as a KFF file
+    const uint32_t k = static_cast<uint32_t>(atol(argv[3]));
+    KffWriter w(argv[2], k);
+    for (int i = 4; i < argc; i++)
+    {
+      uint64_t words[2] = {0, 0};
+      for (uint32_t b = 0; b < k; b++)
+      {
+        const char c = argv[i][b];
+        const uint64_t v = c == 'A' ? 0 : c == 'C' ? 1 : c == 'T' ? 2 : 3;      // kmtricks kmer.hpp:38
+        const uint32_t bit = 2 * (k - 1 - b);
+        words[bit / 64] |= v << (bit % 64);
+      }
+      w.write(words, (k + 31) / 32);
+    }
+    w.close();
     return 0;
   }
   if (cmd == "dev-config" && argc == 5)

@@ -364,3 +364,65 @@ def test_cli_resume_recorrects_from_spill_files(cli, tmp_path):
     # another cutoff: the prefilter changed, everything is redone
     r4 = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "--keep-tmp", "-s", "0.05", "-u", "1000", "-c", "benjamini"])
     assert "Process partitions" in r4.stderr and "[error]" not in r4.stderr, r4.stderr
+
+
+# ---- -f/--kff-output (include/kmdiff/kff_utils.hpp:32-107) -------------------------------------------------
+
+def kff_kmers(raw: bytes, k: int):
+    """minimal KFF reader for the files KffWriter leaves: -> list of k-mer strings"""
+    assert raw[:3] == b"KFF" and raw[-3:] == b"KFF" and raw[5] == 0x1E
+    pos = 8 + 4 + int.from_bytes(raw[8:12], "big")
+    assert raw[pos:pos + 1] == b"v"
+    nvars = int.from_bytes(raw[pos + 1:pos + 9], "big")
+    pos += 9
+    gv = {}
+    for _ in range(nvars):
+        end = raw.index(b"\0", pos)
+        gv[raw[pos:end].decode()] = int.from_bytes(raw[end + 1:end + 9], "big")
+        pos = end + 9
+    assert gv == {"data_size": 0, "k": k, "max": 1}
+    assert raw[pos:pos + 1] == b"r"
+    nblocks = int.from_bytes(raw[pos + 1:pos + 9], "big")
+    pos += 9
+    nbytes, out = (k + 3) // 4, []
+    for _ in range(nblocks):
+        v = int.from_bytes(raw[pos:pos + nbytes], "big")
+        out.append("".join("ACTG"[(v >> (2 * (k - 1 - i))) & 3] for i in range(k)))
+        pos += nbytes
+    assert raw[pos:pos + 1] == b"i"
+    return out
+
+
+def test_kff_writer_matches_reference_files(cli, tmp_path):
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "kff_vectors.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) == 6
+    for c in cases:
+        out = str(tmp_path / "o.kff")
+        assert run([cli, "dev-kff", out, str(c["k"])] + c["kmers"]).returncode == 0
+        with open(out, "rb") as f:
+            got = f.read()
+        assert got == bytes.fromhex(c["kff"]), (c["k"], c["file"])
+        assert kff_kmers(got, c["k"]) == c["kmers"]
+    # 128-bit k-mers (the reference truncates them, SURVEY.md §8 hazard 1): checked by decoding
+    kmer = "ACGT" * 15 + "TGA"
+    out = str(tmp_path / "w.kff")
+    assert run([cli, "dev-kff", out, "63", kmer, kmer[::-1]]).returncode == 0
+    with open(out, "rb") as f:
+        assert kff_kmers(f.read(), 63) == [kmer, kmer[::-1]]
+
+
+@pytest.mark.gpu
+def test_cli_kff_output(cli, tmp_path):
+    n, parts = 60_000, 3
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=parts)
+    out = str(tmp_path / "out")
+    r = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "-f"] + THR_ARGS)
+    assert "[error]" not in r.stderr, r.stderr
+    ctl, case, _ = expected_records(spec, n, parts, "bonferroni")
+    for name, want in (("control", ctl), ("case", case)):
+        with open(os.path.join(out, f"{name}_kmers.kff"), "rb") as f:
+            got = kff_kmers(f.read(), 31)
+        assert sorted(got) == sorted(s for _, s in want) and len(got) > 3
+    assert not os.path.exists(os.path.join(out, "case_kmers.fasta"))
