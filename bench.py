@@ -355,9 +355,13 @@ def bench_b200(args) -> None:
         raise SystemExit("bench.py: no CUDA device — kmdiff_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    saved_stdout = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        # NCCL prints its version banner on stdout: keep fd 1 on stderr until the one JSON line is due
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     cfg_name = args.config
@@ -386,7 +390,10 @@ def bench_b200(args) -> None:
     spec.rows_device(data.data_ptr(), rows, row_base=rank * rows, device=local_rank, stream=stream.cuda_stream)
     torch.cuda.synchronize()
 
-    counts_dev = torch.zeros(3, dtype=torch.int64, device=dev)
+    exchange = None
+    if world > 1:
+        from kmdiff_b200.distributed import DeviceExchange
+        exchange = DeviceExchange(dev)
 
     def pop_stage(timed: bool):
         # do_pop (cmd/diff.hpp:168-224): Gram matrix of the sampled k-mers -> PCs -> null model -> GLM per survivor
@@ -419,23 +426,10 @@ def bench_b200(args) -> None:
         if popstrat:
             pop_stage(True)
         if world > 1:
-            counts_dev.copy_(torch.tensor([c.rows, c.n_control, c.n_case], dtype=torch.int64), non_blocking=True)
-            dist.all_reduce(counts_dev)
-            total_rows = int(counts_dev[0].item())
-        if corr_kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM) and world > 1:
-            # global ascending walk: exchange the ranks' sorted p-values, find the first rejection
-            p_loc = torch.from_numpy(ctx.sorted_pvalues()).to(dev)
-            n_loc = torch.tensor([p_loc.numel()], dtype=torch.int64, device=dev)
-            sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.all_gather(sizes, n_loc)
-            mx = int(max(int(s.item()) for s in sizes))
-            pad = torch.full((mx,), float("inf"), dtype=torch.float64, device=dev)
-            pad[:p_loc.numel()] = p_loc
-            allp = [torch.empty(mx, dtype=torch.float64, device=dev) for _ in range(world)]
-            dist.all_gather(allp, pad)
-            merged = torch.sort(torch.cat([a[:int(s.item())] for a, s in zip(allp, sizes)])).values.cpu().numpy()
-            _, cut = K.first_reject(merged, corr_kind, SIGNIFICANCE, total_rows)
-            return ctx.keep_below(cut), c
+            # m of the correctors = rows of all ranks; BH/Holm: one ascending walk over all ranks' survivors,
+            # exchanged and ranked on the devices (kmdiff_b200.distributed.DeviceExchange)
+            _, kept = exchange.correct(ctx, corr_kind, SIGNIFICANCE)
+            return kept, c
         return ctx.correct(corr_kind, SIGNIFICANCE, total_rows), c
 
     def barrier():
@@ -610,8 +604,12 @@ def bench_b200(args) -> None:
         }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 

@@ -191,6 +191,14 @@ int kmd_significant(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t*
  * rejected p-value with kmd_first_reject, and every rank keeps its survivors with p < p_cut. */
 int kmd_sorted_pvalues(kmd_context* ctx, double* out, uint64_t cap, uint64_t* n);
 int kmd_keep_below(kmd_context* ctx, double p_cut, uint64_t* n_control, uint64_t* n_case);
+/* The same exchange without leaving the devices: the survivors' p-values (accumulator order, unsorted)
+ * copied into a caller-owned DEVICE buffer on the context's stream; and the ascending walk over a
+ * DEVICE array of merged, sorted p-values (+inf padding allowed at the end), one thread per rank
+ * (both rank tests are monotone, so the first failing position is a min-reduction).  n_accepted =
+ * index of the first rejection, p_cut = its p-value (+inf if none).  Synchronises the stream. */
+int kmd_survivor_pvalues_device(kmd_context* ctx, double* d_out, uint64_t cap, uint64_t* n);
+int kmd_first_reject_device(kmd_context* ctx, const double* d_p_sorted, uint64_t n, int correction,
+                            double significance, uint64_t total_rows, uint64_t* n_accepted, double* p_cut);
 /* host helper: walk p_sorted (ascending, all ranks merged) exactly like sorted_aggregator::run;
  * returns the number accepted and writes the first rejected p-value (+inf if none) */
 uint64_t kmd_first_reject(const double* p_sorted, uint64_t n, int correction, double significance,

@@ -27,7 +27,7 @@ SYMBOLS = [
     "kmd_popstrat_enable", "kmd_popstrat_set_draw_index", "kmd_popstrat_sampled", "kmd_popstrat_geno", "kmd_popstrat_gram",
     "kmd_popstrat_gram_ms", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
     "kmd_survivor_counts", "kmd_smartpca_normalize", "kmd_sym_eig", "kmd_smartpca_pcs",
-    "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_rows_host", "kmd_merge_ms",
+    "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_rows_host", "kmd_merge_ms", "kmd_survivor_pvalues_device", "kmd_first_reject_device",
 ]
 
 
@@ -108,6 +108,8 @@ def load() -> C.CDLL:
     L.kmd_significant.argtypes = [vp, vp, u64, pu64]
     L.kmd_sorted_pvalues.argtypes = [vp, vp, u64, pu64]
     L.kmd_keep_below.argtypes = [vp, d, pu64, pu64]
+    L.kmd_survivor_pvalues_device.argtypes = [vp, vp, u64, pu64]
+    L.kmd_first_reject_device.argtypes = [vp, vp, u64, C.c_int, d, u64, pu64, C.POINTER(d)]
     L.kmd_first_reject.argtypes = [vp, u64, C.c_int, d, u64, C.POINTER(d)]
     L.kmd_first_reject.restype = u64
     L.kmd_lf_table_fill.argtypes = [vp, u64]

@@ -307,6 +307,19 @@ class DiffContext:
             self._ck(self._L.kmd_sorted_pvalues(self._h, out.ctypes.data, n.value, C.byref(n)))
         return out
 
+    def survivor_pvalues_device(self, dev_ptr: int, cap: int) -> int:
+        """survivors' p-values (unsorted) copied device-to-device into dev_ptr on the context's stream; -> count"""
+        n = C.c_uint64()
+        self._ck(self._L.kmd_survivor_pvalues_device(self._h, C.c_void_p(dev_ptr) if dev_ptr else None, cap, C.byref(n)))
+        return n.value
+
+    def first_reject_device(self, dev_ptr: int, n: int, correction: int, significance: float, total_rows: int):
+        """sorted_aggregator::run's walk over a device array of merged ascending p-values; -> (n_accepted, p_cut)"""
+        acc, cut = C.c_uint64(), C.c_double()
+        self._ck(self._L.kmd_first_reject_device(self._h, C.c_void_p(dev_ptr), n, int(correction), significance, total_rows,
+                                                 C.byref(acc), C.byref(cut)))
+        return acc.value, cut.value
+
     def keep_below(self, p_cut: float) -> tuple[int, int]:
         nc, nk = C.c_uint64(), C.c_uint64()
         self._ck(self._L.kmd_keep_below(self._h, p_cut, C.byref(nc), C.byref(nk)))

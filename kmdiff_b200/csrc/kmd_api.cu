@@ -165,6 +165,7 @@ struct kmd_context
   int order_state = 0;           // 0 none, 1 row order over all survivors, 2 p order over all survivors
   bool final_valid = false;
   bool final_sorted = false;     // d_order is in output order (row order, or ascending p); else sorted lazily at fetch
+  bool final_by_p = false;       // output order of an unsorted d_order: ascending p (ties by row) instead of row order
   uint64_t max_row_key = 0;      // upper bound of every survivor's row index: bounds the radix passes of a row sort
 
   // host staging for kmd_scan_host / kmd_model_rows_host
@@ -895,24 +896,20 @@ int download_records(kmd_context* ctx, const uint32_t* d_order, uint32_t n, kmd_
 }
 
 // keep survivors (visited in the current order) with p < cut; stable
+// survivors with p < cut, kept in arrival order; kmd_significant puts them in ascending p (ties by row) when asked
 int keep_below_impl(kmd_context* ctx, double cut, uint64_t* n_control, uint64_t* n_case)
 {
-  const uint32_t n = ctx->h_cnt->surv_count;
   KMD_CUDA(ctx, cudaMemsetAsync(&ctx->d_cnt->keep_control, 0, 3 * sizeof(uint32_t), ctx->stream));
-  if (n)
-  {
-    uint32_t* flags = ctx->d_vals[1];
-    flag_below_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->d_vals[0], ctx->surv.p, cut, flags);
-    scan_exclusive_kernel<<<1, 1024, 0, ctx->stream>>>(flags, n, &ctx->d_cnt->keep_total);
-    compact_kernel<<<blocks_for(n), 256, 0, ctx->stream>>>(n, ctx->d_vals[0], flags, ctx->surv.p, cut, ctx->surv.sign, ctx->d_order, ctx->d_cnt);
-    ctx->launches += 3;
-    KMD_CUDA(ctx, cudaGetLastError());
-  }
+  keep_unordered_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_cnt, static_cast<uint32_t>(ctx->cap), ctx->surv.p, cut,
+                                                                     ctx->surv.sign, ctx->d_order);
+  ctx->launches++;
+  KMD_CUDA(ctx, cudaGetLastError());
   int rc = fetch_counters(ctx);
   if (rc) return rc;
-  ctx->n_final = n ? ctx->h_cnt->keep_total : 0;
+  ctx->n_final = ctx->h_cnt->keep_total;
   ctx->final_valid = true;
-  ctx->final_sorted = true;
+  ctx->final_sorted = false;
+  ctx->final_by_p = true;
   if (n_control) *n_control = ctx->h_cnt->keep_control;
   if (n_case) *n_case = ctx->h_cnt->keep_case;
   return KMD_OK;
@@ -1330,6 +1327,7 @@ int kmd_correct(kmd_context* ctx, int correction, double significance, uint64_t 
     ctx->n_final = ctx->h_cnt->keep_total;
     ctx->final_valid = true;
     ctx->final_sorted = false;
+    ctx->final_by_p = false;
     if (n_control) *n_control = ctx->h_cnt->keep_control;
     if (n_case) *n_case = ctx->h_cnt->keep_case;
     return KMD_OK;
@@ -1374,12 +1372,21 @@ int kmd_significant(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t*
   KMD_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!ctx->final_sorted && ctx->n_final > 1)
   {
-    // stateless correctors leave the kept slots in arrival order: put them in row order now
+    // stateless correctors and kmd_keep_below leave the kept slots in arrival order: put them in row order now,
+    // then (kmd_keep_below: BENJAMINI / HOLM output) stably in ascending p
     iota_keys_kernel<<<blocks_for(ctx->n_final), 256, 0, ctx->stream>>>(ctx->n_final, ctx->surv.row, ctx->surv.p, 0, ctx->d_order,
                                                                          ctx->d_keys[0], ctx->d_vals[0]);
     ctx->launches++;
     int rc = radix_sort(ctx, ctx->n_final, row_key_passes(ctx));
     if (rc) return rc;
+    if (ctx->final_by_p)
+    {
+      KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_vals[1], ctx->d_vals[0], ctx->n_final * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+      iota_keys_kernel<<<blocks_for(ctx->n_final), 256, 0, ctx->stream>>>(ctx->n_final, ctx->surv.row, ctx->surv.p, 1, ctx->d_vals[1],
+                                                                           ctx->d_keys[0], ctx->d_vals[0]);
+      ctx->launches++;
+      if ((rc = radix_sort(ctx, ctx->n_final))) return rc;
+    }
     KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_order, ctx->d_vals[0], ctx->n_final * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->order_state = 0;   // the full-survivor ordering in d_vals[0] was overwritten
   }
@@ -1405,12 +1412,54 @@ int kmd_sorted_pvalues(kmd_context* ctx, double* out, uint64_t cap, uint64_t* n)
   return KMD_OK;
 }
 
+int kmd_survivor_pvalues_device(kmd_context* ctx, double* d_out, uint64_t cap, uint64_t* n)
+{
+  if (!ctx || !n) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = fetch_counters(ctx);
+  if (rc) return rc;
+  *n = ctx->h_cnt->surv_count;
+  if (!d_out || *n == 0) return KMD_OK;
+  if (cap < *n) return fail(ctx, KMD_ERR_ARG, "output capacity %llu < %llu survivors", static_cast<unsigned long long>(cap),
+                            static_cast<unsigned long long>(*n));
+  KMD_CUDA(ctx, cudaMemcpyAsync(d_out, ctx->surv.p, *n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return KMD_OK;
+}
+
+int kmd_first_reject_device(kmd_context* ctx, const double* d_p_sorted, uint64_t n, int correction, double significance,
+                            uint64_t total_rows, uint64_t* n_accepted, double* p_cut)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (correction != KMD_CORR_BENJAMINI && correction != KMD_CORR_HOLM) return fail(ctx, KMD_ERR_ARG, "BENJAMINI or HOLM expected");
+  if (n >= (1ull << 32)) return fail(ctx, KMD_ERR_ARG, "too many p-values");
+  if (n && !d_p_sorted) return fail(ctx, KMD_ERR_ARG, "null p-values");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint32_t first = static_cast<uint32_t>(n);
+  double cut = std::numeric_limits<double>::infinity();
+  if (n)
+  {
+    set_u32_kernel<<<1, 1, 0, ctx->stream>>>(&ctx->d_cnt->first_reject, first);
+    first_reject_kernel<<<blocks_for(first), 256, 0, ctx->stream>>>(d_p_sorted, first, correction == KMD_CORR_HOLM, significance,
+                                                                    total_rows, &ctx->d_cnt->first_reject);
+    ctx->launches += 2;
+    KMD_CUDA(ctx, cudaGetLastError());
+    KMD_CUDA(ctx, cudaMemcpyAsync(&first, &ctx->d_cnt->first_reject, sizeof first, cudaMemcpyDeviceToHost, ctx->stream));
+    KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (first < n)
+    {
+      KMD_CUDA(ctx, cudaMemcpyAsync(&cut, d_p_sorted + first, sizeof cut, cudaMemcpyDeviceToHost, ctx->stream));
+      KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  if (n_accepted) *n_accepted = first;
+  if (p_cut) *p_cut = cut;
+  return KMD_OK;
+}
+
 int kmd_keep_below(kmd_context* ctx, double p_cut, uint64_t* n_control, uint64_t* n_case)
 {
   if (!ctx) return KMD_ERR_ARG;
   KMD_CUDA(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_order(ctx, 2);
-  if (rc) return rc;
   return keep_below_impl(ctx, p_cut, n_control, n_case);
 }
 

@@ -81,6 +81,43 @@ def global_cut(p_local_sorted: np.ndarray, correction: int, significance: float,
     return first_reject(merged, correction, significance, total_rows)
 
 
+class DeviceExchange:
+    """BENJAMINI / HOLM across ranks without leaving the GPUs (NCCL): one all-gather of each rank's
+    (rows, controls, cases, survivors), one all-gather of the survivors' p-values padded with +inf, one device
+    sort of the union, kmd_first_reject_device, then every rank keeps its survivors below the cut.
+    Buffers are cached between calls.  The context must run on torch's current stream (ctx.set_stream)."""
+
+    def __init__(self, device, group=None):
+        self.device, self.group = device, group
+        self.world = _world(group)
+        self.meta = torch.zeros(4, dtype=torch.int64, device=device)
+        self.meta_all = torch.zeros(4 * self.world, dtype=torch.int64, device=device)
+        self.pad = None
+        self.allp = None
+
+    def correct(self, ctx, correction: int, significance: float):
+        """-> (total_rows, (n_control, n_case) kept on this rank)"""
+        c = ctx.counters()
+        self.meta.copy_(torch.tensor([c.rows, c.n_control, c.n_case, c.survivors], dtype=torch.int64), non_blocking=True)
+        dist.all_gather_into_tensor(self.meta_all, self.meta, group=self.group)
+        m = self.meta_all.view(self.world, 4).cpu()
+        total_rows = int(m[:, 0].sum())
+        if correction not in (CorrectionType.BENJAMINI, CorrectionType.HOLM):
+            return total_rows, ctx.correct(correction, significance, total_rows)
+        mx = max(1, int(m[:, 3].max()))
+        if self.pad is None or self.pad.numel() < mx:
+            cap = mx + mx // 4
+            self.pad = torch.empty(cap, dtype=torch.float64, device=self.device)
+            self.allp = torch.empty(cap * self.world, dtype=torch.float64, device=self.device)
+        pad, allp = self.pad[:mx], self.allp[:mx * self.world]
+        pad.fill_(float("inf"))
+        ctx.survivor_pvalues_device(pad.data_ptr(), mx)
+        dist.all_gather_into_tensor(allp, pad, group=self.group)
+        merged = torch.sort(allp).values                      # +inf padding sorts last and never passes a rank test
+        _, cut = ctx.first_reject_device(merged.data_ptr(), int(m[:, 3].sum()), correction, significance, total_rows)
+        return total_rows, ctx.keep_below(cut)
+
+
 def correct_sharded(ctx, correction: int, significance: float, device, group=None):
     """do_correction (cmd/diff.hpp:227-260) for one rank's DiffContext when partitions are sharded.
     -> (total_rows, (n_control, n_case) kept on this rank)."""

@@ -330,8 +330,9 @@ struct Partition
 class GpuWorker
 {
  public:
-  GpuWorker(int device, const DiffOptions& o, const RunConfig& cfg, uint64_t sum_controls, uint64_t sum_cases)
-    : m_device(device), m_opt(o)
+  // n_readers threads decode this GPU's partitions (one partition per thread at a time) into pinned buffers
+  GpuWorker(int device, const DiffOptions& o, const RunConfig& cfg, uint64_t sum_controls, uint64_t sum_cases, size_t n_readers = 1)
+    : m_device(device), m_opt(o), m_n_readers(std::max<size_t>(1, n_readers)), m_bufs(2 * std::max<size_t>(1, n_readers) + 1)
   {
     kmd_config c{};
     c.abi_version = KMD_ABI_VERSION;
@@ -390,9 +391,12 @@ class GpuWorker
         ck(m_ctx.get(), kmd_sync(m_ctx.get()), "kmd_sync");
         return;
       }
-      std::thread reader([this] { read_loop(); });
+      m_next_part = 0;
+      m_readers_left = static_cast<int>(m_n_readers);
+      std::vector<std::thread> readers;
+      for (size_t r = 0; r < m_n_readers; r++) readers.emplace_back([this] { read_loop(); });
       feed_loop();
-      reader.join();
+      for (auto& r : readers) r.join();
       if (m_reader_error) std::rethrow_exception(m_reader_error);
       ck(m_ctx.get(), kmd_sync(m_ctx.get()), "kmd_sync");
     }
@@ -559,8 +563,9 @@ class GpuWorker
   {
     try
     {
-      for (const Partition& p : partitions)
+      for (size_t pi; (pi = m_next_part.fetch_add(1)) < partitions.size();)
       {
+        const Partition& p = partitions[pi];
         MatrixFile mf(p.path, m_row_bytes);
         const uint32_t slots = (mf.hdr.kmer_size + 31) / 32;
         if (mf.hdr.nb_counts != m_opt.nb_controls + m_opt.nb_cases)
@@ -585,10 +590,19 @@ class GpuWorker
         logf(L_DEBUG, "partition %u: %llu rows (gpu %d)", p.index, static_cast<unsigned long long>(local), m_device);
       }
     }
-    catch (...) { m_reader_error = std::current_exception(); }
-    Buf* b = acquire_free();
-    b->rows = 0; b->last = true;
-    publish(b);
+    catch (...)
+    {
+      std::lock_guard<std::mutex> lk(m_mu);
+      if (!m_reader_error) m_reader_error = std::current_exception();
+      m_next_part = partitions.size();   // the other readers stop after their current partition
+    }
+    if (m_readers_left.fetch_sub(1) == 1)
+    {
+      // the last reader to finish closes the stream of buffers
+      Buf* b = acquire_free();
+      b->rows = 0; b->last = true;
+      publish(b);
+    }
   }
 
   void feed_loop()
@@ -637,7 +651,10 @@ class GpuWorker
   ctx_ptr m_ctx;
   uint64_t m_row_bytes = 0, m_buf_rows = 0;
   uint64_t m_draw_next = 0;   // count-file mode: Sampler draw index = rows merged so far (one worker, partition order)
-  Buf m_bufs[3];
+  size_t m_n_readers = 1;
+  std::vector<Buf> m_bufs;
+  std::atomic<size_t> m_next_part{0};
+  std::atomic<int> m_readers_left{0};
   std::queue<Buf*> m_free, m_ready;
   std::mutex m_mu;
   std::condition_variable m_cv;
@@ -1206,7 +1223,9 @@ void main_diff(DiffOptions& opt)
   }
 
   std::vector<std::unique_ptr<GpuWorker>> workers;
-  for (int d = 0; d < n_dev; d++) workers.push_back(std::make_unique<GpuWorker>(d, opt, cfg, sum_c, sum_k));
+  // host threads (-t) are split over the devices: each GPU gets its own readers (file read / LZ4 decode -> pinned)
+  const size_t readers_per_gpu = std::max<size_t>(1, std::min<size_t>(8, opt.nb_threads / static_cast<size_t>(n_dev)));
+  for (int d = 0; d < n_dev; d++) workers.push_back(std::make_unique<GpuWorker>(d, opt, cfg, sum_c, sum_k, readers_per_gpu));
 
   if (resumed)
   {

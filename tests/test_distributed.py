@@ -102,3 +102,63 @@ def test_two_ranks_reach_the_single_process_decision(tmp_path):
             got = np.sort(np.concatenate([res[0][key][2], res[1][key][2]]))
             assert np.array_equal(got, np.sort(want["row"][keep]))
     assert 0 < len(oracle.aggregate(want["p"], oracle.BENJAMINI, 0.05, 10**12)) < len(want)
+
+
+# ---- the same decision on real GPUs over NCCL (needs >= 2 devices; run with `gpurun --gpus 2`) ---------
+
+def _nccl_worker(rank: int, world: int, port: int, out_dir: str):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import kmdiff_b200 as K
+        from kmdiff_b200 import distributed as D
+
+        spec, rows, totals = _cohort()
+        R = spec.row_bytes
+        cuts = [0, 10_000, 90_000, 90_001, 130_000, 200_000, 215_000, 240_000]
+        sizes = [b - a for a, b in zip(cuts[:-1], cuts[1:])]
+        mine = D.assign_partitions(sizes, world)[rank]
+        res = {}
+        with K.DiffContext(10, 10, int(totals[:10].sum()), int(totals[10:].sum()), threshold=THR, device=rank) as ctx:
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+            ex = D.DeviceExchange(dev)
+            for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM, K.CorrectionType.BONFERRONI):
+                ctx.reset()
+                for p in mine:
+                    ctx.scan_host(rows[cuts[p] * R:cuts[p + 1] * R], row_base=cuts[p], partition=p)
+                total, kept = ex.correct(ctx, kind, 0.05)
+                sig = ctx.significant()
+                res[int(kind)] = (total, kept, sig["row"].copy(), sig["p_value"].copy())
+                # the host-side exchange (gather + kmd_first_reject) must reach the same decision
+                ctx.reset()
+                for p in mine:
+                    ctx.scan_host(rows[cuts[p] * R:cuts[p + 1] * R], row_base=cuts[p], partition=p)
+                total2, kept2 = D.correct_sharded(ctx, kind, 0.05, dev)
+                assert (total2, kept2) == (total, kept)
+                assert np.array_equal(ctx.significant()["row"], sig["row"])
+        np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.array([res], dtype=object), allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_two_gpus_reach_the_single_process_decision_over_nccl(tmp_path):
+    import kmdiff_b200 as K
+    import oracle
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world = 2
+    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"rank{r}.npy", allow_pickle=True)[0] for r in range(world)]
+    spec, rows, totals = _cohort()
+    want, _, _ = oracle.Model(10, 10, totals).diff(rows, 1, 4, THR)
+    for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM, K.CorrectionType.BONFERRONI):
+        keep = oracle.aggregate(want["p"], int(kind), 0.05, spec.total_rows)
+        assert res[0][int(kind)][0] == res[1][int(kind)][0] == spec.total_rows
+        got = np.sort(np.concatenate([res[0][int(kind)][2], res[1][int(kind)][2]]))
+        assert np.array_equal(got, np.sort(want["row"][keep])) and len(keep) > 10
+        assert sum(sum(r[int(kind)][1]) for r in res) == len(keep)
