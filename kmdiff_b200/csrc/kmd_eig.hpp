@@ -4,16 +4,35 @@
 // dspev through eigx.c:95-114): all eigenvalues, descending, with unit eigenvectors.  The matrix is
 // tiny next to the k-mer stream, so this stays on the host (north_star: "the samples x samples
 // eigensolve stays on host"); LAPACKE headers are not part of this image, hence a self-contained
-// Householder tridiagonalisation + implicit-shift QL iteration.
+// Householder tridiagonalisation + implicit-shift QL iteration.  The reflectors and the QL rotations do not
+// depend on the eigenvector matrix they are accumulated into, so they are recorded while (d, e) is reduced and
+// then applied to Q in their original order by a few threads, each owning a block of rows of Q: every
+// element of Q sees exactly the operation sequence of the textbook loop, only faster.
 #pragma once
 
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <numeric>
+#include <thread>
 #include <vector>
+#if defined(__x86_64__) || defined(__i386__)
+#include <xmmintrin.h>
+#endif
 
 namespace kmd {
+
+// Far from the diagonal the accumulated eigenvector entries decay below 1e-308; x86 handles such subnormal
+// operands in microcode (~100x slower), and they cannot influence a result that is printed with four
+// decimals (pcs.evec), so the accumulation threads flush them to zero.
+struct FlushSubnormals
+{
+#if defined(__x86_64__) || defined(__i386__)
+  unsigned saved;
+  FlushSubnormals() : saved(_mm_getcsr()) { _mm_setcsr(saved | 0x8040u); }   // FTZ | DAZ
+  ~FlushSubnormals() { _mm_setcsr(saved); }
+#endif
+};
 
 // a: n*n row-major symmetric.  evals[j] descending; evecs[j*n + i] = component i of eigenvector j,
 // normalised so that its largest-magnitude component is positive (LAPACK leaves the sign unspecified).
@@ -22,8 +41,17 @@ inline int sym_eig(const double* a, uint32_t n, double* evals, double* evecs)
 {
   if (n == 0) return 0;
   std::vector<double> A(a, a + static_cast<size_t>(n) * n);
-  std::vector<double> Q(static_cast<size_t>(n) * n, 0.0);  // accumulated reflectors, row-major
-  for (uint32_t i = 0; i < n; i++) Q[static_cast<size_t>(i) * n + i] = 1.0;
+  // accumulated reflectors, stored TRANSPOSED (Q[c * n + r] = element (r, c)): every Householder update and every
+  // QL rotation then works on contiguous rows; the arithmetic and its order are those of the plain layout
+  std::vector<double> Q_store(static_cast<size_t>(n) * n + 8, 0.0);
+  // 64-byte aligned, so that the threads' row blocks (multiples of 8 doubles) never share a cache line
+  double* Q = Q_store.data() + ((64 - reinterpret_cast<uintptr_t>(Q_store.data()) % 64) % 64) / sizeof(double);
+  struct Rot { double s, c; uint32_t i; };
+  std::vector<Rot> rot;
+  std::vector<uint32_t> refl_k;
+  std::vector<double> refl_v;
+  rot.reserve(static_cast<size_t>(n) * n * 2);
+  refl_v.reserve(static_cast<size_t>(n) * n / 2 + n);
   std::vector<double> v(n), p(n), d(n), e(n, 0.0);
 
   // ---- Householder: A <- H A H with H = I - 2 v v^T zeroing column k below the sub-diagonal ----
@@ -64,15 +92,9 @@ inline int sym_eig(const double* a, uint32_t n, double* evals, double* evecs)
       A[static_cast<size_t>(k + 1 + i) * n + k] = 0.0;
       A[static_cast<size_t>(k) * n + k + 1 + i] = 0.0;
     }
-    // Q <- Q H (columns k+1.. of Q)
-    for (uint32_t r = 0; r < n; r++)
-    {
-      double* row = &Q[static_cast<size_t>(r) * n + k + 1];
-      double s = 0.0;
-      for (uint32_t j = 0; j < m; j++) s += row[j] * v[j];
-      s *= 2.0;
-      for (uint32_t j = 0; j < m; j++) row[j] -= s * v[j];
-    }
+    // Q <- Q H (columns k+1.. of Q) is applied later: keep the reflector
+    refl_k.push_back(k);
+    refl_v.insert(refl_v.end(), v.begin(), v.begin() + m);
   }
   for (uint32_t i = 0; i < n; i++) d[i] = A[static_cast<size_t>(i) * n + i];
   for (uint32_t i = 0; i + 1 < n; i++) e[i] = A[static_cast<size_t>(i + 1) * n + i];
@@ -117,13 +139,7 @@ inline int sym_eig(const double* a, uint32_t n, double* evals, double* evecs)
           r = (d[i] - g) * s + 2.0 * c * b;
           d[i + 1] = g + (pp = s * r);
           g = c * r - b;
-          for (uint32_t k = 0; k < n; k++)
-          {
-            double* row = &Q[static_cast<size_t>(k) * n];
-            f = row[i + 1];
-            row[i + 1] = s * row[i] + c * f;
-            row[i] = c * row[i] - s * f;
-          }
+          rot.push_back({s, c, static_cast<uint32_t>(i)});   // columns i, i+1 of Q, applied later
         }
         if (r == 0.0 && i >= static_cast<int>(l)) continue;
         d[l] -= pp;
@@ -133,6 +149,68 @@ inline int sym_eig(const double* a, uint32_t n, double* evals, double* evecs)
     } while (m != l);
   }
 
+  // ---- apply the recorded reflectors, then the rotations, to Q: rows [r0, r1) per thread ----
+  {
+    auto apply = [&](uint32_t r0, uint32_t r1) {
+      FlushSubnormals ftz;
+      const uint32_t w = r1 - r0;
+      // private compact copy of the block (n x w, identity rows r0..r1): sequential, cache-resident sweeps
+      std::vector<double> B(static_cast<size_t>(n) * w, 0.0);
+      for (uint32_t r = r0; r < r1; r++) B[static_cast<size_t>(r) * w + (r - r0)] = 1.0;
+      std::vector<double> sacc(w);
+      size_t off = 0;
+      for (uint32_t k : refl_k)
+      {
+        const uint32_t m = n - k - 1;
+        const double* vk = &refl_v[off];
+        off += m;
+        // s_r = 2 sum_j Q(r, k+1+j) v_j in j order, then Q(r, k+1+j) -= s_r v_j
+        std::fill(sacc.begin(), sacc.end(), 0.0);
+        for (uint32_t j = 0; j < m; j++)
+        {
+          const double* col = &B[static_cast<size_t>(k + 1 + j) * w];
+          const double vj = vk[j];
+          for (uint32_t r = 0; r < w; r++) sacc[r] += col[r] * vj;
+        }
+        for (uint32_t r = 0; r < w; r++) sacc[r] *= 2.0;
+        for (uint32_t j = 0; j < m; j++)
+        {
+          double* col = &B[static_cast<size_t>(k + 1 + j) * w];
+          const double vj = vk[j];
+          for (uint32_t r = 0; r < w; r++) col[r] -= sacc[r] * vj;
+        }
+      }
+      for (const Rot& t : rot)
+      {
+        double* __restrict__ ci = &B[static_cast<size_t>(t.i) * w];
+        double* __restrict__ ci1 = ci + w;
+        const double s = t.s, c = t.c;
+        for (uint32_t r = 0; r < w; r++)
+        {
+          const double f = ci1[r];
+          const double g0 = ci[r];
+          ci1[r] = s * g0 + c * f;
+          ci[r] = c * g0 - s * f;
+        }
+      }
+      for (uint32_t c = 0; c < n; c++) std::copy(&B[static_cast<size_t>(c) * w], &B[static_cast<size_t>(c) * w] + w, &Q[static_cast<size_t>(c) * n + r0]);
+    };
+    const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t n_thr = std::max(1u, std::min({hw, 16u, n / 24u}));
+    if (n_thr == 1) apply(0, n);
+    else
+    {
+      std::vector<std::thread> pool;
+      const uint32_t per = ((n + n_thr - 1) / n_thr + 7) / 8 * 8;
+      for (uint32_t t = 0; t < n_thr; t++)
+      {
+        const uint32_t r0 = std::min(n, t * per), r1 = std::min(n, r0 + per);
+        if (r0 < r1) pool.emplace_back(apply, r0, r1);
+      }
+      for (auto& t : pool) t.join();
+    }
+  }
+
   std::vector<uint32_t> order(n);
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return d[x] > d[y]; });
@@ -140,11 +218,12 @@ inline int sym_eig(const double* a, uint32_t n, double* evals, double* evecs)
   {
     const uint32_t col = order[j];
     evals[j] = d[col];
+    const double* qc = &Q[static_cast<size_t>(col) * n];
     uint32_t big = 0;
     for (uint32_t i = 1; i < n; i++)
-      if (std::fabs(Q[static_cast<size_t>(i) * n + col]) > std::fabs(Q[static_cast<size_t>(big) * n + col])) big = i;
-    const double sgn = Q[static_cast<size_t>(big) * n + col] < 0 ? -1.0 : 1.0;
-    for (uint32_t i = 0; i < n; i++) evecs[static_cast<size_t>(j) * n + i] = sgn * Q[static_cast<size_t>(i) * n + col];
+      if (std::fabs(qc[i]) > std::fabs(qc[big])) big = i;
+    const double sgn = qc[big] < 0 ? -1.0 : 1.0;
+    for (uint32_t i = 0; i < n; i++) evecs[static_cast<size_t>(j) * n + i] = sgn * qc[i];
   }
   return rc;
 }

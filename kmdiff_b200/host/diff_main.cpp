@@ -331,8 +331,10 @@ class GpuWorker
 {
  public:
   // n_readers threads decode this GPU's partitions (one partition per thread at a time) into pinned buffers
-  GpuWorker(int device, const DiffOptions& o, const RunConfig& cfg, uint64_t sum_controls, uint64_t sum_cases, size_t n_readers = 1)
-    : m_device(device), m_opt(o), m_n_readers(std::max<size_t>(1, n_readers)), m_bufs(2 * std::max<size_t>(1, n_readers) + 1)
+  // buf_bytes: size of one pinned staging buffer (pinning host memory costs ~0.5 s per GB, so small inputs get small buffers)
+  GpuWorker(int device, const DiffOptions& o, const RunConfig& cfg, uint64_t sum_controls, uint64_t sum_cases, size_t n_readers = 1,
+            size_t buf_bytes = 16u << 20)
+    : m_device(device), m_opt(o), m_n_readers(std::max<size_t>(1, n_readers)), m_bufs(std::max<size_t>(1, n_readers) + 2)
   {
     kmd_config c{};
     c.abi_version = KMD_ABI_VERSION;
@@ -364,9 +366,14 @@ class GpuWorker
       ck(raw, kmd_popstrat_enable(raw, &pc), "kmd_popstrat_enable");
     }
     m_row_bytes = 8ull * c.kmer_words + (o.nb_controls + o.nb_cases) * o.count_bytes;
-    m_buf_rows = std::max<uint64_t>(1, (64ull << 20) / m_row_bytes);
+    m_buf_rows = std::max<uint64_t>(1, buf_bytes / m_row_bytes);
+  }
+  // matrix input only: the pinned staging buffers of the reader threads
+  void alloc_buffers()
+  {
     for (auto& b : m_bufs)
     {
+      if (b.data) continue;
       b.data = static_cast<uint8_t*>(kmd_host_alloc(m_buf_rows * m_row_bytes));
       if (!b.data) throw KmdError("GpuError", "kmd_host_alloc failed");
     }
@@ -391,6 +398,7 @@ class GpuWorker
         ck(m_ctx.get(), kmd_sync(m_ctx.get()), "kmd_sync");
         return;
       }
+      alloc_buffers();
       m_next_part = 0;
       m_readers_left = static_cast<int>(m_n_readers);
       std::vector<std::thread> readers;
@@ -1224,8 +1232,28 @@ void main_diff(DiffOptions& opt)
 
   std::vector<std::unique_ptr<GpuWorker>> workers;
   // host threads (-t) are split over the devices: each GPU gets its own readers (file read / LZ4 decode -> pinned)
-  const size_t readers_per_gpu = std::max<size_t>(1, std::min<size_t>(8, opt.nb_threads / static_cast<size_t>(n_dev)));
-  for (int d = 0; d < n_dev; d++) workers.push_back(std::make_unique<GpuWorker>(d, opt, cfg, sum_c, sum_k, readers_per_gpu));
+  const size_t parts_per_gpu = (parts.size() + static_cast<size_t>(n_dev) - 1) / static_cast<size_t>(n_dev);
+  const size_t readers_per_gpu = std::max<size_t>(1, std::min({size_t{8}, opt.nb_threads / static_cast<size_t>(n_dev), std::max<size_t>(1, parts_per_gpu)}));
+  uint64_t input_bytes = 0;
+  for (const Partition& p : parts) input_bytes += p.bytes;
+  const size_t buf_bytes = static_cast<size_t>(std::min<uint64_t>(16ull << 20, std::max<uint64_t>(1ull << 20,
+                               input_bytes / static_cast<uint64_t>(n_dev) / (2 * (readers_per_gpu + 2)))));
+  // one thread per device: CUDA context creation and the device allocations of kmd_create run side by side
+  workers.resize(static_cast<size_t>(n_dev));
+  {
+    std::vector<std::thread> pool;
+    std::exception_ptr err;
+    std::mutex err_mu;
+    for (int d = 0; d < n_dev; d++)
+      pool.emplace_back([&, d] {
+        try { workers[static_cast<size_t>(d)] = std::make_unique<GpuWorker>(d, opt, cfg, sum_c, sum_k, readers_per_gpu, buf_bytes); }
+        catch (...) { std::lock_guard<std::mutex> lk(err_mu); err = std::current_exception(); }
+      });
+    for (auto& t : pool) t.join();
+    if (err) std::rethrow_exception(err);
+  }
+  logf(L_DEBUG, "%d device context(s) ready (%.3f s), %zu reader thread(s) per device, %zu KiB staging buffers", n_dev,
+       merge_time.seconds(), readers_per_gpu, buf_bytes >> 10);
 
   if (resumed)
   {

@@ -307,3 +307,45 @@ def test_cli_pop_correction(tmp_path, lz4):
     got = sorted((strip_index(h), s) for f in ("control_kmers.fasta", "case_kmers.fasta")
                  for h, s in read_fasta(os.path.join(out, f)))
     assert got == want_recs
+
+
+def test_cli_pop_correction_from_count_files(tmp_path):
+    """--pop-correction on a run directory of per-sample count files (device merge) leaves the same popstrat/
+    files, spill files and FASTA records as on the matrices of the same cohort: the Sampler draws follow the
+    merged row numbering."""
+    import filecmp
+    import os
+    import subprocess
+
+    from kmdiff_b200 import build as kb
+    from kmdiff_b200 import kmtricks_io as kio
+
+    cli = kb.build_cli()
+    nc, nk, npc, m, parts = 24, 24, 3, 40_000, 3
+    n = nc + nk
+    counts, _ = _cohort_with_structure(nc, nk, m, seed=5)
+    counts[:, 0] = np.maximum(counts[:, 0], 1)            # no all-zero row: the merge cannot produce one
+    rows = np.zeros((m, 8 + 4 * n), dtype=np.uint8)
+    rows[:, :8] = (np.arange(m, dtype=np.uint64) * np.uint64(977) + np.uint64(5)).view(np.uint8).reshape(m, 8)
+    rows[:, 8:] = counts.view(np.uint8).reshape(m, 4 * n)
+    totals = counts.sum(0).astype(np.uint64) * np.uint64(1000)
+    spec = K.SynthSpec(nc, nk, kmer_size=31, count_bytes=4, total_rows=m, seed=1)
+    outs = {}
+    for mode in ("matrix", "counts"):
+        d, out = str(tmp_path / f"run_{mode}"), str(tmp_path / f"out_{mode}")
+        kio.write_run_dir(d, spec, m, parts, lz4=True, payload=rows.ravel(), totals=totals, count_files=(mode == "counts"))
+        r = subprocess.run([cli, "diff", "-d", d, "-1", str(nc), "-2", str(nk), "-o", out, "--pop-correction", "--kmer-pca", "0.2",
+                            "--random-seed", "7", "--n-pc", str(npc), "--keep-tmp", "-s", "0.5", "-u", "100000",
+                            "--merge-records", "300000"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "[error]" not in r.stderr, r.stderr
+        assert "Population correction done." in r.stderr
+        outs[mode] = out
+    for rel in ("popstrat/gwas_eigenstratX.geno", "popstrat/gwas_eigenstratX.snp", "popstrat/pcs.evec",
+                "control_kmers.fasta", "case_kmers.fasta"):
+        a, b = os.path.join(outs["matrix"], rel), os.path.join(outs["counts"], rel)
+        assert os.path.getsize(a) > 0 and filecmp.cmp(a, b, shallow=False), rel
+    for p in range(parts):
+        for suffix in ("_uncorrected", "_popstrat_uncorrected"):
+            raw = [subprocess.run([cli, "dev-cat", os.path.join(outs[mode], "partitions", f"p{p}{suffix}"), "0", "lz4"],
+                                  capture_output=True, timeout=60).stdout for mode in ("matrix", "counts")]
+            assert raw[0] == raw[1] and len(raw[0]) > 0
