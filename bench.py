@@ -481,7 +481,10 @@ def bench_b200(args) -> None:
         total = cc.rows * world
         if popstrat:
             pop_stage(False)
-        r = ctx.correct(corr_kind, SIGNIFICANCE, total)
+        if world > 1:
+            _, r = exchange.correct(ctx, corr_kind, SIGNIFICANCE)      # same global decision as the resident step
+        else:
+            r = ctx.correct(corr_kind, SIGNIFICANCE, total)
         sig = ctx.significant()
         d2h = sig.nbytes + 48 * 3
         return r, len(sig)

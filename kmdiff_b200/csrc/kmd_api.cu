@@ -541,28 +541,6 @@ __global__ void gather_p_kernel(uint32_t n, const uint32_t* order, const double*
   if (i < n) out[i] = p[order[i]];
 }
 
-// keep flags of the stateless correctors / of keep_below, over survivors visited in `order`
-__global__ void flag_below_kernel(uint32_t n, const uint32_t* order, const double* p, double cut, uint32_t* flags)
-{
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flags[i] = p[order[i]] < cut ? 1u : 0u;
-}
-
-// stable compaction given exclusive-scanned flags; also counts kept controls / cases
-__global__ void compact_kernel(uint32_t n, const uint32_t* order, const uint32_t* flags_scanned,
-                               const double* p, double cut, const int32_t* sign, uint32_t* out_order,
-                               DeviceCounters* cnt)
-{
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t slot = order[i];
-  if (p[slot] < cut)
-  {
-    out_order[flags_scanned[i]] = slot;
-    if (sign[slot] == KMD_SIGN_CONTROL) atomicAdd(&cnt->keep_control, 1u); else atomicAdd(&cnt->keep_case, 1u);
-  }
-}
-
 __global__ void count_prefix_kernel(uint32_t n, const uint32_t* order, const int32_t* sign, DeviceCounters* cnt)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

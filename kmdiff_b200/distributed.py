@@ -85,7 +85,8 @@ class DeviceExchange:
     """BENJAMINI / HOLM across ranks without leaving the GPUs (NCCL): one all-gather of each rank's
     (rows, controls, cases, survivors), one all-gather of the survivors' p-values padded with +inf, one device
     sort of the union, kmd_first_reject_device, then every rank keeps its survivors below the cut.
-    Buffers are cached between calls.  The context must run on torch's current stream (ctx.set_stream)."""
+    Buffers are cached between calls.  The context's stream and torch's current stream are ordered explicitly
+    (the context may run on its own non-blocking stream: kmd_set_stream(NULL) does not mean the legacy stream)."""
 
     def __init__(self, device, group=None):
         self.device, self.group = device, group
@@ -110,10 +111,17 @@ class DeviceExchange:
             self.pad = torch.empty(cap, dtype=torch.float64, device=self.device)
             self.allp = torch.empty(cap * self.world, dtype=torch.float64, device=self.device)
         pad, allp = self.pad[:mx], self.allp[:mx * self.world]
+        on_gpu = self.device.type == "cuda"
         pad.fill_(float("inf"))
+        if on_gpu:
+            torch.cuda.current_stream(self.device).synchronize()      # the fill precedes the context's copy
         ctx.survivor_pvalues_device(pad.data_ptr(), mx)
+        if on_gpu:
+            ctx.sync()                                                # the copy precedes the all-gather
         dist.all_gather_into_tensor(allp, pad, group=self.group)
         merged = torch.sort(allp).values                      # +inf padding sorts last and never passes a rank test
+        if on_gpu:
+            torch.cuda.current_stream(self.device).synchronize()      # the sorted union precedes the context's walk
         _, cut = ctx.first_reject_device(merged.data_ptr(), int(m[:, 3].sum()), correction, significance, total_rows)
         return total_rows, ctx.keep_below(cut)
 

@@ -162,3 +162,88 @@ def test_two_gpus_reach_the_single_process_decision_over_nccl(tmp_path):
         got = np.sort(np.concatenate([res[0][int(kind)][2], res[1][int(kind)][2]]))
         assert np.array_equal(got, np.sort(want["row"][keep])) and len(keep) > 10
         assert sum(sum(r[int(kind)][1]) for r in res) == len(keep)
+
+
+# ---- DeviceExchange's host logic on CPU: gloo, a stand-in context backed by numpy ------------------------
+
+class _Counters:
+    def __init__(self, rows, n_control, n_case, survivors):
+        self.rows, self.n_control, self.n_case, self.survivors = rows, n_control, n_case, survivors
+
+
+class _NumpyCtx:
+    """what DeviceExchange needs from a DiffContext, over host arrays (the device calls have GPU tests)"""
+
+    def __init__(self, p, sign, rows):
+        self.p, self.sign, self.rows = np.ascontiguousarray(p, dtype=np.float64), sign, rows
+
+    def counters(self):
+        return _Counters(self.rows, int((self.sign == 0).sum()), int((self.sign != 0).sum()), len(self.p))
+
+    def survivor_pvalues_device(self, ptr, cap):
+        import ctypes
+        assert cap >= len(self.p)
+        ctypes.memmove(ptr, self.p.ctypes.data, self.p.nbytes)
+        return len(self.p)
+
+    def first_reject_device(self, ptr, n, corr, sig, total):
+        import ctypes
+        import kmdiff_b200 as K
+        arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(n,)).copy()
+        assert np.all(arr[1:] >= arr[:-1]) and np.all(np.isfinite(arr))
+        return K.first_reject(arr, corr, sig, total)
+
+    def keep_below(self, cut):
+        k = self.p < cut
+        return int((k & (self.sign == 0)).sum()), int((k & (self.sign != 0)).sum())
+
+    def correct(self, corr, sig, total):
+        import oracle
+        keep = oracle.aggregate(self.p, int(corr), sig, total)
+        return int((self.sign[keep] == 0).sum()), int((self.sign[keep] != 0).sum())
+
+
+def _exchange_inputs(rank):
+    rng = np.random.default_rng(100 + rank)
+    n = 5000 - 611 * rank                       # ragged: the shorter ranks are padded with +inf
+    p = np.where(rng.random(n) < 0.6, 10.0 ** rng.uniform(-40, -9, n), rng.uniform(1e-7, 5e-7, n))
+    p[rng.random(n) < 0.1] = 0.0
+    return p, (rng.random(n) < 0.8).astype(np.int32)
+
+
+def _exchange_worker(rank: int, world: int, port: int, out_dir: str):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import kmdiff_b200 as K
+        from kmdiff_b200 import distributed as D
+        p, sign = _exchange_inputs(rank)
+        ex = D.DeviceExchange(torch.device("cpu"))
+        res = {}
+        for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM, K.CorrectionType.BONFERRONI):
+            for rows in (4_000_000, 10**11):
+                res[(int(kind), rows)] = ex.correct(_NumpyCtx(p, sign, rows), kind, 0.05)
+        np.save(os.path.join(out_dir, f"ex{rank}.npy"), np.array([res], dtype=object), allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_device_exchange_logic_three_ranks_gloo(tmp_path):
+    import kmdiff_b200 as K
+    import oracle
+    world = 3
+    mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"ex{r}.npy", allow_pickle=True)[0] for r in range(world)]
+    ps, signs = zip(*[_exchange_inputs(r) for r in range(world)])
+    allp, alls = np.concatenate(ps), np.concatenate(signs)
+    for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM, K.CorrectionType.BONFERRONI):
+        for rows in (4_000_000, 10**11):
+            keep = oracle.aggregate(allp, int(kind), 0.05, rows * world)
+            want = (int((alls[keep] == 0).sum()), int((alls[keep] != 0).sum()))
+            got = [res[r][(int(kind), rows)] for r in range(world)]
+            assert all(g[0] == rows * world for g in got)
+            assert (sum(g[1][0] for g in got), sum(g[1][1] for g in got)) == want, (kind, rows)
+    # the large m makes BH / Holm break early: a strict subset is kept
+    keep = oracle.aggregate(allp, oracle.BENJAMINI, 0.05, 3 * 10**11)
+    assert 0 < len(keep) < len(allp)
