@@ -26,6 +26,7 @@ ORACLE_SO = os.path.join(HERE, "libkmd_oracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libkmdiff_ref.so")
 REF_BIN = os.path.join(HERE, "_ref", "kmdiff")
 REF_BIN16 = os.path.join(HERE, "_ref", "kmdiff_c16")
+REF_SMARTPCA = os.path.join(HERE, "_ref", "smartpca")
 REFERENCE_ROOT = "/root/reference"
 
 CONTROL, CASE, NO = 0, 1, 2
@@ -42,6 +43,10 @@ def build(ref: bool | None = None, refbin: bool = False) -> None:
     if ref:
         targets = ["ref"] + (["refbin"] if refbin else [])
         subprocess.check_call(["make", "-s", "-j8", "-C", HERE] + targets)
+        if refbin:
+            # HAWK's smartpca next to the reference binary: lets the reference's --pop-correction pipeline run here
+            # (needs scipy's bundled OpenBLAS for LAPACK); the parity tests that use it skip when it is absent
+            subprocess.call(["make", "-s", "-j8", "-C", HERE, "smartpca"])
 
 
 class _Model(C.Structure):

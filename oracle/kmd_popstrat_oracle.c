@@ -1,5 +1,5 @@
 /* TEST INFRASTRUCTURE — NOT PRODUCT CODE.  See kmd_popstrat_oracle.h for scope, citations and
- * parity status (sampler / IRLS / pop_strat_corrector pinned; smartpca restatement UNPINNED).
+ * parity status (sampler / IRLS / pop_strat_corrector / smartpca restatement all pinned).
  * Compile with -ffp-contract=off: the reference is built for baseline x86-64 (no FMA). */
 #define _USE_MATH_DEFINES
 #include "kmd_popstrat_oracle.h"
@@ -368,7 +368,7 @@ double kmo_popstrat_apply(const kmo_popstrat* ps, const double* counts, double* 
 }
 
 /* ================================================================================================
- * smartpca (HAWK's EIG6.0.1) — PARITY UNPINNED
+ * smartpca (HAWK's EIG6.0.1) — pinned against the real program, tests/test_smartpca_reference.py
  * ================================================================================================ */
 
 /* getcolxz + fvadjust for one SNP.  Returns 0 if the SNP is ignored (no carrier). */

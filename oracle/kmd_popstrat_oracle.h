@@ -11,10 +11,13 @@
  *     default_random_engine / uniform_real_distribution, src/linear_model.cpp, src/popstrat.cpp),
  *     tests/test_popstrat_oracle.py, plus golden vectors made from that library
  *     (tests/golden/popstrat_vectors.json, generator committed).
- *   smartpca (HAWK's modified EIGENSOFT 6.0.1, thirdparty/hawk/EIG6.0.1-Hawk): PARITY UNPINNED —
- *     the program needs GSL + LAPACKE + OpenBLAS headers that this image lacks, so it cannot be
- *     compiled here; kmo_smartpca_* restates its arithmetic from the source lines cited below and
- *     is cross-checked against numpy.linalg.eigh only.
+ *   smartpca (HAWK's modified EIGENSOFT 6.0.1, thirdparty/hawk/EIG6.0.1-Hawk): PINNED — `make -C oracle
+ *     smartpca` builds the program from the reference's vendored sources (LAPACK from scipy's bundled
+ *     OpenBLAS, the GSL-only "fastmode" stubbed).  tests/test_smartpca_reference.py holds kmo_smartpca_*
+ *     to its pcs.evec / eigenvalue output (tests/golden/smartpca_vectors.json, generator committed): every
+ *     printed digit equal, eigenvector signs aside (LAPACK's dspev leaves them unspecified), and — with
+ *     oracle/_ref/kmdiff next to it — to the reference binary's whole `--pop-correction` run (.geno,
+ *     pcs.evec, LRT and GLM p-values of the spill files, bit for bit).
  *
  * Citations: "popstrat.hpp" = include/kmdiff/popstrat.hpp, "popstrat.cpp" = src/popstrat.cpp,
  * "linear_model.cpp" = src/linear_model.cpp, "smartpca.c" =
@@ -79,7 +82,7 @@ void kmo_popstrat_free(kmo_popstrat* ps);
 double kmo_popstrat_apply(const kmo_popstrat* ps, const double* counts, double* model, int* iters,
                           double* llr);
 
-/* ---- smartpca as HAWK ships it (parity unpinned, see header) -------------------------------- */
+/* ---- smartpca as HAWK ships it (pinned against the real program, see header) ----------------- */
 /* geno: m rows (sampled k-mers) x n individuals, values 0/1 (what EigGenoFile writes,
  * popstrat.hpp:56-80).  Follows smartpca.c:907-1025: per SNP getcolxz (:2598-2700) + fvadjust
  * (:1684-1800, usenorm YES), SNPs with no carrier dropped (:921), XTX += col col^T in input order

@@ -1,7 +1,7 @@
 """Pins oracle/kmd_popstrat_oracle.c (sampler, IRLS, pop_strat_corrector) against golden vectors made
 from the unmodified reference (tests/golden/popstrat_vectors.json <- make_popstrat_golden.py) and,
-where oracle/_ref exists, against the live reference library; checks the (unpinned) smartpca
-restatement against numpy.  CPU only."""
+where oracle/_ref exists, against the live reference library; checks the smartpca restatement against
+numpy (it is pinned against the real smartpca in tests/test_smartpca_reference.py).  CPU only."""
 import json
 import os
 import tempfile
