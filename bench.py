@@ -132,7 +132,7 @@ def make_reference_run_dir(cfg_name: str, sample_rows: int, partitions: int) -> 
     return d, spec.row_bytes
 
 
-def run_reference_once(run_dir: str, cfg_name: str, threads: int) -> float:
+def run_reference_once(run_dir: str, cfg_name: str, threads: int, pop_args=()) -> float:
     import oracle
     nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
     binary = oracle.REF_BIN if b == 4 else oracle.REF_BIN16
@@ -141,7 +141,7 @@ def run_reference_once(run_dir: str, cfg_name: str, threads: int) -> float:
     if os.path.exists(opt):
         os.remove(opt)   # reference quirk: matrix mode truncates it and the next run then fails
     cmd = [binary, "diff", "--km-run", run_dir, "-1", str(nc), "-2", str(nk), "-o", out, "-t", str(threads),
-           "-c", corr, "-s", str(SIGNIFICANCE), "-u", str(CUTOFF)]
+           "-c", corr, "-s", str(SIGNIFICANCE), "-u", str(CUTOFF)] + list(pop_args)
     t0 = time.perf_counter()
     r = subprocess.run(cmd, capture_output=True, text=True)
     dt = time.perf_counter() - t0
@@ -529,20 +529,29 @@ def bench_b200(args) -> None:
 
     # ---- CPU baseline: the reference binary on a bounded prefix of the same matrix (N=1 only) ----
     cpu = None
-    if world == 1 and not args.no_cpu_baseline and not popstrat:
+    import oracle as _oracle_paths                      # paths of the reference binaries only
+    have_smartpca = os.path.exists(_oracle_paths.REF_SMARTPCA)
+    if world == 1 and not args.no_cpu_baseline and (not popstrat or have_smartpca):
         cores = os.cpu_count() or 1
         try:
             if reference_available():
                 sample = reference_sample_rows(cfg_name, cores)
+                pop_args, what = (), "`kmdiff diff"
+                if popstrat:
+                    # the reference's whole --pop-correction pipeline (Sampler, HAWK smartpca, evec2pca.perl, GLM) with
+                    # the workload's sampling rate, on at most ~1 GB of rows
+                    sample = int(min(sample, (1 << 30) // R))
+                    pop_args = ("--pop-correction", "--kmer-pca", repr(C4_SAMPLED / rows), "--n-pc", str(C4_NPC), "--random-seed", "42")
+                    what = "`kmdiff diff --pop-correction` (+ oracle/_ref/smartpca)"
                 parts = max(cores, 8)
                 run_dir, _ = make_reference_run_dir(cfg_name, sample, parts)
                 try:
-                    run_reference_once(run_dir, cfg_name, cores)           # warm the page cache
-                    dt = run_reference_once(run_dir, cfg_name, cores)
+                    run_reference_once(run_dir, cfg_name, cores, pop_args)           # warm the page cache
+                    dt = run_reference_once(run_dir, cfg_name, cores, pop_args)
                 finally:
                     shutil.rmtree(run_dir, ignore_errors=True)
                 cpu = {"value": sample / dt, "unit": "rows/s", "cores": cores, "kind": "reference",
-                       "sample": f"`kmdiff diff -t {cores}` (oracle/_ref/kmdiff) on the first {sample} rows of the "
+                       "sample": f"{what} -t {cores}` (oracle/_ref/kmdiff) on the first {sample} rows of the "
                                  f"workload, {parts} uncompressed partitions, {dt:.2f} s"}
             else:
                 import oracle
