@@ -190,7 +190,9 @@ def bench_reference(args) -> None:
         "config": {"workload": f"{cfg_name}: synthetic {nc}+{nk} samples, k={k}, {b}-byte counts, {corr}",
                    "rows_per_step": sample, "partitions": parts, "row_bytes": R,
                    "note": "reference `kmdiff diff` binary (file read + LRT + correction + FASTA) on a "
-                           "bounded prefix of the workload's synthetic matrix, uncompressed matrices"},
+                           "bounded prefix of the workload's synthetic matrix, " +
+                           ("uncompressed per-sample count files merged by km::KmerMerger" if cfg_name.endswith("m")
+                            else "uncompressed matrices")},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "reference",
                          "sample": f"{sample} rows in {parts} partitions per step"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -163,3 +163,19 @@ def test_sym_eig_and_pcs():
     # the printed coordinates are the unit eigenvectors quantised to 1e-4 (SURVEY.md §7 "GRM")
     assert np.abs(pcs - evecs[:10].T).max() <= 0.5e-4 + 1e-9
     assert np.array_equal(pcs, np.round(pcs, 4))
+
+
+def test_reference_linear_test_goldens():
+    """the golden values of the reference's own tests/linear_test.cpp (TEST(linear, utils) and
+    TEST(linear, lu_decomposition)): sigmoid(1.0), predict({1,2,3},{1,2,3}), and the 4x4 inverse"""
+    L = oracle.lib()
+    assert abs(L.kmo_sigmoid(1.0) - 0.7310585786300048792512) < 1e-15
+    assert abs(L.kmo_sigmoid(14.0) - 0.9999991684719723358679) < 1e-15       # predict = sigmoid(linear_predictor) = sigmoid(14)
+    m = np.array([[1, 2, 1, 1], [1, 1, 6, 1], [1, 0, 1, 0], [1, 0, 1, 1]], dtype=np.float64)
+    want = np.array([[0.1, -0.2, 1, 0.1], [0.5, 0, 0, -0.5], [-0.1, 0.2, 0, -0.1], [0, 0, -1, 1]])
+    inv, singular, is_nan = oracle.inverse(m)
+    assert not singular and not is_nan
+    assert np.abs(inv - want).max() < 1e-15
+    if oracle.ref_available() and hasattr(oracle.ref(), "ref_inverse"):
+        rinv, _, _ = oracle.inverse(m, impl="ref")
+        assert np.array_equal(inv, rinv)
