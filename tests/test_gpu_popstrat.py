@@ -349,3 +349,25 @@ def test_cli_pop_correction_from_count_files(tmp_path):
             raw = [subprocess.run([cli, "dev-cat", os.path.join(outs[mode], "partitions", f"p{p}{suffix}"), "0", "lz4"],
                                   capture_output=True, timeout=60).stdout for mode in ("matrix", "counts")]
             assert raw[0] == raw[1] and len(raw[0]) > 0
+
+
+def test_cli_pop_correction_matches_reference_binary():
+    """`kmdiff-b200 diff --pop-correction` against the reference binary's own run (oracle/_ref/kmdiff + HAWK smartpca +
+    evec2pca.perl) on the same run directory: identical .geno file, PCs equal up to eigenvector sign, identical
+    survivor k-mers, LRT and GLM p-values within 1e-9 relative, identical FASTA k-mer sets."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    if not (os.path.exists(oracle.REF_BIN) and os.path.exists(oracle.REF_SMARTPCA)):
+        pytest.skip("oracle/_ref/kmdiff + smartpca not built")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "profiles", "scripts", "popstrat_vs_reference.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-800:]
+    res = json.loads(r.stdout.strip().split("\n")[-1])
+    assert res["geno_identical"] and res["pcs_equal_up_to_sign"]
+    assert res["kmers_identical_uncorrected"] and res["kmers_identical_popstrat_uncorrected"]
+    assert res["max_rel_p_uncorrected"] <= 1e-9 and res["max_rel_p_popstrat_uncorrected"] <= 1e-9
+    assert res["fasta_kmers_identical_control_kmers.fasta"] and res["fasta_kmers_identical_case_kmers.fasta"]
