@@ -156,6 +156,53 @@ def rows_to_streams(payload, nb_samples: int, kmer_words: int, count_bytes: int)
     return out
 
 
+def iter_kmer_ranges(streams, kmer_words: int, count_bytes: int, max_records: int):
+    """Cut N sorted per-sample record streams into complete k-mer ranges of at most ~max_records records (all
+    samples together), the way `kmdiff-b200 diff` feeds kmd_merge_scan_host (GpuWorker::merge_loop): every stream
+    contributes up to max_records/N buffered records, the smallest "last buffered k-mer" of the streams that still
+    have more bounds the range, records above it wait for the next one.  Yields lists of N uint8 views."""
+    rec = 8 * kmer_words + count_bytes
+    recs = [np.ascontiguousarray(s).view(np.uint8).reshape(-1, rec) for s in streams]
+    n = len(recs)
+    per = max(1, max_records // max(1, n))
+
+    def keys(a):   # ascending sort key per record: (high word, low word)
+        lo = np.ascontiguousarray(a[:, :8]).view("<u8").ravel()
+        if kmer_words == 1:
+            return lo, None
+        return lo, np.ascontiguousarray(a[:, 8:16]).view("<u8").ravel()
+
+    ks = [keys(a) for a in recs]
+    pos = [0] * n
+    while True:
+        end = [min(len(recs[s]), pos[s] + per) for s in range(n)]
+        if all(end[s] == pos[s] for s in range(n)):
+            return
+        bound = None
+        for s in range(n):
+            if end[s] < len(recs[s]):                 # the stream has more: nothing above its last buffered k-mer is complete
+                lo, hi = ks[s]
+                k = (int(hi[end[s] - 1]) if hi is not None else 0, int(lo[end[s] - 1]))
+                if bound is None or k < bound:
+                    bound = k
+        cut = []
+        for s in range(n):
+            if bound is None:
+                cut.append(end[s])
+                continue
+            lo, hi = ks[s]
+            a, b = pos[s], end[s]
+            if hi is None:
+                c = a + int(np.searchsorted(lo[a:b], np.uint64(bound[1]), side="right"))
+            else:
+                c = a + int(np.searchsorted(hi[a:b], np.uint64(bound[0]), side="left"))
+                c2 = a + int(np.searchsorted(hi[a:b], np.uint64(bound[0]), side="right"))
+                c = c + int(np.searchsorted(lo[c:c2], np.uint64(bound[1]), side="right"))
+            cut.append(c)
+        yield [recs[s][pos[s]:cut[s]].ravel() for s in range(n)]
+        pos = cut
+
+
 def write_hist(path: str, kmer_size: int, sample_id: int, total: int, lower: int = 1, upper: int = 255,
                hist_u: np.ndarray | None = None) -> None:
     n = upper - lower + 1

@@ -102,3 +102,33 @@ def test_rows_to_streams_round_trip():
     streams = kio.rows_to_streams(rows, 9, 1, 2)
     got = oracle.kmer_merge(streams, 1, 2)
     assert np.array_equal(got, rows)
+
+
+@pytest.mark.parametrize("kw,b,n,budget", [(1, 4, 20, 5000), (2, 2, 7, 900), (1, 1, 3, 50), (1, 4, 5, 10**9)])
+def test_kmer_range_chunks_cover_the_merge(kw, b, n, budget):
+    """iter_kmer_ranges (the host program's feeding rule): merging the ranges one by one gives the rows of the whole
+    merge, in order, and no range exceeds the record budget by more than one buffer per stream"""
+    rng = np.random.default_rng(kw * 100 + n)
+    m = 30_000
+    lo = np.unique(rng.integers(0, 2**40, size=m, dtype=np.uint64))
+    hi = np.sort(rng.integers(0, 5, size=len(lo), dtype=np.uint64)) if kw == 2 else None
+    if kw == 2:
+        order = np.lexsort((lo, hi))
+        lo, hi = lo[order], hi[order]
+    streams = []
+    for s in range(n):
+        sel = rng.random(len(lo)) < [0.9, 0.05, 0.4][s % 3]
+        rec = np.zeros((int(sel.sum()), 8 * kw + b), dtype=np.uint8)
+        rec[:, :8] = lo[sel].view(np.uint8).reshape(-1, 8)
+        if kw == 2:
+            rec[:, 8:16] = hi[sel].view(np.uint8).reshape(-1, 8)
+        rec[:, 8 * kw:] = rng.integers(1, 200, size=(int(sel.sum()), 1), dtype=np.uint64).view(np.uint8).reshape(-1, 8)[:, :b]
+        streams.append(rec.ravel())
+    whole = oracle.kmer_merge(streams, kw, b)
+    parts, n_chunks = [], 0
+    for chunk in kio.iter_kmer_ranges(streams, kw, b, budget):
+        assert sum(c.size for c in chunk) // (8 * kw + b) <= max(budget, n)
+        parts.append(oracle.kmer_merge(chunk, kw, b))
+        n_chunks += 1
+    assert np.array_equal(np.concatenate(parts), whole)
+    assert n_chunks > 3 or budget >= 10**9
