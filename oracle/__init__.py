@@ -41,7 +41,7 @@ def build(ref: bool | None = None, refbin: bool = False) -> None:
     if ref is None:
         ref = os.path.isdir(REFERENCE_ROOT)
     if ref:
-        targets = ["ref"] + (["refbin"] if refbin else [])
+        targets = ["ref"] + (["refbin", "refbin16"] if refbin else [])
         subprocess.check_call(["make", "-s", "-j8", "-C", HERE] + targets)
         if refbin:
             # HAWK's smartpca next to the reference binary: lets the reference's --pop-correction pipeline run here

@@ -171,3 +171,50 @@ def test_oracle_equals_reference_on_seeded_rows(nc, nk, b, kw):
 def test_oracle_chisqc_equals_reference_on_dense_grid():
     xs = np.exp(np.linspace(np.log(1e-8), np.log(1500.0), 4000))
     assert all(oracle.chisqc(1.0, float(x)) == oracle.ref_chisqc(1.0, float(x)) for x in xs)
+
+
+# ---- the reference BINARIES (4-byte and 2-byte count builds) against the oracle, on the CPU ---------------
+
+@pytest.mark.skipif(not os.path.exists(oracle.REF_BIN), reason="oracle/_ref/kmdiff not built (no /root/reference)")
+@pytest.mark.parametrize("nc,nk,k,b", [(10, 10, 31, 4), (6, 9, 31, 2), (5, 5, 63, 2)])
+def test_reference_binary_spill_files_match_oracle(tmp_path, nc, nk, k, b):
+    """`kmdiff diff --keep-tmp` of the unmodified reference: the prefilter survivors of its spill files (k-mer, p,
+    sign, means) equal the oracle's bit for bit.  k = 63: the reference writes only the low 64 bits of the k-mer
+    (SURVEY.md §8 hazard 1), which is what is compared."""
+    import subprocess
+
+    import kmdiff_b200 as K
+    from kmdiff_b200 import build as kb
+    from kmdiff_b200 import kmtricks_io as kio
+
+    binary = oracle.REF_BIN if b == 4 else oracle.REF_BIN16
+    if not os.path.exists(binary):
+        pytest.skip(f"{binary} not built")
+    n_rows = 60_000
+    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=n_rows, seed=17, enriched_ppm=4000)
+    d, out = str(tmp_path / "run"), str(tmp_path / "out")
+    kio.write_run_dir(d, spec, n_rows, 1)
+    r = subprocess.run([binary, "diff", "--km-run", d, "-1", str(nc), "-2", str(nk), "-o", out, "--keep-tmp", "-t", "1",
+                        "-s", "0.05", "-u", "100000"], capture_output=True, text=True, timeout=600)
+    assert "[error]" not in r.stderr, r.stderr[-600:]
+    rows = spec.rows_host(n_rows)
+    want, n_ctl, n_case = oracle.Model(nc, nk, spec.totals()).diff(rows, spec.kmer_words, b, 0.05 / 100000)
+    assert f"{len(want)}/{n_rows} significant k-mers." in r.stderr
+    assert f"Before correction: {n_ctl} (control), {n_case} (case)." in r.stderr
+    raw = subprocess.run([kb.build_cli(), "dev-cat", os.path.join(out, "partitions", "p0_uncorrected"), "0", "lz4"],
+                         capture_output=True, timeout=60).stdout
+    # the reference dumps 8 k-mer bytes whatever k is; built WITH_POPSTRAT every record also carries `u16 N | N x f64
+    # counts` (kmer.hpp:118-123)
+    n = nc + nk
+    rec = 8 + 28 + 2 + 8 * n
+    assert len(raw) == rec * len(want) and len(want) > 30
+    a = np.frombuffer(raw, dtype=np.uint8).reshape(-1, rec)
+    assert np.array_equal(np.ascontiguousarray(a[:, :8]).view("<u8").ravel(), want["kmer"][:, 0])
+    assert np.array_equal(np.ascontiguousarray(a[:, 8:16]).view("<f8").ravel(), want["p"])
+    assert np.array_equal(np.ascontiguousarray(a[:, 16:20]).view("<i4").ravel(), want["sign"])
+    assert np.array_equal(np.ascontiguousarray(a[:, 20:28]).view("<f8").ravel(), want["mean_control"])
+    assert np.array_equal(np.ascontiguousarray(a[:, 28:36]).view("<f8").ravel(), want["mean_case"])
+    assert np.all(np.ascontiguousarray(a[:, 36:38]).view("<u2").ravel() == n)
+    dt = {2: "<u2", 4: "<u4"}[b]
+    counts = np.ascontiguousarray(rows.reshape(n_rows, -1)[:, 8 * spec.kmer_words:]).view(dt).reshape(n_rows, n)
+    assert np.array_equal(np.ascontiguousarray(a[:, 38:]).view("<f8").reshape(-1, n), counts[want["row"]].astype(np.float64))
