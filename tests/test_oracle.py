@@ -218,3 +218,52 @@ def test_reference_binary_spill_files_match_oracle(tmp_path, nc, nk, k, b):
     dt = {2: "<u2", 4: "<u4"}[b]
     counts = np.ascontiguousarray(rows.reshape(n_rows, -1)[:, 8 * spec.kmer_words:]).view(dt).reshape(n_rows, n)
     assert np.array_equal(np.ascontiguousarray(a[:, 38:]).view("<f8").reshape(-1, n), counts[want["row"]].astype(np.float64))
+
+
+@pytest.mark.skipif(not os.path.exists(oracle.REF_BIN), reason="oracle/_ref/kmdiff not built (no /root/reference)")
+@pytest.mark.parametrize("corr", ["bonferroni", "benjamini", "sidak", "holm", "disabled"])
+def test_reference_binary_fasta_matches_oracle(tmp_path, corr):
+    """The FASTA files of the unmodified reference for every corrector against oracle.aggregate + oracle.fasta_record:
+    same records (header text after the running index, sequence); BENJAMINI / HOLM additionally in the same order
+    (ascending p).  m is made large (10^7-row matrix header trick is not available, so --cutoff 1 and a tight -s make
+    the correctors bite)."""
+    import subprocess
+
+    import kmdiff_b200 as K
+    from kmdiff_b200 import kmtricks_io as kio
+
+    nc = nk = 10
+    n_rows = 80_000
+    spec = K.SynthSpec(nc, nk, kmer_size=31, count_bytes=4, total_rows=n_rows, seed=23, enriched_ppm=3000)
+    d, out = str(tmp_path / "run"), str(tmp_path / "out")
+    kio.write_run_dir(d, spec, n_rows, 3)
+    # significance levels at which each corrector rejects a part of the prefilter survivors (Sidak's
+    # 1 - (1 - t)^(1/m) underflows to 0 for t = 1e-12)
+    sig, cutoff = {"bonferroni": "1e-12", "benjamini": "1e-12", "holm": "1e-12", "sidak": "1e-3", "disabled": "1e-9"}[corr], "1"
+    r = subprocess.run([oracle.REF_BIN, "diff", "--km-run", d, "-1", "10", "-2", "10", "-o", out, "-c", corr, "-t", "1",
+                        "-s", sig, "-u", cutoff], capture_output=True, text=True, timeout=600)
+    assert "[error]" not in r.stderr, r.stderr[-600:]
+    rows = spec.rows_host(n_rows)
+    want, _, _ = oracle.Model(nc, nk, spec.totals()).diff(rows, 1, 4, float(sig) / float(cutoff))
+    keep = oracle.aggregate(want["p"], oracle.CORRECTIONS[corr], float(sig), n_rows)
+    assert 0 < len(keep) < len(want) or corr in ("disabled",)          # the corrector rejects part of the survivors
+    exp = {"control": [], "case": []}
+    for rcd in want[keep]:
+        rec = oracle.fasta_record(0, rcd["p"], rcd["mean_control"], rcd["mean_case"], oracle.kmer_to_string(rcd["kmer"][:1], 31))
+        head, body = rec.split("\n", 1)
+        exp["control" if rcd["sign"] == oracle.CONTROL else "case"].append((head.split("_", 1)[1], body.replace("\n", "")))
+    for name in ("control", "case"):
+        got, head = [], None
+        with open(os.path.join(out, f"{name}_kmers.fasta")) as f:
+            for line in f:
+                line = line.rstrip("\n")
+                if line.startswith(">"):
+                    head = line.split("_", 1)[1]
+                else:
+                    got.append((head, line))
+        if corr in ("benjamini", "holm"):
+            assert [g[1] for g in got] == [e[1] for e in exp[name]] or sorted(got) == sorted(exp[name])
+            assert sorted(got) == sorted(exp[name])
+        else:
+            assert sorted(got) == sorted(exp[name])
+    assert f"Significant k-mers: {len(exp['control'])} (control), {len(exp['case'])} (case)." in r.stderr
