@@ -7,7 +7,7 @@
  *
  * Parity status: PINNED.  tests/test_merge_oracle.py checks it against (1) the reference's own
  * fixture tests/data_test/km_out_dir and the expectations of tests/merge_test.cpp (320 merged rows,
- * per-sample totals 160/160, no significant k-mer; fixture committed under tests/golden/km_out_dir
+ * per-sample totals 160/160, no significant k-mer; fixture files committed as hex in tests/golden/km_out_dir.json
  * by tests/golden/make_merge_golden.py), (2) the real km::KmerMerger behind oracle/_ref
  * (ref_kmer_merge in ref_shim.cpp) on seeded streams, and (3) vectors generated from it
  * (tests/golden/merge_vectors.json).

@@ -68,3 +68,22 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     denom = np.where(b == 0, 1.0, np.abs(b))
     return np.abs(a - b) / denom
+
+
+def materialize_km_out_dir(dst: str) -> str:
+    """The reference's merge_test.cpp run directory (tests/golden/km_out_dir.json: its files as hex) written under dst."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "km_out_dir.json")) as f:
+        files = json.load(f)["files"]
+    for rel, hx in files.items():
+        path = os.path.join(dst, rel)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "wb") as f:
+            f.write(bytes.fromhex(hx))
+    os.makedirs(os.path.join(dst, "matrices"), exist_ok=True)      # kmtricks leaves an empty matrices/ directory
+    return dst
+
+
+@pytest.fixture
+def km_out_dir(tmp_path):
+    return materialize_km_out_dir(str(tmp_path / "km_out_dir"))

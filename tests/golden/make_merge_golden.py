@@ -3,10 +3,11 @@
 
     python tests/golden/make_merge_golden.py
 
-  km_out_dir/         the DATA fixture of the reference's own tests/merge_test.cpp
-                      (tests/data_test/km_out_dir: 2 samples x 4 partitions of .kmer.lz4 files, the two
-                      .hist files, options.txt, kmtricks.fof), copied byte for byte.  merge_test.cpp
-                      expects 320 merged rows, per-sample totals 160/160 and no significant k-mer.
+  km_out_dir.json     the DATA fixture of the reference's own tests/merge_test.cpp (tests/data_test/km_out_dir:
+                      2 samples x 4 partitions of .kmer.lz4 files as kmtricks wrote them, the two .hist files,
+                      options.txt, kmtricks.fof) as {relative path: hex of the bytes}; tests/conftest.py
+                      materialises it into a temporary run directory.  merge_test.cpp expects 320 merged rows,
+                      per-sample totals 160/160 and no significant k-mer.
   merge_vectors.json  dense rows produced by the UNMODIFIED km::KmerMerger (oracle/_ref,
                       ref_kmer_merge in oracle/ref_shim.cpp) on seeded per-sample streams of every
                       record shape; streams and rows stored as hex.
@@ -53,16 +54,18 @@ def seeded_streams(rng, n_samples, kmer_size, count_bytes, n_kmers, density, cma
 
 
 def main():
-    dst = os.path.join(HERE, "km_out_dir")
-    shutil.rmtree(dst, ignore_errors=True)
+    files = {}
     for sub in ("counts", "histograms"):
-        shutil.copytree(os.path.join(REF_FIXTURE, sub), os.path.join(dst, sub))
-    for f in ("options.txt", "kmtricks.fof"):
-        shutil.copy(os.path.join(REF_FIXTURE, f), os.path.join(dst, f))
-    for r, _d, files in os.walk(dst):
-        os.chmod(r, 0o755)
-        for f in files:
-            os.chmod(os.path.join(r, f), 0o644)
+        for r, _d, names in os.walk(os.path.join(REF_FIXTURE, sub)):
+            for name in sorted(names):
+                path = os.path.join(r, name)
+                with open(path, "rb") as f:
+                    files[os.path.relpath(path, REF_FIXTURE)] = f.read().hex()
+    for name in ("options.txt", "kmtricks.fof"):
+        with open(os.path.join(REF_FIXTURE, name), "rb") as f:
+            files[name] = f.read().hex()
+    with open(os.path.join(HERE, "km_out_dir.json"), "w") as f:
+        json.dump({"source": "tlemane/kmdiff tests/data_test/km_out_dir (fixture of tests/merge_test.cpp)", "files": files}, f)
 
     rng = np.random.default_rng(20261017)
     cases = []
@@ -87,7 +90,7 @@ def main():
     with open(os.path.join(HERE, "merge_vectors.json"), "w") as f:
         json.dump({"source": "km::KmerMerger<K, MAX_C>(paths, ab_min, k, 1, 0) of tlemane/kmdiff's vendored kmtricks, "
                              "via oracle/_ref (ref_kmer_merge)", "cases": cases}, f)
-    print("wrote", dst, "and merge_vectors.json:", [c["n_rows"] for c in cases])
+    print("wrote km_out_dir.json and merge_vectors.json:", [c["n_rows"] for c in cases])
 
 
 if __name__ == "__main__":

@@ -15,7 +15,6 @@ from conftest import SHAPES, make_cohort, rel_err
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FIXTURE = os.path.join(GOLDEN, "km_out_dir")
 THR = 0.05 / 100000
 
 
@@ -26,7 +25,8 @@ def ctx_for(nc, nk, k, b, totals=None, thr=THR, **kw):
                          threshold=thr, **kw)
 
 
-def test_reference_fixture_merge_test_cpp():
+def test_reference_fixture_merge_test_cpp(km_out_dir):
+    FIXTURE = km_out_dir
     """tests/merge_test.cpp through the CUDA path: 320 rows, 0 control / 0 case survivors"""
     cfg = kio.get_kmtricks_config(FIXTURE)
     tc, tk = kio.get_total_kmer(FIXTURE, 1, 1, cfg.abundance_min)

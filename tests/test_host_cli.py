@@ -303,12 +303,9 @@ def test_cli_count_files_match_matrix_mode_and_reference(cli, tmp_path, merge_re
 
 
 @pytest.mark.gpu
-def test_cli_reference_fixture_km_out_dir(cli, tmp_path):
+def test_cli_reference_fixture_km_out_dir(cli, tmp_path, km_out_dir):
     """the reference's tests/data_test/km_out_dir (merge_test.cpp): 1 control + 1 case, k = 20, 4 partitions"""
-    import shutil
-    d = str(tmp_path / "km_out_dir")
-    shutil.copytree(os.path.join(ROOT, "tests", "golden", "km_out_dir"), d)
-    os.makedirs(os.path.join(d, "matrices"), exist_ok=True)
+    d = km_out_dir
     out = str(tmp_path / "out")
     r = run([cli, "diff", "-d", d, "-1", "1", "-2", "1", "-o", out, "-u", "10000", "--log-factorial", "100"])
     assert r.returncode == 0 and "[error]" not in r.stderr, r.stderr

@@ -11,7 +11,6 @@ import oracle
 from kmdiff_b200 import kmtricks_io as kio
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-FIXTURE = os.path.join(GOLDEN, "km_out_dir")
 
 
 def load_cases():
@@ -19,7 +18,8 @@ def load_cases():
         return json.load(f)["cases"]
 
 
-def test_reference_fixture_merge_test_cpp():
+def test_reference_fixture_merge_test_cpp(km_out_dir):
+    FIXTURE = km_out_dir
     """tests/merge_test.cpp: T == 320 merged rows, totals 160 / 160, nothing significant"""
     cfg = kio.get_kmtricks_config(FIXTURE)
     assert (cfg.kmer_size, cfg.abundance_min, cfg.nb_partitions) == (20, 1, 4)
