@@ -26,8 +26,8 @@ def ctx_for(nc, nk, k, b, totals=None, thr=THR, **kw):
 
 
 def test_reference_fixture_merge_test_cpp(km_out_dir):
-    FIXTURE = km_out_dir
     """tests/merge_test.cpp through the CUDA path: 320 rows, 0 control / 0 case survivors"""
+    FIXTURE = km_out_dir
     cfg = kio.get_kmtricks_config(FIXTURE)
     tc, tk = kio.get_total_kmer(FIXTURE, 1, 1, cfg.abundance_min)
     with K.DiffContext(1, 1, tc[0], tk[0], kmer_size=cfg.kmer_size, count_bytes=4, threshold=0.05 / 10000, lf_size=100) as ctx:

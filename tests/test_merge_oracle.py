@@ -19,8 +19,8 @@ def load_cases():
 
 
 def test_reference_fixture_merge_test_cpp(km_out_dir):
-    FIXTURE = km_out_dir
     """tests/merge_test.cpp: T == 320 merged rows, totals 160 / 160, nothing significant"""
+    FIXTURE = km_out_dir
     cfg = kio.get_kmtricks_config(FIXTURE)
     assert (cfg.kmer_size, cfg.abundance_min, cfg.nb_partitions) == (20, 1, 4)
     tc, tk = kio.get_total_kmer(FIXTURE, 1, 1, cfg.abundance_min)
