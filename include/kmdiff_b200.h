@@ -199,6 +199,38 @@ int kmd_keep_below(kmd_context* ctx, double p_cut, uint64_t* n_control, uint64_t
 int kmd_survivor_pvalues_device(kmd_context* ctx, double* d_out, uint64_t cap, uint64_t* n);
 int kmd_first_reject_device(kmd_context* ctx, const double* d_p_sorted, uint64_t n, int correction,
                             double significance, uint64_t total_rows, uint64_t* n_accepted, double* p_cut);
+/* The whole multi-GPU correction stream-ordered on the devices, one host synchronisation per run
+ * (replaces global_merge's total, merge.hpp:316 + 390-397, and sorted_aggregator::run's global heap,
+ * aggregator.hpp:282-310, when partitions are sharded over ranks; any corrector):
+ *   kmd_exchange_export   this rank's slot = KMD_EXCHANGE_HEADER u64 {rows, controls, cases, survivors, overflow, 0,0,0}
+ *                         followed by `cap` p-values (accumulator order, +inf padded); d_slot is DEVICE memory of
+ *                         KMD_EXCHANGE_HEADER + cap words.  Asynchronous on the context's stream (kmd_get_stream).
+ *   (caller)              all-gathers the world slots into d_all (NCCL / peer copies), ordered after the export and
+ *                         before the next call with events on that stream.
+ *   kmd_exchange_correct  m = sum of the slots' rows; BENJAMINI / HOLM: device sort of the union, first rejected rank
+ *                         (same walk as kmd_first_reject), p_cut = its p-value; other correctors: p_cut from m;
+ *                         this rank's survivors with p < p_cut are kept.  Asynchronous.
+ *   kmd_exchange_result   synchronises and reports.  overflow != 0: some rank had more than cap survivors, nothing was
+ *                         decided — repeat the three calls with cap >= max_rank_survivors.  Otherwise kmd_significant
+ *                         returns this rank's kept records (ascending p, ties by row, for BENJAMINI / HOLM). */
+#define KMD_EXCHANGE_HEADER 8
+typedef struct kmd_exchange_decision
+{
+  uint64_t total_rows;         /* m: rows tested by all ranks                          */
+  uint64_t total_survivors;    /* prefilter survivors of all ranks                     */
+  uint64_t max_rank_survivors; /* largest per-rank survivor count                      */
+  uint64_t n_accepted;         /* BENJAMINI / HOLM: global number accepted, else 0      */
+  double p_cut;                /* survivors with p < p_cut are significant             */
+  uint64_t kept_control;       /* this rank's significant control / case k-mers        */
+  uint64_t kept_case;
+  uint32_t overflow;
+  uint32_t reserved;
+} kmd_exchange_decision;
+void* kmd_get_stream(kmd_context* ctx); /* the cudaStream_t all work of ctx is ordered on */
+int kmd_exchange_export(kmd_context* ctx, uint64_t* d_slot, uint64_t cap);
+int kmd_exchange_correct(kmd_context* ctx, const uint64_t* d_all, uint32_t world, uint64_t cap, int correction,
+                         double significance);
+int kmd_exchange_result(kmd_context* ctx, kmd_exchange_decision* out);
 /* host helper: walk p_sorted (ascending, all ranks merged) exactly like sorted_aggregator::run;
  * returns the number accepted and writes the first rejected p-value (+inf if none) */
 uint64_t kmd_first_reject(const double* p_sorted, uint64_t n, int correction, double significance,

@@ -28,7 +28,10 @@ SYMBOLS = [
     "kmd_popstrat_gram_ms", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
     "kmd_survivor_counts", "kmd_smartpca_normalize", "kmd_sym_eig", "kmd_smartpca_pcs",
     "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_rows_host", "kmd_merge_ms", "kmd_survivor_pvalues_device", "kmd_first_reject_device",
+    "kmd_get_stream", "kmd_exchange_export", "kmd_exchange_correct", "kmd_exchange_result",
 ]
+
+EXCHANGE_HEADER = 8
 
 
 class Config(C.Structure):
@@ -43,6 +46,12 @@ class Config(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("rows", C.c_uint64), ("candidates", C.c_uint64), ("survivors", C.c_uint64),
                 ("n_control", C.c_uint64), ("n_case", C.c_uint64)]
+
+
+class ExchangeDecision(C.Structure):
+    _fields_ = [("total_rows", C.c_uint64), ("total_survivors", C.c_uint64), ("max_rank_survivors", C.c_uint64),
+                ("n_accepted", C.c_uint64), ("p_cut", C.c_double), ("kept_control", C.c_uint64),
+                ("kept_case", C.c_uint64), ("overflow", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class PopstratConfig(C.Structure):
@@ -110,6 +119,11 @@ def load() -> C.CDLL:
     L.kmd_keep_below.argtypes = [vp, d, pu64, pu64]
     L.kmd_survivor_pvalues_device.argtypes = [vp, vp, u64, pu64]
     L.kmd_first_reject_device.argtypes = [vp, vp, u64, C.c_int, d, u64, pu64, C.POINTER(d)]
+    L.kmd_get_stream.argtypes = [vp]
+    L.kmd_get_stream.restype = vp
+    L.kmd_exchange_export.argtypes = [vp, vp, u64]
+    L.kmd_exchange_correct.argtypes = [vp, vp, u32, u64, C.c_int, d]
+    L.kmd_exchange_result.argtypes = [vp, C.POINTER(ExchangeDecision)]
     L.kmd_first_reject.argtypes = [vp, u64, C.c_int, d, u64, C.POINTER(d)]
     L.kmd_first_reject.restype = u64
     L.kmd_lf_table_fill.argtypes = [vp, u64]

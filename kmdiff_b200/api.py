@@ -320,6 +320,23 @@ class DiffContext:
                                                  C.byref(acc), C.byref(cut)))
         return acc.value, cut.value
 
+    # -- multi-GPU correction, stream-ordered on the device (kmd_exchange_*) --
+    def stream_ptr(self) -> int:
+        """the cudaStream_t (as an integer) all device work of this context is ordered on"""
+        return int(self._L.kmd_get_stream(self._h) or 0)
+
+    def exchange_export(self, slot_dev_ptr: int, cap: int) -> None:
+        self._ck(self._L.kmd_exchange_export(self._h, C.c_void_p(slot_dev_ptr), int(cap)))
+
+    def exchange_correct(self, all_dev_ptr: int, world: int, cap: int, correction: int, significance: float) -> None:
+        self._ck(self._L.kmd_exchange_correct(self._h, C.c_void_p(all_dev_ptr), int(world), int(cap), int(correction),
+                                              float(significance)))
+
+    def exchange_result(self) -> _lib.ExchangeDecision:
+        out = _lib.ExchangeDecision()
+        self._ck(self._L.kmd_exchange_result(self._h, C.byref(out)))
+        return out
+
     def keep_below(self, p_cut: float) -> tuple[int, int]:
         nc, nk = C.c_uint64(), C.c_uint64()
         self._ck(self._L.kmd_keep_below(self._h, p_cut, C.byref(nc), C.byref(nk)))

@@ -118,6 +118,25 @@ struct MergeState
   uint64_t last_records = 0;
 };
 
+// multi-GPU correction (kmd_exchange_*): the union of the ranks' p-values, sorted here, and the decision
+struct ExchangeDecision
+{
+  unsigned long long total_rows, total_survivors, max_rank_survivors, n_accepted;
+  double p_cut;
+  uint32_t first;        // scratch of first_reject_dev_kernel
+  uint32_t overflow;     // some rank had more survivors than `cap`
+};
+
+struct ExchangeState
+{
+  uint64_t* keys[2] = {nullptr, nullptr};
+  size_t keys_cap = 0;
+  ExchangeDecision* d_dec = nullptr;
+  ExchangeDecision* h_dec = nullptr;   // pinned
+  bool pending = false;                // kmd_exchange_correct enqueued, result not read yet
+  bool by_p = false;
+};
+
 }  // namespace
 
 struct kmd_context
@@ -176,12 +195,14 @@ struct kmd_context
 
   PopState pop;
   MergeState mrg;
+  ExchangeState xch;
 };
 
 namespace {
 
 void pop_free(kmd_context* ctx);   // kmd_popstrat_api.inl
 void merge_free(kmd_context* ctx); // kmd_merge_api.inl
+void exchange_free(kmd_context* ctx); // kmd_exchange_api.inl
 int pop_reset(kmd_context* ctx);
 
 int fail(kmd_context* ctx, int code, const char* fmt, ...)
@@ -567,9 +588,11 @@ __global__ void gather_records_kernel(uint32_t n, const uint32_t* order, Survivo
 
 // Stateless correctors (aggregator::worker, aggregator.hpp:137-163): every survivor is tested on its own, so the
 // kept slots are appended in arrival order (warp-aggregated atomics) and only ordered when they are fetched.
+// cut_ptr != null: the cut is read from device memory (multi-GPU exchange, no host round trip).
 __global__ void __launch_bounds__(256) keep_unordered_kernel(DeviceCounters* cnt, uint32_t cap, const double* p, double cut,
-                                                             const int32_t* sign, uint32_t* out_order)
+                                                             const double* cut_ptr, const int32_t* sign, uint32_t* out_order)
 {
+  if (cut_ptr) cut = *cut_ptr;
   const uint32_t n = min(cnt->surv_count, cap);
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t stride = gridDim.x * blockDim.x;
@@ -771,13 +794,15 @@ int fetch_counters(kmd_context* ctx)
   return KMD_OK;
 }
 
-// stable LSD radix sort of the (key, slot) pairs in d_keys[0]/d_vals[0] over the low 8*n_passes key bits
-// (higher bits must be equal in all keys); the sorted slots end up in d_vals[0]
-int radix_sort(kmd_context* ctx, uint32_t n, int n_passes = 8)
+// stable LSD radix sort of (key[, slot]) pairs over the low 8*n_passes key bits (higher bits must be equal in all
+// keys), ping-ponging between the two buffers; *result = index of the buffer that holds the sorted output.
+// vals may be null (keys only).
+int radix_sort_buffers(kmd_context* ctx, uint64_t* const keys[2], uint32_t* const vals[2], uint32_t n, int n_passes, int* result)
 {
+  *result = 0;
   if (n < 2 || n_passes <= 0) return KMD_OK;
-  const uint32_t n_tiles = (n + kSortTile - 1) / kSortTile;
-  const size_t need = static_cast<size_t>(n_tiles) * 256;
+  const uint32_t n_ctas = (n + kSortCtaKeys - 1) / kSortCtaKeys;
+  const size_t need = static_cast<size_t>(n_ctas) * 256;
   if (need > ctx->hist_entries)
   {
     if (ctx->d_hist) cudaFree(ctx->d_hist);
@@ -786,19 +811,28 @@ int radix_sort(kmd_context* ctx, uint32_t n, int n_passes = 8)
     KMD_CUDA(ctx, cudaMalloc(&ctx->d_hist, need * sizeof(uint32_t)));
     ctx->hist_entries = need;
   }
-  const uint32_t blocks = (n_tiles + kSortWarps - 1) / kSortWarps;
   int cur = 0;
   for (int pass = 0; pass < n_passes; pass++)
   {
     const int shift = 8 * pass;
-    sort_hist_kernel<<<blocks, kSortWarps * 32, 0, ctx->stream>>>(ctx->d_keys[cur], n, shift, n_tiles, ctx->d_hist);
+    sort_hist_kernel<<<n_ctas, kSortWarps * 32, 0, ctx->stream>>>(keys[cur], n, shift, n_ctas, ctx->d_hist);
     scan_exclusive_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_hist, static_cast<uint32_t>(need), nullptr);
-    sort_scatter_kernel<<<blocks, kSortWarps * 32, 0, ctx->stream>>>(ctx->d_keys[cur], ctx->d_vals[cur], ctx->d_keys[cur ^ 1],
-                                                                      ctx->d_vals[cur ^ 1], n, shift, n_tiles, ctx->d_hist);
+    sort_scatter_kernel<<<n_ctas, kSortWarps * 32, 0, ctx->stream>>>(keys[cur], vals ? vals[cur] : nullptr, keys[cur ^ 1],
+                                                                     vals ? vals[cur ^ 1] : nullptr, n, shift, n_ctas, ctx->d_hist);
     ctx->launches += 3;
     cur ^= 1;
   }
   KMD_CUDA(ctx, cudaGetLastError());
+  *result = cur;
+  return KMD_OK;
+}
+
+// the context's survivor (key, slot) pairs in d_keys[0]/d_vals[0]; the sorted slots end up in d_vals[0]
+int radix_sort(kmd_context* ctx, uint32_t n, int n_passes = 8)
+{
+  int cur = 0;
+  int rc = radix_sort_buffers(ctx, ctx->d_keys, ctx->d_vals, n, n_passes, &cur);
+  if (rc) return rc;
   if (cur == 1)
     KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_vals[0], ctx->d_vals[1], n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   return KMD_OK;
@@ -879,7 +913,7 @@ int keep_below_impl(kmd_context* ctx, double cut, uint64_t* n_control, uint64_t*
 {
   KMD_CUDA(ctx, cudaMemsetAsync(&ctx->d_cnt->keep_control, 0, 3 * sizeof(uint32_t), ctx->stream));
   keep_unordered_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_cnt, static_cast<uint32_t>(ctx->cap), ctx->surv.p, cut,
-                                                                     ctx->surv.sign, ctx->d_order);
+                                                                     nullptr, ctx->surv.sign, ctx->d_order);
   ctx->launches++;
   KMD_CUDA(ctx, cudaGetLastError());
   int rc = fetch_counters(ctx);
@@ -974,6 +1008,7 @@ void kmd_destroy(kmd_context* ctx)
   cudaFree(ctx->d_hist); cudaFree(ctx->d_p_sorted); cudaFree(ctx->d_out); cudaFree(ctx->d_order);
   pop_free(ctx);
   merge_free(ctx);
+  exchange_free(ctx);
   if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
   if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1297,7 +1332,7 @@ int kmd_correct(kmd_context* ctx, int correction, double significance, uint64_t 
     }
     KMD_CUDA(ctx, cudaMemsetAsync(&ctx->d_cnt->keep_control, 0, 3 * sizeof(uint32_t), ctx->stream));
     keep_unordered_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_cnt, static_cast<uint32_t>(ctx->cap), ctx->surv.p, cut,
-                                                                       ctx->surv.sign, ctx->d_order);
+                                                                       nullptr, ctx->surv.sign, ctx->d_order);
     ctx->launches++;
     KMD_CUDA(ctx, cudaGetLastError());
     int rc0 = fetch_counters(ctx);
@@ -1632,3 +1667,4 @@ int kmd_synth_fill_device(const kmd_synth* s, int device, void* d_rows, uint64_t
 
 #include "kmd_popstrat_api.inl"
 #include "kmd_merge_api.inl"
+#include "kmd_exchange_api.inl"

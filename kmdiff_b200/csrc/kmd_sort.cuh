@@ -5,7 +5,9 @@
 //
 // Sizes here are the prefilter survivors (<= ~1e-3 of the rows), so the sort favours simplicity:
 // 8 passes of 8 bits; each warp owns a tile of consecutive keys, ranks equal digits with
-// __match_any_sync in lane order (=> stable) and keeps running per-digit offsets in shared memory.
+// __match_any_sync in lane order (=> stable) and keeps running per-digit offsets in shared memory;
+// the eight warps of a CTA share one histogram column, so the table that is prefix-summed between the
+// two kernels of a pass has 256 x (n / 4096) entries.
 #pragma once
 
 #include <cstdint>
@@ -14,24 +16,35 @@
 namespace kmd {
 
 constexpr int kSortTile = 512;   // keys per warp
-constexpr int kSortWarps = 8;    // warps per CTA
+constexpr int kSortWarps = 8;    // warps per CTA; a CTA owns kSortTile * kSortWarps consecutive keys
+constexpr int kSortCtaKeys = kSortTile * kSortWarps;
 
-__global__ void __launch_bounds__(kSortWarps * 32)
-sort_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t n_tiles,
-                 uint32_t* __restrict__ hist /* [256][n_tiles] */)
+// digit counts of each warp's sub-tile of the CTA's keys -> counts[warp][digit] (shared memory)
+__device__ __forceinline__ void sort_count_tile(const uint64_t* __restrict__ keys, uint32_t n, int shift,
+                                                uint32_t (*counts)[256])
 {
-  __shared__ uint32_t counts[kSortWarps][256];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tile = blockIdx.x * kSortWarps + warp;
   for (uint32_t d = lane; d < 256; d += 32) counts[warp][d] = 0;
   __syncwarp();
-  if (tile >= n_tiles) return;
-  const uint32_t begin = tile * kSortTile;
+  const uint32_t begin = blockIdx.x * kSortCtaKeys + warp * kSortTile;
   const uint32_t end = min(n, begin + kSortTile);
   for (uint32_t i = begin + lane; i < end; i += 32)
     atomicAdd(&counts[warp][(keys[i] >> shift) & 0xFF], 1u);
-  __syncwarp();
-  for (uint32_t d = lane; d < 256; d += 32) hist[d * n_tiles + tile] = counts[warp][d];
+  __syncthreads();
+}
+
+// one histogram per CTA (not per warp): the table the single-CTA prefix sum walks stays small
+__global__ void __launch_bounds__(kSortWarps * 32)
+sort_hist_kernel(const uint64_t* __restrict__ keys, uint32_t n, int shift, uint32_t n_ctas,
+                 uint32_t* __restrict__ hist /* [256][n_ctas] */)
+{
+  __shared__ uint32_t counts[kSortWarps][256];
+  sort_count_tile(keys, n, shift, counts);
+  const uint32_t d = threadIdx.x;   // kSortWarps * 32 == 256 digits
+  uint32_t s = 0;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; w++) s += counts[w][d];
+  hist[d * n_ctas + blockIdx.x] = s;
 }
 
 // Exclusive prefix sum of `n` u32 values in place, one CTA (n is at most a few hundred thousand).
@@ -64,18 +77,29 @@ __global__ void __launch_bounds__(1024) scan_exclusive_kernel(uint32_t* data, ui
   if (total && t == 1023) *total = partial[1023];
 }
 
+// vals_in == nullptr: keys only
 __global__ void __launch_bounds__(kSortWarps * 32)
 sort_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
-                    int shift, uint32_t n_tiles, const uint32_t* __restrict__ offsets /* scanned hist */)
+                    int shift, uint32_t n_ctas, const uint32_t* __restrict__ offsets /* scanned hist */)
 {
   __shared__ uint32_t base[kSortWarps][256];
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tile = blockIdx.x * kSortWarps + warp;
-  if (tile >= n_tiles) return;
-  for (uint32_t d = lane; d < 256; d += 32) base[warp][d] = offsets[d * n_tiles + tile];
-  __syncwarp();
-  const uint32_t begin = tile * kSortTile;
+  sort_count_tile(keys_in, n, shift, base);
+  {
+    // counts -> first output slot of (warp, digit): the CTA's offset of the digit + the counts of the warps before
+    const uint32_t d = threadIdx.x;
+    uint32_t run = offsets[d * n_ctas + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortWarps; w++)
+    {
+      const uint32_t c = base[w][d];
+      base[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  const uint32_t begin = blockIdx.x * kSortCtaKeys + warp * kSortTile;
   const uint32_t end = min(n, begin + kSortTile);
   for (uint32_t i0 = begin; i0 < end; i0 += 32)
   {
@@ -93,7 +117,7 @@ sort_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
       if (rank == 0) base[warp][d] += __popc(peers);
       __syncwarp(active);
       keys_out[dst] = key;
-      vals_out[dst] = vals_in[i];
+      if (vals_in) vals_out[dst] = vals_in[i];
     }
   }
 }
@@ -108,6 +132,22 @@ __global__ void first_reject_kernel(const double* __restrict__ p_sorted, uint32_
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  bool pass;
+  if (holm)
+    pass = p_sorted[i] < __ddiv_rn(level, static_cast<double>(total - i));
+  else
+    pass = p_sorted[i] < __dmul_rn(__ddiv_rn(static_cast<double>(static_cast<uint64_t>(i) + 1),
+                                             static_cast<double>(total)), level);
+  if (!pass) atomicMin(first, i);
+}
+
+// the same walk with m read from device memory (multi-GPU exchange: m = sum of the ranks' row counts)
+__global__ void first_reject_dev_kernel(const double* __restrict__ p_sorted, uint32_t n, int holm, double level,
+                                        const uint64_t* __restrict__ total_ptr, uint32_t* first)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t total = *total_ptr;
   bool pass;
   if (holm)
     pass = p_sorted[i] < __ddiv_rn(level, static_cast<double>(total - i));
