@@ -7,19 +7,29 @@
 
 One "step" = one pass of the hot path over one batch of synthetic kmtricks-format rows held by each
 GPU: reset -> LRT scan of the batch (screen + exact fp64 test of the candidates + prefilter) ->
-global row count (NCCL all-reduce when N > 1) -> significance correction on the device (sort /
-compaction) -> counts of significant control / case k-mers back on the host.
+device-side exchange (kmdiff_b200.distributed.DeviceExchange: one all-gather of every rank's row /
+survivor counters and survivor p-values, device sort of the union, first rejected rank, keep) -> ONE
+host synchronisation that returns m, the cut and the counts of significant control / case k-mers.
 
-Workload at N=1: BASELINE.json configs[1] ("synthetic 10 control + 10 case, k=31, 1e9 k-mer rows,
-Poisson LRT + Bonferroni"), 88 B/row = 88 GB resident in HBM.  Every rank holds its own 1e9-row
-partition set (weak scaling; partitions are disjoint, no data-path collective).
+Headline workload at every N: BASELINE.json configs[2], the shape the north-star target is quoted on
+("synthetic 100 + 100 samples, k=31, ..., Benjamini-Hochberg correction"), 808 B/row, 1.5e8 rows =
+121 GB resident per GPU (2e9 rows = 1.6 TB do not fit 8 x 180 GB; every rank holds its own disjoint
+partition set: weak scaling, no data-path collective).  The line also carries, under "c2", the same
+measurement of configs[1] ("10 control + 10 case, k=31, 1e9 k-mer rows, Poisson LRT + Bonferroni",
+88 GB resident per GPU), the headline of round 1.
 
-`value`  : rows/s with the rows already resident in HBM (device generated, seeded).
-`e2e`    : rows/s through the C-ABI with HOST buffers (kmd_scan_host from pinned memory, survivors
-           and significant k-mers read back), H2D/D2H inside the timed region, on a smaller batch.
+`value`   : rows/s with the rows already resident in HBM (device generated, seeded).
+`e2e`     : rows/s through the C-ABI with HOST buffers (kmd_scan_host from pinned memory, exchange,
+            significant records read back), H2D/D2H inside the timed region, on a smaller batch.
+`e2e_cli` : the drop-in program itself, file -> FASTA: wall time of `kmdiff-b200 diff` against the
+            reference binary `kmdiff diff -t $(nproc)` on the same run directory (N = 1 only).
 `roofline`: lrt_scan kernel, algorithmic bytes R*rows / its CUDA-event duration vs measured HBM peak.
-`cpu_baseline`: the reference's own `kmdiff diff` binary (oracle/_ref/kmdiff) on the host cores,
-           on a bounded prefix of the same synthetic matrix written as a kmtricks run dir.
+`cpu_baseline`: the reference's own `kmdiff diff` binary (oracle/_ref/kmdiff) on the host cores, on a
+            bounded prefix of the same synthetic matrix written as a kmtricks run dir; its FASTA k-mer
+            set is compared with ours on the same prefix (`parity_on_prefix`).
+`decision_check`: outside the timed region the same survivors are corrected again with the walk on
+            the host (correct_sharded: gather + kmd_first_reject); m, the kept counts and the kept
+            rows must be identical or the bench fails.
 """
 from __future__ import annotations
 
@@ -37,9 +47,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 CONFIGS = {
-    # name: (nb_controls, nb_cases, k, count_bytes, rows, correction)
+    # name: (nb_controls, nb_cases, k, count_bytes, rows per GPU, correction)
     "c2": (10, 10, 31, 4, 1_000_000_000, "bonferroni"),
-    "c3": (100, 100, 31, 4, 150_000_000, "benjamini"),   # 2e9 rows = 1.6 TB do not fit one GPU
+    "c3": (100, 100, 31, 4, 150_000_000, "benjamini"),   # 2e9 rows = 1.6 TB do not fit 8 x 180 GB
     "c5": (50, 50, 63, 2, 500_000_000, "bonferroni"),    # per-GPU share of 4e9 rows over 8 GPUs
     # BASELINE.json configs[3]: population stratification, 10 PCs, 1e6 sampled k-mers, logistic GLM
     "c4": (200, 200, 31, 4, 60_000_000, "bonferroni"),
@@ -47,10 +57,28 @@ CONFIGS = {
     # (BASELINE.json configs[0]'s input layout; km::KmerMerger row of SURVEY.md §8a) — host streams in
     "c2m": (10, 10, 31, 4, 8_000_000, "bonferroni"),
 }
+HEADLINE = "c3"
+SECONDARY = "c2"
 C4_NPC = 10
 C4_SAMPLED = 1_000_000
 SIGNIFICANCE = 0.05
 CUTOFF = 100000
+SEED = 42
+ENRICHED_PPM = 1000
+CLI = os.path.join(ROOT, "kmdiff_b200", "kmdiff-b200")
+
+
+def workload_name(cfg_name: str) -> str:
+    nc, nk, k, b, _, corr = CONFIGS[cfg_name]
+    if cfg_name.endswith("m"):
+        return (f"{cfg_name}: synthetic {nc}+{nk} samples, k={k}, {b}-byte counts as per-sample sorted count streams "
+                f"(no matrices), N-way merge + Poisson LRT + {corr}")
+    return f"{cfg_name}: synthetic {nc}+{nk} samples, k={k}, {b}-byte counts, Poisson LRT + {corr}"
+
+
+def row_bytes(cfg_name: str) -> int:
+    nc, nk, k, b, _, _ = CONFIGS[cfg_name]
+    return 8 * ((k + 31) // 32) + (nc + nk) * b
 
 
 def load_peaks():
@@ -59,6 +87,21 @@ def load_peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def scratch_dir() -> str:
+    """where run directories go: $KMD_TMP, else /dev/shm when it has room (the GPU boxes' / is a slow virtual disk
+    and both arms read the same files), else /tmp"""
+    env = os.environ.get("KMD_TMP")
+    if env:
+        return env
+    try:
+        st = os.statvfs("/dev/shm")
+        if st.f_bavail * st.f_frsize > (64 << 30):
+            return "/dev/shm"
+    except OSError:
+        pass
+    return "/tmp"
 
 
 class ClockSampler(threading.Thread):
@@ -113,47 +156,71 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------
-# reference arm: the unmodified `kmdiff diff` binary on the host cores
+# run directories and the reference binary.  Nothing in this section imports kmdiff_b200 or maps
+# libkmdiff_b200.so into this process: the synthetic rows are written by a `kmdiff-b200 dev-synth`
+# subprocess that has exited before anything is timed.
 # ------------------------------------------------------------------------------------------------------
 
-def reference_available():
-    import oracle
-    return os.path.exists(oracle.REF_BIN)
+def ref_binaries():
+    import oracle      # constants only (paths of the reference binaries under oracle/_ref)
+    return oracle.REF_BIN, oracle.REF_BIN16, oracle.REF_SMARTPCA
 
 
-def make_reference_run_dir(cfg_name: str, sample_rows: int, partitions: int) -> tuple[str, int]:
-    """kmtricks run dir holding rows [0, sample_rows) of the workload's synthetic matrix"""
-    import kmdiff_b200 as K
-    from kmdiff_b200 import kmtricks_io as kio
+def make_run_dir(cfg_name: str, sample_rows: int, partitions: int) -> str:
+    """kmtricks run dir holding rows [0, sample_rows) of the workload's synthetic matrix (raw matrices, or raw
+    per-sample count files for the *m configs)"""
     nc, nk, k, b, rows, _ = CONFIGS[cfg_name]
-    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=rows, seed=42)
-    d = tempfile.mkdtemp(prefix="kmdiff_ref_run_", dir=os.environ.get("KMD_TMP", "/tmp"))
-    kio.write_run_dir(d, spec, sample_rows, partitions, count_files=cfg_name.endswith("m"))
-    return d, spec.row_bytes
+    if not os.path.exists(CLI):
+        raise RuntimeError(f"{CLI} not built (python -m kmdiff_b200.build)")
+    d = tempfile.mkdtemp(prefix="kmdiff_run_", dir=scratch_dir())
+    cmd = [CLI, "dev-synth", d, str(nc), str(nk), str(k), str(b), str(rows), str(SEED), str(ENRICHED_PPM),
+           str(sample_rows), str(partitions), "counts" if cfg_name.endswith("m") else "matrix"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
+    if r.returncode != 0:
+        shutil.rmtree(d, ignore_errors=True)
+        raise RuntimeError(f"dev-synth failed ({r.returncode}): {r.stderr[-300:]}")
+    return d
 
 
-def run_reference_once(run_dir: str, cfg_name: str, threads: int, pop_args=()) -> float:
-    import oracle
+REF_HUNG = [0]      # reference invocations killed by the timeout (the reference has known races, SURVEY.md §5)
+
+
+def run_reference_once(run_dir: str, cfg_name: str, threads: int, pop_args=(), keep_out: bool = False, timeout: float = 240.0):
+    """one `kmdiff diff` of the unmodified reference binary -> (seconds, output dir or None).  A run that hangs is
+    killed after `timeout` seconds and repeated once."""
     nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
-    binary = oracle.REF_BIN if b == 4 else oracle.REF_BIN16
-    out = tempfile.mkdtemp(prefix="kmdiff_ref_out_", dir=os.environ.get("KMD_TMP", "/tmp"))
-    opt = os.path.join(run_dir, "kmdiff-count.opt")
-    if os.path.exists(opt):
-        os.remove(opt)   # reference quirk: matrix mode truncates it and the next run then fails
-    cmd = [binary, "diff", "--km-run", run_dir, "-1", str(nc), "-2", str(nk), "-o", out, "-t", str(threads),
-           "-c", corr, "-s", str(SIGNIFICANCE), "-u", str(CUTOFF)] + list(pop_args)
-    t0 = time.perf_counter()
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    dt = time.perf_counter() - t0
-    shutil.rmtree(out, ignore_errors=True)
-    if r.returncode != 0 or "[error]" in r.stderr:
-        raise RuntimeError(f"reference kmdiff failed: {r.stderr[-500:]}")
-    return dt
+    ref4, ref2, _ = ref_binaries()
+    binary = ref4 if b == 4 else ref2
+    cmd_tail = ["-t", str(threads), "-c", corr, "-s", str(SIGNIFICANCE), "-u", str(CUTOFF)] + list(pop_args)
+    last_err = ""
+    for _attempt in range(2):
+        out = tempfile.mkdtemp(prefix="kmdiff_ref_out_", dir=scratch_dir())
+        opt = os.path.join(run_dir, "kmdiff-count.opt")
+        if os.path.exists(opt) and not cfg_name.endswith("m"):
+            os.remove(opt)   # reference quirk: matrix mode truncates it and the next run then fails
+        cmd = [binary, "diff", "--km-run", run_dir, "-1", str(nc), "-2", str(nk), "-o", out] + cmd_tail
+        t0 = time.perf_counter()
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        except subprocess.TimeoutExpired:
+            REF_HUNG[0] += 1
+            shutil.rmtree(out, ignore_errors=True)
+            last_err = f"timed out after {timeout:.0f} s"
+            continue
+        dt = time.perf_counter() - t0
+        if r.returncode != 0 or "[error]" in r.stderr:
+            shutil.rmtree(out, ignore_errors=True)
+            raise RuntimeError(f"reference kmdiff failed: {r.stderr[-500:]}")
+        if keep_out:
+            return dt, out
+        shutil.rmtree(out, ignore_errors=True)
+        return dt, None
+    raise RuntimeError(f"reference kmdiff hung twice ({last_err})")
 
 
 def reference_sample_rows(cfg_name: str, cores: int) -> int:
     nc, nk, k, b, rows, _ = CONFIGS[cfg_name]
-    # ~3 M rows/s/core at N=20 (SURVEY.md §6), scaling down with the row width; aim at ~5 s per run
+    # ~3 M rows/s/core at N=20 (SURVEY.md §6), scaling down with the row width; aim at a few seconds per run
     per_core = int(3_000_000 * 20 / (nc + nk))
     return int(min(rows, 32_000_000, max(200_000, per_core * min(cores, 64) * 2)))
 
@@ -162,43 +229,52 @@ def bench_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg_name = args.config
+    cfg_name = args.config or HEADLINE
     nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
-    base = {"metric": "kmer_rows_tested_per_sec", "unit": "rows/s", "impl": "reference", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
-    import oracle
-    binary = oracle.REF_BIN if b == 4 else oracle.REF_BIN16
+    ref4, ref2, _ = ref_binaries()
+    binary = ref4 if b == 4 else ref2
     if not os.path.exists(binary):
         print(json.dumps({"impl": "reference", "unavailable": f"{binary} not built (make -C oracle refbin)"}))
         return
     cores = os.cpu_count() or 1
     sample = reference_sample_rows(cfg_name, cores)
     parts = max(cores, 8)
-    run_dir, R = make_reference_run_dir(cfg_name, sample, parts)
+    run_dir = make_run_dir(cfg_name, sample, parts)
     try:
         for _ in range(args.warmup):
             run_reference_once(run_dir, cfg_name, cores)
-        t = [run_reference_once(run_dir, cfg_name, cores) for _ in range(args.steps)]
+        t = [run_reference_once(run_dir, cfg_name, cores)[0] for _ in range(args.steps)]
     finally:
         shutil.rmtree(run_dir, ignore_errors=True)
     total = sum(t)
     value = sample * args.steps / total
-    line = dict(base)
-    line.update({
-        "value": value, "ms_per_step": 1e3 * total / args.steps,
-        "config": {"workload": f"{cfg_name}: synthetic {nc}+{nk} samples, k={k}, {b}-byte counts, {corr}",
-                   "rows_per_step": sample, "partitions": parts, "row_bytes": R,
-                   "note": "reference `kmdiff diff` binary (file read + LRT + correction + FASTA) on a "
-                           "bounded prefix of the workload's synthetic matrix, " +
+    line = {
+        "metric": "kmer_rows_tested_per_sec", "value": value, "unit": "rows/s", "impl": "reference", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg_name), "rows_per_step": sample, "partitions": parts,
+                   "row_bytes": row_bytes(cfg_name), "significance": SIGNIFICANCE, "cutoff": CUTOFF, "hung": REF_HUNG[0],
+                   "note": "the unmodified reference `kmdiff diff` binary (file read + LRT + correction + FASTA) on a "
+                           "bounded prefix of the workload's synthetic matrix in " + scratch_dir() + ", " +
                            ("uncompressed per-sample count files merged by km::KmerMerger" if cfg_name.endswith("m")
-                            else "uncompressed matrices")},
+                            else "uncompressed matrices") + "; the run directory is written by a dev-synth subprocess "
+                           "before anything is timed"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "reference",
                          "sample": f"{sample} rows in {parts} partitions per step"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    })
+    }
     print(json.dumps(line))
+
+
+def fasta_kmers(path: str):
+    """sequence lines of a reference FASTA file as a set of strings"""
+    out = set()
+    with open(path) as f:
+        for line in f:
+            if not line.startswith(">"):
+                out.add(line.strip())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -206,10 +282,13 @@ def bench_reference(args) -> None:
 # ------------------------------------------------------------------------------------------------------
 
 def bench_merge(args) -> None:
+    import ctypes
+
     import numpy as np
     import torch
 
     import kmdiff_b200 as K
+    from kmdiff_b200 import _lib
     from kmdiff_b200 import kmtricks_io as kio
 
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
@@ -221,14 +300,13 @@ def bench_merge(args) -> None:
     if args.rows:
         rows = args.rows
     n = nc + nk
-    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=rows, seed=42)
+    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=CONFIGS[cfg_name][4], seed=SEED, enriched_ppm=ENRICHED_PPM)
     totals = spec.totals()
     kw, rec = spec.kmer_words, 8 * spec.kmer_words + b
     # the host program's reader state, prepared once: every sample's records of a k-mer range per merge call
     # The streams live in pinned host memory, like the reader buffers of `kmdiff-b200 diff`.
-    import ctypes
-    from kmdiff_b200 import _lib
     L = _lib.load()
+    L.kmd_bind_host_thread(0)
     chunk_rows = max(1, min(rows, (24 << 20) // n))
     chunks, n_records, pinned = [], 0, []
     for lo in range(0, rows, chunk_rows):
@@ -294,18 +372,17 @@ def bench_merge(args) -> None:
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         try:
-            if reference_available():
-                sample = min(rows, reference_sample_rows("c2", cores) // 4)
-                parts = max(cores, 8)
-                run_dir, _ = make_reference_run_dir(cfg_name, sample, parts)
-                try:
-                    run_reference_once(run_dir, cfg_name, cores)
-                    dtc = run_reference_once(run_dir, cfg_name, cores)
-                finally:
-                    shutil.rmtree(run_dir, ignore_errors=True)
-                cpu = {"value": sample / dtc, "unit": "rows/s", "cores": cores, "kind": "reference",
-                       "sample": f"`kmdiff diff -t {cores}` (oracle/_ref/kmdiff, km::KmerMerger path) on the first {sample} "
-                                 f"rows as {parts} partitions x {n} uncompressed .kmer files, {dtc:.2f} s"}
+            sample = min(rows, reference_sample_rows("c2", cores) // 4)
+            parts = max(cores, 8)
+            run_dir = make_run_dir(cfg_name, sample, parts)
+            try:
+                run_reference_once(run_dir, cfg_name, cores)
+                dtc, _ = run_reference_once(run_dir, cfg_name, cores)
+            finally:
+                shutil.rmtree(run_dir, ignore_errors=True)
+            cpu = {"value": sample / dtc, "unit": "rows/s", "cores": cores, "kind": "reference",
+                   "sample": f"`kmdiff diff -t {cores}` (oracle/_ref/kmdiff, km::KmerMerger path) on the first {sample} "
+                             f"rows as {parts} partitions x {n} uncompressed .kmer files, {dtc:.2f} s"}
         except Exception as e:
             cpu = {"value": None, "unit": "rows/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
 
@@ -313,8 +390,7 @@ def bench_merge(args) -> None:
         "metric": "kmer_rows_tested_per_sec", "value": value, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{cfg_name}: synthetic {nc}+{nk} samples, k={k}, {b}-byte counts as per-sample sorted count "
-                               f"streams (no matrices), device N-way merge + Poisson LRT + {corr}",
+        "config": {"workload": workload_name(cfg_name),
                    "rows_per_gpu": rows, "records_per_gpu": n_records, "record_bytes": rec, "row_bytes": spec.row_bytes,
                    "merge_calls_per_step": len(chunks), "merge_passes": n_passes[0],
                    "l2": f"every merge call works on {n_records // max(1, len(chunks)) * 32 >> 20} MiB of (key, payload) arrays, above the 126 MB L2",
@@ -342,60 +418,119 @@ def bench_merge(args) -> None:
 # our arm
 # ------------------------------------------------------------------------------------------------------
 
-def bench_b200(args) -> None:
+class Env:
+    """process-wide state of our arm: rank, device, NCCL, stdout kept clean for the one JSON line"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — kmdiff_b200 has no CPU fallback")
+        from kmdiff_b200 import _lib
+        self.L = _lib.load()
+        # CPU affinity + memory policy of this rank's GPU, before anything is pinned
+        self.L.kmd_bind_host_thread(self.local_rank)
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.saved_stdout = None
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            # NCCL prints its version banner on stdout: keep fd 1 on stderr until the one JSON line is due
+            sys.stdout.flush()
+            self.saved_stdout = os.dup(1)
+            os.dup2(2, 1)
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, xs) -> list[int]:
+        t = self.torch.tensor(list(xs), dtype=self.torch.int64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [int(v) for v in t.tolist()]
+
+    def emit(self, line: dict):
+        if self.rank == 0:
+            if self.saved_stdout is not None:
+                sys.stdout.flush()
+                os.dup2(self.saved_stdout, 1)
+            print(json.dumps(line), flush=True)
+            if self.saved_stdout is not None:
+                os.dup2(2, 1)
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def h2d_ceiling_gbs(env: Env, nbytes: int = 1 << 30, reps: int = 4) -> float:
+    """plain cudaMemcpyAsync from pinned memory, all ranks at once: what the PCIe path gives this rank's GPU"""
+    torch = env.torch
+    src = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(nbytes, dtype=torch.uint8, device=env.dev)
+    dst.copy_(src, non_blocking=True)
+    env.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = env.max_over_ranks(e0.elapsed_time(e1))
+    del src, dst
+    return nbytes * reps / (ms * 1e-3) / 1e9
+
+
+def measure(env: Env, args, cfg_name: str, steps: int, warmup: int, full: bool) -> dict:
+    """one workload on this rank's GPU -> the measurement block (rank 0 returns the aggregate).  full = headline:
+    also the CPU baseline + prefix parity and the CLI timing (N = 1, rank 0)."""
+    import ctypes
+
     import numpy as np
-    import torch
-    import torch.distributed as dist
 
     import kmdiff_b200 as K
-    from kmdiff_b200 import _lib
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — kmdiff_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    saved_stdout = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner on stdout: keep fd 1 on stderr until the one JSON line is due
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        dist.init_process_group("nccl", device_id=dev)
-
-    cfg_name = args.config
+    from kmdiff_b200.distributed import DeviceExchange, correct_sharded
+    torch = env.torch
+    rank, world, dev = env.rank, env.world, env.dev
     nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
-    if args.rows:
+    if args.rows and full:
         rows = args.rows
     corr_kind = K.correction_from_str(corr)
-    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=rows * world, seed=42)
+    spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=CONFIGS[cfg_name][4] * max(world, 1), seed=SEED,
+                       enriched_ppm=ENRICHED_PPM)
     R = spec.row_bytes
     totals = spec.totals()
     thr = SIGNIFICANCE / CUTOFF
 
     stream = torch.cuda.current_stream()
     ctx = K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), kmer_size=k, count_bytes=b,
-                        threshold=thr, device=local_rank, max_survivors=max(1 << 22, rows // 200))
+                        threshold=thr, device=env.local_rank, max_survivors=max(1 << 22, rows // 200))
     ctx.set_stream(stream.cuda_stream)
     popstrat = cfg_name == "c4"
     pop_ms = {"gram_kernel": [], "gram_call": [], "pca_host": [], "glm": [], "sampled": 0, "used": 0}
     if popstrat:
         if world > 1:
             raise SystemExit("bench.py: c4 is a single-GPU bench line (the multi-GPU Gram sum is covered by tests)")
-        ctx.popstrat_enable(C4_SAMPLED / rows, seed=42, is_diploid=True, n_pc=C4_NPC, max_sampled=2 * C4_SAMPLED)
+        ctx.popstrat_enable(C4_SAMPLED / rows, seed=SEED, is_diploid=True, n_pc=C4_NPC, max_sampled=2 * C4_SAMPLED)
 
     # ---- resident workload: this rank's rows, generated on the device (seeded, counter-based) ----
     data = torch.empty(rows * R, dtype=torch.uint8, device=dev)
-    spec.rows_device(data.data_ptr(), rows, row_base=rank * rows, device=local_rank, stream=stream.cuda_stream)
+    spec.rows_device(data.data_ptr(), rows, row_base=rank * rows, device=env.local_rank, stream=stream.cuda_stream)
     torch.cuda.synchronize()
-
-    exchange = None
-    if world > 1:
-        from kmdiff_b200.distributed import DeviceExchange
-        exchange = DeviceExchange(dev)
+    exchange = DeviceExchange(dev)
 
     def pop_stage(timed: bool):
         # do_pop (cmd/diff.hpp:168-224): Gram matrix of the sampled k-mers -> PCs -> null model -> GLM per survivor
@@ -420,56 +555,60 @@ def bench_b200(args) -> None:
     last_scan_ms = [0.0]
 
     def step():
+        """-> (m, (kept control, kept case) on this rank); ONE host synchronisation (exchange_result)"""
         ctx.reset()
         ctx.scan_device(data.data_ptr(), rows, row_base=rank * rows, partition=rank)
-        c = ctx.counters()
-        total_rows = c.rows
-        last_scan_ms[0] = ctx.scan_kernel_ms()     # before the Gram kernel reuses the context's event pair
         if popstrat:
+            ctx.sync()
+            last_scan_ms[0] = ctx.scan_kernel_ms()     # before the Gram kernel reuses the context's event pair
             pop_stage(True)
-        if world > 1:
-            # m of the correctors = rows of all ranks; BH/Holm: one ascending walk over all ranks' survivors,
-            # exchanged and ranked on the devices (kmdiff_b200.distributed.DeviceExchange)
-            _, kept = exchange.correct(ctx, corr_kind, SIGNIFICANCE)
-            return kept, c
-        return ctx.correct(corr_kind, SIGNIFICANCE, total_rows), c
+        return exchange.correct(ctx, corr_kind, SIGNIFICANCE)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(3, args.warmup)):
-        res, c = step()
+    for _ in range(max(3, warmup)):
+        total_rows, kept = step()
     launches0 = ctx.launch_count()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(env.local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scan_ms = []
-    barrier()
+    env.barrier()
     ev0.record(stream)
-    for _ in range(args.steps):
-        res, c = step()
-        scan_ms.append(last_scan_ms[0])
+    for _ in range(steps):
+        total_rows, kept = step()
+        scan_ms.append(last_scan_ms[0] if popstrat else ctx.scan_kernel_ms())
     ev1.record(stream)
-    barrier()
+    env.barrier()
     clocks = sampler.stop()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    launches = (ctx.launch_count() - launches0) // args.steps
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = rows * world * args.steps / (elapsed_ms * 1e-3)
+    elapsed_ms = env.max_over_ranks(ev0.elapsed_time(ev1))
+    launches = (ctx.launch_count() - launches0) // steps
+    value = rows * world * steps / (elapsed_ms * 1e-3)
+    assert total_rows == rows * world, (total_rows, rows, world)
+    dec = exchange.last
+    c = ctx.counters()
+
+    # ---- decision check (outside the timed region): the same survivors, the walk on the host ----
+    check = None
+    if not popstrat:
+        sig_dev = ctx.significant()
+        total2, kept2 = correct_sharded(ctx, corr_kind, SIGNIFICANCE, dev)
+        sig_host = ctx.significant()
+        same = (total2 == total_rows and tuple(kept2) == tuple(kept) and len(sig_dev) == len(sig_host) == sum(kept)
+                and np.array_equal(sig_dev["row"], sig_host["row"]) and np.array_equal(sig_dev["p_value"], sig_host["p_value"]))
+        n_bad = env.sum_over_ranks([0 if same else 1])[0]
+        if n_bad:
+            raise SystemExit(f"bench.py: device-side exchange and host walk disagree on {n_bad} rank(s): "
+                             f"{(total_rows, kept)} vs {(total2, kept2)}")
+        check = {"host_walk_equal": True, "compared": "m, kept control/case per rank, kept rows and p-values per rank",
+                 "ranks": world}
+    g_ctl, g_case, g_surv, g_cand = env.sum_over_ranks([kept[0], kept[1], c.survivors, c.candidates])
 
     # ---- end to end through the C-ABI with host buffers ----
-    e2e_rows = min(rows, args.e2e_rows, (8 << 30) // R)      # at most 8 GiB of pinned host rows
-    L = _lib.load()
+    e2e_rows = min(rows, args.e2e_rows, (args.e2e_gib << 30) // R)
+    L = env.L
     hptr = L.kmd_host_alloc(e2e_rows * R)
     if not hptr:
         raise SystemExit("kmd_host_alloc failed")
-    import ctypes
     hbuf = np.ctypeslib.as_array(ctypes.cast(hptr, ctypes.POINTER(ctypes.c_uint8)), shape=(e2e_rows * R,))
     torch.cuda.synchronize()
     hbuf[:] = data[:e2e_rows * R].cpu().numpy()      # same rows as the resident workload's prefix
@@ -479,31 +618,24 @@ def bench_b200(args) -> None:
         nonlocal d2h
         ctx.reset()
         ctx.scan_host(hptr, e2e_rows, row_base=rank * rows, partition=rank)
-        cc = ctx.counters()
-        total = cc.rows * world
         if popstrat:
             pop_stage(False)
-        if world > 1:
-            _, r = exchange.correct(ctx, corr_kind, SIGNIFICANCE)      # same global decision as the resident step
-        else:
-            r = ctx.correct(corr_kind, SIGNIFICANCE, total)
+        _, r = exchange.correct(ctx, corr_kind, SIGNIFICANCE)      # same global decision procedure as the resident step
         sig = ctx.significant()
-        d2h = sig.nbytes + 48 * 3
+        d2h = sig.nbytes + 64 + 48
         return r, len(sig)
 
     for _ in range(2):
         e2e_step()
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         e2e_res, n_sig = e2e_step()
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_rows * world * args.e2e_steps / float(te.item())
+    e2e_s = env.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = e2e_rows * world * args.e2e_steps / e2e_s
     L.kmd_host_free(hptr)
+    ceiling = h2d_ceiling_gbs(env)
 
     # ---- roofline of the dominant kernel (lrt_scan) ----
     peak, peak_src = load_peaks()
@@ -524,76 +656,38 @@ def bench_b200(args) -> None:
         except Exception:
             pass
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    # ---- CPU baseline: the reference binary on a bounded prefix of the same matrix (N=1 only) ----
-    cpu = None
-    import oracle as _oracle_paths                      # paths of the reference binaries only
-    have_smartpca = os.path.exists(_oracle_paths.REF_SMARTPCA)
-    if world == 1 and not args.no_cpu_baseline and (not popstrat or have_smartpca):
-        cores = os.cpu_count() or 1
-        try:
-            if reference_available():
-                sample = reference_sample_rows(cfg_name, cores)
-                pop_args, what = (), "`kmdiff diff"
-                if popstrat:
-                    # the reference's whole --pop-correction pipeline (Sampler, HAWK smartpca, evec2pca.perl, GLM) with
-                    # the workload's sampling rate, on at most ~1 GB of rows
-                    sample = int(min(sample, (1 << 30) // R))
-                    pop_args = ("--pop-correction", "--kmer-pca", repr(C4_SAMPLED / rows), "--n-pc", str(C4_NPC), "--random-seed", "42")
-                    what = "`kmdiff diff --pop-correction` (+ oracle/_ref/smartpca)"
-                parts = max(cores, 8)
-                run_dir, _ = make_reference_run_dir(cfg_name, sample, parts)
-                try:
-                    run_reference_once(run_dir, cfg_name, cores, pop_args)           # warm the page cache
-                    dt = run_reference_once(run_dir, cfg_name, cores, pop_args)
-                finally:
-                    shutil.rmtree(run_dir, ignore_errors=True)
-                cpu = {"value": sample / dt, "unit": "rows/s", "cores": cores, "kind": "reference",
-                       "sample": f"{what} -t {cores}` (oracle/_ref/kmdiff) on the first {sample} rows of the "
-                                 f"workload, {parts} uncompressed partitions, {dt:.2f} s"}
-            else:
-                import oracle
-                sample = min(rows, 2_000_000)
-                hrows = data[:sample * R].cpu().numpy()
-                m = oracle.Model(nc, nk, totals)
-                t0 = time.perf_counter()
-                m.diff(hrows, spec.kmer_words, b, thr)
-                dt = time.perf_counter() - t0
-                cpu = {"value": sample / dt, "unit": "rows/s", "cores": 1, "kind": "port",
-                       "sample": f"oracle/kmd_oracle.c on the first {sample} rows, in memory, {dt:.2f} s"}
-        except Exception as e:  # the baseline must never take the bench line down
-            cpu = {"value": None, "unit": "rows/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
-
-    line = {
-        "metric": "kmer_rows_tested_per_sec", "value": value, "unit": "rows/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": elapsed_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    block = {
+        "value": value, "ms_per_step": elapsed_ms / steps,
         "config": {
-            "workload": f"{cfg_name}: synthetic {nc}+{nk} samples, k={k}, {b}-byte counts, Poisson LRT + {corr}",
+            "workload": workload_name(cfg_name),
             "rows_per_gpu": rows, "row_bytes": R, "bytes_per_gpu": rows * R, "significance": SIGNIFICANCE,
             "cutoff": CUTOFF, "partition_sharding": f"{world} ranks x {rows} rows, disjoint",
             "l2": "inputs (>= 13 GB per step) far exceed the 126 MB L2; no flush needed",
-            "survivors_per_gpu": int(c.survivors), "significant": [int(res[0]), int(res[1])],
-            "screen_candidates": int(c.candidates),
+            "correction_path": "kmdiff_b200.distributed.DeviceExchange (kmd_exchange_export -> NCCL all-gather -> "
+                               "kmd_exchange_correct -> kmd_exchange_result), one host sync per step",
+            "total_rows": int(total_rows), "survivors": g_surv, "screen_candidates": g_cand,
+            "significant": [g_ctl, g_case], "p_cut": float(dec.p_cut), "n_accepted": int(dec.n_accepted),
+            "exchange_slot_cap": exchange.cap, "exchange_retries_in_warmup": exchange.retries,
         },
+        "decision_check": check,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "kernel": "lrt_scan_kernel", "ms_per_launch": scan_avg_ms,
-                     "algorithmic_bytes_per_launch": rows * R, "peak_source": peak_src},
+                     "algorithmic_bytes_per_launch": rows * R, "peak_source": peak_src,
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "step_frac_of_nominal_8TBs": rows * R / (elapsed_ms / steps * 1e-3) / 8e12},
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": e2e_rows * R,
                 "d2h_bytes_per_step": int(d2h), "rows_per_step": e2e_rows, "steps": args.e2e_steps,
-                "api": ("kmd_scan_host + kmd_popstrat_{gram,init,apply} + kmd_correct + kmd_significant" if popstrat else
-                        "kmd_scan_host + kmd_correct + kmd_significant") + " (pinned host buffer)"},
+                "h2d_gbs_per_gpu": e2e_rows * R * args.e2e_steps / e2e_s / 1e9,
+                "h2d_ceiling_gbs_per_gpu": ceiling,
+                "ceiling_note": "plain cudaMemcpyAsync from a pinned 1 GiB buffer, all ranks at once, same run",
+                "api": ("kmd_scan_host + kmd_popstrat_{gram,init,apply}" if popstrat else "kmd_scan_host") +
+                       " + kmd_exchange_* + kmd_significant (pinned host buffer, records read back)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
     if popstrat:
         n = nc + nk
-        k = args.steps
-        avg = lambda v: sum(v[-k:]) / max(1, len(v[-k:]))
+        avg = lambda v: sum(v[-steps:]) / max(1, len(v[-steps:]))
         gram_ms = avg(pop_ms["gram_kernel"])
         used = pop_ms["used"]
         ops = 2.0 * n * n * used                       # algorithmic int8 multiply-adds x2 of X X^T
@@ -604,7 +698,7 @@ def bench_b200(args) -> None:
         except Exception:
             pass
         int8_peak = 2.0 * bf16 if bf16 else 4500.0
-        line["popstrat"] = {
+        block["popstrat"] = {
             "n_pc": C4_NPC, "sampled_kmers_used": used, "survivors_fitted": int(c.survivors),
             "gram": {"bound": "tensor", "kernel": "grm_umma_kernel", "ms_per_launch": gram_ms,
                      "achieved": ops / (gram_ms * 1e-3) / 1e12 if gram_ms else None, "peak": int8_peak, "unit": "TOP/s",
@@ -616,15 +710,155 @@ def bench_b200(args) -> None:
             "glm": {"kernel": "irls_kernel", "ms": avg(pop_ms["glm"]),
                     "kmers_per_s": int(c.survivors) / (avg(pop_ms["glm"]) * 1e-3) if pop_ms["glm"] else None},
         }
-    if cpu is not None:
-        line["cpu_baseline"] = cpu
-    if saved_stdout is not None:
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        os.dup2(2, 1)
-        dist.destroy_process_group()
+
+    # ---- CPU baseline: the reference binary on a bounded prefix of the same matrix, and parity on that prefix ----
+    if full and world == 1 and rank == 0 and not args.no_cpu_baseline:
+        block.update(cpu_baseline_and_parity(env, args, cfg_name, ctx, spec, exchange, popstrat))
+
+    ctx.close()
+    del data
+    torch.cuda.empty_cache()
+    return block
+
+
+def cpu_baseline_and_parity(env: Env, args, cfg_name: str, ctx, spec, exchange, popstrat: bool) -> dict:
+    import numpy as np
+
+    import kmdiff_b200 as K
+    nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
+    R = spec.row_bytes
+    cores = os.cpu_count() or 1
+    out = {}
+    ref4, ref2, smartpca = ref_binaries()
+    binary = ref4 if b == 4 else ref2
+    try:
+        if os.path.exists(binary) and (not popstrat or os.path.exists(smartpca)):
+            sample = reference_sample_rows(cfg_name, cores)
+            pop_args, what = (), "`kmdiff diff"
+            if popstrat:
+                # the reference's whole --pop-correction pipeline (Sampler, HAWK smartpca, evec2pca.perl, GLM) with
+                # the workload's sampling rate, on at most ~1 GB of rows
+                sample = int(min(sample, (1 << 30) // R))
+                pop_args = ("--pop-correction", "--kmer-pca", repr(C4_SAMPLED / rows), "--n-pc", str(C4_NPC), "--random-seed", str(SEED))
+                what = "`kmdiff diff --pop-correction` (+ oracle/_ref/smartpca)"
+            parts = max(cores, 8)
+            run_dir = make_run_dir(cfg_name, sample, parts)
+            ref_out = None
+            try:
+                run_reference_once(run_dir, cfg_name, cores, pop_args)           # warm the page cache
+                dt, ref_out = run_reference_once(run_dir, cfg_name, cores, pop_args, keep_out=True)
+                out["cpu_baseline"] = {
+                    "value": sample / dt, "unit": "rows/s", "cores": cores, "kind": "reference", "hung": REF_HUNG[0],
+                    "sample": f"{what} -t {cores}` (oracle/_ref/kmdiff) on the first {sample} rows of the workload, "
+                              f"{parts} uncompressed partitions in {scratch_dir()}, {dt:.2f} s"}
+                if not popstrat:
+                    # parity on the prefix: the reference's FASTA k-mer set == ours (same rows, same m, same corrector)
+                    ref_set = fasta_kmers(os.path.join(ref_out, "control_kmers.fasta")) | fasta_kmers(os.path.join(ref_out, "case_kmers.fasta"))
+                    hrows = spec.rows_host(sample)
+                    ctx.reset()
+                    ctx.scan_host(hrows, row_base=0, partition=0)
+                    exchange.correct(ctx, K.correction_from_str(corr), SIGNIFICANCE)      # world == 1: m = the prefix's rows
+                    sig = ctx.significant()
+                    ours = {K.kmer_to_string(r["kmer"][:spec.kmer_words], k) for r in sig}
+                    if b != 4 or k > 32:
+                        # the reference truncates k > 32 k-mers to 64 bits in its spill files (SURVEY.md §8 hazard 1)
+                        ours = {s[-32:] for s in ours}
+                        ref_set = {s[-32:] for s in ref_set}
+                    out["parity_on_prefix"] = bool(ours == ref_set)
+                    out["parity_detail"] = {"rows": sample, "reference_significant": len(ref_set), "ours_significant": len(ours),
+                                            "only_reference": len(ref_set - ours), "only_ours": len(ours - ref_set)}
+            finally:
+                shutil.rmtree(run_dir, ignore_errors=True)
+                if ref_out:
+                    shutil.rmtree(ref_out, ignore_errors=True)
+        else:
+            import oracle
+            sample = min(rows, 2_000_000)
+            hrows = spec.rows_host(sample)
+            m = oracle.Model(nc, nk, spec.totals())
+            t0 = time.perf_counter()
+            m.diff(hrows, spec.kmer_words, b, SIGNIFICANCE / CUTOFF)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": sample / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+                                   "sample": f"oracle/kmd_oracle.c on the first {sample} rows, in memory, {dt:.2f} s"}
+    except Exception as e:  # the baseline must never take the bench line down
+        out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+    if not popstrat and not args.no_cli:
+        try:
+            out["e2e_cli"] = cli_end_to_end(cfg_name, args.cli_gib, cores)
+        except Exception as e:
+            out["e2e_cli"] = {"failed": str(e)}
+    return out
+
+
+def cli_end_to_end(cfg_name: str, gib: float, cores: int) -> dict:
+    """file -> FASTA: `kmdiff-b200 diff` vs the reference binary on the same run directory (raw matrices, page
+    cache / tmpfs warm for both; best of 2 runs each).  Wall clock of the whole process, start-up included."""
+    nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
+    R = row_bytes(cfg_name)
+    n_rows = int(min(rows, gib * (1 << 30) // R))
+    parts = max(cores, 8) * 2
+    run_dir = make_run_dir(cfg_name, n_rows, parts)
+    res = {"rows": n_rows, "bytes": n_rows * R, "partitions": parts, "layout": "uncompressed matrices", "dir": scratch_dir(),
+           "host_threads": cores}
+    try:
+        common = ["diff", "--km-run", run_dir, "-1", str(nc), "-2", str(nk), "-t", str(cores), "-c", corr,
+                  "-s", str(SIGNIFICANCE), "-u", str(CUTOFF)]
+        seqs = {}
+        for name, binary, extra in (("reference", ref_binaries()[0 if b == 4 else 1], []),
+                                    ("kmdiff_b200", CLI, ["--gpus", "1", "--count-bytes", str(b)])):
+            if not os.path.exists(binary):
+                continue
+            best = None
+            for i in range(2):
+                opt = os.path.join(run_dir, "kmdiff-count.opt")
+                if os.path.exists(opt):
+                    os.remove(opt)
+                out = tempfile.mkdtemp(prefix="kmdiff_cli_out_", dir=scratch_dir())
+                t0 = time.perf_counter()
+                r = subprocess.run([binary] + common + extra + ["-o", out], capture_output=True, text=True, timeout=900)
+                dt = time.perf_counter() - t0
+                if r.returncode != 0 or "[error]" in r.stderr:
+                    shutil.rmtree(out, ignore_errors=True)
+                    raise RuntimeError(f"{name} failed: {r.stderr[-300:]}")
+                if i == 0:
+                    seqs[name] = fasta_kmers(os.path.join(out, "control_kmers.fasta")) | fasta_kmers(os.path.join(out, "case_kmers.fasta"))
+                shutil.rmtree(out, ignore_errors=True)
+                best = dt if best is None else min(best, dt)
+            res[name + "_s"] = best
+            res[name + "_rows_per_s"] = n_rows / best
+            res[name + "_file_gbs"] = n_rows * R / best / 1e9
+        if "reference_s" in res and "kmdiff_b200_s" in res:
+            res["speedup"] = res["reference_s"] / res["kmdiff_b200_s"]
+            res["same_significant_set"] = bool(seqs["reference"] == seqs["kmdiff_b200"])
+            res["significant"] = len(seqs["kmdiff_b200"])
+    finally:
+        shutil.rmtree(run_dir, ignore_errors=True)
+    return res
+
+
+def bench_b200(args) -> None:
+    env = Env()
+    cfg_name = args.config or HEADLINE
+    head = measure(env, args, cfg_name, args.steps, args.warmup, full=True)
+    secondary = None
+    if not args.config and not args.no_secondary and SECONDARY != cfg_name:
+        secondary = measure(env, args, SECONDARY, args.steps, args.warmup, full=False)
+    line = {
+        "metric": "kmer_rows_tested_per_sec", "value": head["value"], "unit": "rows/s", "n_gpus": env.world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": head["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+    }
+    for key in ("config", "decision_check", "roofline", "e2e", "e2e_cli", "gpu_launches", "clocks", "popstrat", "cpu_baseline",
+                "parity_on_prefix", "parity_detail"):
+        if key in head and head[key] is not None:
+            line[key] = head[key]
+    if secondary is not None:
+        line[SECONDARY] = {key: secondary[key] for key in ("value", "ms_per_step", "config", "decision_check", "roofline", "e2e",
+                                                           "gpu_launches", "clocks") if key in secondary}
+        line[SECONDARY]["unit"] = "rows/s"
+    env.emit(line)
+    env.close()
 
 
 def main():
@@ -633,11 +867,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--config", default="", choices=[""] + list(CONFIGS),
+                    help=f"workload (default: {HEADLINE} as the headline, plus {SECONDARY} under its own key)")
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: the config's)")
     ap.add_argument("--e2e-rows", type=int, default=1 << 25)
+    ap.add_argument("--e2e-gib", type=int, default=8, help="at most this many GiB of pinned host rows in the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cli-gib", type=float, default=16.0, help="size of the run directory of the e2e_cli leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cli", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         bench_reference(args)

@@ -125,6 +125,14 @@ int kmd_scan_device(kmd_context* ctx, const void* d_rows, uint64_t n_rows, uint6
  * has been enqueued and the host buffer is no longer needed. */
 int kmd_scan_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_t row_base,
                   uint32_t partition);
+/* The same without waiting for the copy: returns as soon as the copies and scans are enqueued.  h_rows (pinned) must
+ * stay untouched until kmd_host_wait(ctx, *ticket) returns — the only entry point that may be called from a thread
+ * other than the one driving ctx (reader threads recycling their staging buffers while the feeder keeps enqueuing;
+ * the host-side replacement of the one-row-at-a-time istream reads of matrix_proxy::merge, merge.hpp:194-203).
+ * At most 255 tickets may be outstanding. */
+int kmd_scan_host_async(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_t row_base,
+                        uint32_t partition, uint64_t* ticket);
+int kmd_host_wait(kmd_context* ctx, uint64_t ticket);
 int kmd_counters_get(kmd_context* ctx, kmd_counters* out);
 /* prefilter survivors ordered by row (what the FileAccumulators hold, accumulator.hpp:156-285) */
 int kmd_survivors(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n);
@@ -316,6 +324,13 @@ void kmd_kmer_to_string(const uint64_t* words, uint32_t kmer_words, uint32_t k, 
 size_t kmd_format_fasta(uint64_t index, const kmd_survivor* s, uint32_t kmer_words, uint32_t k,
                         char* out, size_t cap);
 
+/* Bind the calling host thread to `device`: makes it the thread's current CUDA device and — where sysfs exposes the
+ * GPU's NUMA node — restricts the thread to that node's CPUs and prefers its memory, so that staging buffers pinned
+ * by this thread (kmd_host_alloc) and the copies into them stay next to the GPU's PCIe root.  A no-op on single-node
+ * hosts.  Call before kmd_host_alloc; one process per GPU calls it once at start-up. */
+int kmd_bind_host_thread(int device);
+/* create the device's primary CUDA context now (hosts overlap this ~0.5 s with their own start-up work) */
+int kmd_warmup(int device);
 /* pinned host memory for kmd_scan_host / kmd_model_rows_host */
 void* kmd_host_alloc(size_t bytes);
 void kmd_host_free(void* p);

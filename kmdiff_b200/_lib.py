@@ -28,7 +28,7 @@ SYMBOLS = [
     "kmd_popstrat_gram_ms", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
     "kmd_survivor_counts", "kmd_smartpca_normalize", "kmd_sym_eig", "kmd_smartpca_pcs",
     "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_rows_host", "kmd_merge_ms", "kmd_survivor_pvalues_device", "kmd_first_reject_device",
-    "kmd_get_stream", "kmd_exchange_export", "kmd_exchange_correct", "kmd_exchange_result",
+    "kmd_scan_host_async", "kmd_host_wait", "kmd_bind_host_thread", "kmd_warmup", "kmd_get_stream", "kmd_exchange_export", "kmd_exchange_correct", "kmd_exchange_result",
 ]
 
 EXCHANGE_HEADER = 8
@@ -119,6 +119,8 @@ def load() -> C.CDLL:
     L.kmd_keep_below.argtypes = [vp, d, pu64, pu64]
     L.kmd_survivor_pvalues_device.argtypes = [vp, vp, u64, pu64]
     L.kmd_first_reject_device.argtypes = [vp, vp, u64, C.c_int, d, u64, pu64, C.POINTER(d)]
+    L.kmd_scan_host_async.argtypes = [vp, vp, u64, u64, u32, pu64]
+    L.kmd_host_wait.argtypes = [vp, u64]
     L.kmd_get_stream.argtypes = [vp]
     L.kmd_get_stream.restype = vp
     L.kmd_exchange_export.argtypes = [vp, vp, u64]
@@ -135,6 +137,8 @@ def load() -> C.CDLL:
     L.kmd_kmer_to_string.restype = None
     L.kmd_format_fasta.argtypes = [u64, vp, u32, u32, C.c_char_p, C.c_size_t]
     L.kmd_format_fasta.restype = C.c_size_t
+    L.kmd_bind_host_thread.argtypes = [C.c_int]
+    L.kmd_warmup.argtypes = [C.c_int]
     L.kmd_host_alloc.argtypes = [C.c_size_t]
     L.kmd_host_alloc.restype = vp
     L.kmd_host_free.argtypes = [vp]

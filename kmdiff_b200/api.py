@@ -209,6 +209,17 @@ class DiffContext:
             ptr = a.ctypes.data
         self._ck(self._L.kmd_scan_host(self._h, C.c_void_p(ptr), n_rows, row_base, partition))
 
+    def scan_host_async(self, host_ptr: int, n_rows: int, row_base: int = 0, partition: int = 0) -> int:
+        """kmd_scan_host without waiting for the copies; host_ptr (pinned) stays untouched until host_wait(ticket)"""
+        t = C.c_uint64()
+        self._ck(self._L.kmd_scan_host_async(self._h, C.c_void_p(host_ptr), n_rows, row_base, partition, C.byref(t)))
+        return t.value
+
+    def host_wait(self, ticket: int) -> None:
+        rc = self._L.kmd_host_wait(self._h, int(ticket))
+        if rc:
+            raise KmdError(rc, "kmd_host_wait failed")
+
     # -- per-sample count files: km::KmerMerger (kmtricks/merge.hpp:102-361) --
     def _merge_args(self, streams, ab_min):
         n = self.nb_samples

@@ -16,6 +16,10 @@
 #include <thread>
 #include <vector>
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <cuda_runtime.h>
 
 #include "kmd_eig.hpp"
@@ -192,6 +196,11 @@ struct kmd_context
   size_t stage_bytes = 0;
   cudaEvent_t ev_copy[2] = {nullptr, nullptr};
   cudaEvent_t ev_scan[2] = {nullptr, nullptr};
+  int stage_next = 0;             // staging buffer the next chunk goes to (persists across calls: copy i+1 overlaps scan i)
+  // kmd_scan_host_async tickets: event t % kTicketRing is recorded on the copy stream after the last H2D copy of ticket t
+  static constexpr uint64_t kTicketRing = 256;
+  cudaEvent_t ev_ticket[kTicketRing] = {};
+  uint64_t next_ticket = 1;
 
   PopState pop;
   MergeState mrg;
@@ -1006,6 +1015,7 @@ void kmd_destroy(kmd_context* ctx)
     if (ctx->ev_scan[b]) cudaEventDestroy(ctx->ev_scan[b]);
   }
   cudaFree(ctx->d_hist); cudaFree(ctx->d_p_sorted); cudaFree(ctx->d_out); cudaFree(ctx->d_order);
+  for (cudaEvent_t e : ctx->ev_ticket) if (e) cudaEventDestroy(e);
   pop_free(ctx);
   merge_free(ctx);
   exchange_free(ctx);
@@ -1082,16 +1092,19 @@ int kmd_create(const kmd_config* cfg, kmd_context** out)
   ctx->lr_cut = lr_cut_for(cfg->threshold);
 
   KMD_TRY(make_plan(ctx));
-  if (!ctx->direct)
+  // The attribute belongs to the function and the device, not to a context: always raise it to the largest value any
+  // context can need (the 200 KiB ring budget + barriers; 12288 table entries), so that contexts with different
+  // row shapes or table sizes on one device do not lower each other's limit.
   {
-    KMD_CUDA_C(cudaFuncSetAttribute(lrt_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->scan_smem)));
-    KMD_CUDA_C(cudaFuncSetAttribute(lrt_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->scan_smem)));
-    KMD_CUDA_C(cudaFuncSetAttribute(lrt_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->scan_smem)));
+    const int scan_smem_max = static_cast<int>(kBarrierBytes + 200 * 1024 + 128);
+    KMD_CUDA_C(cudaFuncSetAttribute(lrt_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem_max));
+    KMD_CUDA_C(cudaFuncSetAttribute(lrt_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem_max));
+    KMD_CUDA_C(cudaFuncSetAttribute(lrt_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, scan_smem_max));
+    const int lf_smem_bytes = 12288 * static_cast<int>(sizeof(double));
+    KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
+    KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
+    KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
   }
-  const int lf_smem_bytes = static_cast<int>(std::min<uint64_t>(cfg->lf_size, 12288) * sizeof(double));
-  KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
-  KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
-  KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
 
   // buffers
   const size_t cap = ctx->cap;
@@ -1162,21 +1175,21 @@ int kmd_scan_device(kmd_context* ctx, const void* d_rows, uint64_t n_rows, uint6
   return scan_device_impl(ctx, static_cast<const uint8_t*>(d_rows), n_rows, row_base, partition);
 }
 
-int kmd_scan_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_t row_base, uint32_t partition)
+// chunked H2D copies on the copy stream, each followed by the scan of the chunk on the context's stream; the two
+// staging buffers alternate across calls, so the copy of chunk i+1 overlaps the scan of chunk i whatever the
+// size of the caller's buffers
+static int scan_host_enqueue(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_t row_base, uint32_t partition)
 {
-  if (!ctx) return KMD_ERR_ARG;
-  if (n_rows == 0) return KMD_OK;
-  if (!h_rows) return fail(ctx, KMD_ERR_ARG, "null row pointer");
-  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
   int rc = ensure_stage(ctx);
   if (rc) return rc;
   const uint64_t R = ctx->plan.row_bytes;
   const uint64_t chunk_rows = ctx->stage_bytes / R;
   const uint8_t* src = static_cast<const uint8_t*>(h_rows);
   uint64_t done = 0;
-  for (uint64_t c = 0; done < n_rows; c++)
+  while (done < n_rows)
   {
-    const int b = static_cast<int>(c & 1);
+    const int b = ctx->stage_next;
+    ctx->stage_next ^= 1;
     const uint64_t n = std::min(chunk_rows, n_rows - done);
     // the scan that last read this staging buffer (possibly enqueued by an earlier call) must be done;
     // waiting on a never-recorded event is a no-op
@@ -1188,9 +1201,53 @@ int kmd_scan_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_
     KMD_CUDA(ctx, cudaEventRecord(ctx->ev_scan[b], ctx->stream));
     done += n;
   }
+  return KMD_OK;
+}
+
+int kmd_scan_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_t row_base, uint32_t partition)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (n_rows == 0) return KMD_OK;
+  if (!h_rows) return fail(ctx, KMD_ERR_ARG, "null row pointer");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = scan_host_enqueue(ctx, h_rows, n_rows, row_base, partition);
+  if (rc) return rc;
   // the caller may reuse h_rows as soon as we return
   KMD_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   return KMD_OK;
+}
+
+int kmd_scan_host_async(kmd_context* ctx, const void* h_rows, uint64_t n_rows, uint64_t row_base, uint32_t partition,
+                        uint64_t* ticket)
+{
+  if (!ctx || !ticket) return KMD_ERR_ARG;
+  *ticket = 0;
+  if (n_rows == 0) return KMD_OK;
+  if (!h_rows) return fail(ctx, KMD_ERR_ARG, "null row pointer");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = scan_host_enqueue(ctx, h_rows, n_rows, row_base, partition);
+  if (rc) return rc;
+  const uint64_t t = ctx->next_ticket;
+  cudaEvent_t& ev = ctx->ev_ticket[t % kmd_context::kTicketRing];
+  if (!ev) KMD_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  KMD_CUDA(ctx, cudaEventRecord(ev, ctx->copy_stream));
+  // published last: kmd_host_wait may run on another thread and must find the event recorded
+  __atomic_store_n(&ctx->next_ticket, t + 1, __ATOMIC_RELEASE);
+  *ticket = t;
+  return KMD_OK;
+}
+
+int kmd_host_wait(kmd_context* ctx, uint64_t ticket)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (ticket == 0) return KMD_OK;
+  const uint64_t next = __atomic_load_n(&ctx->next_ticket, __ATOMIC_ACQUIRE);
+  if (ticket >= next) return KMD_ERR_ARG;   // (no message: ctx->err belongs to the scanning thread)
+  // the ring holds the last kTicketRing tickets; an older one was overwritten only after kTicketRing later copies
+  // were enqueued behind it on the same stream, and callers keep fewer buffers than that in flight
+  if (ticket + kmd_context::kTicketRing <= next) return KMD_OK;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return KMD_ERR_CUDA;
+  return cudaEventSynchronize(ctx->ev_ticket[ticket % kmd_context::kTicketRing]) == cudaSuccess ? KMD_OK : KMD_ERR_CUDA;
 }
 
 int kmd_counters_get(kmd_context* ctx, kmd_counters* out)
@@ -1292,12 +1349,13 @@ int kmd_model_rows_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, d
   const uint64_t R = ctx->plan.row_bytes;
   // chunk so that rows + 28 bytes of results per row fit one staging buffer
   const uint64_t chunk_rows = std::max<uint64_t>(1, ctx->stage_bytes / (R + 32));
-  double *d_p = nullptr, *d_mc = nullptr, *d_kk = nullptr;
-  int32_t* d_sign = nullptr;
-  KMD_CUDA(ctx, cudaMalloc(&d_p, chunk_rows * 8));
-  KMD_CUDA(ctx, cudaMalloc(&d_mc, chunk_rows * 8));
-  KMD_CUDA(ctx, cudaMalloc(&d_kk, chunk_rows * 8));
-  KMD_CUDA(ctx, cudaMalloc(&d_sign, chunk_rows * 4));
+  // one allocation for the four result arrays: nothing to leak when it fails
+  uint8_t* d_res = nullptr;
+  KMD_CUDA(ctx, cudaMalloc(&d_res, chunk_rows * 28));
+  double* d_p = reinterpret_cast<double*>(d_res);
+  double* d_mc = d_p + chunk_rows;
+  double* d_kk = d_mc + chunk_rows;
+  int32_t* d_sign = reinterpret_cast<int32_t*>(d_kk + chunk_rows);
   const uint8_t* src = static_cast<const uint8_t*>(h_rows);
   for (uint64_t done = 0; done < n_rows && rc == KMD_OK; done += chunk_rows)
   {
@@ -1311,7 +1369,7 @@ int kmd_model_rows_host(kmd_context* ctx, const void* h_rows, uint64_t n_rows, d
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = fail(ctx, KMD_ERR_CUDA, "model_rows_host: %s", cudaGetErrorString(e));
   }
-  cudaFree(d_p); cudaFree(d_mc); cudaFree(d_kk); cudaFree(d_sign);
+  cudaFree(d_res);
   return rc;
 }
 
@@ -1604,6 +1662,67 @@ size_t kmd_format_fasta(uint64_t index, const kmd_survivor* s, uint32_t kmer_wor
   }
   *w = 0;
   return need;
+}
+
+// CPU set "0-3,8,10-11" (sysfs cpulist) -> cpu_set_t restricted to the CPUs the thread may already use
+static bool parse_cpulist(const char* text, const cpu_set_t& allowed, cpu_set_t* out)
+{
+  CPU_ZERO(out);
+  int n = 0;
+  const char* p = text;
+  while (*p)
+  {
+    char* end = nullptr;
+    const long a = strtol(p, &end, 10);
+    if (end == p) break;
+    long b = a;
+    p = end;
+    if (*p == '-') { b = strtol(p + 1, &end, 10); p = end; }
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++)
+      if (c >= 0 && CPU_ISSET(c, &allowed)) { CPU_SET(c, out); n++; }
+    if (*p == ',') p++;
+  }
+  return n > 0;
+}
+
+int kmd_bind_host_thread(int device)
+{
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return KMD_ERR_ARG; }
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return KMD_OK; }
+  for (char* c = bus; *c; c++) *c = static_cast<char>(tolower(*c));
+  auto slurp = [&](const char* leaf, char* buf, size_t cap) {
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/%s", bus, leaf);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    const size_t n = fread(buf, 1, cap - 1, f);
+    fclose(f);
+    buf[n] = 0;
+    return n > 0;
+  };
+  char text[4096];
+  int node = -1;
+  if (slurp("numa_node", text, sizeof text)) node = atoi(text);
+  if (node < 0) return KMD_OK;   // single-node host or a VM that hides the topology: nothing to bind
+  cpu_set_t allowed, want;
+  if (sched_getaffinity(0, sizeof allowed, &allowed) == 0 && slurp("local_cpulist", text, sizeof text) &&
+      parse_cpulist(text, allowed, &want))
+    sched_setaffinity(0, sizeof want, &want);
+  // pages this thread touches from now on (pinned staging buffers above all) come from the GPU's node
+  unsigned long mask[16] = {0};
+  if (node < static_cast<int>(sizeof mask * 8))
+  {
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, mask, sizeof mask * 8);
+  }
+  return KMD_OK;
+}
+
+int kmd_warmup(int device)
+{
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return KMD_ERR_ARG; }
+  return cudaFree(nullptr) == cudaSuccess ? KMD_OK : KMD_ERR_CUDA;
 }
 
 void* kmd_host_alloc(size_t bytes)

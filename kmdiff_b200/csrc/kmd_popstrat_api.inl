@@ -459,7 +459,8 @@ int kmd_popstrat_apply(kmd_context* ctx)
   A.counts = ctx->pop.d_surv_counts;
   A.p_value = ctx->surv.p;  // ks.set_pval(corrected) (popstrat.hpp:330)
   if ((rc = launch_irls(ctx, A, n_surv))) return rc;
-  if (ctx->order_state == 2) ctx->order_state = 1;  // the p order is stale, the row order is not
+  // d_vals[0] holds the p order in state 2 (ensure_order overwrote the row order with it): both orders are rebuilt
+  if (ctx->order_state != 1) ctx->order_state = 0;
   ctx->final_valid = false;
   return KMD_OK;
 }

@@ -5,9 +5,10 @@ The reference's only cross-partition communication is (reference file:line)
   * the control / case survivor counters                           merge.hpp:319-337
   * one global ascending walk over all survivors for BH / Holm     include/kmdiff/aggregator.hpp:282-310, 325-341
 Partitions are disjoint k-mer sets, so there is no data-path collective: each rank scans its own
-partitions, then (1) one all-reduce(sum) of three u64 counters, and for BENJAMINI / HOLM (2) an
-all-gather of the ranks' ascending survivor p-values (<= ~1e-3 of the rows), from which every rank
-derives the same first rejected p-value and keeps its own survivors below it.
+partitions, then ONE all-gather carries every rank's counters and (for BENJAMINI / HOLM) its survivors'
+p-values (<= ~1e-3 of the rows); every rank derives the same m and the same first rejected p-value from
+the gathered bytes and keeps its own survivors below it (DeviceExchange).  correct_sharded is the same
+decision with the walk on the host (gloo / any backend).
 
 Works on any torch.distributed backend: NCCL over NVLink on the GPUs, gloo in the CPU tests.
 """
@@ -82,48 +83,64 @@ def global_cut(p_local_sorted: np.ndarray, correction: int, significance: float,
 
 
 class DeviceExchange:
-    """BENJAMINI / HOLM across ranks without leaving the GPUs (NCCL): one all-gather of each rank's
-    (rows, controls, cases, survivors), one all-gather of the survivors' p-values padded with +inf, one device
-    sort of the union, kmd_first_reject_device, then every rank keeps its survivors below the cut.
-    Buffers are cached between calls.  The context's stream and torch's current stream are ordered explicitly
-    (the context may run on its own non-blocking stream: kmd_set_stream(NULL) does not mean the legacy stream)."""
+    """do_correction (cmd/diff.hpp:227-260) when partitions are sharded over ranks, without leaving the GPUs and with
+    ONE host synchronisation per run (kmd_exchange_* in include/kmdiff_b200.h):
 
-    def __init__(self, device, group=None):
+      export   every rank writes its slot {rows, controls, cases, survivors | cap p-values, +inf padded} on the
+               context's stream — the survivor count is never read back to size anything;
+      gather   one NCCL all-gather of the slots (NVLink), ordered against the context's stream with events;
+      correct  m = sum of the rows; BENJAMINI / HOLM: device sort of the union + first rejected rank + p_cut, the other
+               correctors: p_cut from m; every rank keeps its survivors below p_cut;
+      result   the single read-back: (m, p_cut, kept control / case of this rank, overflow).
+
+    `cap` grows (and the exchange is repeated) when some rank had more survivors than fit a slot; buffers are cached."""
+
+    def __init__(self, device, group=None, cap: int = 1 << 16):
         self.device, self.group = device, group
         self.world = _world(group)
-        self.meta = torch.zeros(4, dtype=torch.int64, device=device)
-        self.meta_all = torch.zeros(4 * self.world, dtype=torch.int64, device=device)
-        self.pad = None
-        self.allp = None
+        self.cap = int(cap)
+        self.slot = None
+        self.all = None
+        self.last = None          # the kmd_exchange_decision of the last run
+        self.retries = 0          # exchanges repeated because a slot overflowed
+
+    def _buffers(self):
+        from ._lib import EXCHANGE_HEADER
+        words = EXCHANGE_HEADER + self.cap
+        if self.slot is None or self.slot.numel() != words:
+            self.slot = torch.zeros(words, dtype=torch.int64, device=self.device)
+            self.all = self.slot if self.world == 1 else torch.zeros(words * self.world, dtype=torch.int64, device=self.device)
+        return self.slot, self.all
 
     def correct(self, ctx, correction: int, significance: float):
-        """-> (total_rows, (n_control, n_case) kept on this rank)"""
-        c = ctx.counters()
-        self.meta.copy_(torch.tensor([c.rows, c.n_control, c.n_case, c.survivors], dtype=torch.int64), non_blocking=True)
-        dist.all_gather_into_tensor(self.meta_all, self.meta, group=self.group)
-        m = self.meta_all.view(self.world, 4).cpu()
-        total_rows = int(m[:, 0].sum())
-        if correction not in (CorrectionType.BENJAMINI, CorrectionType.HOLM):
-            return total_rows, ctx.correct(correction, significance, total_rows)
-        mx = max(1, int(m[:, 3].max()))
-        if self.pad is None or self.pad.numel() < mx:
-            cap = mx + mx // 4
-            self.pad = torch.empty(cap, dtype=torch.float64, device=self.device)
-            self.allp = torch.empty(cap * self.world, dtype=torch.float64, device=self.device)
-        pad, allp = self.pad[:mx], self.allp[:mx * self.world]
+        """-> (total_rows, (n_control, n_case) kept on this rank); ctx.significant() then returns this rank's records"""
         on_gpu = self.device.type == "cuda"
-        pad.fill_(float("inf"))
-        if on_gpu:
-            torch.cuda.current_stream(self.device).synchronize()      # the fill precedes the context's copy
-        ctx.survivor_pvalues_device(pad.data_ptr(), mx)
-        if on_gpu:
-            ctx.sync()                                                # the copy precedes the all-gather
-        dist.all_gather_into_tensor(allp, pad, group=self.group)
-        merged = torch.sort(allp).values                      # +inf padding sorts last and never passes a rank test
-        if on_gpu:
-            torch.cuda.current_stream(self.device).synchronize()      # the sorted union precedes the context's walk
-        _, cut = ctx.first_reject_device(merged.data_ptr(), int(m[:, 3].sum()), correction, significance, total_rows)
-        return total_rows, ctx.keep_below(cut)
+        while True:
+            slot, allb = self._buffers()
+            cs = cur = None
+            if on_gpu:
+                cur = torch.cuda.current_stream(self.device)
+                cs = torch.cuda.ExternalStream(ctx.stream_ptr(), device=self.device)
+                if cs.cuda_stream == cur.cuda_stream:
+                    cs = None
+                else:
+                    cs.wait_stream(cur)           # the buffers may have just been allocated / zeroed on torch's stream
+            ctx.exchange_export(slot.data_ptr(), self.cap)
+            if self.world > 1:
+                if cs is not None:
+                    cur.wait_stream(cs)           # export -> all-gather
+                dist.all_gather_into_tensor(allb, slot, group=self.group)
+                if cs is not None:
+                    cs.wait_stream(cur)           # all-gather -> sort / walk / keep
+            ctx.exchange_correct(allb.data_ptr(), self.world, self.cap, correction, significance)
+            dec = ctx.exchange_result()
+            if not dec.overflow:
+                break
+            self.retries += 1
+            want = int(dec.max_rank_survivors) + int(dec.max_rank_survivors) // 4 + 1
+            self.cap = (want + 4095) // 4096 * 4096
+        self.last = dec
+        return int(dec.total_rows), (int(dec.kept_control), int(dec.kept_case))
 
 
 def correct_sharded(ctx, correction: int, significance: float, device, group=None):

@@ -31,8 +31,10 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <sys/resource.h>
 #include <sys/time.h>
+#include <unistd.h>
 
 #include <kmdiff/imodel.hpp>
 #include <kmdiff_b200.h>
@@ -323,19 +325,27 @@ struct Partition
   uint32_t index;
   uint64_t bytes;
   uint64_t draw_base = 0;
+  bool raw = false;                        // uncompressed matrix: read in slices by several threads
   std::vector<std::string> sample_paths;   // count-file mode: counts/partition_{p}/<sample>.kmer.lz4, fof order
 };
 
-// One GPU's share: a reader thread decodes its partitions into pinned buffers, this thread feeds the GPU.
+// One GPU's share.  Matrix input: reader threads bring slices of the partition files into pinned staging buffers
+// (pread of the page cache for raw matrices — many slices per file, so every -t thread has work whatever the
+// partition count; one sequential LZ4 stream per compressed file), the feeder thread enqueues the asynchronous
+// H2D copy + scan of every buffer (kmd_scan_host_async) and hands the buffer straight back; a reader waits for its
+// buffer's copy (kmd_host_wait) only when it is about to refill it.  Replaces the per-row istream reads of
+// matrix_proxy::merge (merge.hpp:194-203) under global_merge's partition pool (merge.hpp:341-388).
 class GpuWorker
 {
  public:
-  // n_readers threads decode this GPU's partitions (one partition per thread at a time) into pinned buffers
-  // buf_bytes: size of one pinned staging buffer (pinning host memory costs ~0.5 s per GB, so small inputs get small buffers)
+  // buf_bytes: size of one pinned staging buffer; max_bufs: pool limit (buffers are pinned on demand by the reader
+  // threads — pinning costs ~0.3 s per GB and overlaps the first reads)
   GpuWorker(int device, const DiffOptions& o, const RunConfig& cfg, uint64_t sum_controls, uint64_t sum_cases, size_t n_readers = 1,
-            size_t buf_bytes = 16u << 20)
-    : m_device(device), m_opt(o), m_n_readers(std::max<size_t>(1, n_readers)), m_bufs(std::max<size_t>(1, n_readers) + 2)
+            size_t buf_bytes = 16u << 20, size_t max_bufs = 0)
+    : m_device(device), m_opt(o), m_n_readers(std::max<size_t>(1, n_readers)),
+      m_bufs(max_bufs ? max_bufs : 2 * std::max<size_t>(1, n_readers) + 2)
   {
+    kmd_bind_host_thread(device);   // CPU affinity + memory policy of the GPU's NUMA node (no-op when unknown)
     kmd_config c{};
     c.abi_version = KMD_ABI_VERSION;
     c.device = device;
@@ -368,19 +378,10 @@ class GpuWorker
     m_row_bytes = 8ull * c.kmer_words + (o.nb_controls + o.nb_cases) * o.count_bytes;
     m_buf_rows = std::max<uint64_t>(1, buf_bytes / m_row_bytes);
   }
-  // matrix input only: the pinned staging buffers of the reader threads
-  void alloc_buffers()
-  {
-    for (auto& b : m_bufs)
-    {
-      if (b.data) continue;
-      b.data = static_cast<uint8_t*>(kmd_host_alloc(m_buf_rows * m_row_bytes));
-      if (!b.data) throw KmdError("GpuError", "kmd_host_alloc failed");
-    }
-  }
   ~GpuWorker()
   {
     for (auto& b : m_bufs) kmd_host_free(b.data);
+    for (int fd : m_fds) if (fd >= 0) ::close(fd);
   }
 
   kmd_context* ctx() { return m_ctx.get(); }
@@ -398,13 +399,23 @@ class GpuWorker
         ck(m_ctx.get(), kmd_sync(m_ctx.get()), "kmd_sync");
         return;
       }
-      alloc_buffers();
-      m_next_part = 0;
+      plan_items();
+      m_next_item = 0;
       m_readers_left = static_cast<int>(m_n_readers);
       std::vector<std::thread> readers;
       for (size_t r = 0; r < m_n_readers; r++) readers.emplace_back([this] { read_loop(); });
-      feed_loop();
+      std::exception_ptr feed_error;
+      try { feed_loop(false); }
+      catch (...)
+      {
+        // keep recycling the readers' buffers (without scanning) until the last one arrives, so that no reader
+        // stays blocked in acquire_free() and every thread can be joined before the error is reported
+        feed_error = std::current_exception();
+        m_next_item = m_items.size();
+        try { feed_loop(true); } catch (...) {}
+      }
       for (auto& r : readers) r.join();
+      if (feed_error) std::rethrow_exception(feed_error);
       if (m_reader_error) std::rethrow_exception(m_reader_error);
       ck(m_ctx.get(), kmd_sync(m_ctx.get()), "kmd_sync");
     }
@@ -412,7 +423,32 @@ class GpuWorker
   }
 
  private:
-  struct Buf { uint8_t* data = nullptr; uint64_t rows = 0; uint64_t row_base = 0; uint64_t draw_base = 0; uint32_t partition = 0; bool last = false; };
+  struct Buf { uint8_t* data = nullptr; uint64_t rows = 0; uint64_t row_base = 0; uint64_t draw_base = 0; uint32_t partition = 0; bool last = false;
+               uint64_t ticket = 0; /* kmd_scan_host_async ticket of the copy that last read this buffer */ };
+  // one unit of reader work: rows [first_row, first_row + rows) of a raw matrix, or a whole compressed matrix (rows == 0)
+  struct Item { size_t part; uint64_t first_row; uint64_t rows; };
+
+  void plan_items()
+  {
+    m_items.clear();
+    m_fds.assign(partitions.size(), -1);
+    for (size_t pi = 0; pi < partitions.size(); pi++)
+    {
+      const Partition& p = partitions[pi];
+      MatrixFile mf(p.path, m_row_bytes);
+      const uint32_t slots = (mf.hdr.kmer_size + 31) / 32;
+      if (mf.hdr.nb_counts != m_opt.nb_controls + m_opt.nb_cases)
+        throw KmdError("InputError", p.path + ": " + std::to_string(mf.hdr.nb_counts) + " counts per row, expected " +
+                                       std::to_string(m_opt.nb_controls + m_opt.nb_cases));
+      if (mf.hdr.kmer_slots != slots) throw KmdError("InputError", p.path + ": unexpected kmer_slots");
+      if (mf.hdr.compressed) { m_items.push_back({pi, 0, 0}); continue; }
+      if ((p.bytes - kMatrixHeaderBytes) % m_row_bytes) throw KmdError("InputError", p.path + ": truncated row");
+      m_fds[pi] = ::open(p.path.c_str(), O_RDONLY);
+      if (m_fds[pi] < 0) throw KmdError("IOError", "Unable to open " + p.path);
+      for (uint64_t r = 0; r < mf.rows_if_raw; r += m_buf_rows) m_items.push_back({pi, r, std::min(m_buf_rows, mf.rows_if_raw - r)});
+      logf(L_DEBUG, "partition %u: %llu rows (gpu %d)", p.index, static_cast<unsigned long long>(mf.rows_if_raw), m_device);
+    }
+  }
 
   // Run directories without matrices (cmd/diff.hpp:88-95 -> global_merge::merge(), merge.hpp:237-309): every
   // partition is N per-sample files of sorted (k-mer, count) records.  The reference walks them with
@@ -569,23 +605,43 @@ class GpuWorker
 
   void read_loop()
   {
+    kmd_bind_host_thread(m_device);
     try
     {
-      for (size_t pi; (pi = m_next_part.fetch_add(1)) < partitions.size();)
+      for (size_t ii; (ii = m_next_item.fetch_add(1)) < m_items.size();)
       {
-        const Partition& p = partitions[pi];
+        const Item& it = m_items[ii];
+        const Partition& p = partitions[it.part];
+        if (it.rows)
+        {
+          // a slice of a raw matrix: page cache -> pinned buffer
+          Buf* b = acquire_free();
+          const size_t want = it.rows * m_row_bytes;
+          size_t got = 0;
+          while (got < want)
+          {
+            const ssize_t n = ::pread(m_fds[it.part], b->data + got, want - got,
+                                      static_cast<off_t>(kMatrixHeaderBytes + it.first_row * m_row_bytes + got));
+            if (n <= 0) { publish_empty(b); throw KmdError("IOError", p.path + ": short read"); }
+            got += static_cast<size_t>(n);
+          }
+          b->rows = it.rows;
+          b->row_base = (static_cast<uint64_t>(p.index) << kPartShift) + it.first_row;
+          b->draw_base = p.draw_base + it.first_row;
+          b->partition = p.index;
+          publish(b);
+          continue;
+        }
+        // a compressed matrix: one sequential LZ4 frame
         MatrixFile mf(p.path, m_row_bytes);
-        const uint32_t slots = (mf.hdr.kmer_size + 31) / 32;
-        if (mf.hdr.nb_counts != m_opt.nb_controls + m_opt.nb_cases)
-          throw KmdError("InputError", p.path + ": " + std::to_string(mf.hdr.nb_counts) + " counts per row, expected " +
-                                         std::to_string(m_opt.nb_controls + m_opt.nb_cases));
-        if (mf.hdr.kmer_slots != slots) throw KmdError("InputError", p.path + ": unexpected kmer_slots");
         uint64_t local = 0;
         for (;;)
         {
           Buf* b = acquire_free();
-          const size_t got = mf.payload->read(b->data, m_buf_rows * m_row_bytes);
-          if (got % m_row_bytes) throw KmdError("InputError", p.path + ": truncated row");
+          size_t got;
+          try { got = mf.payload->read(b->data, m_buf_rows * m_row_bytes); }
+          catch (...) { publish_empty(b); throw; }
+          if (got % m_row_bytes) { publish_empty(b); throw KmdError("InputError", p.path + ": truncated row"); }
           b->rows = got / m_row_bytes;
           b->row_base = (static_cast<uint64_t>(p.index) << kPartShift) + local;
           b->draw_base = p.draw_base + local;
@@ -602,7 +658,7 @@ class GpuWorker
     {
       std::lock_guard<std::mutex> lk(m_mu);
       if (!m_reader_error) m_reader_error = std::current_exception();
-      m_next_part = partitions.size();   // the other readers stop after their current partition
+      m_next_item = m_items.size();   // the other readers stop after their current item
     }
     if (m_readers_left.fetch_sub(1) == 1)
     {
@@ -613,46 +669,69 @@ class GpuWorker
     }
   }
 
-  void feed_loop()
+  // drain == true: an error is being unwound — buffers are recycled without being scanned
+  void feed_loop(bool drain)
   {
     for (;;)
     {
       Buf* b;
       {
         std::unique_lock<std::mutex> lk(m_mu);
-        m_cv.wait(lk, [this] { return !m_ready.empty(); });
+        m_cv_ready.wait(lk, [this] { return !m_ready.empty(); });
         b = m_ready.front(); m_ready.pop();
       }
       const bool last = b->last;
-      if (b->rows)
+      struct Recycle
+      {
+        GpuWorker* w; Buf* b;
+        ~Recycle()
+        {
+          { std::lock_guard<std::mutex> lk(w->m_mu); b->last = false; b->rows = 0; w->m_free.push(b); }
+          w->m_cv_free.notify_one();
+        }
+      } recycle{this, b};
+      if (b->rows && !drain)
       {
         // Sampler draws follow the reference's `-t 1` visiting order, not the (partition, row) tag
         if (m_opt.pop_correction) ck(m_ctx.get(), kmd_popstrat_set_draw_index(m_ctx.get(), b->draw_base), "kmd_popstrat_set_draw_index");
-        ck(m_ctx.get(), kmd_scan_host(m_ctx.get(), b->data, b->rows, b->row_base, b->partition), "kmd_scan_host");
+        ck(m_ctx.get(), kmd_scan_host_async(m_ctx.get(), b->data, b->rows, b->row_base, b->partition, &b->ticket), "kmd_scan_host_async");
       }
-      {
-        std::lock_guard<std::mutex> lk(m_mu);
-        b->last = false;
-        m_free.push(b);
-      }
-      m_cv.notify_all();
       if (last) break;
     }
   }
 
+  // a free staging buffer whose last copy has completed; pinned on first use, by the reader that needs it
   Buf* acquire_free()
   {
-    std::unique_lock<std::mutex> lk(m_mu);
-    if (!m_init) { for (auto& b : m_bufs) m_free.push(&b); m_init = true; }
-    m_cv.wait(lk, [this] { return !m_free.empty(); });
-    Buf* b = m_free.front(); m_free.pop();
+    Buf* b = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(m_mu);
+      if (m_free.empty() && m_allocated < m_bufs.size()) b = &m_bufs[m_allocated++];
+      else
+      {
+        m_cv_free.wait(lk, [this] { return !m_free.empty(); });
+        b = m_free.front(); m_free.pop();
+      }
+    }
+    if (!b->data)
+    {
+      b->data = static_cast<uint8_t*>(kmd_host_alloc(m_buf_rows * m_row_bytes));
+      if (!b->data) { publish_empty(b); throw KmdError("GpuError", "kmd_host_alloc failed"); }
+    }
+    if (b->ticket)
+    {
+      if (kmd_host_wait(m_ctx.get(), b->ticket) != KMD_OK) { publish_empty(b); throw KmdError("GpuError", "kmd_host_wait failed"); }
+      b->ticket = 0;
+    }
     return b;
   }
   void publish(Buf* b)
   {
     { std::lock_guard<std::mutex> lk(m_mu); m_ready.push(b); }
-    m_cv.notify_all();
+    m_cv_ready.notify_one();
   }
+  // hand a buffer back through the feeder without work (error paths: the pool must stay complete)
+  void publish_empty(Buf* b) { b->rows = 0; b->last = false; publish(b); }
 
   int m_device;
   const DiffOptions& m_opt;
@@ -661,12 +740,14 @@ class GpuWorker
   uint64_t m_draw_next = 0;   // count-file mode: Sampler draw index = rows merged so far (one worker, partition order)
   size_t m_n_readers = 1;
   std::vector<Buf> m_bufs;
-  std::atomic<size_t> m_next_part{0};
+  std::vector<Item> m_items;
+  std::vector<int> m_fds;             // raw matrices, parallel to `partitions`
+  std::atomic<size_t> m_next_item{0};
   std::atomic<int> m_readers_left{0};
   std::queue<Buf*> m_free, m_ready;
+  size_t m_allocated = 0;             // buffers of m_bufs handed out so far
   std::mutex m_mu;
-  std::condition_variable m_cv;
-  bool m_init = false;
+  std::condition_variable m_cv_free, m_cv_ready;
   std::exception_ptr m_reader_error;
 };
 
@@ -1103,6 +1184,33 @@ void main_diff(DiffOptions& opt)
     throw KmdError("IOError", "Unknown gender: the reference rejects every --gender file (src/popstrat.cpp:26-41).");
   if (opt.pop_correction && opt.npc > 10) throw KmdError("OptionError", "--n-pc must be <= 10 (pcs.evec holds 10 components).");
 
+  // CUDA start-up (driver initialisation + one primary context per device, ~0.5 s) runs beside the host-side
+  // start-up work below (run-dir config, N histogram files, P matrix headers, pinning the first staging buffers)
+  struct Warmup
+  {
+    std::thread th;
+    std::atomic<int> n_dev{0};
+    void start(int want)
+    {
+      th = std::thread([this, want] {
+        const int n = std::min(kmd_device_count(), want);
+        std::vector<std::thread> pool;
+        for (int d = 1; d < n; d++) pool.emplace_back([d] { kmd_warmup(d); });
+        if (n > 0) kmd_warmup(0);
+        for (auto& t : pool) t.join();
+        n_dev = n;
+      });
+    }
+    int wait() { if (th.joinable()) th.join(); return n_dev; }
+    ~Warmup() { if (th.joinable()) th.join(); }
+  } warmup;
+  {
+    size_t n_units = list_matrices(opt.kmtricks_dir).size();
+    if (n_units == 0) n_units = 1u << 16;     // count-file mode: the partition count is read below
+    const bool single = !opt.model_lib_path.empty();
+    warmup.start(single ? 1 : static_cast<int>(std::min<size_t>(n_units, opt.gpus > 0 ? static_cast<size_t>(opt.gpus) : 1u << 16)));
+  }
+
   const RunConfig cfg = get_kmtricks_config(opt.kmtricks_dir);
   if (cfg.kmer_size > 64) throw KmdError("OptionError", "k > 64 is not supported (the reference cannot write such k-mers either).");
   const uint32_t kw = (cfg.kmer_size + 31) / 32;
@@ -1152,7 +1260,7 @@ void main_diff(DiffOptions& opt)
     // partition index from the header (matrix_{p}.count[.lz4])
     MatrixFile mf(p, 8ull * kw + (opt.nb_controls + opt.nb_cases) * opt.count_bytes);
     Partition part{};
-    part.path = p; part.index = mf.hdr.partition; part.bytes = static_cast<uint64_t>(fs::file_size(p));
+    part.path = p; part.index = mf.hdr.partition; part.bytes = static_cast<uint64_t>(fs::file_size(p)); part.raw = !mf.hdr.compressed;
     parts.push_back(part);
   }
   if (!from_matrix)
@@ -1180,6 +1288,7 @@ void main_diff(DiffOptions& opt)
   int n_dev = kmd_device_count();
   if (n_dev <= 0) throw KmdError("GpuError", "no CUDA device visible: kmdiff-b200 has no CPU fallback.");
   if (opt.gpus > 0) n_dev = std::min(n_dev, opt.gpus);
+  warmup.wait();
   const bool plugin = !opt.model_lib_path.empty();
   if (plugin)
   {
@@ -1230,13 +1339,19 @@ void main_diff(DiffOptions& opt)
     for (size_t i = 0; i < parts.size(); i++) { parts[i].draw_base = base; base += rows[i]; }
   }
 
-  std::vector<std::unique_ptr<GpuWorker>> workers;
-  // host threads (-t) are split over the devices: each GPU gets its own readers (file read / LZ4 decode -> pinned)
-  const size_t parts_per_gpu = (parts.size() + static_cast<size_t>(n_dev) - 1) / static_cast<size_t>(n_dev);
-  // reading the page cache into pinned memory runs at ~1 GB/s per thread on the B200 hosts: take all the threads -t allows
-  const size_t readers_per_gpu = std::max<size_t>(1, std::min({size_t{32}, opt.nb_threads / static_cast<size_t>(n_dev), std::max<size_t>(1, parts_per_gpu)}));
+  // The workers own pinned staging buffers and device contexts whose orderly release (unpinning, cudaFree, context
+  // teardown) costs more than a short run's scan; the process is about to end, so they are deliberately left to the OS
+  // (main() leaves through _exit once every output file is closed).
+  auto& workers = *new std::vector<std::unique_ptr<GpuWorker>>;
+  // host threads (-t) are split over the devices: each GPU gets its own readers (page cache / LZ4 decode -> pinned).
+  // Raw matrices are read in slices, so the reader count is not limited by the partition count.
   uint64_t input_bytes = 0;
-  for (const Partition& p : parts) input_bytes += p.bytes;
+  bool any_raw = false;
+  for (const Partition& p : parts) { input_bytes += p.bytes; any_raw |= p.raw; }
+  const size_t parts_per_gpu = (parts.size() + static_cast<size_t>(n_dev) - 1) / static_cast<size_t>(n_dev);
+  const size_t reader_cap = any_raw ? size_t{32} : std::max<size_t>(1, parts_per_gpu);
+  const size_t readers_per_gpu = std::max<size_t>(1, std::min({size_t{32}, opt.nb_threads / static_cast<size_t>(n_dev), reader_cap}));
+  // pinning host memory costs ~0.3 s per GB: small inputs get small buffers
   const size_t buf_bytes = static_cast<size_t>(std::min<uint64_t>(16ull << 20, std::max<uint64_t>(1ull << 20,
                                input_bytes / static_cast<uint64_t>(n_dev) / (2 * (readers_per_gpu + 2)))));
   // one thread per device: CUDA context creation and the device allocations of kmd_create run side by side
@@ -1437,6 +1552,7 @@ void main_diff(DiffOptions& opt)
 //   dev-cat FILE SKIP [lz4]  decoded payload of a kmtricks file (SKIP header bytes; LZ4 frame iff its compressed flag is set or "lz4" is given)
 //   dev-pack IN OUT          IN wrapped into one LZ4 frame of stored blocks
 //   dev-config DIR NC NK     run-dir config and per-sample totals
+//   dev-synth OUT ...        a synthetic kmtricks run directory (bench inputs)
 int dev_command(int argc, char** argv)
 {
   const std::string cmd = argv[1];
@@ -1485,6 +1601,110 @@ int dev_command(int argc, char** argv)
     w.close();
     return 0;
   }
+  if (cmd == "dev-synth" && argc >= 12)
+  {
+    // dev-synth OUT NC NK K COUNT_BYTES TOTAL_ROWS SEED PPM N_ROWS PARTITIONS matrix|counts [THREADS]
+    // A kmtricks run directory holding rows [0, N_ROWS) of the seeded synthetic cohort (kmd_synth_*), as raw count
+    // matrices or as per-sample sorted count files: the input of bench.py's reference arm and of the CLI timings,
+    // written by a process of its own so that the timed reference never shares a process with this library.
+    const std::string out = argv[2];
+    kmd_synth sy{};
+    sy.nb_controls = static_cast<uint32_t>(atol(argv[3])); sy.nb_cases = static_cast<uint32_t>(atol(argv[4]));
+    sy.kmer_size = static_cast<uint32_t>(atol(argv[5])); sy.kmer_words = (sy.kmer_size + 31) / 32;
+    sy.count_bytes = static_cast<uint32_t>(atol(argv[6])); sy.total_rows = strtoull(argv[7], nullptr, 10);
+    sy.seed = strtoull(argv[8], nullptr, 10); sy.enriched_ppm = static_cast<uint32_t>(atol(argv[9]));
+    const uint64_t n_rows = strtoull(argv[10], nullptr, 10);
+    const uint32_t parts = static_cast<uint32_t>(std::max(1l, atol(argv[11])));
+    const bool count_files = argc > 12 && !strcmp(argv[12], "counts");
+    const size_t threads = argc > 13 ? static_cast<size_t>(std::max(1l, atol(argv[13]))) : std::max(1u, std::thread::hardware_concurrency());
+    const uint32_t n = sy.nb_controls + sy.nb_cases, kw = sy.kmer_words, B = sy.count_bytes;
+    const size_t R = 8ull * kw + static_cast<size_t>(n) * B;
+    fs::create_directories(out + "/matrices");
+    fs::create_directories(out + "/histograms");
+    std::vector<std::string> ids;
+    for (uint32_t i = 0; i < sy.nb_controls; i++) ids.push_back("C" + std::to_string(i));
+    for (uint32_t i = 0; i < sy.nb_cases; i++) ids.push_back("K" + std::to_string(i));
+    {
+      std::ofstream fof(out + "/kmtricks.fof"), opt(out + "/options.txt");
+      for (const std::string& id : ids) fof << id << " : /dev/null/" << id << ".fa\n";
+      opt << "kmer_size=" << sy.kmer_size << ", c_ab_min=1,\n";
+    }
+    fs::remove(out + "/kmdiff-count.opt");
+    std::vector<uint64_t> totals(n);
+    kmd_synth_totals(&sy, totals.data());
+    for (uint32_t j = 0; j < n; j++)
+    {
+      // km::HistFileHeader + two empty histograms over [1, 255] (hist_file.hpp:31-45, 129-144); only `total` is read
+      FILE* f = fopen((out + "/histograms/" + ids[j] + ".hist").c_str(), "wb");
+      if (!f) return 2;
+#pragma pack(push, 1)
+      struct { uint64_t km_magic; uint32_t version; uint8_t compressed; uint64_t magic; uint32_t k, id;
+               uint64_t lower, upper, uniq, total, oob_ln, oob_lu, oob_un, oob_uu; } h{kKmMagic, 0, 0, kHistMagic, sy.kmer_size, j, 1, 255, 0, totals[j], 0, 0, 0, 0};
+#pragma pack(pop)
+      fwrite(&h, sizeof h, 1, f);
+      const std::vector<uint64_t> zeros(2 * 255, 0);
+      fwrite(zeros.data(), 8, zeros.size(), f);
+      fclose(f);
+    }
+    const uint64_t per = (n_rows + parts - 1) / parts;
+    std::atomic<uint32_t> next{0};
+    std::atomic<bool> failed{false};
+    auto work = [&] {
+      const uint64_t chunk = std::max<uint64_t>(1, (8u << 20) / R);
+      std::vector<uint8_t> rows(chunk * R);
+      for (uint32_t p; (p = next.fetch_add(1)) < parts;)
+      {
+        fs::create_directories(out + "/counts/partition_" + std::to_string(p));
+        const uint64_t lo = std::min(n_rows, p * per), hi = std::min(n_rows, (p + 1) * per);
+        std::vector<FILE*> files;
+        if (count_files)
+        {
+          for (uint32_t j = 0; j < n; j++)
+          {
+            FILE* f = fopen((out + "/counts/partition_" + std::to_string(p) + "/" + ids[j] + ".kmer.lz4").c_str(), "wb");
+            if (!f) { failed = true; return; }
+            const KmerHeader h{kKmMagic, 0, 0, kKmerMagic, sy.kmer_size, kw, B, j, p};
+            fwrite(&h, sizeof h, 1, f);
+            files.push_back(f);
+          }
+        }
+        else
+        {
+          FILE* f = fopen((out + "/matrices/matrix_" + std::to_string(p) + ".count").c_str(), "wb");
+          if (!f) { failed = true; return; }
+          const MatrixHeader h{kKmMagic, 0, 0, kMatrixMagic, sy.kmer_size, kw, B, n, 0, p};
+          fwrite(&h, sizeof h, 1, f);
+          files.push_back(f);
+        }
+        for (uint64_t r = lo; r < hi; r += chunk)
+        {
+          const uint64_t m = std::min(chunk, hi - r);
+          if (kmd_synth_fill_host(&sy, rows.data(), m, r, 1) != KMD_OK) { failed = true; break; }
+          if (!count_files) { fwrite(rows.data(), R, m, files[0]); continue; }
+          // KmerWriter::write (kmer_file.hpp:94-101): one (k-mer, count) record per sample that carries the k-mer
+          for (uint64_t i = 0; i < m; i++)
+          {
+            const uint8_t* row = rows.data() + i * R;
+            for (uint32_t j = 0; j < n; j++)
+            {
+              const uint8_t* c = row + 8ull * kw + static_cast<size_t>(j) * B;
+              bool nz = false;
+              for (uint32_t b = 0; b < B; b++) nz |= c[b] != 0;
+              if (!nz) continue;
+              fwrite(row, 1, 8ull * kw, files[j]);
+              fwrite(c, 1, B, files[j]);
+            }
+          }
+        }
+        for (FILE* f : files) fclose(f);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < std::min<size_t>(threads, parts); t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    return failed ? 2 : 0;
+  }
   if (cmd == "dev-config" && argc == 5)
   {
     const RunConfig c = get_kmtricks_config(argv[2]);
@@ -1525,5 +1745,8 @@ int main(int argc, char** argv)
   {
     logf(L_ERROR, "%s", e.what());
   }
-  return 0;   // like the reference: errors are logged, the exit code stays 0 (main.cc:93-102)
+  // like the reference: errors are logged, the exit code stays 0 (main.cc:93-102).  Every output file has been closed
+  // by its owner; _exit skips the CUDA runtime's exit-time teardown (~0.1-0.2 s for nothing).
+  fflush(nullptr);
+  _exit(0);
 }

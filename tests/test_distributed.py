@@ -104,7 +104,7 @@ def test_two_ranks_reach_the_single_process_decision(tmp_path):
     assert 0 < len(oracle.aggregate(want["p"], oracle.BENJAMINI, 0.05, 10**12)) < len(want)
 
 
-# ---- the same decision on real GPUs over NCCL (needs >= 2 devices; run with `gpurun --gpus 2`) ---------
+# ---- the same decision on real GPUs over NCCL (needs >= 2 devices; run with `gpurun --gpus N`) ---------
 
 def _nccl_worker(rank: int, world: int, port: int, out_dir: str):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -124,14 +124,22 @@ def _nccl_worker(rank: int, world: int, port: int, out_dir: str):
         mine = D.assign_partitions(sizes, world)[rank]
         res = {}
         with K.DiffContext(10, 10, int(totals[:10].sum()), int(totals[10:].sum()), threshold=THR, device=rank) as ctx:
-            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-            ex = D.DeviceExchange(dev)
-            for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM, K.CorrectionType.BONFERRONI):
+            # a small first capacity: the first exchange overflows on some rank and is repeated with a larger one;
+            # the context keeps its OWN non-blocking stream for the first two correctors (event ordering against
+            # torch's stream and NCCL's), torch's current stream for the rest
+            ex = D.DeviceExchange(dev, cap=1024)
+            kinds = (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM, K.CorrectionType.BONFERRONI,
+                     K.CorrectionType.SIDAK, K.CorrectionType.NOTHING)
+            for i, kind in enumerate(kinds):
+                if i == 2:
+                    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
                 ctx.reset()
                 for p in mine:
                     ctx.scan_host(rows[cuts[p] * R:cuts[p + 1] * R], row_base=cuts[p], partition=p)
-                total, kept = ex.correct(ctx, kind, 0.05)
+                for _ in range(3):       # repeated runs reuse the cached buffers: same decision every time
+                    total, kept = ex.correct(ctx, kind, 0.05)
                 sig = ctx.significant()
+                assert len(sig) == sum(kept)
                 res[int(kind)] = (total, kept, sig["row"].copy(), sig["p_value"].copy())
                 # the host-side exchange (gather + kmd_first_reject) must reach the same decision
                 ctx.reset()
@@ -146,22 +154,57 @@ def _nccl_worker(rank: int, world: int, port: int, out_dir: str):
 
 
 @pytest.mark.gpu
-def test_two_gpus_reach_the_single_process_decision_over_nccl(tmp_path):
+def test_all_gpus_reach_the_single_process_decision_over_nccl(tmp_path):
     import kmdiff_b200 as K
     import oracle
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world = 2
+        pytest.skip("needs >= 2 GPUs")
+    world = torch.cuda.device_count()
     mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     res = [np.load(tmp_path / f"rank{r}.npy", allow_pickle=True)[0] for r in range(world)]
     spec, rows, totals = _cohort()
     want, _, _ = oracle.Model(10, 10, totals).diff(rows, 1, 4, THR)
-    for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM, K.CorrectionType.BONFERRONI):
+    for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM, K.CorrectionType.BONFERRONI,
+                 K.CorrectionType.SIDAK, K.CorrectionType.NOTHING):
         keep = oracle.aggregate(want["p"], int(kind), 0.05, spec.total_rows)
-        assert res[0][int(kind)][0] == res[1][int(kind)][0] == spec.total_rows
-        got = np.sort(np.concatenate([res[0][int(kind)][2], res[1][int(kind)][2]]))
+        assert all(r[int(kind)][0] == spec.total_rows for r in res)
+        got = np.sort(np.concatenate([r[int(kind)][2] for r in res]))
         assert np.array_equal(got, np.sort(want["row"][keep])) and len(keep) > 10
         assert sum(sum(r[int(kind)][1]) for r in res) == len(keep)
+        if kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM):
+            for r in res:       # every rank's records come back in ascending p
+                assert np.all(np.diff(r[int(kind)][3]) >= 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("own_stream", [True, False])
+def test_device_exchange_on_one_gpu_equals_kmd_correct(own_stream):
+    """world = 1: the export / sort / walk / keep kernels alone, against kmd_correct and the oracle, for every
+    corrector and for m far above the row count (BH / Holm break early); a tiny first capacity forces the
+    overflow -> repeat path"""
+    import kmdiff_b200 as K
+    import oracle
+    from kmdiff_b200 import distributed as D
+    spec, rows, totals = _cohort()
+    want, _, _ = oracle.Model(10, 10, totals).diff(rows, 1, 4, THR)
+    dev = torch.device("cuda", 0)
+    with K.DiffContext(10, 10, int(totals[:10].sum()), int(totals[10:].sum()), threshold=THR) as ctx:
+        if not own_stream:
+            ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ex = D.DeviceExchange(dev, cap=64)
+        for kind in K.CorrectionType:
+            ctx.reset()
+            ctx.scan_host(rows)
+            total, kept = ex.correct(ctx, kind, 0.05)
+            sig = ctx.significant()
+            keep = oracle.aggregate(want["p"], int(kind), 0.05, spec.total_rows)
+            assert total == spec.total_rows and sum(kept) == len(keep) == len(sig)
+            assert np.array_equal(np.sort(sig["row"]), np.sort(want["row"][keep]))
+            assert (ctx.correct(kind, 0.05, total), ) == (kept, )
+            assert np.array_equal(ctx.significant()["row"], sig["row"])
+            if kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM):
+                assert ex.last.n_accepted == len(keep)
+        assert ex.retries == 1 and ex.cap >= len(want)
 
 
 # ---- DeviceExchange's host logic on CPU: gloo, a stand-in context backed by numpy ------------------------
@@ -172,35 +215,55 @@ class _Counters:
 
 
 class _NumpyCtx:
-    """what DeviceExchange needs from a DiffContext, over host arrays (the device calls have GPU tests)"""
+    """what DeviceExchange needs from a DiffContext — the kmd_exchange_* contract of include/kmdiff_b200.h — restated over
+    host arrays (the device kernels have GPU tests); lets gloo carry the slots between CPU ranks"""
+
+    HEADER = 8
 
     def __init__(self, p, sign, rows):
         self.p, self.sign, self.rows = np.ascontiguousarray(p, dtype=np.float64), sign, rows
+        self._dec = None
 
-    def counters(self):
-        return _Counters(self.rows, int((self.sign == 0).sum()), int((self.sign != 0).sum()), len(self.p))
+    def stream_ptr(self):
+        return 0
 
-    def survivor_pvalues_device(self, ptr, cap):
+    @staticmethod
+    def _view(ptr, words):
         import ctypes
-        assert cap >= len(self.p)
-        ctypes.memmove(ptr, self.p.ctypes.data, self.p.nbytes)
-        return len(self.p)
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint64)), shape=(words,))
 
-    def first_reject_device(self, ptr, n, corr, sig, total):
-        import ctypes
+    def exchange_export(self, ptr, cap):
+        slot = self._view(ptr, self.HEADER + cap)
+        n = len(self.p)
+        slot[:self.HEADER] = [self.rows, int((self.sign == 0).sum()), int((self.sign != 0).sum()), n, int(n > cap), 0, 0, 0]
+        pv = slot[self.HEADER:].view(np.float64)
+        pv[:] = np.inf
+        pv[:min(n, cap)] = self.p[:cap]
+
+    def exchange_correct(self, ptr, world, cap, corr, sig):
         import kmdiff_b200 as K
-        arr = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(n,)).copy()
-        assert np.all(arr[1:] >= arr[:-1]) and np.all(np.isfinite(arr))
-        return K.first_reject(arr, corr, sig, total)
+        from kmdiff_b200 import _lib
+        allb = self._view(ptr, world * (self.HEADER + cap)).reshape(world, self.HEADER + cap)
+        total = int(allb[:, 0].sum())
+        dec = _lib.ExchangeDecision()
+        dec.total_rows, dec.total_survivors = total, int(allb[:, 3].sum())
+        dec.max_rank_survivors, dec.overflow = int(allb[:, 3].max()), int(allb[:, 4].any())
+        if corr in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM):
+            union = np.sort(allb[:, self.HEADER:].copy().view(np.float64).ravel())
+            n_acc, cut = K.first_reject(union, corr, sig, total)
+            dec.n_accepted, dec.p_cut = min(n_acc, dec.total_survivors), (cut if n_acc < union.size else np.inf)
+        elif corr == K.CorrectionType.BONFERRONI:
+            dec.p_cut = sig / total
+        elif corr == K.CorrectionType.SIDAK:
+            dec.p_cut = 1 - (1 - sig) ** (1.0 / total)
+        else:
+            dec.p_cut = sig
+        k = self.p < dec.p_cut
+        dec.kept_control, dec.kept_case = int((k & (self.sign == 0)).sum()), int((k & (self.sign != 0)).sum())
+        self._dec = dec
 
-    def keep_below(self, cut):
-        k = self.p < cut
-        return int((k & (self.sign == 0)).sum()), int((k & (self.sign != 0)).sum())
-
-    def correct(self, corr, sig, total):
-        import oracle
-        keep = oracle.aggregate(self.p, int(corr), sig, total)
-        return int((self.sign[keep] == 0).sum()), int((self.sign[keep] != 0).sum())
+    def exchange_result(self):
+        return self._dec
 
 
 def _exchange_inputs(rank):
@@ -219,11 +282,12 @@ def _exchange_worker(rank: int, world: int, port: int, out_dir: str):
         import kmdiff_b200 as K
         from kmdiff_b200 import distributed as D
         p, sign = _exchange_inputs(rank)
-        ex = D.DeviceExchange(torch.device("cpu"))
+        ex = D.DeviceExchange(torch.device("cpu"), cap=4096)     # rank 0 holds 5000: the first exchange overflows
         res = {}
         for kind in (K.CorrectionType.BENJAMINI, K.CorrectionType.HOLM, K.CorrectionType.BONFERRONI):
             for rows in (4_000_000, 10**11):
                 res[(int(kind), rows)] = ex.correct(_NumpyCtx(p, sign, rows), kind, 0.05)
+        assert ex.retries == 1 and ex.cap >= 5000
         np.save(os.path.join(out_dir, f"ex{rank}.npy"), np.array([res], dtype=object), allow_pickle=True)
     finally:
         dist.destroy_process_group()

@@ -137,6 +137,48 @@ def test_device_resident_scan_equals_host_scan():
         assert ctx.launch_count() >= 2
 
 
+@pytest.mark.parametrize("shape,buf_rows", [("c2", 4099), ("c3", 1000), ("odd", 77)])
+def test_async_host_scan_with_recycled_pinned_buffers(shape, buf_rows):
+    """kmd_scan_host_async + kmd_host_wait the way the host program's readers use them: a small pool of pinned buffers
+    refilled as soon as their copy is done, buffers submitted out of row order, one waiter thread per buffer"""
+    import ctypes
+    import threading
+    from kmdiff_b200 import _lib
+    L = _lib.load()
+    spec, rows, totals = make_cohort(shape, 150_001, seed=21)
+    R = spec.row_bytes
+    want, *_ = oracle_for(spec, totals).diff(rows, spec.kmer_words, spec.count_bytes, THR)
+    n_bufs = 3
+    ptrs = [L.kmd_host_alloc(buf_rows * R) for _ in range(n_bufs)]
+    assert all(ptrs)
+    views = [np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(buf_rows * R,)) for p in ptrs]
+    slices = [(lo, min(buf_rows, 150_001 - lo)) for lo in range(0, 150_001, buf_rows)]
+    rng = np.random.default_rng(3)
+    rng.shuffle(slices)
+    try:
+        with ctx_for(spec, totals) as ctx:
+            tickets = [0] * n_bufs
+            for i, (lo, n) in enumerate(slices):
+                b = i % n_bufs
+                if tickets[b]:
+                    t = threading.Thread(target=ctx.host_wait, args=(tickets[b],))     # from another thread, as documented
+                    t.start()
+                    t.join()
+                views[b][:n * R] = rows[lo * R:(lo + n) * R]
+                tickets[b] = ctx.scan_host_async(ptrs[b], n, row_base=lo)
+                assert tickets[b] == i + 1
+            for t in tickets:
+                ctx.host_wait(t)
+            ctx.host_wait(1)                     # an old ticket is simply done
+            with pytest.raises(K.KmdError):
+                ctx.host_wait(len(slices) + 5)   # a ticket that was never issued
+            assert ctx.counters().rows == 150_001
+            check_survivors(ctx.survivors(), want)
+    finally:
+        for p in ptrs:
+            L.kmd_host_free(p)
+
+
 def test_synthetic_rows_identical_on_host_and_device():
     import torch
     for shape in ("c2", "c5", "b1", "odd"):
