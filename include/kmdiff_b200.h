@@ -53,6 +53,15 @@ enum
   KMD_CORR_HOLM = 4
 };
 
+/* kmd_config.flags */
+enum
+{
+  /* keep the N counts of every prefilter survivor (KmerSign::m_counts_ratio, kmer.hpp:118-123: what a default
+   * WITH_POPSTRAT build of the reference appends to every spill record); read back with kmd_survivor_counts.
+   * Implied by kmd_popstrat_enable.  Costs max_survivors * N * count_bytes of device memory. */
+  KMD_FLAG_KEEP_COUNTS = 1
+};
+
 typedef struct kmd_context kmd_context;
 
 /* Replaces the constructor arguments of PoissonLikelihood (include/kmdiff/model.hpp:105-118),
@@ -66,7 +75,7 @@ typedef struct kmd_config
   uint32_t kmer_size;     /* k                                                             */
   uint32_t kmer_words;    /* on-disk k-mer words = ceil(k/32) (matrix_file.hpp:109); 1 or 2 */
   uint32_t count_bytes;   /* 1, 2 or 4 (compile-time MAX_C in the reference)               */
-  uint32_t flags;         /* reserved, 0                                                   */
+  uint32_t flags;         /* KMD_FLAG_*                                                    */
   uint64_t sum_controls;  /* Σ per-sample totals of the controls (model.hpp:185-186)       */
   uint64_t sum_cases;     /* Σ per-sample totals of the cases (model.hpp:188)              */
   double threshold;       /* prefilter: significance / cutoff (cmd/diff.hpp:146)           */
@@ -142,6 +151,10 @@ int kmd_survivors(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n
  * re-corrected.  Sign counters are updated like merge.hpp:95-98.  The correction, sorting and
  * output stages then treat them exactly like scanned survivors. */
 int kmd_push_survivors(kmd_context* ctx, const kmd_survivor* records, uint64_t n, uint64_t rows_tested);
+/* the same with the records' counts (n x N values of count_bytes, parallel to records; may be NULL): spill files with
+ * the WITH_POPSTRAT tail re-opened for a new correction or a new stratification fit (cmd/diff.hpp:342-348) */
+int kmd_push_survivors2(kmd_context* ctx, const kmd_survivor* records, const void* counts, uint64_t n,
+                        uint64_t rows_tested);
 
 /* ---- per-sample count files instead of matrices: global_merge::merge() -> km::KmerMerger
  *      (merge.hpp:237-309; kmtricks/merge.hpp:102-361; record layout kmtricks/io/kmer_file.hpp:127-137) ---- */

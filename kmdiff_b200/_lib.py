@@ -19,7 +19,7 @@ CORR_NOTHING, CORR_BONFERRONI, CORR_BENJAMINI, CORR_SIDAK, CORR_HOLM = range(5)
 SYMBOLS = [
     "kmd_abi_version", "kmd_device_count", "kmd_create", "kmd_destroy", "kmd_last_error",
     "kmd_set_stream", "kmd_sync", "kmd_reset", "kmd_scan_device", "kmd_scan_host",
-    "kmd_counters_get", "kmd_survivors", "kmd_push_survivors", "kmd_launch_count", "kmd_scan_kernel_ms", "kmd_model_rows_device", "kmd_model_rows_host",
+    "kmd_counters_get", "kmd_survivors", "kmd_push_survivors", "kmd_push_survivors2", "kmd_launch_count", "kmd_scan_kernel_ms", "kmd_model_rows_device", "kmd_model_rows_host",
     "kmd_correct", "kmd_significant", "kmd_sorted_pvalues", "kmd_keep_below", "kmd_first_reject",
     "kmd_lf_table_fill", "kmd_chisqc", "kmd_corrector_apply", "kmd_kmer_to_string",
     "kmd_format_fasta", "kmd_host_alloc", "kmd_host_free", "kmd_synth_fill_host",
@@ -32,6 +32,7 @@ SYMBOLS = [
 ]
 
 EXCHANGE_HEADER = 8
+FLAG_KEEP_COUNTS = 1
 
 
 class Config(C.Structure):
@@ -108,6 +109,7 @@ def load() -> C.CDLL:
     L.kmd_counters_get.argtypes = [vp, C.POINTER(Counters)]
     L.kmd_survivors.argtypes = [vp, vp, u64, pu64]
     L.kmd_push_survivors.argtypes = [vp, vp, u64, u64]
+    L.kmd_push_survivors2.argtypes = [vp, vp, vp, u64, u64]
     L.kmd_launch_count.argtypes = [vp]
     L.kmd_launch_count.restype = u64
     L.kmd_scan_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]

@@ -140,7 +140,7 @@ class DiffContext:
     def __init__(self, nb_controls: int, nb_cases: int, sum_controls: int, sum_cases: int,
                  kmer_size: int = 31, count_bytes: int = 4, threshold: float = 0.05 / 100000,
                  lf_size: int = 10000, lf_table: np.ndarray | None = None, device: int = 0,
-                 max_survivors: int = 0):
+                 max_survivors: int = 0, keep_counts: bool = False):
         self._L = _lib.load()
         self.nb_controls, self.nb_cases = int(nb_controls), int(nb_cases)
         self.kmer_size = int(kmer_size)
@@ -151,7 +151,8 @@ class DiffContext:
         self.device = int(device)
         self._table = None if lf_table is None else np.ascontiguousarray(lf_table, dtype=np.float64)
         cfg = Config(_lib.KMD_ABI_VERSION, self.device, self.nb_controls, self.nb_cases,
-                     self.kmer_size, self.kmer_words, self.count_bytes, 0, int(sum_controls),
+                     self.kmer_size, self.kmer_words, self.count_bytes,
+                     _lib.FLAG_KEEP_COUNTS if keep_counts else 0, int(sum_controls),
                      int(sum_cases), self.threshold,
                      None if self._table is None else self._table.ctypes.data_as(C.POINTER(C.c_double)),
                      int(lf_size if self._table is None else self._table.size), int(max_survivors))
@@ -278,10 +279,15 @@ class DiffContext:
             self._ck(self._L.kmd_survivors(self._h, out.ctypes.data, n.value, C.byref(n)))
         return out
 
-    def push_survivors(self, records: np.ndarray, rows_tested: int = 0) -> None:
-        """append host-side survivor records (plugin models, resumed spill files)"""
+    def push_survivors(self, records: np.ndarray, rows_tested: int = 0, counts: np.ndarray | None = None) -> None:
+        """append host-side survivor records (plugin models, resumed spill files), optionally with their counts"""
         rec = np.ascontiguousarray(records, dtype=SURVIVOR_DTYPE)
-        self._ck(self._L.kmd_push_survivors(self._h, rec.ctypes.data, rec.size, int(rows_tested)))
+        if counts is None:
+            self._ck(self._L.kmd_push_survivors(self._h, rec.ctypes.data, rec.size, int(rows_tested)))
+            return
+        dt = {1: np.uint8, 2: np.uint16, 4: np.uint32}[self.count_bytes]
+        c = np.ascontiguousarray(counts, dtype=dt).reshape(rec.size, self.nb_controls + self.nb_cases)
+        self._ck(self._L.kmd_push_survivors2(self._h, rec.ctypes.data, c.ctypes.data, rec.size, int(rows_tested)))
 
     # -- IModel::process, batched --
     def model_rows(self, rows):

@@ -6,6 +6,7 @@
 #include "../../include/kmdiff_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -232,6 +233,13 @@ int fail(kmd_context* ctx, int code, const char* fmt, ...)
       return fail(ctx, e_ == cudaErrorMemoryAllocation ? KMD_ERR_NOMEM : KMD_ERR_CUDA,           \
                   "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
   } while (0)
+
+struct DeviceBuf
+{
+  void* p = nullptr;
+  ~DeviceBuf() { if (p) cudaFree(p); }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
 
 uint32_t env_u32(const char* name, uint32_t dflt)
 {
@@ -634,12 +642,22 @@ __global__ void __launch_bounds__(256) keep_unordered_kernel(DeviceCounters* cnt
 }
 
 // FileAccumulator::push for records that arrive from the host (plugin models, resumed spill files)
-__global__ void push_records_kernel(uint32_t n, const kmd_survivor* in, SurvivorArrays s, DeviceCounters* cnt, uint32_t cap)
+// counts_in / counts_out (may be null): the records' per-sample counts, counts_bytes each, stored at the record's slot
+__global__ void push_records_kernel(uint32_t n, const kmd_survivor* in, SurvivorArrays s, DeviceCounters* cnt, uint32_t cap,
+                                    const uint8_t* counts_in, uint8_t* counts_out, uint32_t counts_bytes)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const kmd_survivor r = in[i];
   const uint32_t pos = atomicAdd(&cnt->surv_count, 1u);
+  if (pos < cap && counts_out)
+  {
+    uint8_t* dst = counts_out + static_cast<size_t>(pos) * counts_bytes;
+    if (counts_in)
+      for (uint32_t b = 0; b < counts_bytes; b++) dst[b] = counts_in[static_cast<size_t>(i) * counts_bytes + b];
+    else
+      for (uint32_t b = 0; b < counts_bytes; b++) dst[b] = 0;
+  }
   if (r.sign == KMD_SIGN_CONTROL) atomicAdd(&cnt->n_control, 1u); else atomicAdd(&cnt->n_case, 1u);
   if (pos >= cap) { atomicOr(&cnt->overflow, 2u); return; }
   s.kmer0[pos] = r.kmer[0];
@@ -707,7 +725,7 @@ int launch_scan(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, uint64
   A.out = ctx->surv;
   A.cap = static_cast<uint32_t>(ctx->cap);
   A.kmer_words = ctx->cfg.kmer_words;
-  A.counts_out = ctx->pop.enabled ? ctx->pop.d_surv_counts : nullptr;
+  A.counts_out = ctx->pop.d_surv_counts;   // --pop-correction or KMD_FLAG_KEEP_COUNTS, else null
   A.counts_bytes = (ctx->cfg.nb_controls + ctx->cfg.nb_cases) * ctx->cfg.count_bytes;
   lrt_exact_kernel<B><<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(A);
   KMD_CUDA(ctx, cudaGetLastError());
@@ -1036,12 +1054,21 @@ int kmd_create(const kmd_config* cfg, kmd_context** out)
   if (cfg->count_bytes != 1 && cfg->count_bytes != 2 && cfg->count_bytes != 4) return fail(nullptr, KMD_ERR_ARG, "count_bytes must be 1, 2 or 4");
   if (static_cast<uint64_t>(cfg->nb_controls) + cfg->nb_cases > 65536) return fail(nullptr, KMD_ERR_ARG, "more than 65536 samples");
 
+  // KMD_TIMING=1: where the start-up time of a context goes (stderr)
+  const bool timing = env_u32("KMD_TIMING", 0) != 0;
+  const auto t_start = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (timing)
+      fprintf(stderr, "[kmd_create] %-28s +%.3f s\n", what,
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count());
+  };
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
   {
     cudaGetLastError();
     return fail(nullptr, KMD_ERR_NO_DEVICE, "no CUDA device visible: kmdiff_b200 has no CPU fallback");
   }
+  lap("cudaGetDeviceCount");
   if (cfg->device < 0 || cfg->device >= n_dev) return fail(nullptr, KMD_ERR_ARG, "device %d out of range (0..%d)", cfg->device, n_dev - 1);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, KMD_ERR_CUDA, "cudaGetDeviceProperties failed");
@@ -1068,6 +1095,7 @@ int kmd_create(const kmd_config* cfg, kmd_context** out)
   ctx->stream = ctx->own_stream;
   KMD_CUDA_C(cudaEventCreate(&ctx->ev_k0));
   KMD_CUDA_C(cudaEventCreate(&ctx->ev_k1));
+  lap("context + streams");
 
   // model constants + log-factorial table
   std::vector<double> table;
@@ -1090,6 +1118,7 @@ int kmd_create(const kmd_config* cfg, kmd_context** out)
   ctx->model.lf = ctx->d_lf;
   ctx->model.lf_size = cfg->lf_size;
   ctx->lr_cut = lr_cut_for(cfg->threshold);
+  lap("lf table + model constants");
 
   KMD_TRY(make_plan(ctx));
   // The attribute belongs to the function and the device, not to a context: always raise it to the largest value any
@@ -1106,6 +1135,7 @@ int kmd_create(const kmd_config* cfg, kmd_context** out)
     KMD_CUDA_C(cudaFuncSetAttribute(lrt_model_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lf_smem_bytes));
   }
 
+  lap("kernel attributes");
   // buffers
   const size_t cap = ctx->cap;
   KMD_CUDA_C(cudaMalloc(&ctx->d_cnt, sizeof(DeviceCounters)));
@@ -1128,6 +1158,9 @@ int kmd_create(const kmd_config* cfg, kmd_context** out)
   }
   KMD_CUDA_C(cudaMalloc(&ctx->d_p_sorted, cap * 8));
   KMD_CUDA_C(cudaMalloc(&ctx->d_order, cap * 4));
+  if (cfg->flags & KMD_FLAG_KEEP_COUNTS)   // KmerSign::m_counts_ratio of a default (WITH_POPSTRAT) reference build, kmer.hpp:118-123
+    KMD_CUDA_C(cudaMalloc(&ctx->pop.d_surv_counts, cap * (cfg->nb_controls + cfg->nb_cases) * cfg->count_bytes));
+  lap("device buffers");
 #undef KMD_TRY
 #undef KMD_CUDA_C
   *out = ctx;
@@ -1284,28 +1317,43 @@ int kmd_survivors(kmd_context* ctx, kmd_survivor* out, uint64_t cap, uint64_t* n
   return download_records(ctx, ctx->d_vals[0], ctx->h_cnt->surv_count, out, cap, n);
 }
 
-int kmd_push_survivors(kmd_context* ctx, const kmd_survivor* records, uint64_t n, uint64_t rows_tested)
+int kmd_push_survivors2(kmd_context* ctx, const kmd_survivor* records, const void* counts, uint64_t n, uint64_t rows_tested)
 {
   if (!ctx) return KMD_ERR_ARG;
   if (n && !records) return fail(ctx, KMD_ERR_ARG, "null records");
   if (n >= (1ull << 31)) return fail(ctx, KMD_ERR_ARG, "too many records in one call");
+  if (counts && !ctx->pop.d_surv_counts)
+    return fail(ctx, KMD_ERR_STATE, "counts pushed into a context that keeps none (KMD_FLAG_KEEP_COUNTS / kmd_popstrat_enable)");
   KMD_CUDA(ctx, cudaSetDevice(ctx->device));
   if (n)
   {
     int rc = ensure_out(ctx, n);
     if (rc) return rc;
+    const uint32_t counts_bytes = (ctx->cfg.nb_controls + ctx->cfg.nb_cases) * ctx->cfg.count_bytes;
+    DeviceBuf d_counts;
+    if (counts)
+    {
+      KMD_CUDA(ctx, cudaMalloc(&d_counts.p, n * counts_bytes));
+      KMD_CUDA(ctx, cudaMemcpyAsync(d_counts.p, counts, n * counts_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     KMD_CUDA(ctx, cudaMemcpyAsync(ctx->d_out, records, n * sizeof(kmd_survivor), cudaMemcpyHostToDevice, ctx->stream));
     push_records_kernel<<<blocks_for(static_cast<uint32_t>(n)), 256, 0, ctx->stream>>>(static_cast<uint32_t>(n), ctx->d_out, ctx->surv,
-                                                                                       ctx->d_cnt, static_cast<uint32_t>(ctx->cap));
+                                                                                       ctx->d_cnt, static_cast<uint32_t>(ctx->cap),
+                                                                                       d_counts.as<uint8_t>(), ctx->pop.d_surv_counts, counts_bytes);
     ctx->launches++;
     KMD_CUDA(ctx, cudaGetLastError());
-    KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `records` may be pageable and reused by the caller
+    KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `records` / `counts` may be pageable and reused by the caller
   }
   for (uint64_t i = 0; i < n; i++) ctx->max_row_key = std::max(ctx->max_row_key, records[i].row);
   ctx->rows_tested += rows_tested;
   ctx->order_state = 0;
   ctx->final_valid = false;
   return KMD_OK;
+}
+
+int kmd_push_survivors(kmd_context* ctx, const kmd_survivor* records, uint64_t n, uint64_t rows_tested)
+{
+  return kmd_push_survivors2(ctx, records, nullptr, n, rows_tested);
 }
 
 static int model_rows_launch(kmd_context* ctx, const uint8_t* d_rows, uint64_t n_rows, double* p, int32_t* sign, double* mc, double* kk)

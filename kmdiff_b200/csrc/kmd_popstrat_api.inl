@@ -82,13 +82,6 @@ grm::BucketInfo bucket_info(uint32_t c, uint32_t n, bool diploid, uint32_t count
   return b;
 }
 
-struct DeviceBuf
-{
-  void* p = nullptr;
-  ~DeviceBuf() { if (p) cudaFree(p); }
-  template <class T> T* as() { return static_cast<T*>(p); }
-};
-
 // non-owning view of one slot of PopState::gram_scratch
 struct ScratchBuf
 {
@@ -502,7 +495,8 @@ int kmd_popstrat_fit(kmd_context* ctx, const void* counts, uint64_t n_kmers, dou
 int kmd_survivor_counts(kmd_context* ctx, void* out, uint64_t cap, uint64_t* n_out)
 {
   if (!ctx || !n_out) return KMD_ERR_ARG;
-  if (!ctx->pop.enabled) return fail(ctx, KMD_ERR_STATE, "survivor counts are kept only with population stratification enabled");
+  if (!ctx->pop.d_surv_counts)
+    return fail(ctx, KMD_ERR_STATE, "survivor counts are kept only with KMD_FLAG_KEEP_COUNTS or population stratification enabled");
   KMD_CUDA(ctx, cudaSetDevice(ctx->device));
   int rc = ensure_order(ctx, 1);
   if (rc) return rc;

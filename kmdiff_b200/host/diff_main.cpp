@@ -360,6 +360,8 @@ class GpuWorker
     c.lf_table = nullptr;
     c.lf_size = o.log_size;
     c.max_survivors = o.max_survivors;
+    // spill files carry every survivor's counts, like a default (WITH_POPSTRAT) build of the reference (kmer.hpp:118-123)
+    c.flags = (o.keep_tmp || o.save_sk) ? KMD_FLAG_KEEP_COUNTS : 0;
     kmd_context* raw = nullptr;
     const int rc = kmd_create(&c, &raw);
     if (rc != KMD_OK) throw KmdError("GpuError", std::string("kmd_create: ") + kmd_last_error(nullptr));
@@ -843,9 +845,13 @@ void run_plugin_model(PluginModel<MAX_C>& pm, const std::vector<Partition>& part
 
 // ---- spill files: partitions/p{i}_uncorrected (accumulator.hpp:156-285, kmer.hpp:113-127) --------------
 
-// counts != nullptr: the WITH_POPSTRAT tail `u16 N | N x f64 counts` (kmer.hpp:118-123); surv and counts are parallel.
+// KmerSign::dump of a default (WITH_POPSTRAT=ON, CMakeLists.txt:8) build of the reference (kmer.hpp:113-127):
+//   k-mer | f64 p | i32 sign | f64 mean_control | f64 mean_case | u16 N | N x f64 counts
+// in one LZ4 frame per partition.  For k <= 32 the files are interchangeable with the reference's.  For k > 32 the
+// reference writes only 8 of the 16 k-mer bytes (SURVEY.md §8 hazard 1); all words are written here, and both record
+// sizes are accepted on input.
 void write_spill_files(const std::vector<kmd_survivor>& surv, uint32_t nb_partitions, uint32_t kmer_words, const std::string& dir,
-                       const char* suffix = "_uncorrected", const std::vector<double>* counts = nullptr, uint16_t n_counts = 0)
+                       const char* suffix, const std::vector<double>& counts, uint16_t n_counts)
 {
   std::vector<std::unique_ptr<Lz4FrameWriter>> w(nb_partitions);
   std::vector<FILE*> files(nb_partitions, nullptr);
@@ -860,50 +866,71 @@ void write_spill_files(const std::vector<kmd_survivor>& surv, uint32_t nb_partit
     const kmd_survivor& s = surv[i];
     if (s.partition >= nb_partitions) continue;
     Lz4FrameWriter& o = *w[s.partition];
-    o.write(s.kmer, 8 * kmer_words);   // all words: the reference drops the high word for k > 32 (SURVEY.md §8 hazard 1)
+    o.write(s.kmer, 8 * kmer_words);
     o.write(&s.p_value, 8);
     o.write(&s.sign, 4);
     o.write(&s.mean_control, 8);
     o.write(&s.mean_case, 8);
-    if (counts)
-    {
-      o.write(&n_counts, 2);
-      o.write(counts->data() + i * n_counts, 8ull * n_counts);
-    }
+    o.write(&n_counts, 2);
+    o.write(counts.data() + i * n_counts, 8ull * n_counts);
   }
   for (uint32_t p = 0; p < nb_partitions; p++) { w[p]->close(); fclose(files[p]); }
 }
 
-// FileAccumulator::get over a spill file of an earlier run of this program (accumulator.hpp:190-226,
-// KmerSign::load kmer.hpp:101-111): records without the WITH_POPSTRAT tail.  Rows are renumbered in file order.
-std::vector<kmd_survivor> read_spill_file(const std::string& path, uint32_t partition, uint32_t kmer_words)
+// FileAccumulator::get over a spill file of an earlier run — of this program or of the reference
+// (accumulator.hpp:190-226, KmerSign::load kmer.hpp:101-111).  Rows are renumbered in file order.  counts_out
+// receives the records' counts as count_bytes-wide integers (what kmd_push_survivors2 takes).
+std::vector<kmd_survivor> read_spill_file(const std::string& path, uint32_t partition, uint32_t kmer_words, uint32_t n_samples,
+                                          uint32_t count_bytes, std::vector<uint8_t>* counts_out)
 {
   std::vector<kmd_survivor> out;
   FILE* f = fopen(path.c_str(), "rb");
   if (!f) throw KmdError("IOError", "Unable to open " + path);
   struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
   Lz4FrameReader in(f);
-  const size_t rec = 8ull * kmer_words + 28;
-  std::vector<uint8_t> buf(rec * 4096);
-  uint64_t local = 0;
-  for (;;)
+  std::vector<uint8_t> all;
   {
-    const size_t got = in.read(buf.data(), buf.size());
-    if (got % rec) throw KmdError("IOError", path + ": truncated record");
-    for (size_t i = 0; i < got / rec; i++)
-    {
-      const uint8_t* r = buf.data() + i * rec;
-      kmd_survivor s{};
-      memcpy(s.kmer, r, 8ull * kmer_words);
-      memcpy(&s.p_value, r + 8 * kmer_words, 8);
-      memcpy(&s.sign, r + 8 * kmer_words + 8, 4);
-      memcpy(&s.mean_control, r + 8 * kmer_words + 12, 8);
-      memcpy(&s.mean_case, r + 8 * kmer_words + 20, 8);
-      s.partition = partition;
-      s.row = (static_cast<uint64_t>(partition) << kPartShift) + local++;
-      out.push_back(s);
-    }
-    if (got < buf.size()) break;
+    std::vector<uint8_t> buf(1 << 20);
+    for (size_t got; (got = in.read(buf.data(), buf.size())) > 0;) all.insert(all.end(), buf.begin(), buf.begin() + got);
+  }
+  if (all.empty()) return out;
+  // record layout: the k-mer field is 8 * kmer_words bytes in our files, 8 bytes in the reference's whatever k is
+  size_t kbytes = 8ull * kmer_words;
+  auto tail_ok = [&](size_t kb) {
+    uint16_t n = 0;
+    if (all.size() < kb + 30) return false;
+    memcpy(&n, all.data() + kb + 28, 2);
+    return n == n_samples && all.size() % (kb + 30 + 8ull * n_samples) == 0;
+  };
+  if (!tail_ok(kbytes))
+  {
+    if (kmer_words > 1 && tail_ok(8)) kbytes = 8;   // a reference file for k > 32: the high word was never written
+    else throw KmdError("IOError", path + ": not a spill file of this cohort (record size / sample count mismatch)");
+  }
+  const size_t rec = kbytes + 30 + 8ull * n_samples;
+  uint64_t local = 0;
+  for (size_t at = 0; at < all.size(); at += rec)
+  {
+    const uint8_t* r = all.data() + at;
+    kmd_survivor s{};
+    memcpy(s.kmer, r, kbytes);
+    memcpy(&s.p_value, r + kbytes, 8);
+    memcpy(&s.sign, r + kbytes + 8, 4);
+    memcpy(&s.mean_control, r + kbytes + 12, 8);
+    memcpy(&s.mean_case, r + kbytes + 20, 8);
+    s.partition = partition;
+    s.row = (static_cast<uint64_t>(partition) << kPartShift) + local++;
+    out.push_back(s);
+    if (counts_out)
+      for (uint32_t j = 0; j < n_samples; j++)
+      {
+        double v;
+        memcpy(&v, r + kbytes + 30 + 8ull * j, 8);
+        const uint32_t c = v <= 0 ? 0u : v >= 4294967295.0 ? 0xFFFFFFFFu : static_cast<uint32_t>(v);
+        const size_t o = counts_out->size();
+        counts_out->resize(o + count_bytes);
+        memcpy(counts_out->data() + o, &c, count_bytes);
+      }
   }
   return out;
 }
@@ -1223,16 +1250,42 @@ void main_diff(DiffOptions& opt)
   // The reference forgets total_kmers in options.bin and would correct with m = 0; ours stores it.  Spill files
   // of a --pop-correction run carry per-sample counts and are not resumed from: such a run is redone in full.
   const PrevOptions prev = load_opt(opt.output_directory + "/options.bin");
-  bool resumed = false;
+  bool resumed = false;          // the scan is skipped: survivors come from kept spill files
+  bool resumed_pop = false;      // ... and so is the stratification: the GLM p-values are in p{i}_popstrat_uncorrected
+  uint64_t resumed_total = 0;
   unsigned action = 0;
   if (prev.valid)
   {
     action = compare_opt(opt, prev);
-    bool prev_1 = true;
-    for (uint32_t p = 0; p < cfg.nb_partitions && prev_1; p++) prev_1 = fs::exists(part_dir + "/p" + std::to_string(p) + "_uncorrected");
+    bool prev_1 = true, prev_2 = true;
+    for (uint32_t p = 0; p < cfg.nb_partitions; p++)
+    {
+      prev_1 = prev_1 && fs::exists(part_dir + "/p" + std::to_string(p) + "_uncorrected");
+      prev_2 = prev_2 && fs::exists(part_dir + "/p" + std::to_string(p) + "_popstrat_uncorrected");
+    }
     const bool prev_f = fs::exists(opt.output_directory + "/control_kmers.fasta") && fs::exists(opt.output_directory + "/case_kmers.fasta");
-    logf(L_DEBUG, "prev1 -> %d, prevf -> %d, action -> %u", prev_1, prev_f, action);
-    resumed = prev_1 && !(action & 0b1) && !opt.pop_correction && !prev.pop && prev.total_kmers > 0 && opt.model_lib_path.empty() && !opt.save_sk;
+    logf(L_DEBUG, "prev1 -> %d, prev2 -> %d, prevf -> %d, action -> %u", prev_1, prev_2, prev_f, action);
+    // m of the correctors: options.bin of this program stores it; an output directory written by the reference does
+    // not (it would correct with m = 0), but raw matrices give their row count away: (file size - 45) / R
+    resumed_total = prev.total_kmers;
+    if (resumed_total == 0)
+    {
+      const uint64_t R = 8ull * kw + (opt.nb_controls + opt.nb_cases) * opt.count_bytes;
+      uint64_t rows = 0;
+      bool known = true;
+      const auto mats = list_matrices(opt.kmtricks_dir);
+      for (const std::string& mpath : mats)
+      {
+        MatrixFile mf(mpath, R);
+        if (mf.hdr.compressed) { known = false; break; }
+        rows += mf.rows_if_raw;
+      }
+      if (known && !mats.empty()) resumed_total = rows;
+    }
+    const bool pop_kept = opt.pop_correction && prev.pop && prev_2 && !(action & 0b10);
+    resumed = prev_1 && !(action & 0b1) && resumed_total > 0 && opt.model_lib_path.empty() && !opt.save_sk &&
+              (!opt.pop_correction || pop_kept);
+    resumed_pop = resumed && pop_kept;
     if (resumed && prev_f && action == 0)
     {
       logf(L_INFO, "Done in %s, Peak RSS -> %zu MB.", whole.formatted().c_str(), peak_rss_mb());
@@ -1268,7 +1321,6 @@ void main_diff(DiffOptions& opt)
     if (!opt.model_lib_path.empty())
       throw KmdError("OptionError", "--cmodel needs count matrices (`kmtricks pipeline --until merge --mode kmer:count:bin`): "
                                     "per-sample count files are merged on the GPU, user models run on the host.");
-    if (opt.save_sk) throw KmdError("OptionError", "--save-sk needs count matrices as input.");
     for (uint32_t p = 0; p < cfg.nb_partitions; p++)
     {
       Partition part{};
@@ -1289,6 +1341,7 @@ void main_diff(DiffOptions& opt)
   if (n_dev <= 0) throw KmdError("GpuError", "no CUDA device visible: kmdiff-b200 has no CPU fallback.");
   if (opt.gpus > 0) n_dev = std::min(n_dev, opt.gpus);
   warmup.wait();
+  logf(L_DEBUG, "CUDA warm-up joined (%.3f s since start)", whole.seconds());
   const bool plugin = !opt.model_lib_path.empty();
   if (plugin)
   {
@@ -1350,10 +1403,12 @@ void main_diff(DiffOptions& opt)
   for (const Partition& p : parts) { input_bytes += p.bytes; any_raw |= p.raw; }
   const size_t parts_per_gpu = (parts.size() + static_cast<size_t>(n_dev) - 1) / static_cast<size_t>(n_dev);
   const size_t reader_cap = any_raw ? size_t{32} : std::max<size_t>(1, parts_per_gpu);
-  const size_t readers_per_gpu = std::max<size_t>(1, std::min({size_t{32}, opt.nb_threads / static_cast<size_t>(n_dev), reader_cap}));
+  size_t readers_per_gpu = std::max<size_t>(1, std::min({size_t{32}, opt.nb_threads / static_cast<size_t>(n_dev), reader_cap}));
+  if (const char* e = getenv("KMD_READERS")) readers_per_gpu = std::max<size_t>(1, static_cast<size_t>(atol(e)));   // tuning experiments
   // pinning host memory costs ~0.3 s per GB: small inputs get small buffers
-  const size_t buf_bytes = static_cast<size_t>(std::min<uint64_t>(16ull << 20, std::max<uint64_t>(1ull << 20,
-                               input_bytes / static_cast<uint64_t>(n_dev) / (2 * (readers_per_gpu + 2)))));
+  size_t buf_bytes = static_cast<size_t>(std::min<uint64_t>(16ull << 20, std::max<uint64_t>(1ull << 20,
+                         input_bytes / static_cast<uint64_t>(n_dev) / (2 * (readers_per_gpu + 2)))));
+  if (const char* e = getenv("KMD_BUF_MB")) buf_bytes = std::max<size_t>(1, static_cast<size_t>(atol(e))) << 20;
   // one thread per device: CUDA context creation and the device allocations of kmd_create run side by side
   workers.resize(static_cast<size_t>(n_dev));
   {
@@ -1373,12 +1428,18 @@ void main_diff(DiffOptions& opt)
 
   if (resumed)
   {
-    // accumulators re-opened on the kept spill files (cmd/diff.hpp:342-348)
-    uint64_t tested = prev.total_kmers;
+    // accumulators re-opened on the kept spill files (cmd/diff.hpp:342-348); after a stratified run the p-values to
+    // correct are the GLM ones of p{i}_popstrat_uncorrected
+    uint64_t tested = resumed_total;
+    const uint32_t n_samples = static_cast<uint32_t>(opt.nb_controls + opt.nb_cases);
+    const char* suffix = resumed_pop ? "_popstrat_uncorrected" : "_uncorrected";
     for (uint32_t p = 0; p < cfg.nb_partitions; p++)
     {
-      const std::vector<kmd_survivor> recs = read_spill_file(part_dir + "/p" + std::to_string(p) + "_uncorrected", p, kw);
-      ck(workers[0]->ctx(), kmd_push_survivors(workers[0]->ctx(), recs.data(), recs.size(), tested), "kmd_push_survivors");
+      std::vector<uint8_t> counts;
+      const std::vector<kmd_survivor> recs = read_spill_file(part_dir + "/p" + std::to_string(p) + suffix, p, kw, n_samples,
+                                                             static_cast<uint32_t>(opt.count_bytes), opt.keep_tmp ? &counts : nullptr);
+      ck(workers[0]->ctx(), kmd_push_survivors2(workers[0]->ctx(), recs.data(), opt.keep_tmp ? counts.data() : nullptr, recs.size(), tested),
+         "kmd_push_survivors2");
       tested = 0;
     }
     if (tested) ck(workers[0]->ctx(), kmd_push_survivors(workers[0]->ctx(), nullptr, 0, tested), "kmd_push_survivors");
@@ -1414,6 +1475,7 @@ void main_diff(DiffOptions& opt)
     for (auto& w : workers) if (w->error) std::rethrow_exception(w->error);
   }
 
+  logf(L_DEBUG, "scan finished (%.3f s since start)", whole.seconds());
   uint64_t total_kmers = 0, nb_sign = 0, sign_controls = 0, sign_cases = 0;
   for (auto& w : workers)
   {
@@ -1432,25 +1494,64 @@ void main_diff(DiffOptions& opt)
 
   dump_opt(opt, opt.output_directory + "/options.bin");
   const uint16_t n_samples = static_cast<uint16_t>(opt.nb_controls + opt.nb_cases);
-  // spill files of the prefilter survivors; with --pop-correction they carry the counts (the WITH_POPSTRAT tail)
+  // spill files of the prefilter survivors with their counts (the reference's default record layout)
   auto spill = [&](const char* suffix) {
     std::vector<kmd_survivor> all;
     std::vector<double> counts;
     for (auto& w : workers)
     {
       auto s = fetch(w->ctx(), false);
-      if (opt.pop_correction)
-      {
-        auto c = fetch_counts_as_double(w->ctx(), n_samples, opt.count_bytes, s.size());
-        counts.insert(counts.end(), c.begin(), c.end());
-      }
+      auto c = fetch_counts_as_double(w->ctx(), n_samples, opt.count_bytes, s.size());
+      counts.insert(counts.end(), c.begin(), c.end());
       all.insert(all.end(), s.begin(), s.end());
     }
-    write_spill_files(all, nb_partitions, kw, part_dir, suffix, opt.pop_correction ? &counts : nullptr, n_samples);
+    write_spill_files(all, nb_partitions, kw, part_dir, suffix, counts, n_samples);
   };
   if (opt.keep_tmp && !resumed) spill("_uncorrected");
 
-  if (opt.pop_correction)
+  if (opt.save_sk)
+  {
+    // --save-sk (cmd/diff.hpp:137-147, merge.hpp:270-278, 83-86): positive_kmer_matrix/ gets the run directory's
+    // skeleton (copy_kdir, cmd/diff.hpp:52-64) and one matrix_{p}.count.lz4 per partition holding the rows that passed
+    // the PREFILTER (written inside diff_observer::process, before any correction), count_slots = 4 in the header,
+    // rows in partition order.  With --pop-correction the reference passes no writer (merge.hpp:286-289): skeleton only.
+    const std::string root = opt.output_directory + "/positive_kmer_matrix";
+    const std::string dir = root + "/matrices";
+    fs::create_directories(dir);
+    fs::create_directories(root + "/repartition_gatb");
+    fs::create_directories(root + "/config_gatb");
+    std::error_code ec;
+    const auto copts = fs::copy_options::recursive | fs::copy_options::overwrite_existing;
+    for (const char* sub : {"/config_gatb", "/repartition_gatb"})
+      if (fs::exists(opt.kmtricks_dir + sub)) fs::copy(opt.kmtricks_dir + sub, root + sub, copts, ec);
+    for (const char* file : {"/options.txt", "/kmtricks.fof"})
+      if (fs::exists(opt.kmtricks_dir + file)) fs::copy(opt.kmtricks_dir + file, root, copts, ec);
+    if (!opt.pop_correction)
+    {
+      const size_t cb = (opt.nb_controls + opt.nb_cases) * opt.count_bytes;
+      std::vector<std::unique_ptr<MatrixWriter>> w(nb_partitions);
+      for (const Partition& p : parts)
+        w[p.index] = std::make_unique<MatrixWriter>(dir + "/matrix_" + std::to_string(p.index) + ".count.lz4", cfg.kmer_size, kw, 4,
+                                                    static_cast<uint32_t>(opt.nb_controls + opt.nb_cases), p.index);
+      for (auto& wk : workers)
+      {
+        const auto s = fetch(wk->ctx(), false);
+        uint64_t n = 0;
+        ck(wk->ctx(), kmd_survivor_counts(wk->ctx(), nullptr, 0, &n), "kmd_survivor_counts");
+        if (n != s.size()) throw KmdError("GpuError", "survivor counts out of step with the survivor records");
+        std::vector<uint8_t> raw(n * cb);
+        if (n) ck(wk->ctx(), kmd_survivor_counts(wk->ctx(), raw.data(), n, &n), "kmd_survivor_counts");
+        for (size_t i = 0; i < s.size(); i++)
+        {
+          if (s[i].partition >= nb_partitions || !w[s[i].partition]) continue;
+          w[s[i].partition]->write(s[i].kmer, 8ull * kw);
+          w[s[i].partition]->write(raw.data() + i * cb, cb);
+        }
+      }
+    }
+  }
+
+  if (opt.pop_correction && !resumed_pop)
   {
     do_pop(workers, opt, pop_dir, total_controls, total_cases);
     if (opt.keep_tmp) spill("_popstrat_uncorrected");
@@ -1490,6 +1591,7 @@ void main_diff(DiffOptions& opt)
       kept[i] = fetch(workers[i]->ctx(), true);
     }
   }
+  logf(L_DEBUG, "correction done, records fetched (%.3f s since start)", whole.seconds());
   // k-way merge of the per-GPU outputs: ascending p for BH/Holm, (partition, row) otherwise
   std::vector<kmd_survivor> final_records;
   for (auto& k : kept) final_records.insert(final_records.end(), k.begin(), k.end());
@@ -1507,34 +1609,6 @@ void main_diff(DiffOptions& opt)
     logf(L_INFO, "Partitions aggregated (%s)", agg_time.formatted().c_str());
     logf(L_INFO, "Significant k-mers: %llu (control), %llu (case).", static_cast<unsigned long long>(out.n_control),
          static_cast<unsigned long long>(out.n_case));
-  }
-  if (opt.save_sk)
-  {
-    // matrix of the significant k-mers: one pass over the inputs, rows picked by (partition, row)
-    const std::string dir = opt.output_directory + "/positive_kmer_matrix/matrices";
-    fs::create_directories(dir);
-    const size_t R = 8ull * kw + (opt.nb_controls + opt.nb_cases) * opt.count_bytes;
-    std::vector<std::vector<uint64_t>> want(nb_partitions);
-    for (const kmd_survivor& s : final_records) want[s.partition].push_back(s.row & ((1ull << kPartShift) - 1));
-    for (const Partition& p : parts)
-    {
-      auto& rows = want[p.index];
-      std::sort(rows.begin(), rows.end());
-      MatrixWriter w(dir + "/matrix_" + std::to_string(p.index) + ".count", cfg.kmer_size, kw, static_cast<uint32_t>(opt.count_bytes),
-                     static_cast<uint32_t>(opt.nb_controls + opt.nb_cases), p.index);
-      if (rows.empty()) continue;
-      MatrixFile mf(p.path, R);
-      std::vector<uint8_t> buf(R * 4096);
-      uint64_t base = 0; size_t next = 0;
-      for (;;)
-      {
-        const size_t got = mf.payload->read(buf.data(), buf.size());
-        const size_t n = got / R;
-        while (next < rows.size() && rows[next] < base + n) { w.write(buf.data() + (rows[next] - base) * R, R); next++; }
-        base += n;
-        if (got < buf.size() || next == rows.size()) break;
-      }
-    }
   }
   if (!opt.keep_tmp)
   {
@@ -1728,6 +1802,7 @@ int main(int argc, char** argv)
     try { return dev_command(argc, argv); }
     catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 3; }
   }
+  const Timer process_time;
   DiffOptions opt = parse_cli(argc, argv);
   g_level = opt.verbosity == "debug" ? L_DEBUG : opt.verbosity == "info" ? L_INFO : opt.verbosity == "warning" ? L_WARN : L_ERROR;
   if (opt.correction == KMD_CORR_BENJAMINI || opt.correction == KMD_CORR_HOLM)
@@ -1747,6 +1822,7 @@ int main(int argc, char** argv)
   }
   // like the reference: errors are logged, the exit code stays 0 (main.cc:93-102).  Every output file has been closed
   // by its owner; _exit skips the CUDA runtime's exit-time teardown (~0.1-0.2 s for nothing).
+  logf(L_DEBUG, "leaving main (%.3f s since process start)", process_time.seconds());
   fflush(nullptr);
   _exit(0);
 }

@@ -271,7 +271,8 @@ inline std::vector<std::string> get_files_to_merge(const std::string& run_dir, u
   return paths;
 }
 
-// --save-sk: matrix of the significant k-mers, same container (matrix_file.hpp:93-128), uncompressed payload
+// --save-sk: km::MatrixWriter<65536>(path, k, count_size = 4, nb_counts, id = 0, partition, lz4 = true)
+// (include/kmdiff/merge.hpp:270-278, km/io/matrix_file.hpp:93-128): the 45-byte header, then one LZ4 frame of rows
 class MatrixWriter
 {
  public:
@@ -279,13 +280,15 @@ class MatrixWriter
   {
     m_f = fopen(path.c_str(), "wb");
     if (!m_f) throw KmdError("IOError", "Unable to open " + path);
-    MatrixHeader h{kKmMagic, 0, 0, kMatrixMagic, k, kmer_slots, count_slots, nb_counts, 0, partition};
+    MatrixHeader h{kKmMagic, 0, 1, kMatrixMagic, k, kmer_slots, count_slots, nb_counts, 0, partition};
     fwrite(&h, sizeof h, 1, m_f);
+    m_lz4 = std::make_unique<Lz4FrameWriter>(m_f);
   }
-  void write(const void* row, size_t n) { fwrite(row, 1, n, m_f); }
-  ~MatrixWriter() { if (m_f) fclose(m_f); }
+  void write(const void* row, size_t n) { m_lz4->write(row, n); }
+  ~MatrixWriter() { if (m_lz4) m_lz4->close(); if (m_f) fclose(m_f); }
  private:
   FILE* m_f;
+  std::unique_ptr<Lz4FrameWriter> m_lz4;
 };
 
 }  // namespace kmd_host

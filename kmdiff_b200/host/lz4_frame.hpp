@@ -5,9 +5,10 @@
 // Written from the public LZ4 frame / block format descriptions (lz4_Frame_format.md,
 // lz4_Block_format.md); the reference links the vendored liblz4 1.9.3 instead, which is not available
 // to this build.  Reader: any conforming frame (linked or independent blocks, stored blocks, optional
-// checksums are skipped, concatenated frames).  Writer: a conforming frame of stored (uncompressed)
-// blocks — readable by liblz4, hence by the reference, at the cost of no compression; spill files
-// are small (<= 1e-3 of the rows).
+// checksums are skipped, concatenated frames).  Writer: a conforming frame of independent 64 KiB blocks,
+// each compressed with a greedy single-probe hash matcher (stored as is when that does not shrink it) —
+// readable by liblz4, hence by the reference; spill files are small (<= 1e-3 of the rows), so the
+// matcher favours brevity over ratio.
 #pragma once
 
 #include <cstdint>
@@ -195,6 +196,53 @@ class Lz4FrameReader
 };
 
 // Push-style writer: one frame of stored 64 KiB blocks.
+// One LZ4 block (lz4_Block_format.md): sequences of {token, literals, 2-byte offset, match length}; the last five
+// bytes are literals and no match starts within the last twelve.  Returns the compressed size (appended to out).
+inline size_t lz4_compress_block(const uint8_t* src, size_t n, std::vector<uint8_t>& out)
+{
+  const size_t start = out.size();
+  auto rd32 = [&](size_t i) { uint32_t v; memcpy(&v, src + i, 4); return v; };
+  auto put_len = [&](size_t len) { for (; len >= 255; len -= 255) out.push_back(255); out.push_back(static_cast<uint8_t>(len)); };
+  auto emit = [&](size_t anchor, size_t lit_end, size_t offset, size_t match_len) {
+    const size_t lit = lit_end - anchor;
+    const size_t ml = match_len ? match_len - 4 : 0;
+    out.push_back(static_cast<uint8_t>((lit >= 15 ? 15 : lit) << 4 | (match_len ? (ml >= 15 ? 15 : ml) : 0)));
+    if (lit >= 15) put_len(lit - 15);
+    out.insert(out.end(), src + anchor, src + lit_end);
+    if (!match_len) return;
+    out.push_back(static_cast<uint8_t>(offset & 0xFF));
+    out.push_back(static_cast<uint8_t>(offset >> 8));
+    if (ml >= 15) put_len(ml - 15);
+  };
+  size_t anchor = 0;
+  if (n >= 13)
+  {
+    constexpr int kHashBits = 13;
+    uint32_t table[1 << kHashBits];
+    memset(table, 0xFF, sizeof table);
+    const size_t mflimit = n - 12, matchlimit = n - 5;
+    for (size_t ip = 0; ip < mflimit;)
+    {
+      const uint32_t seq = rd32(ip);
+      const uint32_t h = (seq * 2654435761u) >> (32 - kHashBits);
+      const uint32_t ref = table[h];
+      table[h] = static_cast<uint32_t>(ip);
+      if (ref != 0xFFFFFFFFu && ip - ref <= 65535 && rd32(ref) == seq)
+      {
+        size_t ml = 4;
+        while (ip + ml < matchlimit && src[ref + ml] == src[ip + ml]) ml++;
+        emit(anchor, ip, ip - ref, ml);
+        ip += ml;
+        anchor = ip;
+      }
+      else
+        ip++;
+    }
+  }
+  emit(anchor, n, 0, 0);
+  return out.size() - start;
+}
+
 class Lz4FrameWriter
 {
  public:
@@ -234,13 +282,24 @@ class Lz4FrameWriter
   void flush()
   {
     if (m_buf.empty()) return;
-    const uint32_t hdr = static_cast<uint32_t>(m_buf.size()) | 0x80000000u;
-    fwrite(&hdr, 4, 1, m_f);
-    fwrite(m_buf.data(), 1, m_buf.size(), m_f);
+    m_cmp.clear();
+    const size_t c = lz4_compress_block(m_buf.data(), m_buf.size(), m_cmp);
+    if (c < m_buf.size())
+    {
+      const uint32_t hdr = static_cast<uint32_t>(c);
+      fwrite(&hdr, 4, 1, m_f);
+      fwrite(m_cmp.data(), 1, c, m_f);
+    }
+    else
+    {
+      const uint32_t hdr = static_cast<uint32_t>(m_buf.size()) | 0x80000000u;   // stored block
+      fwrite(&hdr, 4, 1, m_f);
+      fwrite(m_buf.data(), 1, m_buf.size(), m_f);
+    }
     m_buf.clear();
   }
   FILE* m_f;
-  std::vector<uint8_t> m_buf;
+  std::vector<uint8_t> m_buf, m_cmp;
 };
 
 }  // namespace kmd_host

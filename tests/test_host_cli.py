@@ -91,6 +91,23 @@ def test_lz4_frame_writer_is_readable_by_liblz4(cli, tmp_path):
     assert back == data.tobytes()
     out = subprocess.run([cli, "dev-cat", str(dst), "0", "lz4"], capture_output=True, timeout=60)
     assert out.stdout == data.tobytes()
+    # compressible inputs go through the block compressor: matrix rows (short matches, long literal runs), long
+    # overlapping matches (period 7), a run of zeros, and sizes around the 64 KiB block and the 12/5-byte end rules
+    spec = K.SynthSpec(10, 10, total_rows=30_000, seed=5)
+    cases = [spec.rows_host(30_000), np.tile(np.arange(7, dtype=np.uint8), 100_003), np.zeros(65536 * 2 + 11, np.uint8)]
+    cases += [np.frombuffer(bytes(range(256)) * 300, np.uint8)[:n] for n in (0, 1, 4, 5, 11, 12, 13, 14, 65535, 65536, 65537)]
+    for data in cases:
+        data.tofile(src)
+        assert run([cli, "dev-pack", str(src), str(dst)]).returncode == 0
+        with pa.CompressedInputStream(pa.OSFile(str(dst)), "lz4") as s:
+            back = s.read()
+        assert back == data.tobytes(), data.size
+        out = subprocess.run([cli, "dev-cat", str(dst), "0", "lz4"], capture_output=True, timeout=60)
+        assert out.stdout == data.tobytes()
+    assert os.path.getsize(dst) < 1000                       # 65537 bytes of a 256-byte period
+    cases[0].tofile(src)
+    run([cli, "dev-pack", str(src), str(dst)])
+    assert os.path.getsize(dst) < 0.8 * cases[0].nbytes      # synthetic count rows really shrink
 
 
 def test_run_dir_config_and_totals(cli, tmp_path):
@@ -207,8 +224,10 @@ def test_cli_other_count_widths_and_wide_kmers(cli, tmp_path, shape, cb):
         with open(os.path.join(out, "case_kmers.fasta")) as f:
             lines = f.read().split("\n")
         assert len(lines[1]) == 60 and len(lines[2]) == 3      # kseq++ wraps sequences at 60 columns
-    # --keep-tmp: spill files in the reference's record layout (kmer words | f64 p | i32 sign | f64 | f64)
-    rec = 8 * spec.kmer_words + 28
+    # --keep-tmp: spill files in the record layout of a default (WITH_POPSTRAT) reference build:
+    # kmer words | f64 p | i32 sign | f64 | f64 | u16 N | N x f64 counts
+    nsamp = shape[0] + shape[1]
+    rec = 8 * spec.kmer_words + 30 + 8 * nsamp
     total = 0
     for p in range(parts):
         raw = subprocess.run([cli, "dev-cat", os.path.join(out, "partitions", f"p{p}_uncorrected"), "0", "lz4"],
@@ -361,6 +380,113 @@ def test_cli_resume_recorrects_from_spill_files(cli, tmp_path):
     # another cutoff: the prefilter changed, everything is redone
     r4 = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "--keep-tmp", "-s", "0.05", "-u", "1000", "-c", "benjamini"])
     assert "Process partitions" in r4.stderr and "[error]" not in r4.stderr, r4.stderr
+
+
+def spill_records(cli, path, kmer_bytes, n_samples):
+    """decoded p{i}_uncorrected file -> structured array (KmerSign::dump, kmer.hpp:113-127, WITH_POPSTRAT layout)"""
+    raw = subprocess.run([cli, "dev-cat", path, "0", "lz4"], capture_output=True, timeout=120).stdout
+    dt = np.dtype([("kmer", f"V{kmer_bytes}"), ("p", "<f8"), ("sign", "<i4"), ("mc", "<f8"), ("kk", "<f8"), ("n", "<u2"),
+                   ("counts", "<f8", (n_samples,))])
+    assert dt.itemsize == kmer_bytes + 30 + 8 * n_samples and len(raw) % dt.itemsize == 0
+    return np.frombuffer(raw, dtype=dt)
+
+
+@pytest.mark.gpu
+def test_spill_files_interchange_with_the_reference(cli, tmp_path):
+    """--keep-tmp spill files (a12): ours and the reference's hold the same records (k-mer, sign, means and counts bit
+    for bit, p within 1e-9); an output directory written by the REFERENCE is re-corrected by kmdiff-b200 with another
+    -c without a scan (f4) — m comes from the raw matrices' sizes, which the reference's options.bin forgets."""
+    if not os.path.exists(oracle.REF_BIN):
+        pytest.skip("oracle/_ref/kmdiff not built")
+    n, parts = 160_000, 6
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=parts, seed=123)
+    out_ref, out_new = str(tmp_path / "ref"), str(tmp_path / "new")
+    common = ["diff", "--km-run", d, "-1", "10", "-2", "10", "-c", "bonferroni", "-t", "4", "--keep-tmp"] + THR_ARGS
+    r = run([oracle.REF_BIN] + common + ["-o", out_ref])
+    assert "[error]" not in r.stderr, r.stderr
+    os.remove(os.path.join(d, "kmdiff-count.opt"))
+    r = run([cli] + common + ["-o", out_new])
+    assert "[error]" not in r.stderr, r.stderr
+    n_rec = 0
+    for p in range(parts):
+        a = spill_records(cli, os.path.join(out_ref, "partitions", f"p{p}_uncorrected"), 8, 20)
+        b = spill_records(cli, os.path.join(out_new, "partitions", f"p{p}_uncorrected"), 8, 20)
+        assert len(a) == len(b)
+        for f in ("kmer", "sign", "mc", "kk", "n", "counts"):
+            assert np.array_equal(a[f], b[f]), (p, f)
+        assert np.all(np.abs(a["p"] - b["p"]) <= 1e-9 * a["p"])
+        n_rec += len(a)
+    assert n_rec > 100
+    # re-correct the REFERENCE's output directory with another corrector: no scan, the spill files are read
+    r2 = run([cli, "diff", "--km-run", d, "-1", "10", "-2", "10", "-c", "benjamini", "-t", "4", "--keep-tmp", "-o", out_ref] + THR_ARGS)
+    assert "[error]" not in r2.stderr and "Process partitions" not in r2.stderr, r2.stderr
+    ctl, case, _ = expected_records(spec, n, parts, "benjamini")
+    got = sorted((strip_index(h), s) for f in ("control_kmers.fasta", "case_kmers.fasta") for h, s in read_fasta(os.path.join(out_ref, f)))
+    assert got == sorted(ctl + case) and len(got) > 50
+    # and the other way round: the reference resumes from OUR spill files (it corrects with m = 0 then, i.e. keeps
+    # every prefilter survivor — SURVEY.md §5 — so only the record count can be checked)
+    os.remove(os.path.join(d, "kmdiff-count.opt")) if os.path.exists(os.path.join(d, "kmdiff-count.opt")) else None
+    r3 = run([oracle.REF_BIN, "diff", "--km-run", d, "-1", "10", "-2", "10", "-c", "benjamini", "-t", "4", "--keep-tmp", "-o", out_new] + THR_ARGS)
+    assert "[error]" not in r3.stderr and "Process partitions" not in r3.stderr, r3.stderr
+    n_ref = sum(len(read_fasta(os.path.join(out_new, f))) for f in ("control_kmers.fasta", "case_kmers.fasta"))
+    assert n_ref == n_rec
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("count_files", [False, True])
+def test_save_sk_matches_the_reference(cli, tmp_path, count_files):
+    """--save-sk (f3): positive_kmer_matrix/matrices/matrix_{p}.count.lz4 hold the rows that passed the prefilter, in
+    km::MatrixWriter<65536>'s container (45-byte header with compressed = 1 and count_slots = 4, then one LZ4 frame);
+    header fields and decoded payloads equal the reference's (merge.hpp:270-278, 83-86)"""
+    n, parts = 90_000, 4
+    spec = K.SynthSpec(10, 10, kmer_size=31, count_bytes=4, total_rows=n, seed=5, enriched_ppm=3000)
+    d = str(tmp_path / "run")
+    kio.write_run_dir(d, spec, n, parts, count_files=count_files)
+    for sub in ("config_gatb", "repartition_gatb"):      # copy_kdir (cmd/diff.hpp:52-64) needs them; kmtricks writes them
+        os.makedirs(os.path.join(d, sub), exist_ok=True)
+        with open(os.path.join(d, sub, "marker.txt"), "w") as f:
+            f.write(sub)
+    out = str(tmp_path / "out")
+    r = run([cli, "diff", "--km-run", d, "-1", "10", "-2", "10", "-o", out, "--save-sk", "-t", "4"] + THR_ARGS)
+    assert "[error]" not in r.stderr, r.stderr
+    root = os.path.join(out, "positive_kmer_matrix")
+    assert os.path.exists(os.path.join(root, "kmtricks.fof")) and os.path.exists(os.path.join(root, "options.txt"))
+    assert os.path.exists(os.path.join(root, "config_gatb", "marker.txt"))
+
+    def load(base):
+        res = {}
+        for p in range(parts):
+            path = os.path.join(base, "positive_kmer_matrix", "matrices", f"matrix_{p}.count.lz4")
+            with open(path, "rb") as f:
+                hdr = kio.MatrixHeader.unpack(f.read(45))
+            body = subprocess.run([cli, "dev-cat", path, "45"], capture_output=True, timeout=120).stdout
+            assert hdr.compressed == 1 and hdr.count_slots == 4 and hdr.nb_counts == 20 and hdr.kmer_size == 31 and hdr.id == 0
+            res[hdr.partition] = body
+        return res
+
+    ours = load(out)
+    # the rows are the oracle's prefilter survivors, partition by partition, in row order
+    rows = spec.rows_host(n).reshape(n, spec.row_bytes)
+    want, _, _ = oracle.Model(10, 10, spec.totals()).diff(rows.ravel(), 1, 4, 0.05 / 100000)
+    per = (n + parts - 1) // parts
+    total = 0
+    for p in range(parts):
+        idx = want["row"][(want["row"] >= p * per) & (want["row"] < (p + 1) * per)]
+        assert ours[p] == rows[idx].tobytes(), p
+        total += len(idx)
+    assert total == len(want) > 50
+    if os.path.exists(oracle.REF_BIN):
+        out_ref = str(tmp_path / "ref")
+        opt = os.path.join(d, "kmdiff-count.opt")
+        if os.path.exists(opt) and not count_files:
+            os.remove(opt)
+        rr = run([oracle.REF_BIN, "diff", "--km-run", d, "-1", "10", "-2", "10", "-o", out_ref, "--save-sk", "-t", "4"] + THR_ARGS)
+        assert "[error]" not in rr.stderr, rr.stderr
+        ref = load(out_ref)
+        # matrix mode names the reference's files by directory-iteration index, not by partition: compare as multisets
+        assert sorted(ref.values()) == sorted(ours.values())
+        if count_files:
+            assert ref == ours
 
 
 # ---- -f/--kff-output (include/kmdiff/kff_utils.hpp:32-107) -------------------------------------------------
