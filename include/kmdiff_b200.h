@@ -252,6 +252,11 @@ int kmd_exchange_export(kmd_context* ctx, uint64_t* d_slot, uint64_t cap);
 int kmd_exchange_correct(kmd_context* ctx, const uint64_t* d_all, uint32_t world, uint64_t cap, int correction,
                          double significance);
 int kmd_exchange_result(kmd_context* ctx, kmd_exchange_decision* out);
+/* The same exchange inside ONE process that drives several devices (n contexts, one per device — the host program):
+ * every context exports its slot, pulls the other contexts' slots with peer-to-peer copies (NVLink where the topology
+ * has it) ordered by events, and corrects.  Synchronises; decisions[i] belongs to ctxs[i]. */
+int kmd_exchange_local(kmd_context* const* ctxs, uint32_t n, int correction, double significance,
+                       kmd_exchange_decision* decisions);
 /* host helper: walk p_sorted (ascending, all ranks merged) exactly like sorted_aggregator::run;
  * returns the number accepted and writes the first rejected p-value (+inf if none) */
 uint64_t kmd_first_reject(const double* p_sorted, uint64_t n, int correction, double significance,

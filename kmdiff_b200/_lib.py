@@ -28,7 +28,7 @@ SYMBOLS = [
     "kmd_popstrat_gram_ms", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
     "kmd_survivor_counts", "kmd_smartpca_normalize", "kmd_sym_eig", "kmd_smartpca_pcs",
     "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_rows_host", "kmd_merge_ms", "kmd_survivor_pvalues_device", "kmd_first_reject_device",
-    "kmd_scan_host_async", "kmd_host_wait", "kmd_bind_host_thread", "kmd_warmup", "kmd_get_stream", "kmd_exchange_export", "kmd_exchange_correct", "kmd_exchange_result",
+    "kmd_scan_host_async", "kmd_host_wait", "kmd_bind_host_thread", "kmd_warmup", "kmd_get_stream", "kmd_exchange_export", "kmd_exchange_correct", "kmd_exchange_result", "kmd_exchange_local",
 ]
 
 EXCHANGE_HEADER = 8
@@ -128,6 +128,7 @@ def load() -> C.CDLL:
     L.kmd_exchange_export.argtypes = [vp, vp, u64]
     L.kmd_exchange_correct.argtypes = [vp, vp, u32, u64, C.c_int, d]
     L.kmd_exchange_result.argtypes = [vp, C.POINTER(ExchangeDecision)]
+    L.kmd_exchange_local.argtypes = [vp, u32, C.c_int, d, C.POINTER(ExchangeDecision)]
     L.kmd_first_reject.argtypes = [vp, u64, C.c_int, d, u64, C.POINTER(d)]
     L.kmd_first_reject.restype = u64
     L.kmd_lf_table_fill.argtypes = [vp, u64]

@@ -140,6 +140,10 @@ struct ExchangeState
   ExchangeDecision* h_dec = nullptr;   // pinned
   bool pending = false;                // kmd_exchange_correct enqueued, result not read yet
   bool by_p = false;
+  // kmd_exchange_local (one process, several devices): this context's gather buffer and "my slot is written" event
+  uint64_t* gather = nullptr;
+  size_t gather_words = 0;
+  cudaEvent_t ev_export = nullptr;
 };
 
 }  // namespace

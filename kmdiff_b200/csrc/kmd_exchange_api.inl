@@ -20,6 +20,8 @@ void exchange_free(kmd_context* ctx)
   cudaFree(x.keys[0]);
   cudaFree(x.keys[1]);
   cudaFree(x.d_dec);
+  cudaFree(x.gather);
+  if (x.ev_export) cudaEventDestroy(x.ev_export);
   if (x.h_dec) cudaFreeHost(x.h_dec);
   x = ExchangeState{};
 }
@@ -134,6 +136,8 @@ int kmd_exchange_export(kmd_context* ctx, uint64_t* d_slot, uint64_t cap)
   return KMD_OK;
 }
 
+int kmd_exchange_result(kmd_context* ctx, kmd_exchange_decision* out);
+
 int kmd_exchange_correct(kmd_context* ctx, const uint64_t* d_all, uint32_t world, uint64_t cap, int correction, double significance)
 {
   if (!ctx || !d_all || !world) return KMD_ERR_ARG;
@@ -188,6 +192,72 @@ int kmd_exchange_correct(kmd_context* ctx, const uint64_t* d_all, uint32_t world
   x.pending = true;
   x.by_p = sorted;
   ctx->final_valid = false;
+  return KMD_OK;
+}
+
+int kmd_exchange_local(kmd_context* const* ctxs, uint32_t n, int correction, double significance, kmd_exchange_decision* decisions)
+{
+  if (!ctxs || !n || !decisions) return KMD_ERR_ARG;
+  for (uint32_t i = 0; i < n; i++)
+    if (!ctxs[i]) return KMD_ERR_ARG;
+  // slot capacity = the largest survivor count (this entry point synchronises anyway)
+  uint64_t cap = 1;
+  for (uint32_t i = 0; i < n; i++)
+  {
+    kmd_context* c = ctxs[i];
+    KMD_CUDA(c, cudaSetDevice(c->device));
+    int rc = fetch_counters(c);
+    if (rc) return rc;
+    cap = std::max<uint64_t>(cap, c->h_cnt->surv_count);
+  }
+  const uint64_t slot_words = KMD_EXCHANGE_HEADER + cap;
+  // every context writes its slot into its OWN gather buffer ...
+  for (uint32_t i = 0; i < n; i++)
+  {
+    kmd_context* c = ctxs[i];
+    ExchangeState& x = c->xch;
+    KMD_CUDA(c, cudaSetDevice(c->device));
+    if (x.gather_words < slot_words * n)
+    {
+      if (x.gather) KMD_CUDA(c, cudaFree(x.gather));
+      x.gather = nullptr;
+      x.gather_words = 0;
+      const size_t want = slot_words * n + slot_words * n / 4;
+      KMD_CUDA(c, cudaMalloc(&x.gather, want * sizeof(uint64_t)));
+      x.gather_words = want;
+    }
+    if (!x.ev_export) KMD_CUDA(c, cudaEventCreateWithFlags(&x.ev_export, cudaEventDisableTiming));
+    for (uint32_t j = 0; j < n; j++)
+      if (j != i && ctxs[j]->device != c->device)
+      {
+        const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[j]->device, 0);   // NVLink P2P when the topology has it
+        if (e != cudaSuccess) cudaGetLastError();                               // already enabled / unsupported: staged copies
+      }
+    int rc = kmd_exchange_export(c, x.gather + i * slot_words, cap);
+    if (rc) return rc;
+    KMD_CUDA(c, cudaEventRecord(x.ev_export, c->stream));
+  }
+  // ... and pulls every other context's slot over the peer link once that slot is written
+  for (uint32_t j = 0; j < n; j++)
+  {
+    kmd_context* c = ctxs[j];
+    KMD_CUDA(c, cudaSetDevice(c->device));
+    for (uint32_t i = 0; i < n; i++)
+    {
+      if (i == j) continue;
+      KMD_CUDA(c, cudaStreamWaitEvent(c->stream, ctxs[i]->xch.ev_export, 0));
+      KMD_CUDA(c, cudaMemcpyPeerAsync(c->xch.gather + i * slot_words, c->device, ctxs[i]->xch.gather + i * slot_words,
+                                      ctxs[i]->device, slot_words * sizeof(uint64_t), c->stream));
+    }
+    int rc = kmd_exchange_correct(c, c->xch.gather, n, cap, correction, significance);
+    if (rc) return rc;
+  }
+  for (uint32_t j = 0; j < n; j++)
+  {
+    int rc = kmd_exchange_result(ctxs[j], &decisions[j]);
+    if (rc) return rc;
+    if (decisions[j].overflow) return fail(ctxs[j], KMD_ERR_STATE, "exchange slot overflow with an exact capacity");
+  }
   return KMD_OK;
 }
 

@@ -248,7 +248,9 @@ __device__ __forceinline__ void row_partial(const ScanParams& P, const Loader& l
 // approximate division 2.4e-7 => relative error of the ratio <= 4.2e-7 => 6.1e-7 in log2;
 // lg2.approx 2.4e-7 absolute + 2.4e-7 relative; products/sum 1.2e-7 relative.  Total
 // <= 8.5e-7*k + 3.6e-7*|k*log2 x| per cohort; the margin charges 2.5e-6 on both, plus 0.08
-// absolute (host slack on LR* included).  tests/test_screen.py attacks this bound.
+// absolute (host slack on LR* included).  tests/test_gpu_parity.py attacks this bound (adversarial rows against
+// the oracle; 1e8 (kc, kk) pairs up to 2^32 - 1 per cohort against the exact kernel) and tests/test_screen_emulation.py
+// replays the same arithmetic in numpy float32 on the CPU.
 __device__ __forceinline__ bool screen_pass(const ScanParams& P, uint64_t sum_ctrl, uint64_t sum_case)
 {
   const float kc = static_cast<float>(sum_ctrl);

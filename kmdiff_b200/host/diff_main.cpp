@@ -1562,26 +1562,18 @@ void main_diff(DiffOptions& opt)
   logf(L_INFO, opt.correction == KMD_CORR_NOTHING ? "Aggregate partitions..." : "Aggregate partitions and apply significance correction...");
   const bool sorted = opt.correction == KMD_CORR_BENJAMINI || opt.correction == KMD_CORR_HOLM;
   std::vector<std::vector<kmd_survivor>> kept(workers.size());
-  if (sorted && workers.size() > 1)
+  if (workers.size() > 1)
   {
-    // one global ascending walk over all GPUs' survivors (aggregator.hpp:282-310)
-    std::vector<double> merged;
-    for (auto& w : workers)
-    {
-      uint64_t n = 0;
-      ck(w->ctx(), kmd_sorted_pvalues(w->ctx(), nullptr, 0, &n), "kmd_sorted_pvalues");
-      const size_t at = merged.size();
-      merged.resize(at + n);
-      if (n) ck(w->ctx(), kmd_sorted_pvalues(w->ctx(), merged.data() + at, n, &n), "kmd_sorted_pvalues");
-      std::inplace_merge(merged.begin(), merged.begin() + at, merged.end());
-    }
-    double cut = 0;
-    kmd_first_reject(merged.data(), merged.size(), opt.correction, opt.threshold, total_kmers, &cut);
-    for (size_t i = 0; i < workers.size(); i++)
-    {
-      ck(workers[i]->ctx(), kmd_keep_below(workers[i]->ctx(), cut, nullptr, nullptr), "kmd_keep_below");
-      kept[i] = fetch(workers[i]->ctx(), true);
-    }
+    // m and (BENJAMINI / HOLM) one global ascending walk over all GPUs' survivors (aggregator.hpp:282-310), on the
+    // devices: every context exports its counters and p-values, pulls the others' over the peer links, sorts the union
+    // and keeps its own survivors below the first rejected p-value (kmd_exchange_local)
+    std::vector<kmd_context*> ctxs;
+    for (auto& w : workers) ctxs.push_back(w->ctx());
+    std::vector<kmd_exchange_decision> dec(ctxs.size());
+    ck(ctxs[0], kmd_exchange_local(ctxs.data(), static_cast<uint32_t>(ctxs.size()), opt.correction, opt.threshold, dec.data()),
+       "kmd_exchange_local");
+    if (dec[0].total_rows != total_kmers) throw KmdError("GpuError", "exchange: row totals out of step");
+    for (size_t i = 0; i < workers.size(); i++) kept[i] = fetch(workers[i]->ctx(), true);
   }
   else
   {

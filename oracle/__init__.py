@@ -27,6 +27,8 @@ REF_SO = os.path.join(HERE, "_ref", "libkmdiff_ref.so")
 REF_BIN = os.path.join(HERE, "_ref", "kmdiff")
 REF_BIN16 = os.path.join(HERE, "_ref", "kmdiff_c16")
 REF_SMARTPCA = os.path.join(HERE, "_ref", "smartpca")
+REF_PLUGIN_OUR_HEADERS = os.path.join(HERE, "_ref", "libref_ex_model.so")     # reference plugin source x this repo's headers
+OUR_PLUGIN_REF_HEADERS = os.path.join(HERE, "_ref", "libex_model_refhdr.so")   # this repo's plugin x the reference's headers
 REFERENCE_ROOT = "/root/reference"
 
 CONTROL, CASE, NO = 0, 1, 2
@@ -47,6 +49,7 @@ def build(ref: bool | None = None, refbin: bool = False) -> None:
             # HAWK's smartpca next to the reference binary: lets the reference's --pop-correction pipeline run here
             # (needs scipy's bundled OpenBLAS for LAPACK); the parity tests that use it skip when it is absent
             subprocess.call(["make", "-s", "-j8", "-C", HERE, "smartpca"])
+            subprocess.call(["make", "-s", "-C", HERE, "plugins"])
 
 
 class _Model(C.Structure):

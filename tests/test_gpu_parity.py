@@ -9,6 +9,9 @@ import pytest
 import kmdiff_b200 as K
 import oracle
 from conftest import SHAPES, make_cohort, rel_err
+from kmdiff_b200 import _lib as _kmd_lib
+
+K._lib = _kmd_lib
 
 pytestmark = pytest.mark.gpu
 
@@ -255,6 +258,61 @@ def adversarial_rows(nc, nk, count_bytes, rng, n):
     rows[:, :8] = kmers.view(np.uint8).reshape(n, 8)
     rows[:, 8:] = counts.view(np.uint8).reshape(n, -1)
     return rows.ravel()
+
+
+@pytest.mark.parametrize("thr,n", [(0.5, 20_000_000), (1e-3, 20_000_000), (5e-7, 100_000_000), (1e-30, 20_000_000),
+                                   (1e-300, 20_000_000)])
+def test_screen_never_drops_a_survivor_over_the_whole_count_range(thr, n):
+    """up to 1e8 (kc, kk) pairs — one control and one case sample, 4-byte counts, so the two counts ARE the cohort sums — from 1
+    to 2^32 - 1 per cohort, most of them placed around the prefilter boundary LR*(thr) at their own magnitude.  The
+    scan (fp32 screen -> exact kernel on the candidates) must keep exactly the rows the exact kernel keeps when it is
+    run on EVERY row (kmd_model_rows_device): the screen may only err towards keeping a row.  Device vs device, so
+    the oracle's O(sum) log-factorial loop is not in the way of sums far beyond the table."""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(int(-np.log10(max(thr, 1e-300))) + 5)
+    sc, sk = 10**9, 12 * 10**8
+    # LR* for this threshold: smallest LR with igamc(0.5, LR) <= thr (bisection on the library's own chi-square tail)
+    lo, hi = 0.0, 1.0
+    while K._lib.load().kmd_chisqc(1.0, 2 * hi) > thr:
+        lo, hi = hi, hi * 2
+    for _ in range(100):
+        mid = 0.5 * (lo + hi)
+        lo, hi = (mid, hi) if K._lib.load().kmd_chisqc(1.0, 2 * mid) > thr else (lo, mid)
+    lr_star = hi
+    # total t log-uniform in [2, 2^32), split around the null proportion by a deviation that puts LR near LR*:
+    # LR ~ d^2 / (2 t f (1 - f)) for kc = f t + d
+    t = torch.exp2(torch.rand(n, generator=g, device="cuda", dtype=torch.float64) * 31.0 + 1.0)
+    f = sc / (sc + sk)
+    d = torch.sqrt(2.0 * lr_star * t * f * (1 - f)) * (0.6 + 0.8 * torch.rand(n, generator=g, device="cuda", dtype=torch.float64))
+    d = d * torch.where(torch.rand(n, generator=g, device="cuda") < 0.5, -1.0, 1.0)
+    kc = torch.clamp(torch.round(t * f + d), 0, 2**32 - 1)
+    kk = torch.clamp(torch.round(t - kc), 0, 2**32 - 1)
+    # a tenth of the rows: anything goes (one-sided, tiny, saturated)
+    wild = torch.rand(n, generator=g, device="cuda") < 0.1
+    kc = torch.where(wild, torch.floor(torch.exp2(torch.rand(n, generator=g, device="cuda", dtype=torch.float64) * 32.0)) - 1, kc)
+    kk = torch.where(wild, torch.floor(torch.exp2(torch.rand(n, generator=g, device="cuda", dtype=torch.float64) * 32.0)) - 1, kk)
+    kk = torch.where((kc == 0) & (kk == 0), torch.ones_like(kk), kk)       # kmtricks never emits an all-zero row
+    rows = torch.zeros((n, 4), dtype=torch.int32, device="cuda")           # 8-byte k-mer | u32 kc | u32 kk
+    rows[:, 0] = torch.arange(n, device="cuda", dtype=torch.int32)
+    rows[:, 2] = kc.to(torch.int64).to(torch.int32)                        # wraps to the u32 bit pattern
+    rows[:, 3] = kk.to(torch.int64).to(torch.int32)
+    del t, d, kc, kk, wild
+    p = torch.empty(n, dtype=torch.float64, device="cuda")
+    sign = torch.empty(n, dtype=torch.int32, device="cuda")
+    mc = torch.empty(n, dtype=torch.float64, device="cuda")
+    mk = torch.empty(n, dtype=torch.float64, device="cuda")
+    with K.DiffContext(1, 1, sc, sk, kmer_size=31, count_bytes=4, threshold=thr, max_survivors=n) as ctx:
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ctx._ck(ctx._L.kmd_model_rows_device(ctx._h, rows.data_ptr(), n, p.data_ptr(), sign.data_ptr(), mc.data_ptr(), mk.data_ptr()))
+        ctx.scan_device(rows.data_ptr(), n)
+        c = ctx.counters()
+        want = torch.nonzero(p <= thr).ravel()
+        assert c.rows == n and c.survivors == want.numel()
+        assert 0.02 * n < c.survivors < 0.98 * n                           # the boundary really runs through the sample
+        got = ctx.survivors()
+        assert np.array_equal(got["row"], want.cpu().numpy().astype(np.uint64))
+        assert np.array_equal(got["p_value"], p[want].cpu().numpy())
+        assert c.candidates >= c.survivors
 
 
 @pytest.mark.parametrize("nc,nk,b", [(10, 10, 4), (3, 17, 2), (8, 8, 1), (100, 100, 4)])

@@ -162,6 +162,77 @@ def test_example_plugin_builds_against_public_header(tmp_path):
         assert re.search(rf"\bT {s}\b", syms)
 
 
+def test_our_plugin_built_against_reference_headers_loads_in_the_reference_binary(tmp_path):
+    """plugin ABI, direction 1 (b2): plugins/ex_model.cpp compiled against the REFERENCE's include/kmdiff/imodel.hpp
+    (oracle/_ref/libex_model_refhdr.so, `make -C oracle plugins`) is loaded by the unmodified reference binary with
+    --cmodel and flags exactly the rows the model's rule flags"""
+    if not (os.path.exists(oracle.REF_BIN) and os.path.exists(oracle.OUR_PLUGIN_REF_HEADERS)):
+        pytest.skip("oracle/_ref/kmdiff or the plugin build is absent")
+    n = 30_000
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=3, ppm=5000)
+    out = str(tmp_path / "out")
+    r = run([oracle.REF_BIN, "diff", "--km-run", d, "-1", "10", "-2", "10", "-o", out, "--cmodel", oracle.OUR_PLUGIN_REF_HEADERS,
+             "--config", "3.0", "-t", "2"])
+    assert "[error]" not in r.stderr and "Plugin 'FoldChangeModel' loaded." in r.stderr, r.stderr
+    counts = spec.rows_host(n).reshape(n, -1)[:, 8:].copy().view(np.uint32).reshape(n, 20).astype(np.float64)
+    mc, mk = counts[:, :10].mean(axis=1), counts[:, 10:].mean(axis=1)
+    up, down = mk > 3.0 * (mc + 1), mc > 3.0 * (mk + 1)
+    assert len(read_fasta(os.path.join(out, "case_kmers.fasta"))) == int(up.sum()) > 0
+    assert len(read_fasta(os.path.join(out, "control_kmers.fasta"))) == int((down & ~up).sum())
+
+
+@pytest.mark.gpu
+def test_reference_plugin_built_against_our_headers_loads_in_the_cli(cli, tmp_path):
+    """plugin ABI, direction 2 (b2): the REFERENCE's plugins/ex_model.cpp compiled against this repo's
+    include/kmdiff/imodel.hpp (oracle/_ref/libref_ex_model.so) is loaded by kmdiff-b200 with --cmodel.  That model
+    calls every row CONTROL with p = 1e-12, so every row is written, with the plain means in the header."""
+    if not os.path.exists(oracle.REF_PLUGIN_OUR_HEADERS):
+        pytest.skip("oracle/_ref/libref_ex_model.so is absent (make -C oracle plugins)")
+    n = 5_000
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=2)
+    out = str(tmp_path / "out")
+    r = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "--cmodel", oracle.REF_PLUGIN_OUR_HEADERS, "-t", "2"])
+    assert "[error]" not in r.stderr and "Plugin 'ExModel' loaded." in r.stderr, r.stderr
+    assert f"{n}/{n} significant k-mers." in r.stderr
+    recs = read_fasta(os.path.join(out, "control_kmers.fasta"))
+    assert len(recs) == n and read_fasta(os.path.join(out, "case_kmers.fasta")) == []
+    rows = spec.rows_host(n).reshape(n, -1)
+    counts = rows[:, 8:].copy().view(np.uint32).reshape(n, 20).astype(np.float64)
+    want = {}
+    for i in range(n):
+        seq = oracle.kmer_to_string(rows[i, :8].copy().view(np.uint64), 31)
+        want[seq] = strip_index(oracle.fasta_record(0, 1e-12, counts[i, :10].mean(), counts[i, 10:].mean(), seq).split("\n")[0])
+    assert {s: strip_index(h) for h, s in recs} == want
+    if os.path.exists(oracle.REF_BIN):      # and the reference binary with its own plugin says the same
+        out_ref = str(tmp_path / "ref")
+        os.remove(os.path.join(d, "kmdiff-count.opt"))
+        rr = run([oracle.REF_BIN, "diff", "--km-run", d, "-1", "10", "-2", "10", "-o", out_ref, "--cmodel", oracle.REF_PLUGIN_OUR_HEADERS, "-t", "2"])
+        assert "[error]" not in rr.stderr, rr.stderr
+        assert sorted((strip_index(h), s) for h, s in read_fasta(os.path.join(out_ref, "control_kmers.fasta"))) == \
+            sorted((strip_index(h), s) for h, s in recs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("corr", ["benjamini", "bonferroni", "sidak"])
+def test_cli_on_all_gpus_equals_one_gpu(cli, tmp_path, corr):
+    """partitions sharded over every visible device: m and the BENJAMINI walk go through kmd_exchange_local (slots pulled
+    over the peer links); the FASTA files must be the one-GPU run's, byte for byte"""
+    from kmdiff_b200 import _lib
+    n_dev = _lib.load().kmd_device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n, parts = 300_000, 11
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=parts, seed=17)
+    outs = {}
+    for g in (1, n_dev):
+        out = str(tmp_path / f"out{g}")
+        r = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", out, "-c", corr, "--gpus", str(g), "-v", "debug"] + THR_ARGS)
+        assert "[error]" not in r.stderr, r.stderr
+        assert f"{g} device context(s) ready" in r.stderr
+        outs[g] = [open(os.path.join(out, f)).read() for f in ("control_kmers.fasta", "case_kmers.fasta")]
+    assert outs[1] == outs[n_dev] and len(outs[1][1]) > 1000
+
+
 # ---- GPU: whole runs ---------------------------------------------------------------------------------
 
 def expected_records(spec, n_rows, parts, corr, sig=0.05, cutoff=100000):
