@@ -295,6 +295,14 @@ int kmd_popstrat_geno(kmd_context* ctx, uint8_t* geno, uint64_t* rows, uint64_t 
  * trace/(N-1) (smartpca.c:1019-1023); multi-GPU callers sum the un-normalised matrices of all ranks
  * first and call kmd_smartpca_normalize.  n_used = SNPs with at least one carrier. */
 int kmd_popstrat_gram(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used);
+/* Multi-GPU form (partitions, hence sampled k-mers, sharded over ranks): the INTEGER parts only — G_c, the co-carrier
+ * counts of the SNPs with c carriers, written to d_G + (c - 1) * N * N (DEVICE memory of N^3 int32, caller-owned), and the
+ * carrier histogram d_hist[0..N] (u64, DEVICE).  The ranks sum both (NCCL all-reduce: exact and order-free), then every
+ * rank calls kmd_popstrat_gram_combine on the sums and obtains the XTX a single context would have computed from all the
+ * sampled k-mers, bit for bit.  (smartpca.c:907-1025 accumulates the same sums SNP by SNP.) */
+int kmd_popstrat_gram_partial(kmd_context* ctx, int32_t* d_G, uint64_t* d_hist);
+int kmd_popstrat_gram_combine(kmd_context* ctx, const int32_t* d_G, const uint64_t* d_hist, double* xtx, int normalize,
+                              uint64_t* n_used);
 /* device time (ms) of the tensor-core kernel of the last kmd_popstrat_gram */
 int kmd_popstrat_gram_ms(kmd_context* ctx, float* ms);
 /* pop_strat_corrector: load_Z/load_Y + init_global_features (src/popstrat.cpp:153-171, 270-370),

@@ -398,6 +398,18 @@ class DiffContext:
         self._ck(self._L.kmd_popstrat_gram(self._h, xtx.ctypes.data, int(normalize), C.byref(used)))
         return xtx, used.value
 
+    def popstrat_gram_partial(self, g_dev_ptr: int, hist_dev_ptr: int) -> None:
+        """integer Gram matrices by carrier count ([N, N, N] int32) + carrier histogram ([N + 1] u64) into DEVICE memory"""
+        self._ck(self._L.kmd_popstrat_gram_partial(self._h, C.c_void_p(g_dev_ptr), C.c_void_p(hist_dev_ptr)))
+
+    def popstrat_gram_combine(self, g_dev_ptr: int, hist_dev_ptr: int, normalize: bool = True) -> tuple[np.ndarray, int]:
+        """XTX from (globally summed) integer Gram matrices and histogram; -> (xtx, n_used)"""
+        xtx = np.zeros((self.nb_samples, self.nb_samples), dtype=np.float64)
+        used = C.c_uint64()
+        self._ck(self._L.kmd_popstrat_gram_combine(self._h, C.c_void_p(g_dev_ptr), C.c_void_p(hist_dev_ptr), xtx.ctypes.data,
+                                                   int(normalize), C.byref(used)))
+        return xtx, used.value
+
     def popstrat_gram_ms(self) -> float:
         ms = C.c_float()
         self._ck(self._L.kmd_popstrat_gram_ms(self._h, C.byref(ms)))

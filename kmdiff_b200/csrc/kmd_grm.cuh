@@ -318,7 +318,9 @@ struct BucketInfo
   double count;    // N_c (SNPs in the bucket)
 };
 
-__global__ void grm_combine_kernel(const int32_t* G, const BucketInfo* info, uint32_t n_buckets, uint32_t n, double* xtx)
+// slot (may be null): G slot of bucket b (dense-by-carrier-count layouts); default b
+__global__ void grm_combine_kernel(const int32_t* G, const BucketInfo* info, const uint32_t* slot, uint32_t n_buckets, uint32_t n,
+                                   double* xtx)
 {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = blockIdx.y;
@@ -326,7 +328,7 @@ __global__ void grm_combine_kernel(const int32_t* G, const BucketInfo* info, uin
   double acc = 0.0;
   for (uint32_t b = 0; b < n_buckets; b++)
   {
-    const int32_t* g = G + static_cast<size_t>(b) * n * n;
+    const int32_t* g = G + static_cast<size_t>(slot ? slot[b] : b) * n * n;
     const double gij = static_cast<double>(g[static_cast<size_t>(i) * n + j]);
     const double ri = static_cast<double>(g[static_cast<size_t>(i) * n + i]);
     const double rj = static_cast<double>(g[static_cast<size_t>(j) * n + j]);
@@ -335,6 +337,12 @@ __global__ void grm_combine_kernel(const int32_t* G, const BucketInfo* info, uin
     acc += bi.weight * inner;
   }
   xtx[static_cast<size_t>(i) * n + j] = acc;
+}
+
+__global__ void hist_to_u64_kernel(const uint32_t* hist, uint32_t n, uint64_t* out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hist[i];
 }
 
 }  // namespace grm

@@ -103,16 +103,24 @@ int gram_scratch(kmd_context* ctx, int slot, size_t bytes, ScratchBuf* out)
   return KMD_OK;
 }
 
-int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used)
+// dense_G == null: this context's XTX (integer Gram matrices of the carrier-count buckets + fp64 combination).
+// dense_G != null (multi-GPU): only the integers — G_c of bucket c goes to dense_G + (c - 1) * n * n (caller-owned
+// DEVICE memory of n^3 int32, zeroed here) and the carrier histogram to dense_hist[0..n] (u64) — for the ranks to sum.
+int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used, int32_t* dense_G = nullptr, uint64_t* dense_hist = nullptr)
 {
   PopState& ps = ctx->pop;
   const uint32_t n = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
   uint64_t m = 0;
   int rc = pop_sampled(ctx, &m);
   if (rc) return rc;
-  std::fill(xtx, xtx + static_cast<size_t>(n) * n, 0.0);
+  if (xtx) std::fill(xtx, xtx + static_cast<size_t>(n) * n, 0.0);
   if (n_used) *n_used = 0;
   ps.gram_ms = 0;
+  if (dense_G)
+  {
+    KMD_CUDA(ctx, cudaMemsetAsync(dense_G, 0, static_cast<size_t>(n) * n * n * sizeof(int32_t), ctx->stream));
+    KMD_CUDA(ctx, cudaMemsetAsync(dense_hist, 0, (n + 1) * sizeof(uint64_t), ctx->stream));
+  }
   if (m == 0) return KMD_OK;
   if (m >= (1ull << 32)) return fail(ctx, KMD_ERR_ARG, "more than 2^32 sampled k-mers");
 
@@ -138,7 +146,7 @@ int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used)
     koff[c] = k_pad;
     if (!hist[c]) continue;
     used += hist[c];
-    const uint32_t bucket = static_cast<uint32_t>(info.size());
+    const uint32_t bucket = dense_G ? c - 1 : static_cast<uint32_t>(info.size());
     info.push_back(bucket_info(c, n, ps.cfg.is_diploid != 0, hist[c]));
     const uint32_t kblocks = (hist[c] + grm::kBlockK - 1) / grm::kBlockK;
     for (uint32_t kb = 0; kb < kblocks; kb += grm::kMaxKBlocks)
@@ -161,12 +169,12 @@ int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used)
   // longest items first: the persistent CTAs take items round-robin
   std::stable_sort(items.begin(), items.end(), [](const grm::WorkItem& a, const grm::WorkItem& b) { return a.kb_cnt > b.kb_cnt; });
 
-  const size_t g_bytes = info.size() * static_cast<size_t>(n) * n * sizeof(int32_t);
+  const size_t g_bytes = dense_G ? 0 : info.size() * static_cast<size_t>(n) * n * sizeof(int32_t);
   if ((rc = gram_scratch(ctx, 1, (n + 1) * sizeof(uint64_t), &d_koff))) return rc;
   if ((rc = gram_scratch(ctx, 2, (n + 1) * sizeof(uint32_t), &d_cursor))) return rc;
   if ((rc = gram_scratch(ctx, 3, k_pad * sizeof(uint32_t), &d_perm))) return rc;
   if ((rc = gram_scratch(ctx, 4, static_cast<size_t>(rows_alloc) * k_pad, &d_pt))) return rc;
-  if ((rc = gram_scratch(ctx, 5, g_bytes, &d_G))) return rc;
+  if (!dense_G && (rc = gram_scratch(ctx, 5, g_bytes, &d_G))) return rc;
   if ((rc = gram_scratch(ctx, 6, info.size() * sizeof(grm::BucketInfo), &d_info))) return rc;
   if ((rc = gram_scratch(ctx, 7, items.size() * sizeof(grm::WorkItem), &d_items))) return rc;
   if ((rc = gram_scratch(ctx, 8, static_cast<size_t>(n) * n * sizeof(double), &d_xtx))) return rc;
@@ -175,7 +183,7 @@ int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used)
   KMD_CUDA(ctx, cudaMemcpyAsync(d_items.p, items.data(), items.size() * sizeof(grm::WorkItem), cudaMemcpyHostToDevice, ctx->stream));
   KMD_CUDA(ctx, cudaMemsetAsync(d_cursor.p, 0, (n + 1) * sizeof(uint32_t), ctx->stream));
   KMD_CUDA(ctx, cudaMemsetAsync(d_perm.p, 0xFF, k_pad * sizeof(uint32_t), ctx->stream));
-  KMD_CUDA(ctx, cudaMemsetAsync(d_G.p, 0, g_bytes, ctx->stream));
+  if (!dense_G) KMD_CUDA(ctx, cudaMemsetAsync(d_G.p, 0, g_bytes, ctx->stream));
 
   grm::carriers_scatter_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ps.d_carriers, m, d_koff.as<uint64_t>(),
                                                                          d_cursor.as<uint32_t>(), d_perm.as<uint32_t>());
@@ -192,7 +200,7 @@ int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used)
   G.n = n;
   G.n_pad16 = n_pad16;
   G.rows_alloc = rows_alloc;
-  G.G = d_G.as<int32_t>();
+  G.G = dense_G ? dense_G : d_G.as<int32_t>();
   KMD_CUDA(ctx, cudaFuncSetAttribute(grm::grm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(grm::kSmemBytes)));
   const uint32_t grid = std::min<uint32_t>(G.n_items, ctx->sm_count);
   cudaEventRecord(ctx->ev_k0, ctx->stream);
@@ -200,10 +208,19 @@ int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used)
   cudaEventRecord(ctx->ev_k1, ctx->stream);
   KMD_CUDA(ctx, cudaGetLastError());
   ctx->scan_timed = false;
+  if (dense_G)
+  {
+    grm::hist_to_u64_kernel<<<(n + 256) / 256, 256, 0, ctx->stream>>>(d_hist.as<uint32_t>(), n + 1, dense_hist);
+    ctx->launches += 5;
+    KMD_CUDA(ctx, cudaGetLastError());
+    KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    KMD_CUDA(ctx, cudaEventElapsedTime(&ps.gram_ms, ctx->ev_k0, ctx->ev_k1));
+    return KMD_OK;
+  }
 
   // ---- fp64 combination, buckets in ascending carrier count ----
   const dim3 cgrid((n + 127) / 128, n);
-  grm::grm_combine_kernel<<<cgrid, 128, 0, ctx->stream>>>(d_G.as<int32_t>(), d_info.as<grm::BucketInfo>(),
+  grm::grm_combine_kernel<<<cgrid, 128, 0, ctx->stream>>>(d_G.as<int32_t>(), d_info.as<grm::BucketInfo>(), nullptr,
                                                           static_cast<uint32_t>(info.size()), n, d_xtx.as<double>());
   ctx->launches += 5;
   KMD_CUDA(ctx, cudaGetLastError());
@@ -341,6 +358,55 @@ int kmd_popstrat_gram(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_
   if (!ctx->pop.enabled) return fail(ctx, KMD_ERR_STATE, "population stratification is not enabled on this context");
   KMD_CUDA(ctx, cudaSetDevice(ctx->device));
   return gram_impl(ctx, xtx, normalize, n_used);
+}
+
+int kmd_popstrat_gram_partial(kmd_context* ctx, int32_t* d_G, uint64_t* d_hist)
+{
+  if (!ctx || !d_G || !d_hist) return KMD_ERR_ARG;
+  if (!ctx->pop.enabled) return fail(ctx, KMD_ERR_STATE, "population stratification is not enabled on this context");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return gram_impl(ctx, nullptr, 0, nullptr, d_G, d_hist);
+}
+
+int kmd_popstrat_gram_combine(kmd_context* ctx, const int32_t* d_G, const uint64_t* d_hist, double* xtx, int normalize, uint64_t* n_used)
+{
+  if (!ctx || !d_G || !d_hist || !xtx) return KMD_ERR_ARG;
+  if (!ctx->pop.enabled) return fail(ctx, KMD_ERR_STATE, "population stratification is not enabled on this context");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t n = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
+  std::vector<uint64_t> hist(n + 1);
+  KMD_CUDA(ctx, cudaMemcpyAsync(hist.data(), d_hist, (n + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::vector<grm::BucketInfo> info;
+  std::vector<uint32_t> slot;
+  uint64_t used = 0;
+  for (uint32_t c = 1; c <= n; c++)
+  {
+    if (!hist[c]) continue;
+    if (hist[c] >= (1ull << 31)) return fail(ctx, KMD_ERR_ARG, "carrier-count bucket %u overflows int32 (%llu SNPs)", c, static_cast<unsigned long long>(hist[c]));
+    used += hist[c];
+    info.push_back(bucket_info(c, n, ctx->pop.cfg.is_diploid != 0, static_cast<uint32_t>(hist[c])));
+    slot.push_back(c - 1);
+  }
+  if (n_used) *n_used = used;
+  std::fill(xtx, xtx + static_cast<size_t>(n) * n, 0.0);
+  if (info.empty()) return KMD_OK;
+  ScratchBuf d_info, d_slot, d_xtx;
+  int rc;
+  if ((rc = gram_scratch(ctx, 6, info.size() * sizeof(grm::BucketInfo), &d_info))) return rc;
+  if ((rc = gram_scratch(ctx, 2, std::max<size_t>((n + 1), slot.size()) * sizeof(uint32_t), &d_slot))) return rc;
+  if ((rc = gram_scratch(ctx, 8, static_cast<size_t>(n) * n * sizeof(double), &d_xtx))) return rc;
+  KMD_CUDA(ctx, cudaMemcpyAsync(d_info.p, info.data(), info.size() * sizeof(grm::BucketInfo), cudaMemcpyHostToDevice, ctx->stream));
+  KMD_CUDA(ctx, cudaMemcpyAsync(d_slot.p, slot.data(), slot.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  const dim3 cgrid((n + 127) / 128, n);
+  grm::grm_combine_kernel<<<cgrid, 128, 0, ctx->stream>>>(d_G, d_info.as<grm::BucketInfo>(), d_slot.as<uint32_t>(),
+                                                          static_cast<uint32_t>(info.size()), n, d_xtx.as<double>());
+  ctx->launches++;
+  KMD_CUDA(ctx, cudaGetLastError());
+  KMD_CUDA(ctx, cudaMemcpyAsync(xtx, d_xtx.p, static_cast<size_t>(n) * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (normalize) kmd_smartpca_normalize(xtx, n);
+  return KMD_OK;
 }
 
 int kmd_popstrat_gram_ms(kmd_context* ctx, float* ms)

@@ -143,6 +143,31 @@ class DeviceExchange:
         return int(dec.total_rows), (int(dec.kept_control), int(dec.kept_case))
 
 
+def global_gram(ctx, device, group=None, normalize: bool = True) -> tuple[np.ndarray, int]:
+    """smartpca's XTX over the sampled k-mers of ALL ranks (--pop-correction with sharded partitions): every rank computes
+    the integer co-carrier matrices of its own sampled k-mers per carrier count on the tensor cores
+    (kmd_popstrat_gram_partial), one NCCL all-reduce(sum) of those int32 matrices and of the carrier histogram — exact and
+    order-free — and the fp64 combination of the sums (kmd_popstrat_gram_combine): bit for bit the matrix one GPU would
+    compute from all the k-mers.  The reference accumulates the same sums SNP by SNP in one process
+    (thirdparty/hawk/EIG6.0.1-Hawk/src/eigensrc/smartpca.c:907-1025).  -> (xtx, n_used)"""
+    if _world(group) == 1:
+        return ctx.popstrat_gram(normalize)
+    n = ctx.nb_samples
+    if n ** 3 * 4 > (2 << 30):
+        raise ValueError(f"{n} samples: the dense integer exchange would need {n ** 3 * 4 >> 20} MiB per rank")
+    G = torch.empty(n * n * n, dtype=torch.int32, device=device)
+    hist = torch.empty(n + 1, dtype=torch.int64, device=device)
+    on_gpu = device.type == "cuda"
+    if on_gpu:
+        torch.cuda.current_stream(device).synchronize()
+    ctx.popstrat_gram_partial(G.data_ptr(), hist.data_ptr())      # synchronises the context's stream
+    dist.all_reduce(G, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    if on_gpu:
+        torch.cuda.current_stream(device).synchronize()
+    return ctx.popstrat_gram_combine(G.data_ptr(), hist.data_ptr(), normalize)
+
+
 def correct_sharded(ctx, correction: int, significance: float, device, group=None):
     """do_correction (cmd/diff.hpp:227-260) for one rank's DiffContext when partitions are sharded.
     -> (total_rows, (n_control, n_case) kept on this rank)."""

@@ -176,6 +176,48 @@ def test_all_gpus_reach_the_single_process_decision_over_nccl(tmp_path):
                 assert np.all(np.diff(r[int(kind)][3]) >= 0)
 
 
+def _gram_worker(rank: int, world: int, port: int, out_dir: str):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import kmdiff_b200 as K
+        from kmdiff_b200 import distributed as D
+        spec, rows, totals = _cohort()
+        R = spec.row_bytes
+        per = (spec.total_rows // world) // 16 * 16
+        a, b = rank * per, (spec.total_rows if rank == world - 1 else (rank + 1) * per)
+        with K.DiffContext(10, 10, int(totals[:10].sum()), int(totals[10:].sum()), threshold=THR, device=rank) as ctx:
+            ctx.popstrat_enable(0.05, seed=9, n_pc=2)
+            ctx.scan_host(rows[a * R:b * R], row_base=a)
+            xtx, used = D.global_gram(ctx, dev)
+        np.save(os.path.join(out_dir, f"gram{rank}.npy"), np.array([{"xtx": xtx, "used": used}], dtype=object), allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_global_gram_over_nccl_equals_one_gpu(tmp_path):
+    """--pop-correction with partitions sharded over every GPU: the all-reduced integer Gram matrices give every rank the
+    XTX one GPU computes from all the rows, bit for bit"""
+    import kmdiff_b200 as K
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = torch.cuda.device_count()
+    mp.spawn(_gram_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    res = [np.load(tmp_path / f"gram{r}.npy", allow_pickle=True)[0] for r in range(world)]
+    spec, rows, totals = _cohort()
+    with K.DiffContext(10, 10, int(totals[:10].sum()), int(totals[10:].sum()), threshold=THR) as ctx:
+        ctx.popstrat_enable(0.05, seed=9, n_pc=2)
+        ctx.scan_host(rows)
+        want, used = ctx.popstrat_gram()
+    assert used > 1000
+    for r in res:
+        assert r["used"] == used and np.array_equal(r["xtx"], want)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("own_stream", [True, False])
 def test_device_exchange_on_one_gpu_equals_kmd_correct(own_stream):

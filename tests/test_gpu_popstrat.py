@@ -118,6 +118,54 @@ def test_gram_matches_oracle(shape, n_rows, v, diploid):
     assert np.abs(xtx_raw - ref_raw).max() <= 1e-10 * np.abs(ref_raw).max()
 
 
+@pytest.mark.parametrize("shape,n_rows,v,splits", [("c2", 200_000, 0.05, 3), ("c4", 30_000, 0.3, 2), ("odd", 50_000, 0.2, 5)])
+def test_sharded_gram_equals_single_context_bit_for_bit(shape, n_rows, v, splits):
+    """the multi-GPU Gram exchange without NCCL: the rows are split over several contexts (the sampler draws by global
+    row index, so the sampled set is the same), each computes its integer co-carrier matrices per carrier count
+    (kmd_popstrat_gram_partial), the integers are summed — what the all-reduce does — and combined in fp64
+    (kmd_popstrat_gram_combine): the matrix equals the single-context kmd_popstrat_gram bit for bit, normalised or not"""
+    import torch
+    spec, rows, totals = make_cohort(shape, n_rows, seed=19)
+    R, n = spec.row_bytes, spec.nb_controls + spec.nb_cases
+    with ctx_for(spec, totals) as ctx:
+        ctx.popstrat_enable(v, seed=5, n_pc=2)
+        ctx.scan_host(rows)
+        want, used = ctx.popstrat_gram(normalize=False)
+        want_n, _ = ctx.popstrat_gram(normalize=True)
+        # one context through the partial / combine pair: same bits
+        G = torch.empty(n * n * n, dtype=torch.int32, device="cuda")
+        H = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        ctx.popstrat_gram_partial(G.data_ptr(), H.data_ptr())
+        got, used1 = ctx.popstrat_gram_combine(G.data_ptr(), H.data_ptr(), normalize=False)
+        assert used1 == used > 100 and np.array_equal(got, want)
+        assert int(H.sum()) >= used and int(G.view(n, n, n).diagonal(dim1=1, dim2=2).sum()) > 0
+    cuts = [0] + sorted(int(x) // 16 * 16 for x in np.random.default_rng(1).integers(1, n_rows, splits - 1)) + [n_rows]
+    Gs = torch.zeros(n * n * n, dtype=torch.int32, device="cuda")
+    Hs = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    last = None
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        c2 = ctx_for(spec, totals)
+        c2.popstrat_enable(v, seed=5, n_pc=2)
+        if b > a:
+            c2.scan_host(rows[a * R:b * R], row_base=a)
+        Gp = torch.empty_like(Gs)
+        Hp = torch.empty_like(Hs)
+        torch.cuda.synchronize()
+        c2.popstrat_gram_partial(Gp.data_ptr(), Hp.data_ptr())
+        Gs += Gp
+        Hs += Hp
+        if last is not None:
+            last.close()
+        last = c2
+    torch.cuda.synchronize()
+    got, used2 = last.popstrat_gram_combine(Gs.data_ptr(), Hs.data_ptr(), normalize=False)
+    got_n, _ = last.popstrat_gram_combine(Gs.data_ptr(), Hs.data_ptr(), normalize=True)
+    last.close()
+    assert used2 == used
+    assert np.array_equal(got, want) and np.array_equal(got_n, want_n)
+
+
 def test_gram_empty_and_all_present():
     spec, rows, totals = make_cohort("c2", 5_000, seed=8)
     with ctx_for(spec, totals) as ctx:
