@@ -502,7 +502,7 @@ def measure(env: Env, args, cfg_name: str, steps: int, warmup: int, full: bool) 
     import numpy as np
 
     import kmdiff_b200 as K
-    from kmdiff_b200.distributed import DeviceExchange, correct_sharded
+    from kmdiff_b200.distributed import DeviceExchange, correct_sharded, global_gram
     torch = env.torch
     rank, world, dev = env.rank, env.world, env.dev
     nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
@@ -522,9 +522,8 @@ def measure(env: Env, args, cfg_name: str, steps: int, warmup: int, full: bool) 
     popstrat = cfg_name == "c4"
     pop_ms = {"gram_kernel": [], "gram_call": [], "pca_host": [], "glm": [], "sampled": 0, "used": 0}
     if popstrat:
-        if world > 1:
-            raise SystemExit("bench.py: c4 is a single-GPU bench line (the multi-GPU Gram sum is covered by tests)")
-        ctx.popstrat_enable(C4_SAMPLED / rows, seed=SEED, is_diploid=True, n_pc=C4_NPC, max_sampled=2 * C4_SAMPLED)
+        # 1e6 sampled k-mers over ALL ranks (BASELINE.json configs[3]); every rank samples its own rows
+        ctx.popstrat_enable(C4_SAMPLED / (rows * world), seed=SEED, is_diploid=True, n_pc=C4_NPC, max_sampled=2 * C4_SAMPLED)
 
     # ---- resident workload: this rank's rows, generated on the device (seeded, counter-based) ----
     data = torch.empty(rows * R, dtype=torch.uint8, device=dev)
@@ -535,7 +534,8 @@ def measure(env: Env, args, cfg_name: str, steps: int, warmup: int, full: bool) 
     def pop_stage(timed: bool):
         # do_pop (cmd/diff.hpp:168-224): Gram matrix of the sampled k-mers -> PCs -> null model -> GLM per survivor
         t0 = time.perf_counter()
-        xtx, used = ctx.popstrat_gram()
+        # world > 1: integer Gram matrices per carrier count, NCCL all-reduce(sum), fp64 combination of the sums
+        xtx, used = global_gram(ctx, dev)
         t1 = time.perf_counter()
         _, Z = K.smartpca_pcs(xtx, 10)
         t2 = time.perf_counter()

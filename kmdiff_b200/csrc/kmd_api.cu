@@ -116,6 +116,7 @@ struct MergeState
   uint64_t* stream_off = nullptr; size_t off_cap = 0;
   uint32_t* ab_min = nullptr; size_t ab_cap = 0;
   uint32_t* plan = nullptr; size_t plan_cap = 0;
+  uint32_t* split = nullptr; size_t split_cap = 0;   // merge-path split of every tile of the pass in flight
   uint32_t* total = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // unpack | merge passes | row numbering + dense rows
   bool timed = false;

@@ -21,7 +21,7 @@ namespace kmd {
 namespace mrg {
 
 constexpr int kThreads = 256;
-constexpr int kItems = 6;
+constexpr int kItems = 8;
 constexpr int kTile = kThreads * kItems;   // outputs per CTA of a merge pass
 constexpr int kScanTile = 4096;            // flags per CTA of the row-numbering scan
 
@@ -142,44 +142,84 @@ __device__ inline uint32_t merge_path(uint32_t diag, uint32_t len_a, uint32_t le
   return lo;
 }
 
+// pair and tile geometry of CTA `cta` of a pass
 template <int W>
-__global__ void __launch_bounds__(kThreads) merge_pass_kernel(const MergeArgs<W> A)
-{
-  __shared__ uint64_t s_lo[kTile];
-  __shared__ uint64_t s_hi[W == 2 ? kTile : 1];
-  __shared__ uint64_t s_pay[kTile];
-  __shared__ uint32_t s_split[2];
+struct TileGeom { uint32_t a0, b0, len_a, len_b, d0, d1; };
 
-  // which pair does this CTA work on
+template <int W>
+__device__ inline TileGeom<W> tile_geom(const MergeArgs<W>& A, uint32_t cta)
+{
   uint32_t ql = 0, qh = A.n_pairs;
   while (qh - ql > 1)
   {
     const uint32_t mid = (ql + qh) >> 1;
-    if (A.pair_tile[mid] <= blockIdx.x) ql = mid; else qh = mid;
+    if (A.pair_tile[mid] <= cta) ql = mid; else qh = mid;
   }
   const uint32_t q = ql;
-  const uint32_t a0 = A.run_off[2 * q], a1 = A.run_off[2 * q + 1];
-  const uint32_t b0 = a1, b1 = (2 * q + 2 <= A.n_runs) ? A.run_off[2 * q + 2] : a1;
-  const uint32_t len_a = a1 - a0, len_b = b1 - b0;
-  const uint32_t d0 = (blockIdx.x - A.pair_tile[q]) * kTile;
-  const uint32_t d1 = min(d0 + kTile, len_a + len_b);
+  TileGeom<W> g;
+  g.a0 = A.run_off[2 * q];
+  const uint32_t a1 = A.run_off[2 * q + 1];
+  g.b0 = a1;
+  const uint32_t b1 = (2 * q + 2 <= A.n_runs) ? A.run_off[2 * q + 2] : a1;
+  g.len_a = a1 - g.a0;
+  g.len_b = b1 - g.b0;
+  g.d0 = (cta - A.pair_tile[q]) * kTile;
+  g.d1 = min(g.d0 + kTile, g.len_a + g.len_b);
+  return g;
+}
 
-  auto ga = [&](uint32_t i) { return A.in.get(a0 + i); };
-  auto gb = [&](uint32_t i) { return A.in.get(b0 + i); };
-  if (threadIdx.x < 2)
-    s_split[threadIdx.x] = merge_path<W>(threadIdx.x ? d1 : d0, len_a, len_b, ga, gb);
-  __syncthreads();
-  const uint32_t ai0 = s_split[0], ai1 = s_split[1];
-  const uint32_t bi0 = d0 - ai0, bi1 = d1 - ai1;
+// split[cta] = how many records of run A lie before the first output of tile `cta` (merge-path search in global
+// memory, one thread per tile): the merge kernel then starts without a search or a barrier of its own
+template <int W>
+__global__ void __launch_bounds__(128) merge_partition_kernel(const MergeArgs<W> A, uint32_t tiles, uint32_t* __restrict__ split)
+{
+  const uint32_t cta = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cta >= tiles) return;
+  const TileGeom<W> g = tile_geom<W>(A, cta);
+  auto ga = [&](uint32_t i) { return A.in.get(g.a0 + i); };
+  auto gb = [&](uint32_t i) { return A.in.get(g.b0 + i); };
+  split[cta] = merge_path<W>(g.d0, g.len_a, g.len_b, ga, gb);
+}
+
+// shared memory of one merge_pass_kernel CTA: the staged input slices and a per-warp output staging area
+constexpr int kOutTile = kTile + kTile / kItems;   // output staging, skewed by one slot per kItems (bank conflicts)
+__device__ __forceinline__ uint32_t out_slot(uint32_t i) { return i + i / kItems; }
+template <int W>
+constexpr size_t merge_smem_bytes() { return static_cast<size_t>(kTile + kOutTile) * 8 * (W + 1); }
+
+// One tile of kTile outputs: stage both input slices in shared memory (coalesced), ONE block barrier, every thread
+// finds its merge-path start in shared memory and merges kItems consecutive outputs in registers, each warp stages its
+// 32 * kItems outputs in its own slice of a second buffer (warp barrier only) and stores them coalesced.
+template <int W>
+__global__ void __launch_bounds__(kThreads) merge_pass_kernel(const MergeArgs<W> A, const uint32_t* __restrict__ split)
+{
+  extern __shared__ __align__(16) uint64_t smem[];
+  uint64_t* s_lo = smem;
+  uint64_t* s_hi = s_lo + (W == 2 ? kTile : 0);      // W == 1: aliases s_lo, never touched
+  uint64_t* s_pay = s_hi + kTile;
+  uint64_t* o_lo = s_pay + kTile;
+  uint64_t* o_hi = o_lo + (W == 2 ? kOutTile : 0);
+  uint64_t* o_pay = o_hi + kOutTile;
+
+  const TileGeom<W> g = tile_geom<W>(A, blockIdx.x);
+  const uint32_t ai0 = split[blockIdx.x];
+  const uint32_t ai1 = g.d1 == g.len_a + g.len_b ? g.len_a : split[blockIdx.x + 1];
+  const uint32_t bi0 = g.d0 - ai0, bi1 = g.d1 - ai1;
   const uint32_t na = ai1 - ai0, nb = bi1 - bi0, nt = na + nb;   // nt == d1 - d0 <= kTile
 
   // stage the two input slices: A's slice first, then B's
-  for (uint32_t i = threadIdx.x; i < nt; i += kThreads)
+  const uint32_t src_a = g.a0 + ai0, src_b = g.b0 + bi0;
+#pragma unroll
+  for (int e = 0; e < kItems; e++)
   {
-    const uint32_t src = i < na ? a0 + ai0 + i : b0 + bi0 + (i - na);
-    s_lo[i] = A.in.lo[src];
-    if constexpr (W == 2) s_hi[i] = A.in.hi[src];
-    s_pay[i] = A.pay_in[src];
+    const uint32_t i = threadIdx.x + e * kThreads;
+    if (i < nt)
+    {
+      const uint32_t src = i < na ? src_a + i : src_b + (i - na);
+      s_lo[i] = A.in.lo[src];
+      if constexpr (W == 2) s_hi[i] = A.in.hi[src];
+      s_pay[i] = A.pay_in[src];
+    }
   }
   __syncthreads();
 
@@ -192,46 +232,46 @@ __global__ void __launch_bounds__(kThreads) merge_pass_kernel(const MergeArgs<W>
   auto sa = [&](uint32_t i) { return sk(i); };
   auto sb = [&](uint32_t i) { return sk(na + i); };
 
-  // every thread merges kItems consecutive outputs into registers
   const uint32_t t0 = min(threadIdx.x * kItems, nt);
   const uint32_t t1 = min(t0 + kItems, nt);
   uint32_t ia = merge_path<W>(t0, na, nb, sa, sb);
   uint32_t ib = t0 - ia;
-  Key<W> rk[kItems];
-  uint64_t rp[kItems];
+  // the two heads live in registers; every step reloads only the side that advanced
+  Key<W> ka{}, kb{};
+  if (ia < na) ka = sa(ia);
+  if (ib < nb) kb = sb(ib);
 #pragma unroll
   for (int e = 0; e < kItems; e++)
   {
     if (t0 + e < t1)
     {
-      bool take_a;
-      if (ia >= na) take_a = false;
-      else if (ib >= nb) take_a = true;
-      else take_a = sa(ia) <= sb(ib);
+      const bool take_a = ib >= nb || (ia < na && ka <= kb);
       const uint32_t src = take_a ? ia : na + ib;
-      rk[e] = sk(src);
-      rp[e] = s_pay[src];
-      if (take_a) ia++; else ib++;
+      // thread t owns outputs [t * kItems, (t + 1) * kItems): slot stride kItems + 1 between lanes, conflict-free
+      const uint32_t o = t0 + t0 / kItems + e;
+      o_lo[o] = take_a ? ka.lo : kb.lo;
+      if constexpr (W == 2) o_hi[o] = take_a ? ka.hi : kb.hi;
+      o_pay[o] = s_pay[src];
+      if (take_a) { ia++; if (ia < na) ka = sa(ia); }
+      else { ib++; if (ib < nb) kb = sb(ib); }
     }
   }
-  __syncthreads();
+  __syncwarp();
+  // the warp's 32 * kItems outputs are contiguous in the output staging area: coalesced stores
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t w0 = (threadIdx.x & ~31u) * kItems;
+  const uint32_t o0 = g.a0 + g.d0;
 #pragma unroll
   for (int e = 0; e < kItems; e++)
   {
-    if (t0 + e < t1)
+    const uint32_t i = w0 + e * 32 + lane;
+    if (i < nt)
     {
-      s_lo[t0 + e] = rk[e].lo;
-      if constexpr (W == 2) s_hi[t0 + e] = rk[e].hi;
-      s_pay[t0 + e] = rp[e];
+      const uint32_t o = out_slot(i);
+      A.out.lo[o0 + i] = o_lo[o];
+      if constexpr (W == 2) A.out.hi[o0 + i] = o_hi[o];
+      A.pay_out[o0 + i] = o_pay[o];
     }
-  }
-  __syncthreads();
-  const uint32_t o0 = a0 + d0;
-  for (uint32_t i = threadIdx.x; i < nt; i += kThreads)
-  {
-    A.out.lo[o0 + i] = s_lo[i];
-    if constexpr (W == 2) A.out.hi[o0 + i] = s_hi[i];
-    A.pay_out[o0 + i] = s_pay[i];
   }
 }
 

@@ -23,7 +23,7 @@ void merge_free(kmd_context* ctx)
   cudaFree(m.raw);
   for (int b = 0; b < 2; b++) { cudaFree(m.klo[b]); cudaFree(m.khi[b]); cudaFree(m.pay[b]); }
   cudaFree(m.flag); cudaFree(m.tile); cudaFree(m.head_pos); cudaFree(m.rows); cudaFree(m.stream_off);
-  cudaFree(m.ab_min); cudaFree(m.plan); cudaFree(m.total);
+  cudaFree(m.ab_min); cudaFree(m.plan); cudaFree(m.total); cudaFree(m.split);
   for (cudaEvent_t e : m.ev) if (e) cudaEventDestroy(e);
   m = MergeState{};
 }
@@ -34,6 +34,12 @@ template <int W>
 int merge_passes(kmd_context* ctx, const std::vector<MergePass>& passes, int* final_buf)
 {
   MergeState& m = ctx->mrg;
+  uint32_t max_tiles = 0;
+  for (const MergePass& ps : passes) max_tiles = std::max(max_tiles, ps.tiles);
+  int rc = grow(ctx, m.split, m.split_cap, static_cast<size_t>(max_tiles) + 1);
+  if (rc) return rc;
+  const size_t smem = mrg::merge_smem_bytes<W>();
+  KMD_CUDA(ctx, cudaFuncSetAttribute(mrg::merge_pass_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int cur = 0;
   for (const MergePass& ps : passes)
   {
@@ -48,8 +54,9 @@ int merge_passes(kmd_context* ctx, const std::vector<MergePass>& passes, int* fi
     A.n_pairs = ps.n_pairs;
     if (ps.tiles)
     {
-      mrg::merge_pass_kernel<W><<<ps.tiles, mrg::kThreads, 0, ctx->stream>>>(A);
-      ctx->launches++;
+      mrg::merge_partition_kernel<W><<<(ps.tiles + 127) / 128, 128, 0, ctx->stream>>>(A, ps.tiles, m.split);
+      mrg::merge_pass_kernel<W><<<ps.tiles, mrg::kThreads, smem, ctx->stream>>>(A, m.split);
+      ctx->launches += 2;
     }
     cur ^= 1;
   }

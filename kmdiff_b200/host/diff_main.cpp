@@ -1771,6 +1771,44 @@ int dev_command(int argc, char** argv)
     for (auto& t : pool) t.join();
     return failed ? 2 : 0;
   }
+  if (cmd == "dev-lz4bench" && argc >= 4)
+  {
+    // dev-lz4bench THREADS FILE...: decode the payloads of the given kmtricks files (45-byte matrix or 41-byte k-mer
+    // header, then one LZ4 frame) with THREADS host threads, one file per thread at a time, and print the rates
+    const size_t threads = static_cast<size_t>(std::max(1l, atol(argv[2])));
+    std::vector<std::string> files(argv + 3, argv + argc);
+    std::atomic<size_t> next{0};
+    std::atomic<uint64_t> out_bytes{0}, in_bytes{0};
+    const Timer t;
+    auto work = [&] {
+      std::vector<uint8_t> buf(4u << 20);
+      for (size_t i; (i = next.fetch_add(1)) < files.size();)
+      {
+        FILE* f = fopen(files[i].c_str(), "rb");
+        if (!f) continue;
+        uint8_t head[45];
+        if (fread(head, 1, 21, f) != 21) { fclose(f); continue; }
+        uint64_t magic; memcpy(&magic, head + 13, 8);
+        const size_t rest = magic == kMatrixMagic ? 45 - 21 : 41 - 21;
+        if (fread(head + 21, 1, rest, f) != rest) { fclose(f); continue; }
+        PayloadReader pr(f, head[12] != 0);
+        uint64_t n = 0;
+        for (size_t got; (got = pr.read(buf.data(), buf.size())) > 0;) n += got;
+        out_bytes += n;
+        in_bytes += static_cast<uint64_t>(fs::file_size(files[i]));
+        fclose(f);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (size_t i = 1; i < threads; i++) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    const double s = t.seconds();
+    printf("{\"threads\": %zu, \"files\": %zu, \"compressed_bytes\": %llu, \"decoded_bytes\": %llu, \"seconds\": %.4f, "
+           "\"decoded_gbs\": %.3f, \"compressed_gbs\": %.3f}\n", threads, files.size(), static_cast<unsigned long long>(in_bytes.load()),
+           static_cast<unsigned long long>(out_bytes.load()), s, out_bytes.load() / s / 1e9, in_bytes.load() / s / 1e9);
+    return 0;
+  }
   if (cmd == "dev-config" && argc == 5)
   {
     const RunConfig c = get_kmtricks_config(argv[2]);

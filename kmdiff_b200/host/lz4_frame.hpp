@@ -51,12 +51,18 @@ inline uint32_t xxh32(const uint8_t* p, size_t len, uint32_t seed)
 
 // Decodes one LZ4 block into dst[0, cap); matches may reach back before dst (linked blocks: the caller
 // guarantees `history` valid bytes precede dst).  Returns the decoded size.
+// kLz4Slack bytes past src + n must be readable and kLz4Slack bytes past dst + cap writable: short literal runs and
+// matches are copied 16 bytes at a time without trimming the last chunk ("wild copy"), which is where the speed of an
+// LZ4 decoder comes from — kmtricks rows are short sequences (a k-mer's repeated high bytes, a few literal counts).
+constexpr size_t kLz4Slack = 32;
+
 inline size_t lz4_block_decode(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, size_t history)
 {
   const uint8_t* ip = src;
   const uint8_t* const iend = src + n;
   uint8_t* op = dst;
   uint8_t* const oend = dst + cap;
+  auto copy16 = [](uint8_t* d, const uint8_t* s_) { uint64_t a, b; memcpy(&a, s_, 8); memcpy(&b, s_ + 8, 8); memcpy(d, &a, 8); memcpy(d + 8, &b, 8); };
   while (ip < iend)
   {
     const unsigned token = *ip++;
@@ -67,7 +73,13 @@ inline size_t lz4_block_decode(const uint8_t* src, size_t n, uint8_t* dst, size_
       do { if (ip >= iend) throw std::runtime_error("lz4: truncated literal length"); b = *ip++; lit += b; } while (b == 255);
     }
     if (lit > static_cast<size_t>(iend - ip) || lit > static_cast<size_t>(oend - op)) throw std::runtime_error("lz4: literal run overflows");
-    memcpy(op, ip, lit);
+    if (lit <= 32)
+    {
+      copy16(op, ip);                       // within the slack of both buffers
+      if (lit > 16) copy16(op + 16, ip + 16);
+    }
+    else
+      memcpy(op, ip, lit);
     op += lit; ip += lit;
     if (ip >= iend) break;  // the last sequence has no match part
     if (iend - ip < 2) throw std::runtime_error("lz4: truncated offset");
@@ -83,8 +95,20 @@ inline size_t lz4_block_decode(const uint8_t* src, size_t n, uint8_t* dst, size_
     if (off == 0 || off > static_cast<size_t>(op - dst) + history) throw std::runtime_error("lz4: offset out of window");
     if (ml > static_cast<size_t>(oend - op)) throw std::runtime_error("lz4: match overflows");
     const uint8_t* m = op - off;
-    if (off >= ml) { memcpy(op, m, ml); op += ml; }
-    else for (size_t i = 0; i < ml; i++) *op++ = m[i];  // overlapping run
+    if (off >= 16)
+    {
+      // source and destination chunks never overlap: 16 bytes at a time, the last chunk may run into the slack
+      uint8_t* const end = op + ml;
+      do { copy16(op, m); op += 16; m += 16; } while (op < end);
+      op = end;
+    }
+    else if (off >= 8)
+    {
+      uint8_t* const end = op + ml;
+      do { uint64_t a; memcpy(&a, m, 8); memcpy(op, &a, 8); op += 8; m += 8; } while (op < end);
+      op = end;
+    }
+    else for (size_t i = 0; i < ml; i++) *op++ = m[i];  // short-period run
   }
   return static_cast<size_t>(op - dst);
 }
@@ -141,7 +165,7 @@ class Lz4FrameReader
     const unsigned bs = (bd >> 4) & 7;
     if (bs < 4) throw std::runtime_error("lz4: bad block size code");
     m_block_max = static_cast<size_t>(1) << (8 + 2 * bs);
-    m_win.resize(kHistory + m_block_max);
+    m_win.resize(kHistory + m_block_max + kLz4Slack);
     m_hist = 0; m_pos = m_end = kHistory;
     m_in_frame = true;
     return true;
@@ -179,7 +203,7 @@ class Lz4FrameReader
       }
       else
       {
-        m_src.resize(n);
+        if (m_src.size() < n + kLz4Slack) m_src.resize(n + kLz4Slack);
         if (!fill(m_src.data(), n)) throw std::runtime_error("lz4: truncated block");
         out = lz4_block_decode(m_src.data(), n, m_win.data() + kHistory, m_block_max, m_linked ? m_hist : 0);
       }
