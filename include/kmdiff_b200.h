@@ -170,6 +170,21 @@ int kmd_push_survivors2(kmd_context* ctx, const kmd_survivor* records, const voi
  * numbered row_base, row_base+1, ... in ascending k-mer order.  Synchronous for the host buffers. */
 int kmd_merge_scan_host(kmd_context* ctx, const void* const* streams, const uint64_t* n_records,
                         const uint32_t* ab_min, uint64_t row_base, uint32_t partition, uint64_t* n_rows);
+/* The same for the samples' files of a WHOLE partition as they lie on disk: frames[s] = the payload of
+ * counts/partition_p/<sample>.kmer.lz4 after its 41-byte header (HOST; pinned for full PCIe rate), frame_bytes[s] its
+ * size; compressed[s] (NULL = all) says whether it is an LZ4 frame (km::lz4_stream: 64 KiB linked blocks,
+ * kmtricks/io/lz4_stream.hpp:42,128-140) or raw records.  Compressed payloads cross PCIe compressed and are decoded on
+ * the device, one warp per stream — the host decoder manages ~1 GB/s per thread, a GPU ingests ~55 GB/s.
+ * max_records != 0: when the partition decodes to more records than that, nothing is merged and KMD_ERR_OVERFLOW is
+ * returned (*n_records says how many): the caller then streams the partition in k-mer ranges through
+ * kmd_merge_scan_host.  n_rows / n_records may be NULL. */
+int kmd_merge_scan_lz4_host(kmd_context* ctx, const void* const* frames, const uint64_t* frame_bytes,
+                            const uint8_t* compressed, const uint32_t* ab_min, uint64_t row_base, uint32_t partition,
+                            uint64_t max_records, uint64_t* n_rows, uint64_t* n_records);
+/* the device LZ4 decoder alone: nb_controls + nb_cases frames in, their decoded records back to back out (HOST);
+ * device_ms (may be NULL) = device time of the two decode passes (tests, tools) */
+int kmd_lz4_decode_host(kmd_context* ctx, const void* const* frames, const uint64_t* frame_bytes, void* records_out,
+                        uint64_t cap_records, uint64_t* n_records, float* device_ms);
 /* The merged rows themselves (what KmerMerger::write_as_bin would put in a matrix file,
  * kmtricks/merge.hpp:262-272), copied back to the host: tests, tools.  No test is run. */
 int kmd_merge_rows_host(kmd_context* ctx, const void* const* streams, const uint64_t* n_records,

@@ -242,6 +242,35 @@ class DiffContext:
         self._ck(self._L.kmd_merge_scan_host(self._h, ptrs, cnt, ab.ctypes.data, row_base, partition, C.byref(n)))
         return n.value
 
+    def _frame_args(self, frames):
+        n = self.nb_samples
+        assert len(frames) == n, f"{n} frames expected (controls first)"
+        arrs = [_as_u8(f) for f in frames]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data if a.size else None for a in arrs])
+        sizes = (C.c_uint64 * n)(*[a.size for a in arrs])
+        return arrs, ptrs, sizes
+
+    def merge_scan_lz4_host(self, frames, compressed=None, ab_min=1, row_base: int = 0, partition: int = 0,
+                            max_records: int = 0) -> tuple[int, int]:
+        """one partition's count files as they lie on disk (payloads after the 41-byte header; LZ4 frames are decoded
+        on the device) -> (rows, records)"""
+        arrs, ptrs, sizes = self._frame_args(frames)
+        ab = np.ascontiguousarray(np.broadcast_to(np.asarray(ab_min, dtype=np.uint32), (self.nb_samples,)))
+        comp = None if compressed is None else np.ascontiguousarray(compressed, dtype=np.uint8)
+        rows, recs = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.kmd_merge_scan_lz4_host(self._h, ptrs, sizes, None if comp is None else comp.ctypes.data, ab.ctypes.data,
+                                                 row_base, partition, int(max_records), C.byref(rows), C.byref(recs)))
+        return rows.value, recs.value
+
+    def lz4_decode_host(self, frames, cap_records: int) -> tuple[np.ndarray, float]:
+        """the device LZ4-frame decoder alone: -> (decoded records of all streams back to back as bytes, device ms)"""
+        arrs, ptrs, sizes = self._frame_args(frames)
+        rec = 8 * self.kmer_words + self.count_bytes
+        out = np.zeros(max(1, cap_records) * rec, dtype=np.uint8)
+        n, ms = C.c_uint64(), C.c_float()
+        self._ck(self._L.kmd_lz4_decode_host(self._h, ptrs, sizes, out.ctypes.data, cap_records, C.byref(n), C.byref(ms)))
+        return out[:n.value * rec], ms.value
+
     def merge_ms(self) -> dict:
         """device times of the last merge call: {'unpack', 'passes', 'rows'} in ms, 'n_passes', 'n_records'"""
         a, b, c = C.c_float(), C.c_float(), C.c_float()

@@ -25,6 +25,7 @@
 
 #include "kmd_eig.hpp"
 #include "kmd_grm.cuh"
+#include "kmd_lz4.cuh"
 #include "kmd_math.cuh"
 #include "kmd_merge.cuh"
 #include "kmd_popstrat.cuh"
@@ -117,6 +118,12 @@ struct MergeState
   uint32_t* ab_min = nullptr; size_t ab_cap = 0;
   uint32_t* plan = nullptr; size_t plan_cap = 0;
   uint32_t* split = nullptr; size_t split_cap = 0;   // merge-path split of every tile of the pass in flight
+  // device LZ4 decode of compressed count files (kmd_merge_scan_lz4_host): the frames and their per-stream tables
+  uint8_t* lz_in = nullptr; size_t lz_in_cap = 0;
+  uint64_t* lz_tab = nullptr; size_t lz_tab_cap = 0;   // [5][n]: in_off, in_size, out_off, out_cap, out_size
+  uint32_t* lz_status = nullptr; size_t lz_status_cap = 0;
+  cudaEvent_t lz_ev[2] = {nullptr, nullptr};
+  float last_lz4_ms = 0;
   uint32_t* total = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // unpack | merge passes | row numbering + dense rows
   bool timed = false;

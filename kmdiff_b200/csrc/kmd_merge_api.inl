@@ -24,7 +24,9 @@ void merge_free(kmd_context* ctx)
   for (int b = 0; b < 2; b++) { cudaFree(m.klo[b]); cudaFree(m.khi[b]); cudaFree(m.pay[b]); }
   cudaFree(m.flag); cudaFree(m.tile); cudaFree(m.head_pos); cudaFree(m.rows); cudaFree(m.stream_off);
   cudaFree(m.ab_min); cudaFree(m.plan); cudaFree(m.total); cudaFree(m.split);
+  cudaFree(m.lz_in); cudaFree(m.lz_tab); cudaFree(m.lz_status);
   for (cudaEvent_t e : m.ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : m.lz_ev) if (e) cudaEventDestroy(e);
   m = MergeState{};
 }
 
@@ -98,21 +100,16 @@ int merge_rows(kmd_context* ctx, int buf, uint32_t n, uint32_t* n_rows_out)
   return KMD_OK;
 }
 
-// streams[s] = n_records[s] records of sample s (kmer_words*8 bytes of k-mer, count_bytes of count), ascending
-// and unique per stream.  Leaves the dense rows in ctx->mrg.rows.
-int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min, uint32_t* n_rows)
+// off[s] .. off[s + 1]: records of sample s inside the chunk (ascending and unique per stream); fill_raw() enqueues
+// whatever brings those records to m.raw + off[s] * rec (H2D copies of host records, or the device LZ4 decoder).
+// Leaves the dense rows in ctx->mrg.rows.
+template <class FillRaw>
+int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const uint32_t* ab_min, uint32_t* n_rows, FillRaw&& fill_raw)
 {
   MergeState& m = ctx->mrg;
   const uint32_t N = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
   const uint32_t W = ctx->cfg.kmer_words, B = ctx->cfg.count_bytes;
   const size_t rec = 8ull * W + B;
-  if (N > 0xFFFFu) return fail(ctx, KMD_ERR_ARG, "more than 65535 samples");
-  std::vector<uint64_t> off(N + 1, 0);
-  for (uint32_t s = 0; s < N; s++)
-  {
-    if (n_records[s] && !streams[s]) return fail(ctx, KMD_ERR_ARG, "null stream pointer (sample %u)", s);
-    off[s + 1] = off[s] + n_records[s];
-  }
   const uint64_t n64 = off[N];
   *n_rows = 0;
   if (n64 == 0) return KMD_OK;
@@ -120,7 +117,7 @@ int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_r
   const uint32_t n = static_cast<uint32_t>(n64);
 
   int rc;
-  if ((rc = grow(ctx, m.raw, m.raw_cap, n * rec))) return rc;
+  if ((rc = grow(ctx, m.raw, m.raw_cap, n * rec + 16))) return rc;
   for (int b = 0; b < 2; b++)
   {
     if ((rc = grow(ctx, m.klo[b], m.klo_cap[b], n))) return rc;
@@ -167,9 +164,7 @@ int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_r
   KMD_CUDA(ctx, cudaMemcpyAsync(m.ab_min, ab_min, N * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   if (!plan.empty())
     KMD_CUDA(ctx, cudaMemcpyAsync(m.plan, plan.data(), plan.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  for (uint32_t s = 0; s < N; s++)
-    if (n_records[s])
-      KMD_CUDA(ctx, cudaMemcpyAsync(m.raw + off[s] * rec, streams[s], n_records[s] * rec, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = fill_raw())) return rc;
 
   KMD_CUDA(ctx, cudaEventRecord(m.ev[0], ctx->stream));
   mrg::UnpackArgs U{};
@@ -196,6 +191,151 @@ int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_r
   return KMD_OK;
 }
 
+// streams[s] = n_records[s] HOST records of sample s
+int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min, uint32_t* n_rows)
+{
+  const uint32_t N = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
+  if (N > 0xFFFFu) return fail(ctx, KMD_ERR_ARG, "more than 65535 samples");
+  const size_t rec = 8ull * ctx->cfg.kmer_words + ctx->cfg.count_bytes;
+  std::vector<uint64_t> off(N + 1, 0);
+  for (uint32_t s = 0; s < N; s++)
+  {
+    if (n_records[s] && !streams[s]) return fail(ctx, KMD_ERR_ARG, "null stream pointer (sample %u)", s);
+    off[s + 1] = off[s] + n_records[s];
+  }
+  return merge_from_offsets(ctx, off, ab_min, n_rows, [&]() -> int {
+    for (uint32_t s = 0; s < N; s++)
+      if (n_records[s])
+        KMD_CUDA(ctx, cudaMemcpyAsync(ctx->mrg.raw + off[s] * rec, streams[s], n_records[s] * rec, cudaMemcpyHostToDevice, ctx->stream));
+    return KMD_OK;
+  });
+}
+
+// The samples' files of one partition as they lie on disk: frames[s] = the payload after the 41-byte header (HOST),
+// an LZ4 frame when compressed[s] != 0, raw records otherwise.  Compressed payloads are uploaded as they are and
+// decoded on the device, one warp per stream (kmd_lz4.cuh); the decoded records land where the merge tree reads them.
+// records_out (host, may be null): when given, the decoded records of every stream are copied there back to back
+// and no merge is run (tests / tools).
+int merge_lz4_impl(kmd_context* ctx, const void* const* frames, const uint64_t* frame_bytes, const uint8_t* compressed,
+                   const uint32_t* ab_min, uint64_t max_records, uint32_t* n_rows, uint64_t* n_records_out, void* records_out,
+                   uint64_t records_cap)
+{
+  MergeState& m = ctx->mrg;
+  const uint32_t N = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
+  if (N > 0xFFFFu) return fail(ctx, KMD_ERR_ARG, "more than 65535 samples");
+  const size_t rec = 8ull * ctx->cfg.kmer_words + ctx->cfg.count_bytes;
+  *n_rows = 0;
+  // ---- upload the compressed frames, 16-byte aligned ----
+  std::vector<uint64_t> tab(5ull * N, 0);
+  uint64_t* in_off = tab.data();
+  uint64_t* in_size = in_off + N;
+  uint64_t* out_off = in_size + N;
+  uint64_t* out_cap = out_off + N;
+  uint64_t* out_size = out_cap + N;
+  uint64_t in_total = 0;
+  uint32_t n_lz = 0;
+  for (uint32_t s = 0; s < N; s++)
+  {
+    if (frame_bytes[s] && !frames[s]) return fail(ctx, KMD_ERR_ARG, "null stream pointer (sample %u)", s);
+    const bool lz = !compressed || compressed[s];
+    in_off[s] = in_total;
+    in_size[s] = lz ? frame_bytes[s] : 0;
+    if (lz) { in_total += (frame_bytes[s] + 15) / 16 * 16; n_lz++; }
+    else
+    {
+      if (frame_bytes[s] % rec) return fail(ctx, KMD_ERR_ARG, "sample %u: payload is not a whole number of records", s);
+      out_size[s] = frame_bytes[s];
+    }
+  }
+  int rc;
+  if ((rc = grow(ctx, m.lz_in, m.lz_in_cap, in_total + 16))) return rc;
+  if ((rc = grow(ctx, m.lz_tab, m.lz_tab_cap, 5ull * N))) return rc;
+  if ((rc = grow(ctx, m.lz_status, m.lz_status_cap, N))) return rc;
+  for (cudaEvent_t& e : m.lz_ev) if (!e) KMD_CUDA(ctx, cudaEventCreate(&e));
+  for (uint32_t s = 0; s < N; s++)
+    if (in_size[s])
+      KMD_CUDA(ctx, cudaMemcpyAsync(m.lz_in + in_off[s], frames[s], in_size[s], cudaMemcpyHostToDevice, ctx->stream));
+  KMD_CUDA(ctx, cudaMemcpyAsync(m.lz_tab, tab.data(), 5ull * N * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  lz4::Args A{};
+  A.in = m.lz_in;
+  A.in_off = m.lz_tab;
+  A.in_size = m.lz_tab + N;
+  A.out_off = m.lz_tab + 2ull * N;
+  A.out_cap = m.lz_tab + 3ull * N;
+  A.out_size = m.lz_tab + 4ull * N;
+  A.status = m.lz_status;
+  A.n = N;
+  std::vector<uint32_t> status(N, 0);
+  const uint32_t grid = (N + lz4::kWarps - 1) / lz4::kWarps;
+  cudaEvent_t lz0 = m.lz_ev[0], lz1 = m.lz_ev[1];
+  KMD_CUDA(ctx, cudaEventRecord(lz0, ctx->stream));
+  if (n_lz)
+  {
+    // ---- pass 1: decoded sizes (the frames carry no content size) ----
+    A.out = nullptr;
+    lz4::frames_kernel<<<grid, lz4::kWarps * 32, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    KMD_CUDA(ctx, cudaGetLastError());
+    std::vector<uint64_t> sizes(N);
+    KMD_CUDA(ctx, cudaMemcpyAsync(sizes.data(), A.out_size, N * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KMD_CUDA(ctx, cudaMemcpyAsync(status.data(), m.lz_status, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t s = 0; s < N; s++)
+    {
+      if (!in_size[s]) continue;
+      if (status[s]) return fail(ctx, KMD_ERR_ARG, "sample %u: malformed LZ4 frame (decoder status %u)", s, status[s]);
+      if (sizes[s] % rec) return fail(ctx, KMD_ERR_ARG, "sample %u: decoded payload is not a whole number of records", s);
+      out_size[s] = sizes[s];
+    }
+  }
+  std::vector<uint64_t> off(N + 1, 0);
+  for (uint32_t s = 0; s < N; s++) off[s + 1] = off[s] + out_size[s] / rec;
+  if (n_records_out) *n_records_out = off[N];
+  if (max_records && off[N] > max_records)
+    return fail(ctx, KMD_ERR_OVERFLOW, "partition holds %llu records, more than the %llu one merge call may take: stream it in k-mer ranges",
+                static_cast<unsigned long long>(off[N]), static_cast<unsigned long long>(max_records));
+  for (uint32_t s = 0; s < N; s++) { out_off[s] = off[s] * rec; out_cap[s] = out_size[s]; }
+
+  auto fill = [&]() -> int {
+    // ---- pass 2: decode into the merge tree's record buffer; raw streams are plain copies ----
+    KMD_CUDA(ctx, cudaMemcpyAsync(m.lz_tab, tab.data(), 5ull * N * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_lz)
+    {
+      lz4::Args D = A;
+      D.out = m.raw;
+      lz4::frames_kernel<<<grid, lz4::kWarps * 32, 0, ctx->stream>>>(D);
+      ctx->launches++;
+      KMD_CUDA(ctx, cudaGetLastError());
+    }
+    for (uint32_t s = 0; s < N; s++)
+      if (!in_size[s] && out_size[s])
+        KMD_CUDA(ctx, cudaMemcpyAsync(m.raw + out_off[s], frames[s], out_size[s], cudaMemcpyHostToDevice, ctx->stream));
+    KMD_CUDA(ctx, cudaEventRecord(lz1, ctx->stream));
+    return KMD_OK;
+  };
+  if (records_out)
+  {
+    if (off[N] > records_cap) return fail(ctx, KMD_ERR_ARG, "output holds %llu records, the streams decode to %llu",
+                                          static_cast<unsigned long long>(records_cap), static_cast<unsigned long long>(off[N]));
+    if ((rc = grow(ctx, m.raw, m.raw_cap, off[N] * rec + 16))) return rc;
+    if ((rc = fill())) return rc;
+    KMD_CUDA(ctx, cudaMemcpyAsync(records_out, m.raw, off[N] * rec, cudaMemcpyDeviceToHost, ctx->stream));
+    KMD_CUDA(ctx, cudaMemcpyAsync(status.data(), m.lz_status, N * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint32_t s = 0; s < N; s++)
+      if (in_size[s] && status[s]) return fail(ctx, KMD_ERR_ARG, "sample %u: LZ4 decode failed (status %u)", s, status[s]);
+    KMD_CUDA(ctx, cudaEventElapsedTime(&m.last_lz4_ms, lz0, lz1));
+    return KMD_OK;
+  }
+  rc = merge_from_offsets(ctx, off, ab_min, n_rows, fill);
+  if (rc) return rc;
+  // merge_from_offsets synchronised the stream (row count read-back): the decode status is final
+  KMD_CUDA(ctx, cudaMemcpy(status.data(), m.lz_status, N * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  for (uint32_t s = 0; s < N; s++)
+    if (in_size[s] && status[s]) return fail(ctx, KMD_ERR_ARG, "sample %u: LZ4 decode failed (status %u)", s, status[s]);
+  return KMD_OK;
+}
+
 int merge_check(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min)
 {
   if (!ctx) return KMD_ERR_ARG;
@@ -218,6 +358,32 @@ int kmd_merge_scan_host(kmd_context* ctx, const void* const* streams, const uint
   if (n_rows) *n_rows = rows;
   if (rows == 0) return KMD_OK;
   return scan_device_impl(ctx, ctx->mrg.rows, rows, row_base, partition);
+}
+
+int kmd_merge_scan_lz4_host(kmd_context* ctx, const void* const* frames, const uint64_t* frame_bytes, const uint8_t* compressed,
+                            const uint32_t* ab_min, uint64_t row_base, uint32_t partition, uint64_t max_records, uint64_t* n_rows,
+                            uint64_t* n_records)
+{
+  int rc = merge_check(ctx, frames, frame_bytes, ab_min);
+  if (rc) return rc;
+  uint32_t rows = 0;
+  if ((rc = merge_lz4_impl(ctx, frames, frame_bytes, compressed, ab_min, max_records, &rows, n_records, nullptr, 0))) return rc;
+  if (n_rows) *n_rows = rows;
+  if (rows == 0) return KMD_OK;
+  return scan_device_impl(ctx, ctx->mrg.rows, rows, row_base, partition);
+}
+
+int kmd_lz4_decode_host(kmd_context* ctx, const void* const* frames, const uint64_t* frame_bytes, void* records_out,
+                        uint64_t cap_records, uint64_t* n_records, float* device_ms)
+{
+  if (!ctx || !frames || !frame_bytes || !records_out || !n_records) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint32_t rows = 0;
+  const std::vector<uint32_t> ab(ctx->cfg.nb_controls + ctx->cfg.nb_cases, 1);
+  int rc = merge_lz4_impl(ctx, frames, frame_bytes, nullptr, ab.data(), 0, &rows, n_records, records_out, cap_records);
+  if (rc) return rc;
+  if (device_ms) *device_ms = ctx->mrg.last_lz4_ms;
+  return KMD_OK;
 }
 
 int kmd_merge_ms(kmd_context* ctx, float* unpack_ms, float* passes_ms, float* rows_ms, uint32_t* n_passes, uint64_t* n_records)

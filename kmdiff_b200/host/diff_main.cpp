@@ -383,6 +383,7 @@ class GpuWorker
   ~GpuWorker()
   {
     for (auto& b : m_bufs) kmd_host_free(b.data);
+    kmd_host_free(m_arena);
     for (int fd : m_fds) if (fd >= 0) ::close(fd);
   }
 
@@ -491,6 +492,7 @@ class GpuWorker
     for (const Partition& p : partitions)
     {
       if (p.sample_paths.size() != N) throw KmdError("ConfigError", "kmtricks.fof does not list --nb-controls + --nb-cases samples.");
+      if (merge_whole_partition(p, N, kw, B, budget)) continue;
       std::vector<Stream> st(N);
       struct Returner { std::vector<Stream>& st; std::vector<std::unique_ptr<PinnedBuf>>& pins;
                         ~Returner() { for (size_t s = 0; s < st.size(); s++) if (st[s].pin) pins[s] = std::move(st[s].pin); } } returner{st, pins};
@@ -603,6 +605,92 @@ class GpuWorker
       }
       logf(L_DEBUG, "partition %u: %llu rows merged from %u count files (gpu %d)", p.index, static_cast<unsigned long long>(local), N, m_device);
     }
+  }
+
+  // A partition whose files are small enough goes to the device as it lies on disk: the N files are read whole into
+  // one pinned arena (the -t threads share them), cross PCIe still compressed, and are decoded there — one warp per
+  // sample stream (kmd_merge_scan_lz4_host) — then merged and tested in one call.  Returns false when the partition has
+  // to be streamed in k-mer ranges by the loop above instead (too many records for one call, or a count width on
+  // disk that differs from this run's).
+  bool merge_whole_partition(const Partition& p, uint32_t N, uint32_t kw, uint32_t B, uint64_t budget)
+  {
+    if (getenv("KMD_HOST_LZ4")) return false;   // A/B switch: decode on the host threads
+    const size_t rec = 8ull * kw + B;
+    std::vector<uint64_t> fsize(N), foff(N + 1, 0);
+    for (uint32_t s = 0; s < N; s++)
+    {
+      std::error_code ec;
+      fsize[s] = static_cast<uint64_t>(fs::file_size(p.sample_paths[s], ec));
+      if (ec || fsize[s] < kKmerHeaderBytes) throw KmdError("IOError", "Unable to open " + p.sample_paths[s]);
+      foff[s + 1] = foff[s] + (fsize[s] + 63) / 64 * 64;
+    }
+    // compressed k-mer records shrink to no less than ~1/4: do not even read a partition that cannot fit
+    if (foff[N] / rec > 4 * budget) return false;
+    if (foff[N] > m_arena_bytes)
+    {
+      kmd_host_free(m_arena);
+      m_arena = nullptr; m_arena_bytes = 0;
+      const size_t want = static_cast<size_t>(foff[N] + foff[N] / 4 + (1u << 20));
+      m_arena = static_cast<uint8_t*>(kmd_host_alloc(want));
+      if (!m_arena) throw KmdError("GpuError", "kmd_host_alloc failed");
+      m_arena_bytes = want;
+    }
+    std::atomic<uint32_t> next{0};
+    std::exception_ptr err;
+    std::mutex err_mu;
+    auto slurp = [&] {
+      for (uint32_t s; (s = next.fetch_add(1)) < N;)
+      {
+        try
+        {
+          const int fd = ::open(p.sample_paths[s].c_str(), O_RDONLY);
+          if (fd < 0) throw KmdError("IOError", "Unable to open " + p.sample_paths[s]);
+          size_t got = 0;
+          while (got < fsize[s])
+          {
+            const ssize_t n = ::pread(fd, m_arena + foff[s] + got, fsize[s] - got, static_cast<off_t>(got));
+            if (n <= 0) { ::close(fd); throw KmdError("IOError", p.sample_paths[s] + ": short read"); }
+            got += static_cast<size_t>(n);
+          }
+          ::close(fd);
+        }
+        catch (...) { std::lock_guard<std::mutex> lk(err_mu); err = std::current_exception(); }
+      }
+    };
+    {
+      const size_t n_thr = std::max<size_t>(1, std::min<size_t>(m_opt.nb_threads, N));
+      std::vector<std::thread> pool;
+      for (size_t t = 1; t < n_thr; t++) pool.emplace_back(slurp);
+      slurp();
+      for (auto& t : pool) t.join();
+      if (err) std::rethrow_exception(err);
+    }
+    std::vector<const void*> frames(N);
+    std::vector<uint64_t> bytes(N);
+    std::vector<uint8_t> compressed(N);
+    for (uint32_t s = 0; s < N; s++)
+    {
+      KmerHeader h;
+      memcpy(&h, m_arena + foff[s], sizeof h);
+      if (h.km_magic != kKmMagic || h.kmer_magic != kKmerMagic) throw KmdError("IOError", "Invalid file format: " + p.sample_paths[s]);
+      if (h.kmer_slots != kw) throw KmdError("InputError", p.sample_paths[s] + ": unexpected kmer_slots");
+      if (h.count_slots != B) return false;   // widened / narrowed record by record on the host
+      frames[s] = m_arena + foff[s] + kKmerHeaderBytes;
+      bytes[s] = fsize[s] - kKmerHeaderBytes;
+      compressed[s] = h.compressed != 0;
+    }
+    const std::vector<uint32_t> ab_min(N, 1);   // as cmd/diff.hpp:109 passes it
+    if (m_opt.pop_correction)
+      ck(m_ctx.get(), kmd_popstrat_set_draw_index(m_ctx.get(), m_draw_next), "kmd_popstrat_set_draw_index");
+    uint64_t n_rows = 0, n_rec = 0;
+    const int rc = kmd_merge_scan_lz4_host(m_ctx.get(), frames.data(), bytes.data(), compressed.data(), ab_min.data(),
+                                           static_cast<uint64_t>(p.index) << kPartShift, p.index, budget, &n_rows, &n_rec);
+    if (rc == KMD_ERR_OVERFLOW) return false;
+    ck(m_ctx.get(), rc, "kmd_merge_scan_lz4_host");
+    m_draw_next += n_rows;
+    logf(L_DEBUG, "partition %u: %llu rows merged from %u count files, %llu records decoded on the device (gpu %d)", p.index,
+         static_cast<unsigned long long>(n_rows), N, static_cast<unsigned long long>(n_rec), m_device);
+    return true;
   }
 
   void read_loop()
@@ -739,6 +827,8 @@ class GpuWorker
   const DiffOptions& m_opt;
   ctx_ptr m_ctx;
   uint64_t m_row_bytes = 0, m_buf_rows = 0;
+  uint8_t* m_arena = nullptr;   // count-file mode: pinned arena holding one partition's files
+  size_t m_arena_bytes = 0;
   uint64_t m_draw_next = 0;   // count-file mode: Sampler draw index = rows merged so far (one worker, partition order)
   size_t m_n_readers = 1;
   std::vector<Buf> m_bufs;
