@@ -268,12 +268,18 @@ def bench_reference(args) -> None:
 
 
 def fasta_kmers(path: str):
-    """sequence lines of a reference FASTA file as a set of strings"""
-    out = set()
+    """the sequences of a reference FASTA file (kseq++ wraps them at 60 columns) as a set of strings"""
+    out, cur = set(), []
     with open(path) as f:
         for line in f:
-            if not line.startswith(">"):
-                out.add(line.strip())
+            if line.startswith(">"):
+                if cur:
+                    out.add("".join(cur))
+                cur = []
+            else:
+                cur.append(line.strip())
+    if cur:
+        out.add("".join(cur))
     return out
 
 
@@ -714,6 +720,12 @@ def measure(env: Env, args, cfg_name: str, steps: int, warmup: int, full: bool) 
     # ---- CPU baseline: the reference binary on a bounded prefix of the same matrix, and parity on that prefix ----
     if full and world == 1 and rank == 0 and not args.no_cpu_baseline:
         block.update(cpu_baseline_and_parity(env, args, cfg_name, ctx, spec, exchange, popstrat))
+    elif not full and world == 1 and rank == 0 and not args.no_cli and not args.no_cpu_baseline and not popstrat:
+        # the secondary workload: only the drop-in program's file -> FASTA time (17.6 GB = 2e8 rows of c2)
+        try:
+            block["e2e_cli"] = cli_end_to_end(cfg_name, 2e8 * R / (1 << 30), os.cpu_count() or 1)
+        except Exception as e:
+            block["e2e_cli"] = {"failed": str(e)}
 
     ctx.close()
     del data
@@ -784,23 +796,22 @@ def cpu_baseline_and_parity(env: Env, args, cfg_name: str, ctx, spec, exchange, 
     except Exception as e:  # the baseline must never take the bench line down
         out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
     if not popstrat and not args.no_cli:
-        try:
-            out["e2e_cli"] = cli_end_to_end(cfg_name, args.cli_gib, cores)
-        except Exception as e:
-            out["e2e_cli"] = {"failed": str(e)}
+        out["e2e_cli"] = cli_points(args, cfg_name, cores)
     return out
 
 
 def cli_end_to_end(cfg_name: str, gib: float, cores: int) -> dict:
     """file -> FASTA: `kmdiff-b200 diff` vs the reference binary on the same run directory (raw matrices, page
-    cache / tmpfs warm for both; best of 2 runs each).  Wall clock of the whole process, start-up included."""
+    cache / tmpfs warm for both; best of 2 runs each).  Wall clock of the whole process, start-up (CUDA context
+    creation: ~0.6 s) and exit included.  A second is left between runs: the driver tears the previous process's
+    GPU context and pinned memory down after it has exited, and the next CUDA initialisation would wait for that."""
     nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
     R = row_bytes(cfg_name)
     n_rows = int(min(rows, gib * (1 << 30) // R))
     parts = max(cores, 8) * 2
     run_dir = make_run_dir(cfg_name, n_rows, parts)
-    res = {"rows": n_rows, "bytes": n_rows * R, "partitions": parts, "layout": "uncompressed matrices", "dir": scratch_dir(),
-           "host_threads": cores}
+    res = {"workload": workload_name(cfg_name), "rows": n_rows, "bytes": n_rows * R, "partitions": parts,
+           "layout": "uncompressed matrices", "dir": scratch_dir(), "host_threads": cores}
     try:
         common = ["diff", "--km-run", run_dir, "-1", str(nc), "-2", str(nk), "-t", str(cores), "-c", corr,
                   "-s", str(SIGNIFICANCE), "-u", str(CUTOFF)]
@@ -815,6 +826,7 @@ def cli_end_to_end(cfg_name: str, gib: float, cores: int) -> dict:
                 if os.path.exists(opt):
                     os.remove(opt)
                 out = tempfile.mkdtemp(prefix="kmdiff_cli_out_", dir=scratch_dir())
+                time.sleep(1.0)
                 t0 = time.perf_counter()
                 r = subprocess.run([binary] + common + extra + ["-o", out], capture_output=True, text=True, timeout=900)
                 dt = time.perf_counter() - t0
@@ -837,6 +849,21 @@ def cli_end_to_end(cfg_name: str, gib: float, cores: int) -> dict:
     return res
 
 
+def cli_points(args, cfg_name: str, cores: int) -> dict:
+    """e2e_cli at every size of --cli-gib (start-up amortises with size); the largest is the headline object"""
+    sizes = sorted({float(x) for x in str(args.cli_gib).split(",") if x})
+    points = []
+    for g in sizes:
+        try:
+            points.append(cli_end_to_end(cfg_name, g, cores))
+        except Exception as e:
+            points.append({"gib": g, "failed": str(e)})
+    out = dict(points[-1]) if points else {"failed": "no size given"}
+    if len(points) > 1:
+        out["smaller_runs"] = points[:-1]
+    return out
+
+
 def bench_b200(args) -> None:
     env = Env()
     cfg_name = args.config or HEADLINE
@@ -855,7 +882,7 @@ def bench_b200(args) -> None:
             line[key] = head[key]
     if secondary is not None:
         line[SECONDARY] = {key: secondary[key] for key in ("value", "ms_per_step", "config", "decision_check", "roofline", "e2e",
-                                                           "gpu_launches", "clocks") if key in secondary}
+                                                           "e2e_cli", "gpu_launches", "clocks") if key in secondary}
         line[SECONDARY]["unit"] = "rows/s"
     env.emit(line)
     env.close()
@@ -873,7 +900,7 @@ def main():
     ap.add_argument("--e2e-rows", type=int, default=1 << 25)
     ap.add_argument("--e2e-gib", type=int, default=8, help="at most this many GiB of pinned host rows in the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cli-gib", type=float, default=16.0, help="size of the run directory of the e2e_cli leg")
+    ap.add_argument("--cli-gib", default="16,64", help="size(s) in GiB of the run directories of the e2e_cli leg, comma separated")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")

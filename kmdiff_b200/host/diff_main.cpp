@@ -343,7 +343,7 @@ class GpuWorker
   GpuWorker(int device, const DiffOptions& o, const RunConfig& cfg, uint64_t sum_controls, uint64_t sum_cases, size_t n_readers = 1,
             size_t buf_bytes = 16u << 20, size_t max_bufs = 0)
     : m_device(device), m_opt(o), m_n_readers(std::max<size_t>(1, n_readers)),
-      m_bufs(max_bufs ? max_bufs : 2 * std::max<size_t>(1, n_readers) + 2)
+      m_bufs(max_bufs ? max_bufs : std::max<size_t>(1, n_readers) + 8)
   {
     kmd_bind_host_thread(device);   // CPU affinity + memory policy of the GPU's NUMA node (no-op when unknown)
     kmd_config c{};
@@ -1136,6 +1136,45 @@ struct FastaPair
     }
     (is_control ? n_control : n_case)++;
   }
+  // FASTA only: the records are formatted by `threads` threads (the running index of a record = its rank among the
+  // records of its own file, aggregator.hpp:55-62) and written in order
+  void write_all(const std::vector<kmd_survivor>& recs, uint32_t kmer_words, uint32_t k, size_t threads)
+  {
+    const size_t n = recs.size();
+    threads = std::max<size_t>(1, std::min<size_t>(threads, 32));
+    const size_t per = (n + threads - 1) / threads;
+    // per chunk: how many control / case records precede it
+    std::vector<uint64_t> ctl_before(threads + 1, 0), case_before(threads + 1, 0);
+    for (size_t t = 0; t < threads; t++)
+    {
+      uint64_t c = 0, k2 = 0;
+      for (size_t i = std::min(n, t * per); i < std::min(n, (t + 1) * per); i++) (recs[i].sign == KMD_SIGN_CONTROL ? c : k2)++;
+      ctl_before[t + 1] = ctl_before[t] + c;
+      case_before[t + 1] = case_before[t] + k2;
+    }
+    std::vector<std::string> ctl_text(threads), case_text(threads);
+    auto work = [&](size_t t) {
+      uint64_t ic = n_control + ctl_before[t], ik = n_case + case_before[t];
+      char buf[1024];
+      for (size_t i = std::min(n, t * per); i < std::min(n, (t + 1) * per); i++)
+      {
+        const bool is_control = recs[i].sign == KMD_SIGN_CONTROL;
+        const size_t len = kmd_format_fasta(is_control ? ic++ : ik++, &recs[i], kmer_words, k, buf, sizeof buf);
+        (is_control ? ctl_text[t] : case_text[t]).append(buf, len);
+      }
+    };
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < threads; t++) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    for (size_t t = 0; t < threads; t++)
+    {
+      fwrite(ctl_text[t].data(), 1, ctl_text[t].size(), control);
+      fwrite(case_text[t].data(), 1, case_text[t].size(), cases);
+    }
+    n_control += ctl_before[threads];
+    n_case += case_before[threads];
+  }
   ~FastaPair() { if (control) fclose(control); if (cases) fclose(cases); }
 };
 
@@ -1495,8 +1534,10 @@ void main_diff(DiffOptions& opt)
   const size_t reader_cap = any_raw ? size_t{32} : std::max<size_t>(1, parts_per_gpu);
   size_t readers_per_gpu = std::max<size_t>(1, std::min({size_t{32}, opt.nb_threads / static_cast<size_t>(n_dev), reader_cap}));
   if (const char* e = getenv("KMD_READERS")) readers_per_gpu = std::max<size_t>(1, static_cast<size_t>(atol(e)));   // tuning experiments
-  // pinning host memory costs ~0.3 s per GB: small inputs get small buffers
-  size_t buf_bytes = static_cast<size_t>(std::min<uint64_t>(16ull << 20, std::max<uint64_t>(1ull << 20,
+  // Pinning host memory costs ~0.3 s per GB when it is allocated and again when the process exits, so the staging
+  // pool is kept small: 4 MiB buffers (a 76 us copy at PCIe rate, far above the launch overhead; measured best of
+  // 4 / 16 / 32 MiB, profiles/r02d), readers + 8 of them; small inputs get smaller ones.
+  size_t buf_bytes = static_cast<size_t>(std::min<uint64_t>(4ull << 20, std::max<uint64_t>(1ull << 20,
                          input_bytes / static_cast<uint64_t>(n_dev) / (2 * (readers_per_gpu + 2)))));
   if (const char* e = getenv("KMD_BUF_MB")) buf_bytes = std::max<size_t>(1, static_cast<size_t>(atol(e))) << 20;
   // one thread per device: CUDA context creation and the device allocations of kmd_create run side by side
@@ -1687,7 +1728,10 @@ void main_diff(DiffOptions& opt)
   }
   {
     FastaPair out(opt.output_directory, opt.kff, cfg.kmer_size);
-    for (const kmd_survivor& s : final_records) out.write(s, kw, cfg.kmer_size);
+    if (opt.kff || final_records.size() < 4096)
+      for (const kmd_survivor& s : final_records) out.write(s, kw, cfg.kmer_size);
+    else
+      out.write_all(final_records, kw, cfg.kmer_size, opt.nb_threads);
     logf(L_INFO, "Partitions aggregated (%s)", agg_time.formatted().c_str());
     logf(L_INFO, "Significant k-mers: %llu (control), %llu (case).", static_cast<unsigned long long>(out.n_control),
          static_cast<unsigned long long>(out.n_case));
