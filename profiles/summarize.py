@@ -48,6 +48,7 @@ def main():
     ap.add_argument("--rep")
     ap.add_argument("--launches")
     ap.add_argument("--tag", default="lrt_scan")
+    ap.add_argument("--command", default="", help="the profiled command line, recorded in the summary")
     args = ap.parse_args()
 
     if args.rep:
@@ -71,8 +72,8 @@ def main():
         summary = {
             "round": args.round, "config": args.config, "rows": args.rows, "row_bytes": args.row_bytes,
             "kernel": launches[0]["kernel"], "launches_captured": n,
-            "command": "ncu --set full --clock-control none --import-source on -k regex:lrt_scan -s 3 -c 2 python bench.py "
-                       f"--steps 2 --warmup 3 --rows {args.rows} --no-cpu-baseline --e2e-steps 1 --e2e-rows 4194304",
+            "command": args.command or ("ncu --set full --clock-control none --import-source on -k regex:lrt_scan -s 3 -c 2 python bench.py "
+                                        f"--steps 2 --warmup 3 --rows {args.rows} --no-cpu-baseline --e2e-steps 1 --e2e-rows 4194304"),
             "algorithmic_bytes_per_launch": alg, "dram_bytes_per_launch": dram, "traffic_over_algorithmic": dram / alg,
             "duration_s_under_ncu": t, "gbps_under_ncu": alg / t / 1e9,
             "metrics_mean": {k: mean(k) for k in KEEP if all(x.get(k) is not None for x in launches)},
