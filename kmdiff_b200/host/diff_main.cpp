@@ -105,7 +105,7 @@ struct DiffOptions
   double kmer_pca = 0.001;
   size_t ploidy = 2, npc = 2, seed = 0, log_size = 10000;
   // extensions of this implementation
-  int gpus = 0;               // 0 = every visible device
+  int gpus = 0;               // 0 = chosen from the input size: one device per 64 GiB
   size_t count_bytes = 4;     // the reference fixes this at compile time (MAX_C); here a runtime option
   size_t max_survivors = 0;
   size_t max_sampled = 0;     // capacity of the per-GPU presence matrix (--pop-correction); 0 = 2097152
@@ -145,7 +145,7 @@ struct DiffOptions
     "  -v/--verbose STR        debug|info|warning|error {info}\n"
     "  -h/--help  --version\n"
     " [this implementation]\n"
-    "  --gpus INT              GPUs to shard the partitions over. {all visible}\n"
+    "  --gpus INT              GPUs to shard the partitions over. {one per 64 GiB of input}\n"
     "  --count-bytes INT       count width of the matrices: 1, 2 or 4 (the reference's compile-time MAX_C). {4}\n"
     "  --max-survivors INT     capacity of the per-GPU survivor buffers. {4194304}\n"
     "  --max-sampled INT       capacity of the per-GPU sampled k-mer buffer (--pop-correction). {2097152}\n",
@@ -1329,6 +1329,31 @@ void do_pop(std::vector<std::unique_ptr<GpuWorker>>& workers, const DiffOptions&
   logf(L_INFO, "Population correction done. (%s).", pop_time.formatted().c_str());
 }
 
+// Hide all but the first n devices from the CUDA driver (must run before the first CUDA call of the process).
+void restrict_visible_devices(size_t n)
+{
+  if (n == 0) return;
+  std::vector<std::string> ids;
+  if (const char* cur = getenv("CUDA_VISIBLE_DEVICES"))
+  {
+    std::stringstream ss(cur);
+    for (std::string item; std::getline(ss, item, ',');) if (!item.empty()) ids.push_back(item);
+  }
+  else
+  {
+    std::error_code ec;
+    size_t count = 0;
+    if (fs::is_directory("/proc/driver/nvidia/gpus", ec))
+      for (auto& e : fs::directory_iterator("/proc/driver/nvidia/gpus", ec)) { (void)e; count++; }
+    for (size_t i = 0; i < count; i++) ids.push_back(std::to_string(i));
+  }
+  if (ids.size() <= n) return;
+  std::string v;
+  for (size_t i = 0; i < n; i++) v += (i ? "," : "") + ids[i];
+  setenv("CUDA_VISIBLE_DEVICES", v.c_str(), 1);
+  logf(L_DEBUG, "CUDA_VISIBLE_DEVICES=%s (%zu of %zu devices)", v.c_str(), n, ids.size());
+}
+
 // ---- main_diff (cmd/diff.hpp:262-377) ---------------------------------------------------------------------
 
 void main_diff(DiffOptions& opt)
@@ -1361,10 +1386,28 @@ void main_diff(DiffOptions& opt)
     ~Warmup() { if (th.joinable()) th.join(); }
   } warmup;
   {
-    size_t n_units = list_matrices(opt.kmtricks_dir).size();
-    if (n_units == 0) n_units = 1u << 16;     // count-file mode: the partition count is read below
+    // How many devices: --gpus, else one per 64 GiB of input — the host side (page cache -> pinned memory at ~40 GB/s on
+    // a 16-32 core box) feeds one or two GPUs at most, and every further device costs start-up time.  The choice is made
+    // BEFORE the CUDA driver is initialised and the other devices are hidden from it (CUDA_VISIBLE_DEVICES): the
+    // driver's initialisation time grows with every visible device (measured: 0.6 s with 1, 5-7 s with 8 B200s visible).
+    const auto mats = list_matrices(opt.kmtricks_dir);
+    size_t n_units = mats.size();
+    uint64_t bytes = 0;
+    std::error_code ec;
+    for (const std::string& mpath : mats) { const auto sz = fs::file_size(mpath, ec); if (!ec) bytes += sz; }
+    if (n_units == 0)
+    {
+      n_units = 1u << 16;     // count-file mode: the partition count is read below
+      if (fs::is_directory(opt.kmtricks_dir + "/counts"))
+        for (auto& e : fs::recursive_directory_iterator(opt.kmtricks_dir + "/counts", ec))
+          if (e.is_regular_file(ec)) bytes += static_cast<uint64_t>(e.file_size(ec));
+    }
     const bool single = !opt.model_lib_path.empty();
-    warmup.start(single ? 1 : static_cast<int>(std::min<size_t>(n_units, opt.gpus > 0 ? static_cast<size_t>(opt.gpus) : 1u << 16)));
+    size_t want = opt.gpus > 0 ? static_cast<size_t>(opt.gpus) : std::max<uint64_t>(1, bytes >> 36);
+    want = single ? 1 : std::min(want, n_units);
+    restrict_visible_devices(want);
+    if (opt.gpus == 0) opt.gpus = static_cast<int>(want);
+    warmup.start(static_cast<int>(want));
   }
 
   const RunConfig cfg = get_kmtricks_config(opt.kmtricks_dir);
