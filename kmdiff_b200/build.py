@@ -15,8 +15,10 @@ HOST = os.path.join(PKG, "host")
 LIB = os.path.join(PKG, "libkmdiff_b200.so")
 CLI = os.path.join(PKG, "kmdiff-b200")
 
+# host side: AVX2 (every B200 host has it) for the auto-vectorised sweeps of the eigensolver and the LZ4 / table
+# code, but no FMA contraction — host arithmetic must round like the reference's and the oracle's
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-mavx2", "-Xcompiler", "-ffp-contract=off"]
 
 
 def _nvcc() -> str:

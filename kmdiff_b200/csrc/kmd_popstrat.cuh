@@ -224,6 +224,10 @@ struct IrlsWarp
 //   xl[n] mu[n] eta[n] d2[n] H[p*p] LU[p*p] INV[p*p] v[p] w[p] weight[p]
 __host__ __device__ inline size_t irls_warp_doubles(uint32_t n, uint32_t p) { return 4ull * n + 3ull * p * p + 3ull * p; }
 
+// NQ > 0: the features are staged in shared memory and every lane owns exactly NQ slots of [hessian | X^T S z]
+// (NQ = ceil((p*p + p) / 32)): the row walk is straight-line code on shared-memory byte offsets.  NQ == 0: generic
+// form (features in global memory: cohorts too large for shared memory).
+template <int NQ>
 __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArgs A)
 {
   extern __shared__ double sm[];
@@ -279,6 +283,28 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
     el_v[q] = is_v;
   }
 
+  // NQ > 0: the same slots as shared-memory BYTE offsets (relative to sm) of row 0 and byte strides per row.  A slot of
+  // X^T S z multiplies by z[k] (kept in eta[] during the walk): g * z is the very product the generic form reads back
+  // as gz, so both slot kinds are  acc += x_a[k] * (g[k] * x_b[k])  and the walk has no per-slot branch.
+  uint32_t of_a[NQ > 0 ? NQ : 1], of_b[NQ > 0 ? NQ : 1], st_a[NQ > 0 ? NQ : 1], st_b[NQ > 0 ? NQ : 1];
+  if constexpr (NQ > 0)
+  {
+#pragma unroll
+    for (int q = 0; q < NQ; q++)
+    {
+      const uint32_t e = lane + 32 * q;
+      const bool is_v = e >= pp && e < pp + p;
+      const bool dead = e >= pp + p;
+      uint32_t a = dead ? 0 : (is_v ? e - pp : e / p), b = (dead || is_v) ? 0 : e - (e / p) * p;
+      const bool own_a = A.own_last && a == p - 1, own_b = A.own_last && b == p - 1;
+      of_a[q] = static_cast<uint32_t>((own_a ? xl : F + a) - sm) * 8u;
+      st_a[q] = (own_a ? 1u : A.ldf) * 8u;
+      of_b[q] = is_v ? static_cast<uint32_t>(eta - sm) * 8u : static_cast<uint32_t>((own_b ? xl : F + b) - sm) * 8u;
+      st_b[q] = (is_v || own_b) ? 8u : A.ldf * 8u;
+    }
+  }
+  const char* const smb = reinterpret_cast<const char*>(sm);
+
   const uint32_t warps_per_block = blockDim.x >> 5;
   for (uint32_t item = blockIdx.x * warps_per_block + warp; item < n_items; item += gridDim.x * warps_per_block)
   {
@@ -320,7 +346,7 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
         d2[i] = mul(d, d);
         const double z = add(eta[i], div(d, add(g, 1e-305)));
         mu[i] = g;
-        eta[i] = mul(g, z);
+        eta[i] = NQ > 0 ? z : mul(g, z);
       }
       __syncwarp();
 
@@ -330,6 +356,35 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
       //   (X^T S z)[j]  = sum_{good k} X[k][j] * (S[k] * z[k])      (element p*p + j)
       double error = 0.0;
       uint32_t n_good = 0;
+      if constexpr (NQ > 0)
+      {
+        double acc[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) acc[q] = 0.0;
+#pragma unroll 2
+        for (uint32_t k = 0; k < n; k++)
+        {
+          error = add(error, d2[k]);
+          const double g = mu[k];
+          if (!(g > 1e-305)) continue;   // warp-uniform
+          n_good++;
+#pragma unroll
+          for (int q = 0; q < NQ; q++)
+          {
+            const double xa = *reinterpret_cast<const double*>(smb + (k * st_a[q] + of_a[q]));
+            const double xb = *reinterpret_cast<const double*>(smb + (k * st_b[q] + of_b[q]));
+            acc[q] = add(acc[q], mul(xa, mul(g, xb)));
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; q++)
+        {
+          const uint32_t e = lane + 32 * q;
+          if (e < pp) H[e] = acc[q];
+          else if (e < pp + p) v[e - pp] = acc[q];
+        }
+      }
+      else
       {
         double acc[kIrlsQ];
 #pragma unroll

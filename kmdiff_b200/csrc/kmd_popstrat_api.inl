@@ -252,9 +252,29 @@ int launch_irls(kmd_context* ctx, pop::IrlsArgs A, uint32_t n_items_host)
   const size_t smem = irls_smem(A.n, A.p, A.ldf, in_smem, warps);
   if (smem > budget) return fail(ctx, KMD_ERR_ARG, "cohort of %u samples does not fit the GLM kernel's shared memory", A.n);
   A.feat_in_smem = in_smem;
-  KMD_CUDA(ctx, cudaFuncSetAttribute(pop::glm_irls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>((n_items_host + warps - 1) / warps, ctx->sm_count));
-  pop::glm_irls_kernel<<<blocks, warps * 32, smem, ctx->stream>>>(A);
+  const uint32_t nq = in_smem ? (A.p * A.p + A.p + 31) / 32 : 0;   // slots of [hessian | X^T S z] per lane
+  auto launch = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kernel<<<blocks, warps * 32, smem, ctx->stream>>>(A);
+    return cudaGetLastError();
+  };
+  cudaError_t le;
+  switch (nq)
+  {
+    case 1: le = launch(pop::glm_irls_kernel<1>); break;
+    case 2: le = launch(pop::glm_irls_kernel<2>); break;
+    case 3: le = launch(pop::glm_irls_kernel<3>); break;
+    case 4: le = launch(pop::glm_irls_kernel<4>); break;
+    case 5: le = launch(pop::glm_irls_kernel<5>); break;
+    case 6: le = launch(pop::glm_irls_kernel<6>); break;
+    case 7: le = launch(pop::glm_irls_kernel<7>); break;
+    case 8: le = launch(pop::glm_irls_kernel<8>); break;
+    case 9: le = launch(pop::glm_irls_kernel<9>); break;
+    default: le = launch(pop::glm_irls_kernel<0>); break;
+  }
+  KMD_CUDA(ctx, le);
   ctx->launches++;
   KMD_CUDA(ctx, cudaGetLastError());
   return KMD_OK;
@@ -601,8 +621,10 @@ int kmd_sym_eig(const double* a, uint32_t n, double* evals, double* evecs)
 int kmd_smartpca_pcs(const double* xtx, uint32_t n, uint32_t numeigs, double* evals_out, double* pcs)
 {
   if (!xtx || !pcs || numeigs > n) return KMD_ERR_ARG;
-  std::vector<double> evals(n), evecs(static_cast<size_t>(n) * n);
-  if (kmd::sym_eig(xtx, n, evals.data(), evecs.data())) return KMD_ERR_STATE;
+  // all eigenvalues, but only the numeigs leading eigenvectors (inverse iteration: O(n^2) each instead of accumulating
+  // all n through the QL sweeps)
+  std::vector<double> evals(n), evecs(static_cast<size_t>(std::max<uint32_t>(numeigs, 1)) * n);
+  if (kmd::sym_eig_top(xtx, n, numeigs, evals.data(), evecs.data())) return KMD_ERR_STATE;
   if (evals_out) memcpy(evals_out, evals.data(), n * sizeof(double));
   // fxvecs[j] = X X^T fvecs[j] (smartpca.c:1186-1228: ffvecs = X^T fvecs, then one dot product per
   // individual), rescaled to unit length (fxscal, :1230-1240) and written "%10.4f" (:1296-1329)
