@@ -40,7 +40,7 @@ def _sources(d: str, exts: tuple[str, ...]) -> list[str]:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    srcs = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "kmdiff_b200.h")]
+    srcs = _sources(CSRC, (".cu", ".cuh", ".inl", ".hpp")) + [os.path.join(ROOT, "include", "kmdiff_b200.h"), os.path.abspath(__file__)]
     if force or _stale(LIB, srcs):
         cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, os.path.join(CSRC, "kmd_api.cu")]
         if verbose:
