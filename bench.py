@@ -721,11 +721,9 @@ def measure(env: Env, args, cfg_name: str, steps: int, warmup: int, full: bool) 
     if full and world == 1 and rank == 0 and not args.no_cpu_baseline:
         block.update(cpu_baseline_and_parity(env, args, cfg_name, ctx, spec, exchange, popstrat))
     elif not full and world == 1 and rank == 0 and not args.no_cli and not args.no_cpu_baseline and not popstrat:
-        # the secondary workload: only the drop-in program's file -> FASTA time (17.6 GB = 2e8 rows of c2)
-        try:
-            block["e2e_cli"] = cli_end_to_end(cfg_name, 2e8 * R / (1 << 30), os.cpu_count() or 1)
-        except Exception as e:
-            block["e2e_cli"] = {"failed": str(e)}
+        # the secondary workload: only the drop-in program's file -> FASTA time, at 2e8 rows (17.6 GB) and at 64 GiB
+        sec = argparse.Namespace(cli_gib=f"{2e8 * R / (1 << 30)},{args.cli_gib_secondary_max}")
+        block["e2e_cli"] = cli_points(sec, cfg_name, os.cpu_count() or 1)
 
     ctx.close()
     del data
@@ -855,12 +853,18 @@ def cli_points(args, cfg_name: str, cores: int) -> dict:
     points = []
     for g in sizes:
         try:
+            st = os.statvfs(scratch_dir())
+            if g * (1 << 30) > 0.6 * st.f_bavail * st.f_frsize:
+                points.append({"gib": g, "skipped": f"{scratch_dir()} has {st.f_bavail * st.f_frsize >> 30} GiB free"})
+                continue
             points.append(cli_end_to_end(cfg_name, g, cores))
         except Exception as e:
             points.append({"gib": g, "failed": str(e)})
-    out = dict(points[-1]) if points else {"failed": "no size given"}
-    if len(points) > 1:
-        out["smaller_runs"] = points[:-1]
+    done = [p for p in points if "speedup" in p]
+    out = dict(done[-1]) if done else (dict(points[-1]) if points else {"failed": "no size given"})
+    rest = [p for p in points if p is not (done[-1] if done else points[-1])]
+    if rest:
+        out["other_runs"] = rest
     return out
 
 
@@ -901,6 +905,7 @@ def main():
     ap.add_argument("--e2e-gib", type=int, default=8, help="at most this many GiB of pinned host rows in the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cli-gib", default="16,64", help="size(s) in GiB of the run directories of the e2e_cli leg, comma separated")
+    ap.add_argument("--cli-gib-secondary-max", type=float, default=64.0, help="largest e2e_cli run directory of the secondary (c2) workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cli", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
