@@ -340,7 +340,11 @@ def bench_merge(args) -> None:
     def step(timed=False):
         ctx.reset()
         base = 0
-        for streams in chunks:
+        if not timed:
+            ctx.merge_prefetch(chunks[0])
+        for ci, streams in enumerate(chunks):
+            if not timed and ci + 1 < len(chunks):
+                ctx.merge_prefetch(chunks[ci + 1])      # the next range crosses PCIe while this one is merged
             base += ctx.merge_scan_host(streams, row_base=base)
             if timed:
                 m = ctx.merge_ms()
@@ -408,8 +412,8 @@ def bench_merge(args) -> None:
                      "stage_ms_per_step": stage_ms},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": n_records * rec, "d2h_bytes_per_step": int(sig.nbytes + 48),
                 "rows_per_step": rows, "steps": args.steps,
-                "api": "kmd_merge_scan_host (host record streams) + kmd_correct + kmd_significant; this path has no "
-                       "device-resident variant, value == e2e"},
+                "api": "kmd_merge_prefetch (next range's H2D on the copy stream) + kmd_merge_scan_host (host record streams) + "
+                       "kmd_correct + kmd_significant; this path has no device-resident variant, value == e2e"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if cpu is not None:

@@ -181,6 +181,12 @@ int kmd_merge_scan_host(kmd_context* ctx, const void* const* streams, const uint
 int kmd_merge_scan_lz4_host(kmd_context* ctx, const void* const* frames, const uint64_t* frame_bytes,
                             const uint8_t* compressed, const uint32_t* ab_min, uint64_t row_base, uint32_t partition,
                             uint64_t max_records, uint64_t* n_rows, uint64_t* n_records);
+/* Start the host->device copies of the NEXT kmd_merge_scan_host (frames == 0: blobs[s] = the records of sample s,
+ * blob_bytes[s] = n_records[s] * record size) or kmd_merge_scan_lz4_host (frames != 0: all payloads compressed) call on
+ * the copy stream and return at once: they overlap the merge the context is still busy with.  The next merge call
+ * that is given exactly these pointers and sizes uses the prefetched copy; any other call ignores it.  The host
+ * buffers must stay untouched until that call has returned. */
+int kmd_merge_prefetch(kmd_context* ctx, const void* const* blobs, const uint64_t* blob_bytes, int frames);
 /* the device LZ4 decoder alone: nb_controls + nb_cases frames in, their decoded records back to back out (HOST);
  * device_ms (may be NULL) = device time of the two decode passes (tests, tools) */
 int kmd_lz4_decode_host(kmd_context* ctx, const void* const* frames, const uint64_t* frame_bytes, void* records_out,

@@ -271,6 +271,18 @@ class DiffContext:
         self._ck(self._L.kmd_lz4_decode_host(self._h, ptrs, sizes, out.ctypes.data, cap_records, C.byref(n), C.byref(ms)))
         return out[:n.value * rec], ms.value
 
+    def merge_prefetch(self, blobs, frames: bool = False):
+        """start the H2D copies of the next merge_scan_host (record streams) / merge_scan_lz4_host (frames) call on the
+        copy stream; returns the arrays whose memory must stay untouched (and be passed again) until that call"""
+        if frames:
+            arrs, ptrs, sizes = self._frame_args(blobs)
+        else:
+            arrs, ptrs, cnt, _ = self._merge_args(blobs, 1)
+            rec = 8 * self.kmer_words + self.count_bytes
+            sizes = (C.c_uint64 * self.nb_samples)(*[c * rec for c in cnt])
+        self._ck(self._L.kmd_merge_prefetch(self._h, ptrs, sizes, int(bool(frames))))
+        return arrs
+
     def merge_ms(self) -> dict:
         """device times of the last merge call: {'unpack', 'passes', 'rows'} in ms, 'n_passes', 'n_records'"""
         a, b, c = C.c_float(), C.c_float(), C.c_float()

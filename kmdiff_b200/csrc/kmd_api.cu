@@ -124,6 +124,16 @@ struct MergeState
   uint32_t* lz_status = nullptr; size_t lz_status_cap = 0;
   cudaEvent_t lz_ev[2] = {nullptr, nullptr};
   float last_lz4_ms = 0;
+  // kmd_merge_prefetch: the NEXT call's host blobs, already on their way to the device on the copy stream
+  // (two slots: the chunk about to be merged and the one after it)
+  struct Prefetch
+  {
+    uint8_t* buf = nullptr; size_t cap = 0;
+    std::vector<const void*> ptrs;
+    std::vector<uint64_t> bytes;
+    int kind = -1;                  // -1 free, 0 records back to back, 1 frames at 16-byte aligned offsets
+    cudaEvent_t done = nullptr;
+  } pf[2];
   uint32_t* total = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // unpack | merge passes | row numbering + dense rows
   bool timed = false;

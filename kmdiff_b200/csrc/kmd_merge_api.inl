@@ -25,6 +25,7 @@ void merge_free(kmd_context* ctx)
   cudaFree(m.flag); cudaFree(m.tile); cudaFree(m.head_pos); cudaFree(m.rows); cudaFree(m.stream_off);
   cudaFree(m.ab_min); cudaFree(m.plan); cudaFree(m.total); cudaFree(m.split);
   cudaFree(m.lz_in); cudaFree(m.lz_tab); cudaFree(m.lz_status);
+  for (auto& f : m.pf) { cudaFree(f.buf); if (f.done) cudaEventDestroy(f.done); }
   for (cudaEvent_t e : m.ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m.lz_ev) if (e) cudaEventDestroy(e);
   m = MergeState{};
@@ -191,6 +192,25 @@ int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const
   return KMD_OK;
 }
 
+// If (ptrs, bytes) is exactly what kmd_merge_prefetch put on the copy stream, make `dst` that buffer (the old one becomes
+// the next prefetch target) and order the context's stream behind the copies.  Returns true when taken.
+bool take_prefetch(kmd_context* ctx, int kind, const void* const* ptrs, const uint64_t* bytes, uint32_t n, uint8_t*& dst, size_t& dst_cap)
+{
+  for (auto& f : ctx->mrg.pf)
+  {
+    if (f.kind != kind || f.ptrs.size() != n) continue;
+    bool same = true;
+    for (uint32_t s = 0; s < n && same; s++) same = f.ptrs[s] == ptrs[s] && f.bytes[s] == bytes[s];
+    if (!same) continue;
+    std::swap(dst, f.buf);
+    std::swap(dst_cap, f.cap);
+    f.kind = -1;
+    cudaStreamWaitEvent(ctx->stream, f.done, 0);
+    return true;
+  }
+  return false;
+}
+
 // streams[s] = n_records[s] HOST records of sample s
 int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min, uint32_t* n_rows)
 {
@@ -203,7 +223,12 @@ int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_r
     if (n_records[s] && !streams[s]) return fail(ctx, KMD_ERR_ARG, "null stream pointer (sample %u)", s);
     off[s + 1] = off[s] + n_records[s];
   }
+  std::vector<uint64_t> bytes(N);
+  for (uint32_t s = 0; s < N; s++) bytes[s] = n_records[s] * rec;
+  // a prefetched chunk is already (on its way) in the other record buffer: swap it in before the buffers are sized
+  const bool prefetched = take_prefetch(ctx, 0, streams, bytes.data(), N, ctx->mrg.raw, ctx->mrg.raw_cap);
   return merge_from_offsets(ctx, off, ab_min, n_rows, [&]() -> int {
+    if (prefetched) return KMD_OK;
     for (uint32_t s = 0; s < N; s++)
       if (n_records[s])
         KMD_CUDA(ctx, cudaMemcpyAsync(ctx->mrg.raw + off[s] * rec, streams[s], n_records[s] * rec, cudaMemcpyHostToDevice, ctx->stream));
@@ -248,11 +273,13 @@ int merge_lz4_impl(kmd_context* ctx, const void* const* frames, const uint64_t* 
     }
   }
   int rc;
-  if ((rc = grow(ctx, m.lz_in, m.lz_in_cap, in_total + 16))) return rc;
+  bool prefetched = false;
+  if (n_lz == N) prefetched = take_prefetch(ctx, 1, frames, frame_bytes, N, m.lz_in, m.lz_in_cap);
+  if (!prefetched && (rc = grow(ctx, m.lz_in, m.lz_in_cap, in_total + 16))) return rc;
   if ((rc = grow(ctx, m.lz_tab, m.lz_tab_cap, 5ull * N))) return rc;
   if ((rc = grow(ctx, m.lz_status, m.lz_status_cap, N))) return rc;
   for (cudaEvent_t& e : m.lz_ev) if (!e) KMD_CUDA(ctx, cudaEventCreate(&e));
-  for (uint32_t s = 0; s < N; s++)
+  for (uint32_t s = 0; s < N && !prefetched; s++)
     if (in_size[s])
       KMD_CUDA(ctx, cudaMemcpyAsync(m.lz_in + in_off[s], frames[s], in_size[s], cudaMemcpyHostToDevice, ctx->stream));
   KMD_CUDA(ctx, cudaMemcpyAsync(m.lz_tab, tab.data(), 5ull * N * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -358,6 +385,38 @@ int kmd_merge_scan_host(kmd_context* ctx, const void* const* streams, const uint
   if (n_rows) *n_rows = rows;
   if (rows == 0) return KMD_OK;
   return scan_device_impl(ctx, ctx->mrg.rows, rows, row_base, partition);
+}
+
+int kmd_merge_prefetch(kmd_context* ctx, const void* const* blobs, const uint64_t* blob_bytes, int frames)
+{
+  if (!ctx || !blobs || !blob_bytes) return KMD_ERR_ARG;
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  MergeState& m = ctx->mrg;
+  const uint32_t N = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
+  uint64_t total = 0;
+  std::vector<uint64_t> at(N);
+  for (uint32_t s = 0; s < N; s++)
+  {
+    if (blob_bytes[s] && !blobs[s]) return fail(ctx, KMD_ERR_ARG, "null blob pointer (sample %u)", s);
+    at[s] = total;
+    total += frames ? (blob_bytes[s] + 15) / 16 * 16 : blob_bytes[s];
+  }
+  // a free slot: its buffer was the record / frame buffer of an earlier call whose readers (unpack / decode) completed
+  // before that call returned, so the copy stream may overwrite it at once
+  MergeState::Prefetch* f = nullptr;
+  for (auto& cand : m.pf) if (cand.kind == -1) { f = &cand; break; }
+  if (!f) return fail(ctx, KMD_ERR_STATE, "two prefetched chunks are already waiting for their merge calls");
+  int rc;
+  if ((rc = grow(ctx, f->buf, f->cap, total + 16))) return rc;
+  if (!f->done) KMD_CUDA(ctx, cudaEventCreateWithFlags(&f->done, cudaEventDisableTiming));
+  for (uint32_t s = 0; s < N; s++)
+    if (blob_bytes[s])
+      KMD_CUDA(ctx, cudaMemcpyAsync(f->buf + at[s], blobs[s], blob_bytes[s], cudaMemcpyHostToDevice, ctx->copy_stream));
+  KMD_CUDA(ctx, cudaEventRecord(f->done, ctx->copy_stream));
+  f->ptrs.assign(blobs, blobs + N);
+  f->bytes.assign(blob_bytes, blob_bytes + N);
+  f->kind = frames ? 1 : 0;
+  return KMD_OK;
 }
 
 int kmd_merge_scan_lz4_host(kmd_context* ctx, const void* const* frames, const uint64_t* frame_bytes, const uint8_t* compressed,

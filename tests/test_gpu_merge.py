@@ -144,3 +144,56 @@ def test_chunked_merge_equals_whole_partition():
         b = ctx.merge_rows_host(second)
     assert len(a) == 41_235
     assert np.array_equal(np.concatenate([a, b]), dense)
+
+
+@pytest.mark.parametrize("frames", [False, True])
+def test_prefetched_chunks_merge_like_plain_calls(frames):
+    """kmd_merge_prefetch: the next chunk's H2D copies run on the copy stream while the current chunk is merged; a merge
+    call given the prefetched pointers uses that copy, any other call ignores it — results identical either way"""
+    import ctypes
+    import pyarrow as pa
+    from kmdiff_b200 import _lib
+    L = _lib.load()
+    spec, rows, totals = make_cohort("c2", 90_000, seed=4)
+    R = spec.row_bytes
+    want, *_ = oracle.Model(10, 10, totals).diff(rows, 1, 4, THR)
+    cuts = [0, 20_000, 20_001, 55_000, 90_000]
+    chunks, keep = [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        streams = kio.rows_to_streams(rows[a * R:b * R], 20, 1, 4)
+        if frames:
+            streams = [np.frombuffer(pa.compress(s.tobytes(), codec="lz4", asbytes=True), dtype=np.uint8) for s in streams]
+        # pinned copies, like the host program's buffers
+        pinned = []
+        for s_ in streams:
+            ptr = L.kmd_host_alloc(max(1, s_.size))
+            view = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(max(1, s_.size),))[:s_.size]
+            view[:] = s_
+            pinned.append(view)
+            keep.append(ptr)
+        chunks.append(pinned)
+    merge = (lambda ctx, st, base: ctx.merge_scan_lz4_host(st, row_base=base)[0]) if frames else \
+            (lambda ctx, st, base: ctx.merge_scan_host(st, row_base=base))
+    try:
+        with ctx_for(10, 10, 31, 4, totals) as ctx:
+            base = 0
+            ctx.merge_prefetch(chunks[0], frames=frames)
+            for i, st in enumerate(chunks):
+                if i + 1 < len(chunks):
+                    ctx.merge_prefetch(chunks[i + 1], frames=frames)
+                if i == 2:
+                    # a call with OTHER buffers in between must not pick the waiting prefetch up ...
+                    other = [np.array(s_) for s_ in st]
+                    assert merge(ctx, other, base) == cuts[i + 1] - cuts[i]
+                    ctx.reset()
+                    base = 0
+                    # ... and everything is redone from the start without prefetching: the stale slots are simply reused
+                    for j, st2 in enumerate(chunks[:i]):
+                        base += merge(ctx, [np.array(s_) for s_ in st2], base)
+                base += merge(ctx, st, base)
+            assert ctx.counters().rows == 90_000
+            got = ctx.survivors()
+        assert np.array_equal(got["row"], want["row"]) and np.array_equal(got["kmer"], want["kmer"])
+    finally:
+        for ptr in keep:
+            L.kmd_host_free(ptr)
