@@ -73,27 +73,51 @@ __global__ void carriers_scatter_kernel(const uint32_t* carriers, uint64_t m, co
   }
 }
 
-// Pt[i][k] = geno[perm[k]][i]: 32 x 32 tiles through shared memory, coalesced on both sides
-__global__ void __launch_bounds__(1024) transpose_presence_kernel(const uint8_t* geno, uint32_t n, const uint32_t* perm,
-                                                                 uint64_t k_pad, uint8_t* pt)
+// Pt[i][k] = geno[perm[k]][i].  A lane owns 4 consecutive SNPs k and walks the samples 4 at a time: four 32-bit loads
+// (one per SNP; the rows are read front to back, so the 32-byte sectors they touch are reused from L1), a 4 x 4 byte
+// transpose in registers (PRMT) and four 32-bit stores — the warp's stores of one sample are 128 contiguous bytes.
+// Rows n .. rows_alloc-1 and columns without a SNP are written as zeros.
+__global__ void __launch_bounds__(256) transpose_presence_kernel(const uint8_t* __restrict__ geno, uint32_t n,
+                                                                const uint32_t* __restrict__ perm, uint64_t k_pad,
+                                                                uint32_t rows_alloc, uint8_t* __restrict__ pt)
 {
-  __shared__ uint8_t tile[32][33];
-  const uint64_t k0 = static_cast<uint64_t>(blockIdx.x) * 32;
-  const uint32_t i0 = blockIdx.y * 32;
-  const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const uint64_t k0 = (static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x) * 4;
+  if (k0 >= k_pad) return;   // k_pad is a multiple of 4
+  const uint8_t* src[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++)
   {
-    const uint64_t k = k0 + ty;
-    uint8_t v = 0;
-    if (k < k_pad)
-    {
-      const uint32_t s = perm[k];
-      if (s != 0xFFFFFFFFu && i0 + tx < n) v = geno[static_cast<uint64_t>(s) * n + i0 + tx];
-    }
-    tile[ty][tx] = v;
+    const uint32_t s = perm[k0 + q];
+    src[q] = s != 0xFFFFFFFFu ? geno + static_cast<uint64_t>(s) * n : nullptr;
   }
-  __syncthreads();
-  const uint64_t k = k0 + tx;
-  if (k < k_pad) pt[static_cast<uint64_t>(i0 + ty) * k_pad + k] = tile[tx][ty];  // rows >= n stay zero
+  const bool words = (n & 3u) == 0;
+  for (uint32_t i = 0; i < rows_alloc; i += 4)
+  {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+    {
+      w[q] = 0;
+      if (src[q] && i < n)
+      {
+        if (words) w[q] = *reinterpret_cast<const uint32_t*>(src[q] + i);
+        else
+          for (uint32_t b = 0; b < 4 && i + b < n; b++) w[q] |= static_cast<uint32_t>(src[q][i + b]) << (8 * b);
+      }
+    }
+    // o[j] = (w0.byte j, w1.byte j, w2.byte j, w3.byte j)
+    const uint32_t t0 = __byte_perm(w[0], w[1], 0x5140);   // w0.b0 w1.b0 w0.b1 w1.b1
+    const uint32_t t1 = __byte_perm(w[2], w[3], 0x5140);
+    const uint32_t t2 = __byte_perm(w[0], w[1], 0x7362);   // w0.b2 w1.b2 w0.b3 w1.b3
+    const uint32_t t3 = __byte_perm(w[2], w[3], 0x7362);
+    const uint32_t o0 = __byte_perm(t0, t1, 0x5410), o1 = __byte_perm(t0, t1, 0x7632);
+    const uint32_t o2 = __byte_perm(t2, t3, 0x5410), o3 = __byte_perm(t2, t3, 0x7632);
+    uint8_t* dst = pt + static_cast<uint64_t>(i) * k_pad + k0;
+    *reinterpret_cast<uint32_t*>(dst) = o0;
+    *reinterpret_cast<uint32_t*>(dst + k_pad) = o1;
+    *reinterpret_cast<uint32_t*>(dst + 2 * k_pad) = o2;
+    *reinterpret_cast<uint32_t*>(dst + 3 * k_pad) = o3;
+  }
 }
 
 // ---- tcgen05 / TMA PTX ----------------------------------------------------------------------------

@@ -224,14 +224,17 @@ struct IrlsWarp
 //   xl[n] mu[n] eta[n] d2[n] H[p*p] LU[p*p] INV[p*p] v[p] w[p] weight[p]
 __host__ __device__ inline size_t irls_warp_doubles(uint32_t n, uint32_t p) { return 4ull * n + 3ull * p * p + 3ull * p; }
 
-// NQ > 0: the features are staged in shared memory and every lane owns exactly NQ slots of [hessian | X^T S z]
-// (NQ = ceil((p*p + p) / 32)): the row walk is straight-line code on shared-memory byte offsets.  NQ == 0: generic
-// form (features in global memory: cohorts too large for shared memory).
-template <int NQ>
+// P > 0: p == P features, staged in shared memory; every lane owns exactly NQ = ceil((P*P + P) / 32) slots of
+// [hessian | X^T S z] and the row walk is straight-line code on shared-memory byte offsets.  P == 0: generic form
+// (any p; features in global memory when the cohort is too large for shared memory).
+template <int P>
 __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArgs A)
 {
+  // P > 0: the feature count is a compile-time constant (the host dispatches on it when the features fit shared memory):
+  // the lanes' slot count NQ and every loop over features have fixed trip counts
+  constexpr int NQ = P > 0 ? (P * P + P + 31) / 32 : 0;
   extern __shared__ double sm[];
-  const uint32_t n = A.n, p = A.p;
+  const uint32_t n = A.n, p = P > 0 ? static_cast<uint32_t>(P) : A.p;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* cursor = sm;
   const double* F = A.features;

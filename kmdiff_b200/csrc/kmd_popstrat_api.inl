@@ -187,8 +187,8 @@ int gram_impl(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_used, in
 
   grm::carriers_scatter_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ps.d_carriers, m, d_koff.as<uint64_t>(),
                                                                          d_cursor.as<uint32_t>(), d_perm.as<uint32_t>());
-  const dim3 tgrid(static_cast<uint32_t>((k_pad + 31) / 32), rows_alloc / 32);
-  grm::transpose_presence_kernel<<<tgrid, 1024, 0, ctx->stream>>>(ps.d_geno, n, d_perm.as<uint32_t>(), k_pad, d_pt.as<uint8_t>());
+  const uint32_t tgrid = static_cast<uint32_t>((k_pad / 4 + 255) / 256);
+  grm::transpose_presence_kernel<<<tgrid, 256, 0, ctx->stream>>>(ps.d_geno, n, d_perm.as<uint32_t>(), k_pad, rows_alloc, d_pt.as<uint8_t>());
   KMD_CUDA(ctx, cudaGetLastError());
 
   // ---- exact integer Gram matrices on the tensor cores ----
@@ -253,17 +253,16 @@ int launch_irls(kmd_context* ctx, pop::IrlsArgs A, uint32_t n_items_host)
   if (smem > budget) return fail(ctx, KMD_ERR_ARG, "cohort of %u samples does not fit the GLM kernel's shared memory", A.n);
   A.feat_in_smem = in_smem;
   const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>((n_items_host + warps - 1) / warps, ctx->sm_count));
-  const uint32_t nq = in_smem ? (A.p * A.p + A.p + 31) / 32 : 0;   // slots of [hessian | X^T S z] per lane
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
     kernel<<<blocks, warps * 32, smem, ctx->stream>>>(A);
     return cudaGetLastError();
   };
+  // the feature count as a template parameter (null model: n_pc + 2, alternative model: n_pc + 3; --n-pc is 2..10)
   cudaError_t le;
-  switch (nq)
+  switch (in_smem ? A.p : 0u)
   {
-    case 1: le = launch(pop::glm_irls_kernel<1>); break;
     case 2: le = launch(pop::glm_irls_kernel<2>); break;
     case 3: le = launch(pop::glm_irls_kernel<3>); break;
     case 4: le = launch(pop::glm_irls_kernel<4>); break;
@@ -272,6 +271,10 @@ int launch_irls(kmd_context* ctx, pop::IrlsArgs A, uint32_t n_items_host)
     case 7: le = launch(pop::glm_irls_kernel<7>); break;
     case 8: le = launch(pop::glm_irls_kernel<8>); break;
     case 9: le = launch(pop::glm_irls_kernel<9>); break;
+    case 10: le = launch(pop::glm_irls_kernel<10>); break;
+    case 11: le = launch(pop::glm_irls_kernel<11>); break;
+    case 12: le = launch(pop::glm_irls_kernel<12>); break;
+    case 13: le = launch(pop::glm_irls_kernel<13>); break;
     default: le = launch(pop::glm_irls_kernel<0>); break;
   }
   KMD_CUDA(ctx, le);

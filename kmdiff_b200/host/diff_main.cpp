@@ -109,6 +109,7 @@ struct DiffOptions
   size_t count_bytes = 4;     // the reference fixes this at compile time (MAX_C); here a runtime option
   size_t max_survivors = 0;
   size_t max_sampled = 0;     // capacity of the per-GPU presence matrix (--pop-correction); 0 = 2097152
+  bool device_lz4 = false;    // count files: decode the LZ4 frames on the device whatever the cohort size
   size_t merge_records = 32u << 20;   // count-file input: records merged on the device per call (all samples together)
   size_t total_kmers = 0;
 };
@@ -148,7 +149,8 @@ struct DiffOptions
     "  --gpus INT              GPUs to shard the partitions over. {one per 64 GiB of input}\n"
     "  --count-bytes INT       count width of the matrices: 1, 2 or 4 (the reference's compile-time MAX_C). {4}\n"
     "  --max-survivors INT     capacity of the per-GPU survivor buffers. {4194304}\n"
-    "  --max-sampled INT       capacity of the per-GPU sampled k-mer buffer (--pop-correction). {2097152}\n",
+    "  --max-sampled INT       capacity of the per-GPU sampled k-mer buffer (--pop-correction). {2097152}\n"
+    "  --device-lz4            count files: decode the LZ4 frames on the GPU (default from 2048 samples on).\n",
     code ? stderr : stdout);
   exit(code);
 }
@@ -247,6 +249,7 @@ DiffOptions parse_cli(int argc, char** argv)
     else if (a == "--max-survivors") o.max_survivors = number();
     else if (a == "--max-sampled") o.max_sampled = number();
     else if (a == "--merge-records") o.merge_records = number();
+    else if (a == "--device-lz4") o.device_lz4 = true;
     else cli_error("unknown parameter " + a);
   }
   if (!have_d) cli_error("-d/--km-run is required");
@@ -614,7 +617,12 @@ class GpuWorker
   // disk that differs from this run's).
   bool merge_whole_partition(const Partition& p, uint32_t N, uint32_t kw, uint32_t B, uint64_t budget)
   {
-    if (getenv("KMD_HOST_LZ4")) return false;   // A/B switch: decode on the host threads
+    // One warp decodes one stream at ~10 MB/s (a serial chain of short sequences; profiles/r02g), a host thread at
+    // ~2 GB/s: the device path pays off only with thousands of streams in flight, so it is taken from 2048 samples per
+    // partition on (or on request: --device-lz4 / KMD_DEVICE_LZ4=1); smaller cohorts are decoded by the -t host threads.
+    const char* force = getenv("KMD_DEVICE_LZ4");
+    const bool on = force ? atoi(force) != 0 : (m_opt.device_lz4 || N >= 2048);
+    if (!on) return false;
     const size_t rec = 8ull * kw + B;
     std::vector<uint64_t> fsize(N), foff(N + 1, 0);
     for (uint32_t s = 0; s < N; s++)

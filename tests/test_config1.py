@@ -84,16 +84,18 @@ def read_seqs(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("threads", [1, 8])
-def test_cli_reproduces_the_reference_goldens(run_dir, tmp_path, threads):
-    """`kmdiff-b200 diff --km-run kc_dir -1 10 -2 10 --output-dir out -s 0.01` (examples/run.sh:5)"""
+@pytest.mark.parametrize("threads,extra", [(1, []), (8, []), (4, ["--device-lz4"])])
+def test_cli_reproduces_the_reference_goldens(run_dir, tmp_path, threads, extra):
+    """`kmdiff-b200 diff --km-run kc_dir -1 10 -2 10 --output-dir out -s 0.01` (examples/run.sh:5); the `.kmer.lz4` files
+    decoded by the host threads (default for 20 samples) and on the device (--device-lz4)"""
     cli = kb.build_cli()
     out = str(tmp_path / "out")
     r = subprocess.run([cli, "diff", "--km-run", run_dir, "-1", "10", "-2", "10", "--output-dir", out, "-s", "0.01",
-                        "-t", str(threads)], capture_output=True, text=True, timeout=600)
+                        "-t", str(threads), "-v", "debug"] + extra, capture_output=True, text=True, timeout=600)
     log = r.stdout + r.stderr
     assert r.returncode == 0 and "[error]" not in log, log
     assert f"{PREFILTER}/{ROWS} significant k-mers" in log, log
+    assert ("records decoded on the device" in log) == bool(extra)
     assert f"Before correction: {BEFORE[0]} (control), {BEFORE[1]} (case)." in log
     assert f"Significant k-mers: {AFTER[0]} (control), {AFTER[1]} (case)." in log
     for name, want in (("control", AFTER[0]), ("case", AFTER[1])):
