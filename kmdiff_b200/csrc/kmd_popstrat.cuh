@@ -224,15 +224,14 @@ struct IrlsWarp
 //   xl[n] mu[n] eta[n] d2[n] H[p*p] LU[p*p] INV[p*p] v[p] w[p] weight[p]
 __host__ __device__ inline size_t irls_warp_doubles(uint32_t n, uint32_t p) { return 4ull * n + 3ull * p * p + 3ull * p; }
 
-// P > 0: p == P features, staged in shared memory; every lane owns exactly NQ = ceil((P*P + P) / 32) slots of
-// [hessian | X^T S z] and the row walk is straight-line code on shared-memory byte offsets.  P == 0: generic form
+// P > 0: p == P features, staged in shared memory; every lane owns a 2 x 4 block of [hessian | X^T S z] and the row
+// walk is straight-line code on shared-memory byte offsets.  P == 0: generic form
 // (any p; features in global memory when the cohort is too large for shared memory).
 template <int P>
 __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArgs A)
 {
   // P > 0: the feature count is a compile-time constant (the host dispatches on it when the features fit shared memory):
-  // the lanes' slot count NQ and every loop over features have fixed trip counts
-  constexpr int NQ = P > 0 ? (P * P + P + 31) / 32 : 0;
+  // the lanes' blocks of the hessian and every loop over features have fixed shapes
   extern __shared__ double sm[];
   const uint32_t n = A.n, p = P > 0 ? static_cast<uint32_t>(P) : A.p;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -286,24 +285,36 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
     el_v[q] = is_v;
   }
 
-  // NQ > 0: the same slots as shared-memory BYTE offsets (relative to sm) of row 0 and byte strides per row.  A slot of
-  // X^T S z multiplies by z[k] (kept in eta[] during the walk): g * z is the very product the generic form reads back
-  // as gz, so both slot kinds are  acc += x_a[k] * (g[k] * x_b[k])  and the walk has no per-slot branch.
-  uint32_t of_a[NQ > 0 ? NQ : 1], of_b[NQ > 0 ? NQ : 1], st_a[NQ > 0 ? NQ : 1], st_b[NQ > 0 ? NQ : 1];
-  if constexpr (NQ > 0)
+  // P > 0: a lane owns a 2 x 4 block of the p x (p + 1) matrix [hessian | X^T S z] — rows (2r, 2r+1), columns 4c .. 4c+3,
+  // lane = r * ceil((p + 1) / 4) + c — so one row of the walk costs it 2 + 4 shared-memory loads for 8 slots, and the
+  // four products S_k x_b are shared by its two rows.  Column p is X^T S z: it multiplies by z[k] (kept in eta[]
+  // during the walk); S_k * z_k is the very product the generic form reads back as gz, so every slot is
+  // acc += x_a[k] * (S_k * x_b[k]) and the walk has no per-slot branch.  Each slot still sums over k in row order with
+  // the reference's operands, whatever lane holds it.  Offsets are shared-memory BYTE offsets (relative to sm) of row 0,
+  // strides bytes per row; slots outside the matrix read a valid address and are dropped.
+  constexpr int kCQ = P > 0 ? (P + 1 + 3) / 4 : 1;
+  static_assert(P == 0 || ((P + 1) / 2) * kCQ <= 32, "the 2 x 4 blocks of [H | v] must fit one warp");
+  uint32_t of_a[2], st_a[2], of_b[4], st_b[4];
+  const uint32_t blk_r = lane / kCQ, blk_c = lane - blk_r * kCQ;
+  if constexpr (P > 0)
   {
 #pragma unroll
-    for (int q = 0; q < NQ; q++)
+    for (int i = 0; i < 2; i++)
     {
-      const uint32_t e = lane + 32 * q;
-      const bool is_v = e >= pp && e < pp + p;
-      const bool dead = e >= pp + p;
-      uint32_t a = dead ? 0 : (is_v ? e - pp : e / p), b = (dead || is_v) ? 0 : e - (e / p) * p;
-      const bool own_a = A.own_last && a == p - 1, own_b = A.own_last && b == p - 1;
-      of_a[q] = static_cast<uint32_t>((own_a ? xl : F + a) - sm) * 8u;
-      st_a[q] = (own_a ? 1u : A.ldf) * 8u;
-      of_b[q] = is_v ? static_cast<uint32_t>(eta - sm) * 8u : static_cast<uint32_t>((own_b ? xl : F + b) - sm) * 8u;
-      st_b[q] = (is_v || own_b) ? 8u : A.ldf * 8u;
+      uint32_t a = 2 * blk_r + i;
+      if (a >= p) a = 0;
+      const bool own = A.own_last && a == p - 1;
+      of_a[i] = static_cast<uint32_t>((own ? xl : F + a) - sm) * 8u;
+      st_a[i] = (own ? 1u : A.ldf) * 8u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+    {
+      uint32_t c = 4 * blk_c + j;
+      if (c > p) c = 0;
+      const bool is_v = c == p, own = A.own_last && c == p - 1;
+      of_b[j] = static_cast<uint32_t>((is_v ? eta : (own ? xl : F + c)) - sm) * 8u;
+      st_b[j] = (is_v || own) ? 8u : A.ldf * 8u;
     }
   }
   const char* const smb = reinterpret_cast<const char*>(sm);
@@ -349,7 +360,7 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
         d2[i] = mul(d, d);
         const double z = add(eta[i], div(d, add(g, 1e-305)));
         mu[i] = g;
-        eta[i] = NQ > 0 ? z : mul(g, z);
+        eta[i] = P > 0 ? z : mul(g, z);
       }
       __syncwarp();
 
@@ -359,33 +370,42 @@ __global__ void __launch_bounds__(kIrlsWarps * 32) glm_irls_kernel(const IrlsArg
       //   (X^T S z)[j]  = sum_{good k} X[k][j] * (S[k] * z[k])      (element p*p + j)
       double error = 0.0;
       uint32_t n_good = 0;
-      if constexpr (NQ > 0)
+      if constexpr (P > 0)
       {
-        double acc[NQ];
+        double acc[2][4];
 #pragma unroll
-        for (int q = 0; q < NQ; q++) acc[q] = 0.0;
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) acc[i][j] = 0.0;
 #pragma unroll 2
         for (uint32_t k = 0; k < n; k++)
         {
           error = add(error, d2[k]);
-          const double g = mu[k];
-          if (!(g > 1e-305)) continue;   // warp-uniform
-          n_good++;
+          // a row with S_k <= 1e-305 is skipped by the reference; here it adds x_a * (0 * x_b) = +-0 to every slot, which
+          // leaves a sum unchanged (the features are finite) — no branch in the walk
+          const double gk = mu[k];
+          const bool good = gk > 1e-305;
+          n_good += good;
+          const double g = good ? gk : 0.0;
+          const double xa0 = *reinterpret_cast<const double*>(smb + (k * st_a[0] + of_a[0]));
+          const double xa1 = *reinterpret_cast<const double*>(smb + (k * st_a[1] + of_a[1]));
 #pragma unroll
-          for (int q = 0; q < NQ; q++)
+          for (int j = 0; j < 4; j++)
           {
-            const double xa = *reinterpret_cast<const double*>(smb + (k * st_a[q] + of_a[q]));
-            const double xb = *reinterpret_cast<const double*>(smb + (k * st_b[q] + of_b[q]));
-            acc[q] = add(acc[q], mul(xa, mul(g, xb)));
+            const double gx = mul(g, *reinterpret_cast<const double*>(smb + (k * st_b[j] + of_b[j])));
+            acc[0][j] = add(acc[0][j], mul(xa0, gx));
+            acc[1][j] = add(acc[1][j], mul(xa1, gx));
           }
         }
 #pragma unroll
-        for (int q = 0; q < NQ; q++)
-        {
-          const uint32_t e = lane + 32 * q;
-          if (e < pp) H[e] = acc[q];
-          else if (e < pp + p) v[e - pp] = acc[q];
-        }
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+          {
+            const uint32_t a = 2 * blk_r + i, c = 4 * blk_c + j;
+            if (a < p && c < p) H[a * p + c] = acc[i][j];
+            else if (a < p && c == p) v[a] = acc[i][j];
+          }
       }
       else
       {

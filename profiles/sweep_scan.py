@@ -69,6 +69,13 @@ def main():
         for (groups, warps), tile in itertools.product(((1, 24), (2, 12), (2, 15), (3, 8), (3, 10), (4, 7), (5, 6)),
                                                        (16384, 32768)):
             settings.append({"KMD_SCAN_GROUPS": groups, "KMD_SCAN_WARPS": warps, "KMD_SCAN_TILE_BYTES": tile})
+        if os.environ.get("SWEEP_COMBO"):
+            settings = []
+            for (groups, warps), tile, g in itertools.product(((3, 8), (3, 10), (5, 6), (6, 5), (2, 15)), (16384, 24576, 32768), (0, 4, 8, 16, 32)):
+                env = {"KMD_SCAN_GROUPS": groups, "KMD_SCAN_WARPS": warps, "KMD_SCAN_TILE_BYTES": tile}
+                if g:
+                    env["KMD_SCAN_G"] = g
+                settings.append(env)
         for env in settings:
             gbps, ns2 = measure(spec, totals, data, rows, env)
             if gbps is None:
@@ -79,7 +86,7 @@ def main():
             out.append({"config": name, "env": env, "gbps": gbps})
         del data
         torch.cuda.empty_cache()
-    with open(os.path.join(ROOT, "gpurun_out", "sweep_scan.json"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", os.environ.get("SWEEP_OUT", "sweep_scan.json")), "w") as f:
         json.dump(out, f, indent=1)
 
 

@@ -213,6 +213,29 @@ def test_reference_plugin_built_against_our_headers_loads_in_the_cli(cli, tmp_pa
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("lz4", [False, True])
+def test_cli_reports_device_errors_and_input_errors_without_hanging(cli, tmp_path, lz4):
+    """an error raised while the reader threads are running (here: the survivor buffers overflow; a truncated matrix)
+    must end the run with the reference's `[error] Name - message` line and exit code 0 — every reader joined, no
+    std::terminate from a joinable thread, no reader left waiting for a buffer"""
+    n = 400_000
+    spec, d = make_run_dir(tmp_path, n_rows=n, parts=6, lz4=lz4, ppm=20_000)
+    r = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", str(tmp_path / "o1"), "-t", "8", "--max-survivors", "64"] + THR_ARGS)
+    assert r.returncode == 0 and re.search(r"\[error\] GpuError - .*overflow", r.stderr), r.stderr
+    assert "terminate" not in r.stderr
+    # a matrix cut in the middle of a row
+    victim = sorted(os.listdir(os.path.join(d, "matrices")))[2]
+    path = os.path.join(d, "matrices", victim)
+    size = os.path.getsize(path)
+    with open(path, "r+b") as f:
+        f.truncate(size - 37)
+    os.remove(os.path.join(d, "kmdiff-count.opt")) if os.path.exists(os.path.join(d, "kmdiff-count.opt")) else None
+    r = run([cli, "diff", "-d", d, "-1", "10", "-2", "10", "-o", str(tmp_path / "o2"), "-t", "8"] + THR_ARGS)
+    assert r.returncode == 0 and "[error]" in r.stderr and "terminate" not in r.stderr, r.stderr
+    assert not os.path.exists(tmp_path / "o2" / "case_kmers.fasta")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("corr", ["benjamini", "bonferroni", "sidak"])
 def test_cli_on_all_gpus_equals_one_gpu(cli, tmp_path, corr):
     """partitions sharded over every visible device: m and the BENJAMINI walk go through kmd_exchange_local (slots pulled
