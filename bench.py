@@ -724,10 +724,12 @@ def measure(env: Env, args, cfg_name: str, steps: int, warmup: int, full: bool) 
     # ---- CPU baseline: the reference binary on a bounded prefix of the same matrix, and parity on that prefix ----
     if full and world == 1 and rank == 0 and not args.no_cpu_baseline:
         block.update(cpu_baseline_and_parity(env, args, cfg_name, ctx, spec, exchange, popstrat))
-    elif not full and world == 1 and rank == 0 and not args.no_cli and not args.no_cpu_baseline and not popstrat:
-        # the secondary workload: only the drop-in program's file -> FASTA time, at 2e8 rows (17.6 GB) and at 64 GiB
-        sec = argparse.Namespace(cli_gib=f"{2e8 * R / (1 << 30)},{args.cli_gib_secondary_max}")
-        block["e2e_cli"] = cli_points(sec, cfg_name, os.cpu_count() or 1)
+    elif not full and world == 1 and rank == 0 and not args.no_cpu_baseline and not popstrat:
+        # the secondary workload: the same CPU baseline + prefix parity, and the drop-in program's file -> FASTA time at
+        # 2e8 rows (17.6 GB) and at 64 GiB
+        sec = argparse.Namespace(**vars(args))
+        sec.cli_gib = f"{2e8 * R / (1 << 30)},{args.cli_gib_secondary_max}"
+        block.update(cpu_baseline_and_parity(env, sec, cfg_name, ctx, spec, exchange, popstrat))
 
     ctx.close()
     del data
@@ -890,7 +892,8 @@ def bench_b200(args) -> None:
             line[key] = head[key]
     if secondary is not None:
         line[SECONDARY] = {key: secondary[key] for key in ("value", "ms_per_step", "config", "decision_check", "roofline", "e2e",
-                                                           "e2e_cli", "gpu_launches", "clocks") if key in secondary}
+                                                           "e2e_cli", "cpu_baseline", "parity_on_prefix", "parity_detail",
+                                                           "gpu_launches", "clocks") if key in secondary}
         line[SECONDARY]["unit"] = "rows/s"
     env.emit(line)
     env.close()
