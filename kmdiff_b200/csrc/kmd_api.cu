@@ -384,9 +384,16 @@ int make_plan(kmd_context* ctx)
   P.words_ctrl = P.fast ? c.nb_controls * B / 8 : 0;
   P.straddle_elems = P.fast ? (c.nb_controls * B % 8) / B : 0;
 
-  // consumer geometry: `groups` groups of `gw` warps; a group sums one tile at a time
-  uint32_t groups = std::max<uint32_t>(1, env_u32("KMD_SCAN_GROUPS", 3));
-  uint32_t gw = std::max<uint32_t>(1, env_u32("KMD_SCAN_WARPS", 8));
+  // consumer geometry: `groups` groups of `gw` warps; a group sums one tile at a time.  Presets by row size, from the
+  // sweep of profiles/r02j (scan GB/s on 10+10 / 50+50 / 100+100 / 200+200 cohorts: more consumer warps pay for narrow
+  // and for ~1 KB rows, the 3 x 8 geometry for the sizes between, 16 lanes per row for very wide rows); every knob can
+  // still be overridden from the environment.
+  struct Preset { uint32_t max_row_bytes, groups, warps, tile_bytes, lanes; };
+  static const Preset presets[] = {{128, 3, 10, 32768, 0}, {512, 3, 8, 24576, 0}, {1024, 5, 6, 32768, 0}, {0xFFFFFFFFu, 3, 8, 24576, 16}};
+  const Preset* preset = presets;
+  while (P.row_bytes > preset->max_row_bytes) preset++;
+  uint32_t groups = std::max<uint32_t>(1, env_u32("KMD_SCAN_GROUPS", preset->groups));
+  uint32_t gw = std::max<uint32_t>(1, env_u32("KMD_SCAN_WARPS", preset->warps));
   if (groups * gw > kMaxConsumerWarps) return fail(ctx, KMD_ERR_ARG, "KMD_SCAN_GROUPS x KMD_SCAN_WARPS exceeds 31 consumer warps");
   const uint32_t warps = groups * gw;
   ctx->consumer_warps = warps;
@@ -395,7 +402,7 @@ int make_plan(kmd_context* ctx)
   P.group_warps = gw;
 
   const uint32_t ring_budget = 200 * 1024;
-  const uint32_t target_tile = env_u32("KMD_SCAN_TILE_BYTES", 24 * 1024);
+  const uint32_t target_tile = env_u32("KMD_SCAN_TILE_BYTES", preset->tile_bytes);
   const uint32_t units = P.fast ? P.words_total : N;
 
   // lanes per row: cheapest estimated issue cost among the choices whose full pass fits the ring
@@ -412,7 +419,7 @@ int make_plan(kmd_context* ctx)
     const double cost = per_pass * g / 32.0;
     if (cost < best_cost) { best_cost = cost; best_g = g; }
   }
-  P.lanes_per_row = env_u32("KMD_SCAN_G", best_g);
+  P.lanes_per_row = env_u32("KMD_SCAN_G", preset->lanes ? preset->lanes : best_g);
   if (P.lanes_per_row == 0 || (P.lanes_per_row & (P.lanes_per_row - 1)) || P.lanes_per_row > 32)
     return fail(ctx, KMD_ERR_ARG, "KMD_SCAN_G must be a power of two in [1,32]");
 
