@@ -221,6 +221,39 @@ def test_glm_matches_oracle(nc, nk, npc):
     print(f"glm {nc}+{nk} npc={npc}: max rel p err {worst:.2e}")
 
 
+def test_row_order_survives_a_p_sort_followed_by_the_glm():
+    """sorted_pvalues() / a BENJAMINI correct() leave the survivor slots in p order; popstrat_apply then rewrites the
+    p-values, which invalidates that order — survivors() and survivor_counts() must come back in ROW order again, and a
+    later p-sort must break ties by row, not by the stale order"""
+    nc, nk, npc, m = 30, 30, 3, 40_000
+    n = nc + nk
+    counts, _ = _cohort_with_structure(nc, nk, m, seed=5)
+    counts[:, 0] = np.maximum(counts[:, 0], 1)
+    rows = np.zeros((m, 8 + 4 * n), dtype=np.uint8)
+    rows[:, :8] = (np.arange(m, dtype=np.uint64) * np.uint64(13) + np.uint64(1)).view(np.uint8).reshape(m, 8)
+    rows[:, 8:] = counts.view(np.uint8).reshape(m, 4 * n)
+    totals = counts.sum(0).astype(np.uint64) * np.uint64(1000)
+    with K.DiffContext(nc, nk, int(totals[:nc].sum()), int(totals[nc:].sum()), count_bytes=4, threshold=THR) as ctx:
+        ctx.popstrat_enable(0.2, seed=3, n_pc=npc)
+        ctx.scan_host(rows.ravel())
+        first = ctx.survivors()
+        assert len(first) > 20 and np.all(np.diff(first["row"].astype(np.int64)) > 0)
+        xtx, _ = ctx.popstrat_gram()
+        _, Z = K.smartpca_pcs(xtx, 10)
+        ctx.popstrat_init(Z, totals)
+        ps = ctx.sorted_pvalues()                                   # slots now in p order
+        assert np.all(np.diff(ps) >= 0)
+        ctx.correct(K.CorrectionType.BENJAMINI, 0.05, m)
+        ctx.popstrat_apply()                                        # p-values replaced
+        after = ctx.survivors()
+        sc = ctx.survivor_counts()
+        assert np.array_equal(after["row"], first["row"])          # row order, not the stale p order
+        assert np.array_equal(sc, counts[first["row"].astype(np.int64)])
+        assert not np.array_equal(after["p_value"], first["p_value"])
+        ps2 = ctx.sorted_pvalues()
+        assert np.array_equal(ps2, np.sort(after["p_value"]))
+
+
 def test_pop_correction_end_to_end():
     """scan (+sampler) -> Gram -> PCs -> null model -> GLM on every survivor -> Bonferroni, against the
     same pipeline assembled from oracle pieces."""
