@@ -1169,8 +1169,10 @@ int kmd_create(const kmd_config* cfg, kmd_context** out)
   const size_t cap = ctx->cap;
   KMD_CUDA_C(cudaMalloc(&ctx->d_cnt, sizeof(DeviceCounters)));
   KMD_CUDA_C(cudaMemset(ctx->d_cnt, 0, sizeof(DeviceCounters)));
+  lap("first cudaMalloc + memset");
   KMD_CUDA_C(cudaMallocHost(&ctx->h_cnt, sizeof(DeviceCounters)));
   memset(ctx->h_cnt, 0, sizeof(DeviceCounters));
+  lap("first cudaMallocHost");
   KMD_CUDA_C(cudaMalloc(&ctx->d_cand, cap * sizeof(uint32_t)));
   KMD_CUDA_C(cudaMalloc(&ctx->surv.kmer0, cap * 8));
   KMD_CUDA_C(cudaMalloc(&ctx->surv.kmer1, cap * 8));
