@@ -468,7 +468,12 @@ class GpuWorker
     const uint32_t B = static_cast<uint32_t>(m_opt.count_bytes);
     const size_t rec = 8ull * kw + B;
     const uint64_t budget = std::max<uint64_t>(1ull << 12, m_opt.merge_records);
-    const size_t per = static_cast<size_t>(std::max<uint64_t>(1024, budget / N));
+    // per-stream buffer: the call budget shared by the samples, but no more than the largest stream can decode to
+    // (LZ4 shrinks sorted records to no less than ~1/6): pinning costs ~0.4 s per GB
+    uint64_t max_file = 0;
+    for (const Partition& p : partitions)
+      for (const std::string& sp : p.sample_paths) { std::error_code ec; const auto sz = fs::file_size(sp, ec); if (!ec) max_file = std::max<uint64_t>(max_file, sz); }
+    const size_t per = static_cast<size_t>(std::max<uint64_t>(1024, std::min<uint64_t>(budget / N, max_file * 6 / rec + 1024)));
     const std::vector<uint32_t> ab_min(N, 1);
     // record buffers in pinned memory: the H2D copies of kmd_merge_scan_host then run at PCIe rate
     struct PinnedBuf
@@ -481,8 +486,6 @@ class GpuWorker
       uint8_t* data() const { return p; }
     };
     struct Stream { std::unique_ptr<KmerFile> file; std::unique_ptr<PinnedBuf> pin; std::vector<uint8_t> disk; size_t n = 0; bool eof = false; };
-    std::vector<std::unique_ptr<PinnedBuf>> pins(N);
-    for (auto& pb : pins) pb = std::make_unique<PinnedBuf>(per * rec);
     auto key_less = [kw](const uint8_t* a, const uint8_t* b) {
       for (int w = static_cast<int>(kw) - 1; w >= 0; w--)
       {
@@ -492,122 +495,154 @@ class GpuWorker
       }
       return false;
     };
-    for (const Partition& p : partitions)
-    {
-      if (p.sample_paths.size() != N) throw KmdError("ConfigError", "kmtricks.fof does not list --nb-controls + --nb-cases samples.");
-      if (merge_whole_partition(p, N, kw, B, budget)) continue;
-      std::vector<Stream> st(N);
-      struct Returner { std::vector<Stream>& st; std::vector<std::unique_ptr<PinnedBuf>>& pins;
-                        ~Returner() { for (size_t s = 0; s < st.size(); s++) if (st[s].pin) pins[s] = std::move(st[s].pin); } } returner{st, pins};
-      for (uint32_t s = 0; s < N; s++)
+    // Two lanes take partitions in turn: while one lane's range is merged and tested on the device (the context is used
+    // by one thread at a time: m_gpu_mu), the other lane reads and decodes its next range on the host threads.  The
+    // Sampler's draw index follows the rows merged so far, so --pop-correction keeps one lane (one ordered stream).
+    const size_t n_lanes = (m_opt.pop_correction || partitions.size() < 2) ? 1 : 2;
+    const size_t fill_threads = std::max<size_t>(1, std::min<size_t>(m_opt.nb_threads / n_lanes, N));
+    std::atomic<size_t> next_part{0};
+    std::exception_ptr lane_error;
+    std::mutex lane_mu;
+    auto lane = [&] {
+      kmd_bind_host_thread(m_device);
+      try
       {
-        st[s].pin = std::move(pins[s]);
-        st[s].file = std::make_unique<KmerFile>(p.sample_paths[s]);
-        const KmerHeader& h = st[s].file->hdr;
-        if (h.kmer_slots != kw) throw KmdError("InputError", p.sample_paths[s] + ": unexpected kmer_slots");
-        if (h.count_slots == 0 || h.count_slots > 4) throw KmdError("InputError", p.sample_paths[s] + ": unexpected count_slots");
-      }
-      uint64_t local = 0;
-      for (;;)
-      {
-        // refill every open stream up to `per` buffered records, the samples spread over the reader threads
-        std::atomic<uint32_t> next{0};
-        std::exception_ptr err;
-        std::mutex err_mu;
-        auto fill = [&] {
-          for (uint32_t s; (s = next.fetch_add(1)) < N;)
+        std::vector<std::unique_ptr<PinnedBuf>> pins(N);
+        for (auto& pb : pins) pb = std::make_unique<PinnedBuf>(per * rec);
+        for (size_t pi; (pi = next_part.fetch_add(1)) < partitions.size();)
+        {
+          { std::lock_guard<std::mutex> lk(lane_mu); if (lane_error) break; }
+          const Partition& p = partitions[pi];
           {
-            Stream& t = st[s];
-            if (t.eof || t.n >= per) continue;
-            try
+            if (p.sample_paths.size() != N) throw KmdError("ConfigError", "kmtricks.fof does not list --nb-controls + --nb-cases samples.");
             {
-              const size_t want = per - t.n;
-              const uint32_t cs = t.file->hdr.count_slots;
-              size_t got_rec;
-              if (cs == B)
-              {
-                const size_t got = t.file->payload->read(t.pin->data() + t.n * rec, want * rec);
-                if (got % rec) throw KmdError("InputError", p.sample_paths[s] + ": truncated record");
-                got_rec = got / rec;
-              }
-              else
-              {
-                // count stored narrower or wider than this run's count type: KmerReader::read copies count_slots
-                // bytes into a count_type (kmer_file.hpp:132); widen with zeros / keep the low bytes
-                const size_t drec = 8ull * kw + cs;
-                t.disk.resize(want * drec);
-                const size_t got = t.file->payload->read(t.disk.data(), want * drec);
-                if (got % drec) throw KmdError("InputError", p.sample_paths[s] + ": truncated record");
-                got_rec = got / drec;
-                for (size_t i = 0; i < got_rec; i++)
+              std::lock_guard<std::mutex> gpu(m_gpu_mu);
+              if (merge_whole_partition(p, N, kw, B, budget)) continue;
+            }
+            std::vector<Stream> st(N);
+            struct Returner { std::vector<Stream>& st; std::vector<std::unique_ptr<PinnedBuf>>& pins;
+                              ~Returner() { for (size_t s = 0; s < st.size(); s++) if (st[s].pin) pins[s] = std::move(st[s].pin); } } returner{st, pins};
+            for (uint32_t s = 0; s < N; s++)
+            {
+              st[s].pin = std::move(pins[s]);
+              st[s].file = std::make_unique<KmerFile>(p.sample_paths[s]);
+              const KmerHeader& h = st[s].file->hdr;
+              if (h.kmer_slots != kw) throw KmdError("InputError", p.sample_paths[s] + ": unexpected kmer_slots");
+              if (h.count_slots == 0 || h.count_slots > 4) throw KmdError("InputError", p.sample_paths[s] + ": unexpected count_slots");
+            }
+            uint64_t local = 0;
+            for (;;)
+            {
+              // refill every open stream up to `per` buffered records, the samples spread over the reader threads
+              std::atomic<uint32_t> next{0};
+              std::exception_ptr err;
+              std::mutex err_mu;
+              auto fill = [&] {
+                for (uint32_t s; (s = next.fetch_add(1)) < N;)
                 {
-                  uint8_t* dst = t.pin->data() + (t.n + i) * rec;
-                  memset(dst, 0, rec);
-                  memcpy(dst, t.disk.data() + i * drec, 8ull * kw + std::min<uint32_t>(cs, B));
+                  Stream& t = st[s];
+                  if (t.eof || t.n >= per) continue;
+                  try
+                  {
+                    const size_t want = per - t.n;
+                    const uint32_t cs = t.file->hdr.count_slots;
+                    size_t got_rec;
+                    if (cs == B)
+                    {
+                      const size_t got = t.file->payload->read(t.pin->data() + t.n * rec, want * rec);
+                      if (got % rec) throw KmdError("InputError", p.sample_paths[s] + ": truncated record");
+                      got_rec = got / rec;
+                    }
+                    else
+                    {
+                      // count stored narrower or wider than this run's count type: KmerReader::read copies count_slots
+                      // bytes into a count_type (kmer_file.hpp:132); widen with zeros / keep the low bytes
+                      const size_t drec = 8ull * kw + cs;
+                      t.disk.resize(want * drec);
+                      const size_t got = t.file->payload->read(t.disk.data(), want * drec);
+                      if (got % drec) throw KmdError("InputError", p.sample_paths[s] + ": truncated record");
+                      got_rec = got / drec;
+                      for (size_t i = 0; i < got_rec; i++)
+                      {
+                        uint8_t* dst = t.pin->data() + (t.n + i) * rec;
+                        memset(dst, 0, rec);
+                        memcpy(dst, t.disk.data() + i * drec, 8ull * kw + std::min<uint32_t>(cs, B));
+                      }
+                    }
+                    t.n += got_rec;
+                    if (got_rec < want) t.eof = true;
+                  }
+                  catch (...) { std::lock_guard<std::mutex> lk(err_mu); err = std::current_exception(); }
                 }
-              }
-              t.n += got_rec;
-              if (got_rec < want) t.eof = true;
-            }
-            catch (...) { std::lock_guard<std::mutex> lk(err_mu); err = std::current_exception(); }
-          }
-        };
-        const size_t n_thr = std::max<size_t>(1, std::min<size_t>(m_opt.nb_threads, N));
-        std::vector<std::thread> pool;
-        for (size_t t = 1; t < n_thr; t++) pool.emplace_back(fill);
-        fill();
-        for (auto& t : pool) t.join();
-        if (err) std::rethrow_exception(err);
+              };
+              const size_t n_thr = fill_threads;
+              std::vector<std::thread> pool;
+              for (size_t t = 1; t < n_thr; t++) pool.emplace_back(fill);
+              fill();
+              for (auto& t : pool) t.join();
+              if (err) std::rethrow_exception(err);
 
-        // every stream still open may later deliver k-mers above its last buffered one only
-        const uint8_t* bound = nullptr;
-        for (const Stream& t : st)
-          if (!t.eof && t.n)
-          {
-            const uint8_t* last = t.pin->data() + (t.n - 1) * rec;
-            if (!bound || key_less(last, bound)) bound = last;
-          }
-        std::vector<uint8_t> bound_key;
-        if (bound) bound_key.assign(bound, bound + 8 * kw);
-        std::vector<const void*> ptrs(N);
-        std::vector<uint64_t> cnt(N);
-        uint64_t total = 0;
-        for (uint32_t s = 0; s < N; s++)
-        {
-          size_t cut = st[s].n;
-          if (bound)
-          {
-            // first record whose k-mer is > bound
-            size_t lo = 0, hi = st[s].n;
-            while (lo < hi)
-            {
-              const size_t mid = (lo + hi) / 2;
-              if (key_less(bound_key.data(), st[s].pin->data() + mid * rec)) hi = mid; else lo = mid + 1;
+              // every stream still open may later deliver k-mers above its last buffered one only
+              const uint8_t* bound = nullptr;
+              for (const Stream& t : st)
+                if (!t.eof && t.n)
+                {
+                  const uint8_t* last = t.pin->data() + (t.n - 1) * rec;
+                  if (!bound || key_less(last, bound)) bound = last;
+                }
+              std::vector<uint8_t> bound_key;
+              if (bound) bound_key.assign(bound, bound + 8 * kw);
+              std::vector<const void*> ptrs(N);
+              std::vector<uint64_t> cnt(N);
+              uint64_t total = 0;
+              for (uint32_t s = 0; s < N; s++)
+              {
+                size_t cut = st[s].n;
+                if (bound)
+                {
+                  // first record whose k-mer is > bound
+                  size_t lo = 0, hi = st[s].n;
+                  while (lo < hi)
+                  {
+                    const size_t mid = (lo + hi) / 2;
+                    if (key_less(bound_key.data(), st[s].pin->data() + mid * rec)) hi = mid; else lo = mid + 1;
+                  }
+                  cut = lo;
+                }
+                ptrs[s] = st[s].pin->data();
+                cnt[s] = cut;
+                total += cut;
+              }
+              if (total == 0) break;   // every stream is exhausted
+              uint64_t n_rows = 0;
+              {
+                std::lock_guard<std::mutex> gpu(m_gpu_mu);
+                if (m_opt.pop_correction)
+                  ck(m_ctx.get(), kmd_popstrat_set_draw_index(m_ctx.get(), m_draw_next), "kmd_popstrat_set_draw_index");
+                ck(m_ctx.get(), kmd_merge_scan_host(m_ctx.get(), ptrs.data(), cnt.data(), ab_min.data(),
+                                                    (static_cast<uint64_t>(p.index) << kPartShift) + local, p.index, &n_rows),
+                   "kmd_merge_scan_host");
+                m_draw_next += n_rows;
+              }
+              local += n_rows;
+              for (uint32_t s = 0; s < N; s++)
+              {
+                Stream& t = st[s];
+                if (cnt[s] && cnt[s] < t.n) memmove(t.pin->data(), t.pin->data() + cnt[s] * rec, (t.n - cnt[s]) * rec);
+                t.n -= cnt[s];
+              }
             }
-            cut = lo;
+            logf(L_DEBUG, "partition %u: %llu rows merged from %u count files (gpu %d)", p.index, static_cast<unsigned long long>(local), N, m_device);
           }
-          ptrs[s] = st[s].pin->data();
-          cnt[s] = cut;
-          total += cut;
-        }
-        if (total == 0) break;   // every stream is exhausted
-        if (m_opt.pop_correction)
-          ck(m_ctx.get(), kmd_popstrat_set_draw_index(m_ctx.get(), m_draw_next), "kmd_popstrat_set_draw_index");
-        uint64_t n_rows = 0;
-        ck(m_ctx.get(), kmd_merge_scan_host(m_ctx.get(), ptrs.data(), cnt.data(), ab_min.data(),
-                                            (static_cast<uint64_t>(p.index) << kPartShift) + local, p.index, &n_rows),
-           "kmd_merge_scan_host");
-        local += n_rows;
-        m_draw_next += n_rows;
-        for (uint32_t s = 0; s < N; s++)
-        {
-          Stream& t = st[s];
-          if (cnt[s] && cnt[s] < t.n) memmove(t.pin->data(), t.pin->data() + cnt[s] * rec, (t.n - cnt[s]) * rec);
-          t.n -= cnt[s];
         }
       }
-      logf(L_DEBUG, "partition %u: %llu rows merged from %u count files (gpu %d)", p.index, static_cast<unsigned long long>(local), N, m_device);
-    }
+      catch (...) { std::lock_guard<std::mutex> lk(lane_mu); if (!lane_error) lane_error = std::current_exception(); }
+    };
+    std::vector<std::thread> lanes;
+    for (size_t l = 1; l < n_lanes; l++) lanes.emplace_back(lane);
+    lane();
+    for (auto& t : lanes) t.join();
+    if (lane_error) std::rethrow_exception(lane_error);
   }
 
   // A partition whose files are small enough goes to the device as it lies on disk: the N files are read whole into
@@ -835,6 +870,7 @@ class GpuWorker
   const DiffOptions& m_opt;
   ctx_ptr m_ctx;
   uint64_t m_row_bytes = 0, m_buf_rows = 0;
+  std::mutex m_gpu_mu;          // count-file mode: the lanes take turns on the context
   uint8_t* m_arena = nullptr;   // count-file mode: pinned arena holding one partition's files
   size_t m_arena_bytes = 0;
   uint64_t m_draw_next = 0;   // count-file mode: Sampler draw index = rows merged so far (one worker, partition order)
