@@ -324,6 +324,9 @@ int kmd_popstrat_gram(kmd_context* ctx, double* xtx, int normalize, uint64_t* n_
 int kmd_popstrat_gram_partial(kmd_context* ctx, int32_t* d_G, uint64_t* d_hist);
 int kmd_popstrat_gram_combine(kmd_context* ctx, const int32_t* d_G, const uint64_t* d_hist, double* xtx, int normalize,
                               uint64_t* n_used);
+/* The same inside ONE process that drives several devices (the host program): partials on every context, summed on
+ * ctxs[0]'s device over peer copies, combined there.  xtx: N*N row-major (host). */
+int kmd_popstrat_gram_local(kmd_context* const* ctxs, uint32_t n_ctx, double* xtx, int normalize, uint64_t* n_used);
 /* device time (ms) of the tensor-core kernel of the last kmd_popstrat_gram */
 int kmd_popstrat_gram_ms(kmd_context* ctx, float* ms);
 /* pop_strat_corrector: load_Z/load_Y + init_global_features (src/popstrat.cpp:153-171, 270-370),

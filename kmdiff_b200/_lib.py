@@ -25,7 +25,7 @@ SYMBOLS = [
     "kmd_format_fasta", "kmd_host_alloc", "kmd_host_free", "kmd_synth_fill_host",
     "kmd_synth_fill_device", "kmd_synth_totals",
     "kmd_popstrat_enable", "kmd_popstrat_set_draw_index", "kmd_popstrat_sampled", "kmd_popstrat_geno", "kmd_popstrat_gram",
-    "kmd_popstrat_gram_ms", "kmd_popstrat_gram_partial", "kmd_popstrat_gram_combine", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
+    "kmd_popstrat_gram_ms", "kmd_popstrat_gram_partial", "kmd_popstrat_gram_combine", "kmd_popstrat_gram_local", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
     "kmd_survivor_counts", "kmd_smartpca_normalize", "kmd_sym_eig", "kmd_smartpca_pcs",
     "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_scan_lz4_host", "kmd_merge_prefetch", "kmd_lz4_decode_host", "kmd_merge_rows_host", "kmd_merge_ms", "kmd_survivor_pvalues_device", "kmd_first_reject_device",
     "kmd_scan_host_async", "kmd_host_wait", "kmd_bind_host_thread", "kmd_warmup", "kmd_get_stream", "kmd_exchange_export", "kmd_exchange_correct", "kmd_exchange_result", "kmd_exchange_local",
@@ -160,6 +160,7 @@ def load() -> C.CDLL:
     L.kmd_popstrat_gram.argtypes = [vp, vp, C.c_int, pu64]
     L.kmd_popstrat_gram_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.kmd_popstrat_gram_partial.argtypes = [vp, vp, vp]
+    L.kmd_popstrat_gram_local.argtypes = [vp, u32, vp, C.c_int, pu64]
     L.kmd_popstrat_gram_combine.argtypes = [vp, vp, vp, vp, C.c_int, pu64]
     L.kmd_popstrat_init.argtypes = [vp, vp, vp, vp]
     L.kmd_popstrat_apply.argtypes = [vp]

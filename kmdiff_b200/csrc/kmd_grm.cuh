@@ -363,6 +363,18 @@ __global__ void grm_combine_kernel(const int32_t* G, const BucketInfo* info, con
   xtx[static_cast<size_t>(i) * n + j] = acc;
 }
 
+__global__ void add_i32_kernel(int32_t* __restrict__ dst, const int32_t* __restrict__ src, size_t n)
+{
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    dst[i] += src[i];
+}
+
+__global__ void add_u64_kernel(uint64_t* __restrict__ dst, const uint64_t* __restrict__ src, uint32_t n)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
 __global__ void hist_to_u64_kernel(const uint32_t* hist, uint32_t n, uint64_t* out)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -432,6 +432,54 @@ int kmd_popstrat_gram_combine(kmd_context* ctx, const int32_t* d_G, const uint64
   return KMD_OK;
 }
 
+int kmd_popstrat_gram_local(kmd_context* const* ctxs, uint32_t n_ctx, double* xtx, int normalize, uint64_t* n_used)
+{
+  if (!ctxs || !n_ctx || !xtx) return KMD_ERR_ARG;
+  for (uint32_t i = 0; i < n_ctx; i++)
+    if (!ctxs[i] || !ctxs[i]->pop.enabled) return KMD_ERR_ARG;
+  kmd_context* c0 = ctxs[0];
+  if (n_ctx == 1) return kmd_popstrat_gram(c0, xtx, normalize, n_used);
+  const uint32_t n = c0->cfg.nb_controls + c0->cfg.nb_cases;
+  const size_t g_words = static_cast<size_t>(n) * n * n;
+  if (g_words * sizeof(int32_t) > (2ull << 30))
+    return fail(c0, KMD_ERR_ARG, "%u samples: the dense integer Gram exchange would need %zu MiB per device", n, g_words * 4 >> 20);
+  // every context: its integer co-carrier matrices by carrier count + its carrier histogram, on its own device
+  std::vector<DeviceBuf> G(n_ctx), H(n_ctx);
+  for (uint32_t i = 0; i < n_ctx; i++)
+  {
+    kmd_context* c = ctxs[i];
+    KMD_CUDA(c, cudaSetDevice(c->device));
+    KMD_CUDA(c, cudaMalloc(&G[i].p, g_words * sizeof(int32_t)));
+    KMD_CUDA(c, cudaMalloc(&H[i].p, (n + 1) * sizeof(uint64_t)));
+    int rc = gram_impl(c, nullptr, 0, nullptr, G[i].as<int32_t>(), H[i].as<uint64_t>());   // synchronises c's stream
+    if (rc) return rc;
+  }
+  // exact sum on device 0 (peer copies; the integers make the order irrelevant), then one fp64 combination
+  KMD_CUDA(c0, cudaSetDevice(c0->device));
+  DeviceBuf tg, th;
+  KMD_CUDA(c0, cudaMalloc(&tg.p, g_words * sizeof(int32_t)));
+  KMD_CUDA(c0, cudaMalloc(&th.p, (n + 1) * sizeof(uint64_t)));
+  for (uint32_t i = 1; i < n_ctx; i++)
+  {
+    KMD_CUDA(c0, cudaMemcpyPeerAsync(tg.p, c0->device, G[i].p, ctxs[i]->device, g_words * sizeof(int32_t), c0->stream));
+    KMD_CUDA(c0, cudaMemcpyPeerAsync(th.p, c0->device, H[i].p, ctxs[i]->device, (n + 1) * sizeof(uint64_t), c0->stream));
+    grm::add_i32_kernel<<<c0->sm_count * 8, 256, 0, c0->stream>>>(G[0].as<int32_t>(), tg.as<int32_t>(), g_words);
+    grm::add_u64_kernel<<<(n + 256) / 256, 256, 0, c0->stream>>>(H[0].as<uint64_t>(), th.as<uint64_t>(), n + 1);
+    c0->launches += 2;
+    KMD_CUDA(c0, cudaGetLastError());
+  }
+  int rc = kmd_popstrat_gram_combine(c0, G[0].as<int32_t>(), H[0].as<uint64_t>(), xtx, normalize, n_used);
+  // the buffers of the other devices are freed on their own devices
+  for (uint32_t i = 1; i < n_ctx; i++)
+  {
+    cudaSetDevice(ctxs[i]->device);
+    cudaFree(G[i].p); G[i].p = nullptr;
+    cudaFree(H[i].p); H[i].p = nullptr;
+  }
+  cudaSetDevice(c0->device);
+  return rc;
+}
+
 int kmd_popstrat_gram_ms(kmd_context* ctx, float* ms)
 {
   if (!ctx || !ms) return KMD_ERR_ARG;

@@ -1320,15 +1320,14 @@ void do_pop(std::vector<std::unique_ptr<GpuWorker>>& workers, const DiffOptions&
   }
   logf(L_DEBUG, "%zu k-mers sampled for the PCA", sampled.size());
 
-  // smartpca (run_eigenstrat_smartpca, src/popstrat.cpp:98-137): XTX summed over the GPUs, one host eigensolve
-  std::vector<double> xtx(static_cast<size_t>(n) * n, 0.0), part(static_cast<size_t>(n) * n);
+  // smartpca (run_eigenstrat_smartpca, src/popstrat.cpp:98-137): the GPUs' integer co-carrier matrices summed exactly
+  // on one device, one fp64 combination, one host eigensolve — the XTX of a one-GPU run, bit for bit
+  std::vector<double> xtx(static_cast<size_t>(n) * n, 0.0);
   uint64_t used = 0;
-  for (auto& w : workers)
   {
-    uint64_t u = 0;
-    ck(w->ctx(), kmd_popstrat_gram(w->ctx(), part.data(), 0, &u), "kmd_popstrat_gram");
-    for (size_t i = 0; i < xtx.size(); i++) xtx[i] += part[i];
-    used += u;
+    std::vector<kmd_context*> ctxs;
+    for (auto& w : workers) ctxs.push_back(w->ctx());
+    ck(ctxs[0], kmd_popstrat_gram_local(ctxs.data(), static_cast<uint32_t>(ctxs.size()), xtx.data(), 0, &used), "kmd_popstrat_gram_local");
   }
   if (used == 0 || n < 2) throw KmdError("EigenStratError", "eigenstrat/smartpca failed.");
   kmd_smartpca_normalize(xtx.data(), n);

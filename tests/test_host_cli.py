@@ -256,6 +256,29 @@ def test_cli_on_all_gpus_equals_one_gpu(cli, tmp_path, corr):
     assert outs[1] == outs[n_dev] and len(outs[1][1]) > 1000
 
 
+@pytest.mark.gpu
+def test_cli_pop_correction_on_all_gpus_equals_one_gpu(cli, tmp_path):
+    """--pop-correction with the partitions (hence the sampled k-mers) spread over every device: the integer Gram
+    partials are summed exactly (kmd_popstrat_gram_local), so the .geno file, the PCs and the FASTA files are the
+    one-GPU run's, byte for byte"""
+    from kmdiff_b200 import _lib
+    n_dev = _lib.load().kmd_device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n, parts = 200_000, 9
+    spec, d = make_run_dir(tmp_path, shape=(12, 12, 31, 4), n_rows=n, parts=parts, seed=23, ppm=4000)
+    outs = {}
+    for g in (1, n_dev):
+        out = str(tmp_path / f"out{g}")
+        r = run([cli, "diff", "-d", d, "-1", "12", "-2", "12", "-o", out, "--gpus", str(g), "--pop-correction", "--kmer-pca", "0.02",
+                 "--n-pc", "3", "--random-seed", "7", "-t", "1"] + THR_ARGS)
+        assert "[error]" not in r.stderr, r.stderr
+        outs[g] = [open(os.path.join(out, f)).read() for f in ("control_kmers.fasta", "case_kmers.fasta", "popstrat/pcs.evec",
+                                                                "popstrat/gwas_eigenstratX.geno", "popstrat/gwas_eigenstrat.eval")]
+    assert outs[1] == outs[n_dev]
+    assert len(outs[1][3]) > 10_000 and len(outs[1][0]) + len(outs[1][1]) > 500
+
+
 # ---- GPU: whole runs ---------------------------------------------------------------------------------
 
 def expected_records(spec, n_rows, parts, corr, sig=0.05, cutoff=100000):
