@@ -498,7 +498,8 @@ class GpuWorker
     // Two lanes take partitions in turn: while one lane's range is merged and tested on the device (the context is used
     // by one thread at a time: m_gpu_mu), the other lane reads and decodes its next range on the host threads.  The
     // Sampler's draw index follows the rows merged so far, so --pop-correction keeps one lane (one ordered stream).
-    const size_t n_lanes = (m_opt.pop_correction || partitions.size() < 2) ? 1 : 2;
+    size_t n_lanes = (m_opt.pop_correction || partitions.size() < 2) ? 1 : 2;
+    if (const char* e = getenv("KMD_MERGE_LANES")) n_lanes = m_opt.pop_correction ? 1 : std::max<size_t>(1, static_cast<size_t>(atol(e)));   // tuning experiments
     const size_t fill_threads = std::max<size_t>(1, std::min<size_t>(m_opt.nb_threads / n_lanes, N));
     std::atomic<size_t> next_part{0};
     std::exception_ptr lane_error;
