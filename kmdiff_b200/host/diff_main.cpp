@@ -495,11 +495,15 @@ class GpuWorker
       }
       return false;
     };
-    // Two lanes take partitions in turn: while one lane's range is merged and tested on the device (the context is used
-    // by one thread at a time: m_gpu_mu), the other lane reads and decodes its next range on the host threads.  The
-    // Sampler's draw index follows the rows merged so far, so --pop-correction keeps one lane (one ordered stream).
-    size_t n_lanes = (m_opt.pop_correction || partitions.size() < 2) ? 1 : 2;
-    if (const char* e = getenv("KMD_MERGE_LANES")) n_lanes = m_opt.pop_correction ? 1 : std::max<size_t>(1, static_cast<size_t>(atol(e)));   // tuning experiments
+    // Lanes take partitions in turn: while one lane's range is merged and tested on the device (the context is used by
+    // one thread at a time: m_gpu_mu), another lane can read and decode its next range on the host threads.  Measured
+    // (profiles/r02m: 1.6e7 rows as 32 x 20 LZ4 count files): one lane 0.85 s, two 1.1-1.3 s, three 2.2 s — the lanes'
+    // pinned allocations and copies contend inside the driver for more than the overlap wins, so ONE lane is the
+    // default and KMD_MERGE_LANES the knob.  The Sampler's draw index follows the rows merged so far, so
+    // --pop-correction always keeps one lane (one ordered stream).
+    size_t n_lanes = 1;
+    if (const char* e = getenv("KMD_MERGE_LANES")) n_lanes = std::max<size_t>(1, static_cast<size_t>(atol(e)));
+    if (m_opt.pop_correction || partitions.size() < 2) n_lanes = 1;
     const size_t fill_threads = std::max<size_t>(1, std::min<size_t>(m_opt.nb_threads / n_lanes, N));
     std::atomic<size_t> next_part{0};
     std::exception_ptr lane_error;
