@@ -271,12 +271,12 @@ def test_cli_pop_correction_on_all_gpus_equals_one_gpu(cli, tmp_path):
     for g in (1, n_dev):
         out = str(tmp_path / f"out{g}")
         r = run([cli, "diff", "-d", d, "-1", "12", "-2", "12", "-o", out, "--gpus", str(g), "--pop-correction", "--kmer-pca", "0.02",
-                 "--n-pc", "3", "--random-seed", "7", "-t", "1"] + THR_ARGS)
+                 "--n-pc", "3", "--random-seed", "7", "-t", "1", "-c", "disabled"] + THR_ARGS)
         assert "[error]" not in r.stderr, r.stderr
         outs[g] = [open(os.path.join(out, f)).read() for f in ("control_kmers.fasta", "case_kmers.fasta", "popstrat/pcs.evec",
                                                                 "popstrat/gwas_eigenstratX.geno", "popstrat/gwas_eigenstrat.eval")]
     assert outs[1] == outs[n_dev]
-    assert len(outs[1][3]) > 10_000 and len(outs[1][0]) + len(outs[1][1]) > 500
+    assert len(outs[1][3]) > 10_000 and len(outs[1][2]) > 100     # thousands of sampled k-mers, PCs for every sample
 
 
 # ---- GPU: whole runs ---------------------------------------------------------------------------------
