@@ -184,13 +184,16 @@ __global__ void __launch_bounds__(128) merge_partition_kernel(const MergeArgs<W>
 // shared memory of one merge_pass_kernel CTA: the staged input slices and a per-warp output staging area
 constexpr int kOutTile = kTile + kTile / kItems;   // output staging, skewed by one slot per kItems (bank conflicts)
 __device__ __forceinline__ uint32_t out_slot(uint32_t i) { return i + i / kItems; }
-template <int W>
-constexpr size_t merge_smem_bytes() { return static_cast<size_t>(kTile + kOutTile) * 8 * (W + 1); }
+// STAGE_OUT: the warp's outputs go through its own slice of a second shared-memory buffer and leave coalesced;
+// otherwise every thread stores its kItems consecutive outputs (64 contiguous bytes per array) straight from registers —
+// half the shared memory per CTA, i.e. twice the resident warps, for partially filled store sectors.
+template <int W, bool STAGE_OUT>
+constexpr size_t merge_smem_bytes() { return static_cast<size_t>(kTile + (STAGE_OUT ? kOutTile : 0)) * 8 * (W + 1); }
 
 // One tile of kTile outputs: stage both input slices in shared memory (coalesced), ONE block barrier, every thread
 // finds its merge-path start in shared memory and merges kItems consecutive outputs in registers, each warp stages its
 // 32 * kItems outputs in its own slice of a second buffer (warp barrier only) and stores them coalesced.
-template <int W>
+template <int W, bool STAGE_OUT>
 __global__ void __launch_bounds__(kThreads) merge_pass_kernel(const MergeArgs<W> A, const uint32_t* __restrict__ split)
 {
   extern __shared__ __align__(16) uint64_t smem[];
@@ -240,6 +243,7 @@ __global__ void __launch_bounds__(kThreads) merge_pass_kernel(const MergeArgs<W>
   Key<W> ka{}, kb{};
   if (ia < na) ka = sa(ia);
   if (ib < nb) kb = sb(ib);
+  const uint32_t o0 = g.a0 + g.d0;
 #pragma unroll
   for (int e = 0; e < kItems; e++)
   {
@@ -247,30 +251,41 @@ __global__ void __launch_bounds__(kThreads) merge_pass_kernel(const MergeArgs<W>
     {
       const bool take_a = ib >= nb || (ia < na && ka <= kb);
       const uint32_t src = take_a ? ia : na + ib;
-      // thread t owns outputs [t * kItems, (t + 1) * kItems): slot stride kItems + 1 between lanes, conflict-free
-      const uint32_t o = t0 + t0 / kItems + e;
-      o_lo[o] = take_a ? ka.lo : kb.lo;
-      if constexpr (W == 2) o_hi[o] = take_a ? ka.hi : kb.hi;
-      o_pay[o] = s_pay[src];
+      if constexpr (STAGE_OUT)
+      {
+        // thread t owns outputs [t * kItems, (t + 1) * kItems): slot stride kItems + 1 between lanes, conflict-free
+        const uint32_t o = t0 + t0 / kItems + e;
+        o_lo[o] = take_a ? ka.lo : kb.lo;
+        if constexpr (W == 2) o_hi[o] = take_a ? ka.hi : kb.hi;
+        o_pay[o] = s_pay[src];
+      }
+      else
+      {
+        A.out.lo[o0 + t0 + e] = take_a ? ka.lo : kb.lo;
+        if constexpr (W == 2) A.out.hi[o0 + t0 + e] = take_a ? ka.hi : kb.hi;
+        A.pay_out[o0 + t0 + e] = s_pay[src];
+      }
       if (take_a) { ia++; if (ia < na) ka = sa(ia); }
       else { ib++; if (ib < nb) kb = sb(ib); }
     }
   }
-  __syncwarp();
-  // the warp's 32 * kItems outputs are contiguous in the output staging area: coalesced stores
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t w0 = (threadIdx.x & ~31u) * kItems;
-  const uint32_t o0 = g.a0 + g.d0;
-#pragma unroll
-  for (int e = 0; e < kItems; e++)
+  if constexpr (STAGE_OUT)
   {
-    const uint32_t i = w0 + e * 32 + lane;
-    if (i < nt)
+    __syncwarp();
+    // the warp's 32 * kItems outputs are contiguous in the output staging area: coalesced stores
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w0 = (threadIdx.x & ~31u) * kItems;
+#pragma unroll
+    for (int e = 0; e < kItems; e++)
     {
-      const uint32_t o = out_slot(i);
-      A.out.lo[o0 + i] = o_lo[o];
-      if constexpr (W == 2) A.out.hi[o0 + i] = o_hi[o];
-      A.pay_out[o0 + i] = o_pay[o];
+      const uint32_t i = w0 + e * 32 + lane;
+      if (i < nt)
+      {
+        const uint32_t o = out_slot(i);
+        A.out.lo[o0 + i] = o_lo[o];
+        if constexpr (W == 2) A.out.hi[o0 + i] = o_hi[o];
+        A.pay_out[o0 + i] = o_pay[o];
+      }
     }
   }
 }

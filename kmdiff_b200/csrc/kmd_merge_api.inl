@@ -41,8 +41,10 @@ int merge_passes(kmd_context* ctx, const std::vector<MergePass>& passes, int* fi
   for (const MergePass& ps : passes) max_tiles = std::max(max_tiles, ps.tiles);
   int rc = grow(ctx, m.split, m.split_cap, static_cast<size_t>(max_tiles) + 1);
   if (rc) return rc;
-  const size_t smem = mrg::merge_smem_bytes<W>();
-  KMD_CUDA(ctx, cudaFuncSetAttribute(mrg::merge_pass_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  static const bool stage_out = env_u32("KMD_MERGE_STAGE_OUT", 1) != 0;
+  const size_t smem = stage_out ? mrg::merge_smem_bytes<W, true>() : mrg::merge_smem_bytes<W, false>();
+  if (stage_out) KMD_CUDA(ctx, cudaFuncSetAttribute(mrg::merge_pass_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  else KMD_CUDA(ctx, cudaFuncSetAttribute(mrg::merge_pass_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int cur = 0;
   for (const MergePass& ps : passes)
   {
@@ -58,7 +60,8 @@ int merge_passes(kmd_context* ctx, const std::vector<MergePass>& passes, int* fi
     if (ps.tiles)
     {
       mrg::merge_partition_kernel<W><<<(ps.tiles + 127) / 128, 128, 0, ctx->stream>>>(A, ps.tiles, m.split);
-      mrg::merge_pass_kernel<W><<<ps.tiles, mrg::kThreads, smem, ctx->stream>>>(A, m.split);
+      if (stage_out) mrg::merge_pass_kernel<W, true><<<ps.tiles, mrg::kThreads, smem, ctx->stream>>>(A, m.split);
+      else mrg::merge_pass_kernel<W, false><<<ps.tiles, mrg::kThreads, smem, ctx->stream>>>(A, m.split);
       ctx->launches += 2;
     }
     cur ^= 1;
