@@ -336,47 +336,85 @@ def bench_merge(args) -> None:
     corr_kind = K.correction_from_str(corr)
     stage_ms = {"unpack": 0.0, "passes": 0.0, "rows": 0.0, "scan": 0.0}
     n_passes = [0]
+    tree = {"algo": None, "rows": None, "keys_in": 0, "keys_out": 0}
+    # the same records resident in HBM (kmd_merge_scan_device): `value`; the host streams above: `e2e`
+    dev_chunks = []
+    for views in chunks:
+        cat = np.concatenate(views) if views else np.empty(0, np.uint8)
+        dev_chunks.append((torch.from_numpy(cat).cuda(), [v.size // rec for v in views]))
 
-    def step(timed=False):
-        ctx.reset()
-        base = 0
-        if not timed:
-            ctx.merge_prefetch(chunks[0])
-        for ci, streams in enumerate(chunks):
-            if not timed and ci + 1 < len(chunks):
-                ctx.merge_prefetch(chunks[ci + 1])      # the next range crosses PCIe while this one is merged
-            base += ctx.merge_scan_host(streams, row_base=base)
-            if timed:
-                m = ctx.merge_ms()
-                for key in ("unpack", "passes", "rows"):
-                    stage_ms[key] += m[key]
-                n_passes[0] = m["n_passes"]
-                ctx.sync()
-                stage_ms["scan"] += ctx.scan_kernel_ms()
+    def finish():
         c = ctx.counters()
         res = ctx.correct(corr_kind, SIGNIFICANCE, c.rows)
         sig = ctx.significant()
         return res, c, sig
 
-    for _ in range(max(3, args.warmup)):
-        res, c, sig = step()
-    assert c.rows == rows, (c.rows, rows)
-    launches0 = ctx.launch_count()
+    def step_device(timed=False):
+        ctx.reset()
+        base = 0
+        for d, cnt in dev_chunks:
+            base += ctx.merge_scan_device(d.data_ptr(), cnt, row_base=base)
+            if timed:
+                m = ctx.merge_ms()
+                for key in ("unpack", "passes", "rows"):
+                    stage_ms[key] += m[key]
+                n_passes[0] = m["n_passes"]
+                info = ctx.merge_info()
+                tree["algo"] = info["algo"]
+                tree["rows"] = info["rows"]
+                tree["keys_in"] += info["keys_in"]
+                tree["keys_out"] += info["keys_out"]
+                ctx.sync()
+                stage_ms["scan"] += ctx.scan_kernel_ms()
+        return finish()
+
+    def step_host():
+        ctx.reset()
+        base = 0
+        ctx.merge_prefetch(chunks[0])
+        for ci, streams in enumerate(chunks):
+            if ci + 1 < len(chunks):
+                ctx.merge_prefetch(chunks[ci + 1])      # the next range crosses PCIe while this one is merged
+            base += ctx.merge_scan_host(streams, row_base=base)
+        return finish()
+
+    def timed_loop(step):
+        for _ in range(max(3, args.warmup)):
+            res, c, sig = step()
+        assert c.rows == rows, (c.rows, rows)
+        launches0 = ctx.launch_count()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res, c, sig = step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        return dt, (ctx.launch_count() - launches0) // args.steps, res, c, sig
+
     sampler = ClockSampler(0)
     sampler.start()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        res, c, sig = step()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    dt, launches, res, c, sig = timed_loop(step_device)
     clocks = sampler.stop()
-    launches = (ctx.launch_count() - launches0) // args.steps
-    step(timed=True)                      # per-stage device times, outside the timed region (adds syncs)
+    dt_host, _, res_h, c_h, sig_h = timed_loop(step_host)
+    assert (res_h[0], res_h[1], c_h.survivors) == (res[0], res[1], c.survivors), "host streams and device records disagree"
+    step_device(timed=True)               # per-stage device times, outside the timed region (adds syncs)
     value = rows * args.steps / dt
+    e2e_value = rows * args.steps / dt_host
     peak, peak_src = load_peaks()
-    pass_bytes = n_passes[0] * n_records * 2 * (8 * kw + 8)     # every pass reads and writes (key, payload)
+    calls = max(1, len(chunks))
+    if tree["algo"] == "union":
+        # every level reads the keys of its input runs and writes the keys of its output runs, once
+        pass_bytes = (tree["keys_in"] + tree["keys_out"]) * 8 * kw
+        kernel = "uni::union_level_kernel"
+        launches_of_kernel = max(1, n_passes[0] * calls)
+    else:
+        pass_bytes = n_passes[0] * n_records * 2 * (8 * kw + 8)     # every pass reads and writes (key, payload)
+        kernel = "mrg::merge_pass_kernel"
+        launches_of_kernel = max(1, n_passes[0] * calls)
     achieved = pass_bytes / (stage_ms["passes"] * 1e-3) / 1e9 if stage_ms["passes"] else None
+    # the whole device stage (keys + tree + rows + scan) against what it must move at least: the records in, the rows out and in again
+    stage_total_ms = sum(stage_ms.values())
+    min_bytes = n_records * rec + 2 * rows * spec.row_bytes
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -402,18 +440,24 @@ def bench_merge(args) -> None:
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(cfg_name),
                    "rows_per_gpu": rows, "records_per_gpu": n_records, "record_bytes": rec, "row_bytes": spec.row_bytes,
-                   "merge_calls_per_step": len(chunks), "merge_passes": n_passes[0],
-                   "l2": f"every merge call works on {n_records // max(1, len(chunks)) * 32 >> 20} MiB of (key, payload) arrays, above the 126 MB L2",
+                   "merge_calls_per_step": len(chunks), "merge_algo": tree["algo"], "merge_rows": tree["rows"], "merge_levels": n_passes[0],
+                   "level_keys_in_per_step": tree["keys_in"], "level_keys_out_per_step": tree["keys_out"],
+                   "l2": f"every merge call works on {n_records // calls * rec >> 20} MiB of records and "
+                         f"{n_records // calls * 8 * kw >> 20} MiB of leaf keys, above the 126 MB L2",
                    "survivors_per_gpu": int(c.survivors), "significant": [int(res[0]), int(res[1])]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if achieved else None, "traffic": None, "kernel": "mrg::merge_pass_kernel",
-                     "ms_per_launch": stage_ms["passes"] / max(1, n_passes[0] * len(chunks)),
-                     "algorithmic_bytes_per_launch": pass_bytes // max(1, n_passes[0] * len(chunks)), "peak_source": peak_src,
-                     "stage_ms_per_step": stage_ms},
-        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": n_records * rec, "d2h_bytes_per_step": int(sig.nbytes + 48),
-                "rows_per_step": rows, "steps": args.steps,
+                     "frac": achieved / peak if achieved else None, "traffic": None, "kernel": kernel,
+                     "ms_per_launch": stage_ms["passes"] / launches_of_kernel,
+                     "algorithmic_bytes_per_launch": pass_bytes // launches_of_kernel, "peak_source": peak_src,
+                     "stage_ms_per_step": stage_ms,
+                     "device_stage": {"ms_per_step": stage_total_ms, "min_bytes_per_step": min_bytes,
+                                      "gbs": min_bytes / (stage_total_ms * 1e-3) / 1e9 if stage_total_ms else None,
+                                      "note": "keys + tree + rows + scan against records in + rows written and read once"}},
+        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": n_records * rec, "d2h_bytes_per_step": int(sig.nbytes + 48),
+                "rows_per_step": rows, "steps": args.steps, "ms_per_step": 1e3 * dt_host / args.steps,
+                "h2d_gbs": n_records * rec * args.steps / dt_host / 1e9,
                 "api": "kmd_merge_prefetch (next range's H2D on the copy stream) + kmd_merge_scan_host (host record streams) + "
-                       "kmd_correct + kmd_significant; this path has no device-resident variant, value == e2e"},
+                       "kmd_correct + kmd_significant; value = the same ranges through kmd_merge_scan_device, records resident in HBM"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if cpu is not None:

@@ -181,6 +181,11 @@ int kmd_merge_scan_host(kmd_context* ctx, const void* const* streams, const uint
 int kmd_merge_scan_lz4_host(kmd_context* ctx, const void* const* frames, const uint64_t* frame_bytes,
                             const uint8_t* compressed, const uint32_t* ab_min, uint64_t row_base, uint32_t partition,
                             uint64_t max_records, uint64_t* n_rows, uint64_t* n_records);
+/* kmd_merge_scan_host for records that are already in device memory: d_records = the streams' records back to back
+ * (sample 0's n_records[0] records, then sample 1's, ...), 4-byte aligned; it is only read and must stay untouched
+ * until the call returns (the call synchronises once, for the row count). */
+int kmd_merge_scan_device(kmd_context* ctx, const void* d_records, const uint64_t* n_records, const uint32_t* ab_min,
+                          uint64_t row_base, uint32_t partition, uint64_t* n_rows);
 /* Start the host->device copies of the NEXT kmd_merge_scan_host (frames == 0: blobs[s] = the records of sample s,
  * blob_bytes[s] = n_records[s] * record size) or kmd_merge_scan_lz4_host (frames != 0: all payloads compressed) call on
  * the copy stream and return at once: they overlap the merge the context is still busy with.  The next merge call
@@ -201,6 +206,15 @@ int kmd_merge_rows_host(kmd_context* ctx, const void* const* streams, const uint
  * row count); the number of passes and records of that call.  Any output may be NULL. */
 int kmd_merge_ms(kmd_context* ctx, float* unpack_ms, float* passes_ms, float* rows_ms, uint32_t* n_passes,
                  uint64_t* n_records);
+
+/* Which merge the last kmd_merge_* call ran and what its tree moved.  algo: 0 = union tree (kmd_union.cuh: the k-mers
+ * are merged pairwise with the duplicates dropped, the counts are scattered into the rows; taken when every record is
+ * solid), 1 = pairwise tree of (k-mer, payload) pairs (kmd_merge.cuh; also with KMD_MERGE_PAIRWISE=1 in the
+ * environment).  rows_mode (union tree): 1 = the rows were assembled in shared memory and written whole (dense cohorts),
+ * 2 = the counts were scattered into zeroed rows (sparse ones); KMD_UNION_ROWS=1|2 forces one.  keys_in / keys_out: keys
+ * read / written by all levels of the union tree (0 for algo 1, where every pass reads and writes every record).  kmd_merge_ms' three times are then: key extraction | levels | zeroing the rows
+ * + scatter (incl. the host round trip for the row count).  Any output may be NULL. */
+int kmd_merge_info(kmd_context* ctx, uint32_t* algo, uint32_t* rows_mode, uint64_t* keys_in, uint64_t* keys_out);
 
 /* diagnostics for bench.py: kernels launched on behalf of ctx so far, and the device time of the
  * most recent lrt_scan kernel launch (CUDA events on the context's stream) */

@@ -27,7 +27,7 @@ SYMBOLS = [
     "kmd_popstrat_enable", "kmd_popstrat_set_draw_index", "kmd_popstrat_sampled", "kmd_popstrat_geno", "kmd_popstrat_gram",
     "kmd_popstrat_gram_ms", "kmd_popstrat_gram_partial", "kmd_popstrat_gram_combine", "kmd_popstrat_gram_local", "kmd_popstrat_init", "kmd_popstrat_apply", "kmd_popstrat_fit",
     "kmd_survivor_counts", "kmd_smartpca_normalize", "kmd_sym_eig", "kmd_smartpca_pcs",
-    "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_scan_lz4_host", "kmd_merge_prefetch", "kmd_lz4_decode_host", "kmd_merge_rows_host", "kmd_merge_ms", "kmd_survivor_pvalues_device", "kmd_first_reject_device",
+    "kmd_sampler_rows", "kmd_merge_scan_host", "kmd_merge_scan_lz4_host", "kmd_merge_prefetch", "kmd_lz4_decode_host", "kmd_merge_rows_host", "kmd_merge_ms", "kmd_merge_scan_device", "kmd_merge_info", "kmd_survivor_pvalues_device", "kmd_first_reject_device",
     "kmd_scan_host_async", "kmd_host_wait", "kmd_bind_host_thread", "kmd_warmup", "kmd_get_stream", "kmd_exchange_export", "kmd_exchange_correct", "kmd_exchange_result", "kmd_exchange_local",
 ]
 
@@ -105,6 +105,8 @@ def load() -> C.CDLL:
     L.kmd_scan_host.argtypes = [vp, vp, u64, u64, u32]
     L.kmd_merge_scan_host.argtypes = [vp, vp, vp, vp, u64, u32, pu64]
     L.kmd_merge_rows_host.argtypes = [vp, vp, vp, vp, vp, u64, pu64]
+    L.kmd_merge_scan_device.argtypes = [vp, vp, vp, vp, u64, u32, pu64]
+    L.kmd_merge_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), pu64, pu64]
     L.kmd_merge_scan_lz4_host.argtypes = [vp, vp, vp, vp, vp, u64, u32, u64, pu64, pu64]
     L.kmd_merge_prefetch.argtypes = [vp, vp, vp, C.c_int]
     L.kmd_lz4_decode_host.argtypes = [vp, vp, vp, vp, u64, pu64, C.POINTER(C.c_float)]

@@ -242,6 +242,27 @@ class DiffContext:
         self._ck(self._L.kmd_merge_scan_host(self._h, ptrs, cnt, ab.ctypes.data, row_base, partition, C.byref(n)))
         return n.value
 
+    def merge_scan_device(self, d_records: int, n_records, ab_min=1, row_base: int = 0, partition: int = 0) -> int:
+        """merge_scan_host for records that already lie in device memory: d_records = device address of the samples'
+        records back to back, n_records[s] = records of sample s; -> rows"""
+        n = self.nb_samples
+        assert len(n_records) == n, f"{n} streams expected (controls first)"
+        cnt = (C.c_uint64 * n)(*[int(c) for c in n_records])
+        ab = np.ascontiguousarray(np.broadcast_to(np.asarray(ab_min, dtype=np.uint32), (n,)))
+        rows = C.c_uint64()
+        self._ck(self._L.kmd_merge_scan_device(self._h, C.c_void_p(int(d_records)), cnt, ab.ctypes.data, row_base, partition,
+                                               C.byref(rows)))
+        return rows.value
+
+    def merge_info(self) -> dict:
+        """the last merge call: 'algo' ('union' = k-mers merged with duplicates dropped + counts scattered,
+        'pairwise' = (k-mer, payload) merge tree), 'rows' ('assembled' in shared memory / 'scattered' into zeroed rows),
+        keys read / written by the union tree's levels"""
+        algo, mode, kin, kout = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        self._ck(self._L.kmd_merge_info(self._h, C.byref(algo), C.byref(mode), C.byref(kin), C.byref(kout)))
+        return {"algo": "union" if algo.value == 0 else "pairwise", "rows": {0: None, 1: "assembled", 2: "scattered"}[mode.value],
+                "keys_in": kin.value, "keys_out": kout.value}
+
     def _frame_args(self, frames):
         n = self.nb_samples
         assert len(frames) == n, f"{n} frames expected (controls first)"

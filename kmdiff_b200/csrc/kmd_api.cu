@@ -28,6 +28,7 @@
 #include "kmd_lz4.cuh"
 #include "kmd_math.cuh"
 #include "kmd_merge.cuh"
+#include "kmd_union.cuh"
 #include "kmd_popstrat.cuh"
 #include "kmd_scan.cuh"
 #include "kmd_sort.cuh"
@@ -139,6 +140,17 @@ struct MergeState
   bool timed = false;
   uint32_t last_passes = 0;
   uint64_t last_records = 0;
+  // the union tree (kmd_union.cuh): tile descriptors, look-back words (+ the ticket), the scatter's splits, flags
+  uni::TileDesc* udesc = nullptr; size_t udesc_cap = 0;
+  unsigned long long* ustatus = nullptr; size_t ustatus_cap = 0;
+  uint32_t* usplit = nullptr; size_t usplit_cap = 0;
+  uint32_t* uflags = nullptr;
+  int algo = -1;            // 0 union tree (pairwise tree when a record is not solid), 1 pairwise tree; -1 = ask KMD_MERGE_PAIRWISE
+  int last_algo = 1;        // what the last call ran
+  bool asm_attr_set[2] = {false, false};
+  uint32_t knob_rows = 0, knob_smem = 56 << 10, knob_scatter_tile = 1024;   // KMD_UNION_ROWS / _SMEM_KB / _SCATTER_TILE
+  int last_rows_mode = 0;   // union tree: 1 rows assembled in shared memory, 2 scattered into zeroed rows
+  uint64_t last_keys_in = 0, last_keys_out = 0;   // keys read / written by the levels of the last union tree
 };
 
 // multi-GPU correction (kmd_exchange_*): the union of the ranks' p-values, sorted here, and the decision
@@ -844,6 +856,8 @@ int fetch_counters(kmd_context* ctx)
 {
   KMD_CUDA(ctx, cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, ctx->stream));
   KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_cnt->overflow & 4u)
+    return fail(ctx, KMD_ERR_STATE, "internal error: a record's k-mer was not among the merged rows (kmd_union.cuh)");
   if (ctx->h_cnt->overflow)
     return fail(ctx, KMD_ERR_OVERFLOW, "%s buffer overflow: raise kmd_config.max_survivors (now %llu)",
                 (ctx->h_cnt->overflow & 1) ? "candidate" : "survivor", static_cast<unsigned long long>(ctx->cap));

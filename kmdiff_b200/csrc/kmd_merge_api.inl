@@ -25,6 +25,7 @@ void merge_free(kmd_context* ctx)
   cudaFree(m.flag); cudaFree(m.tile); cudaFree(m.head_pos); cudaFree(m.rows); cudaFree(m.stream_off);
   cudaFree(m.ab_min); cudaFree(m.plan); cudaFree(m.total); cudaFree(m.split);
   cudaFree(m.lz_in); cudaFree(m.lz_tab); cudaFree(m.lz_status);
+  cudaFree(m.udesc); cudaFree(m.ustatus); cudaFree(m.usplit); cudaFree(m.uflags);
   for (auto& f : m.pf) { cudaFree(f.buf); if (f.done) cudaEventDestroy(f.done); }
   for (cudaEvent_t e : m.ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m.lz_ev) if (e) cudaEventDestroy(e);
@@ -104,11 +105,195 @@ int merge_rows(kmd_context* ctx, int buf, uint32_t n, uint32_t* n_rows_out)
   return KMD_OK;
 }
 
+struct UnionLevel { size_t run_base, run_len, pair_tile, out_len; uint32_t n_runs, n_pairs, tiles; };
+
+// The rows of a chunk by the union tree of kmd_union.cuh: keys -> levels -> (one synchronisation: row count) -> scatter.
+// *used = false (and no rows) when a record lies below its sample's abundance_min: the caller then runs the pairwise
+// tree, which carries the solid flags along.
+template <int W>
+int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t>& off, const uint32_t* ab_min, uint32_t n,
+                uint32_t* n_rows_out, bool* used)
+{
+  MergeState& m = ctx->mrg;
+  const uint32_t N = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
+  const uint32_t B = ctx->cfg.count_bytes;
+  *used = false;
+
+  // the tree: a run's start is the sum of the leaf lengths before it (host), its length is the level's output (device)
+  std::vector<uint32_t> plan;
+  std::vector<UnionLevel> levels;
+  {
+    std::vector<uint32_t> base(N), ub(N);
+    for (uint32_t s = 0; s < N; s++) { base[s] = static_cast<uint32_t>(off[s]); ub[s] = static_cast<uint32_t>(off[s + 1] - off[s]); }
+    bool leaves = true;
+    while (base.size() > 1)
+    {
+      const uint32_t n_runs = static_cast<uint32_t>(base.size()), n_pairs = (n_runs + 1) / 2;
+      UnionLevel lv{};
+      lv.n_runs = n_runs; lv.n_pairs = n_pairs;
+      lv.run_base = plan.size();
+      plan.insert(plan.end(), base.begin(), base.end());
+      lv.run_len = plan.size();
+      if (leaves) plan.insert(plan.end(), ub.begin(), ub.end()); else plan.insert(plan.end(), n_runs, 0u);
+      leaves = false;
+      lv.pair_tile = plan.size();
+      std::vector<uint32_t> nbase(n_pairs), nub(n_pairs);
+      uint32_t tiles = 0;
+      for (uint32_t q = 0; q < n_pairs; q++)
+      {
+        nbase[q] = base[2 * q];
+        nub[q] = ub[2 * q] + (2 * q + 1 < n_runs ? ub[2 * q + 1] : 0u);
+        plan.push_back(tiles);
+        tiles += (nub[q] + uni::kTile - 1) / uni::kTile;
+      }
+      plan.push_back(tiles);
+      lv.tiles = tiles;
+      if (!levels.empty()) levels.back().out_len = lv.run_len;
+      levels.push_back(lv);
+      base.swap(nbase);
+      ub.swap(nub);
+    }
+    if (!levels.empty()) { levels.back().out_len = plan.size(); plan.push_back(0u); }
+  }
+  uint32_t max_tiles = 0;
+  for (const UnionLevel& lv : levels) max_tiles = std::max(max_tiles, lv.tiles);
+  int rc;
+  if ((rc = grow(ctx, m.plan, m.plan_cap, std::max<size_t>(1, plan.size())))) return rc;
+  if ((rc = grow(ctx, m.udesc, m.udesc_cap, std::max<size_t>(1, max_tiles)))) return rc;
+  if ((rc = grow(ctx, m.ustatus, m.ustatus_cap, static_cast<size_t>(max_tiles) + 1))) return rc;
+  if (!m.uflags) KMD_CUDA(ctx, cudaMalloc(&m.uflags, 4 * sizeof(uint32_t)));
+  KMD_CUDA(ctx, cudaMemsetAsync(m.uflags, 0, 4 * sizeof(uint32_t), ctx->stream));
+  if (!plan.empty())
+    KMD_CUDA(ctx, cudaMemcpyAsync(m.plan, plan.data(), plan.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+  // leaves = klo[0] / khi[0]; the levels alternate between klo[1] / khi[1] and pay[0] / pay[1]
+  mrg::KeyArrays<W> leaf{m.klo[0], m.khi[0]};
+  mrg::KeyArrays<W> ping{m.klo[1], m.khi[1]}, pong{m.pay[0], m.pay[1]};
+  KMD_CUDA(ctx, cudaEventRecord(m.ev[0], ctx->stream));
+  {
+    uni::KeysArgs K{};
+    K.raw = raw; K.stream_off = m.stream_off; K.ab_min = m.ab_min; K.n_streams = N; K.n = n;
+    K.kmer_words = W; K.count_bytes = B;
+    K.ab_min_max = *std::max_element(ab_min, ab_min + N);
+    K.klo = leaf.lo; K.khi = leaf.hi; K.nonsolid = m.uflags;
+    const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>((n + 255) / 256, ctx->sm_count * 8));
+    uni::keys_kernel<<<blocks, 256, 0, ctx->stream>>>(K);
+    ctx->launches++;
+  }
+  KMD_CUDA(ctx, cudaEventRecord(m.ev[1], ctx->stream));
+  mrg::KeyArrays<W> cur = leaf;
+  int flip = 0;
+  for (const UnionLevel& lv : levels)
+  {
+    if (lv.tiles == 0) continue;   // nothing but empty runs
+    uni::LevelArgs<W> A{};
+    A.in = cur;
+    A.out = flip ? pong : ping;
+    A.run_base = m.plan + lv.run_base;
+    A.run_len = m.plan + lv.run_len;
+    A.pair_tile = m.plan + lv.pair_tile;
+    A.out_len = m.plan + lv.out_len;
+    A.n_runs = lv.n_runs; A.n_pairs = lv.n_pairs; A.tiles = lv.tiles;
+    A.desc = m.udesc;
+    A.status = m.ustatus;
+    A.ticket = reinterpret_cast<uint32_t*>(m.ustatus + lv.tiles);
+    KMD_CUDA(ctx, cudaMemsetAsync(m.ustatus, 0, (static_cast<size_t>(lv.tiles) + 1) * sizeof(unsigned long long), ctx->stream));
+    uni::level_partition_kernel<W><<<(lv.tiles + 127) / 128, 128, 0, ctx->stream>>>(A);
+    uni::union_level_kernel<W><<<lv.tiles, uni::kThreads, 0, ctx->stream>>>(A);
+    ctx->launches += 2;
+    cur = A.out;
+    flip ^= 1;
+  }
+  KMD_CUDA(ctx, cudaGetLastError());
+  KMD_CUDA(ctx, cudaEventRecord(m.ev[2], ctx->stream));
+
+  uint32_t flags[4] = {0, 0, 0, 0};
+  KMD_CUDA(ctx, cudaMemcpyAsync(flags, m.uflags, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!plan.empty())
+    KMD_CUDA(ctx, cudaMemcpyAsync(plan.data(), m.plan, plan.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  KMD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // also: every H2D copy of the caller's streams is done
+  if (flags[0]) return KMD_OK;
+  *used = true;
+  uint32_t n_rows = n;   // one stream: its keys are the rows
+  m.last_keys_in = m.last_keys_out = 0;
+  if (!levels.empty())
+  {
+    n_rows = plan[levels.back().out_len];
+    for (const UnionLevel& lv : levels)
+    {
+      for (uint32_t r = 0; r < lv.n_runs; r++) m.last_keys_in += plan[lv.run_len + r];
+      for (uint32_t q = 0; q < lv.n_pairs; q++) m.last_keys_out += plan[lv.out_len + q];
+    }
+  }
+  m.last_passes = static_cast<uint32_t>(levels.size());
+  *n_rows_out = n_rows;
+  if (n_rows == 0) return KMD_OK;
+
+  // Rows assembled in shared memory (whole rows written once) when the cohort is dense enough to fill them, scattered
+  // into zeroed rows otherwise (a sparse row is mostly the zeros).  KMD_UNION_ROWS: 0 choose, 1 shared memory, 2 scatter.
+  const size_t row_bytes = ctx->plan.row_bytes;
+  const uint32_t rows_mode = m.knob_rows, smem_budget = m.knob_smem, scatter_tile = m.knob_scatter_tile;
+  uint32_t asm_tile = 0;
+  if (N <= static_cast<uint32_t>(uni::kMaxFlat) && smem_budget > (2ull * N + 2) * 4)
+    asm_tile = static_cast<uint32_t>(std::min<size_t>(uni::kRowTile, (smem_budget - (2ull * N + 2) * 4 - 16) / (row_bytes + 8 * W)) / 16 * 16);
+  const bool dense = static_cast<uint64_t>(n) * 4 >= static_cast<uint64_t>(n_rows) * N;   // a quarter of the cells or more
+  const bool assemble = asm_tile >= 16 && (rows_mode == 1 || (rows_mode == 0 && dense));
+  const uint32_t row_tile = assemble ? asm_tile : scatter_tile;
+  const uint32_t row_tiles = (n_rows + row_tile - 1) / row_tile;
+  if ((rc = grow(ctx, m.rows, m.rows_cap, static_cast<size_t>(n_rows) * row_bytes + 16))) return rc;
+  if ((rc = grow(ctx, m.usplit, m.usplit_cap, (static_cast<size_t>(row_tiles) + 1) * N))) return rc;
+  uni::ScatterArgs<W> S{};
+  S.leaf = leaf;
+  S.rows_key = cur;
+  S.raw = raw; S.stream_off = m.stream_off; S.ab_min = m.ab_min; S.split = m.usplit;
+  S.n_streams = N; S.n_rows = n_rows; S.tiles = row_tiles; S.row_tile = row_tile;
+  S.rec = 8 * W + B; S.row_bytes = static_cast<uint32_t>(row_bytes);
+  S.rows = m.rows;
+  S.err = &ctx->d_cnt->overflow;
+  const uint64_t splits = (static_cast<uint64_t>(row_tiles) + 1) * N;
+  uni::scatter_partition_kernel<W><<<static_cast<uint32_t>((splits + 255) / 256), 256, 0, ctx->stream>>>(S);
+  if (assemble)
+  {
+    const size_t smem = uni::assemble_smem_bytes<W>(row_tile, S.row_bytes, N);
+    bool& attr_set = m.asm_attr_set[W - 1];   // the attribute belongs to (function, device): once per context is enough
+    if (!attr_set)
+    {
+      const int most = 200 << 10;
+      KMD_CUDA(ctx, cudaFuncSetAttribute(uni::assemble_rows_kernel<W, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+      KMD_CUDA(ctx, cudaFuncSetAttribute(uni::assemble_rows_kernel<W, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+      KMD_CUDA(ctx, cudaFuncSetAttribute(uni::assemble_rows_kernel<W, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+      attr_set = true;
+    }
+    switch (B)
+    {
+      case 1: uni::assemble_rows_kernel<W, 1><<<row_tiles, 256, smem, ctx->stream>>>(S); break;
+      case 2: uni::assemble_rows_kernel<W, 2><<<row_tiles, 256, smem, ctx->stream>>>(S); break;
+      default: uni::assemble_rows_kernel<W, 4><<<row_tiles, 256, smem, ctx->stream>>>(S); break;
+    }
+  }
+  else
+  {
+    KMD_CUDA(ctx, cudaMemsetAsync(m.rows, 0, static_cast<size_t>(n_rows) * row_bytes, ctx->stream));
+    switch (B)
+    {
+      case 1: uni::scatter_rows_kernel<W, 1><<<row_tiles, 256, 0, ctx->stream>>>(S); break;
+      case 2: uni::scatter_rows_kernel<W, 2><<<row_tiles, 256, 0, ctx->stream>>>(S); break;
+      default: uni::scatter_rows_kernel<W, 4><<<row_tiles, 256, 0, ctx->stream>>>(S); break;
+    }
+  }
+  m.last_rows_mode = assemble ? 1 : 2;
+  ctx->launches += 2;
+  KMD_CUDA(ctx, cudaGetLastError());
+  return KMD_OK;
+}
+
 // off[s] .. off[s + 1]: records of sample s inside the chunk (ascending and unique per stream); fill_raw() enqueues
 // whatever brings those records to m.raw + off[s] * rec (H2D copies of host records, or the device LZ4 decoder).
 // Leaves the dense rows in ctx->mrg.rows.
+// ext_raw (device, may be null): the records are already there, back to back, and fill_raw has nothing to bring.
 template <class FillRaw>
-int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const uint32_t* ab_min, uint32_t* n_rows, FillRaw&& fill_raw)
+int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const uint32_t* ab_min, uint32_t* n_rows, FillRaw&& fill_raw,
+                       const uint8_t* ext_raw = nullptr)
 {
   MergeState& m = ctx->mrg;
   const uint32_t N = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
@@ -121,7 +306,8 @@ int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const
   const uint32_t n = static_cast<uint32_t>(n64);
 
   int rc;
-  if ((rc = grow(ctx, m.raw, m.raw_cap, n * rec + 16))) return rc;
+  if (!ext_raw && (rc = grow(ctx, m.raw, m.raw_cap, n * rec + 16))) return rc;
+  const uint8_t* raw = ext_raw ? ext_raw : m.raw;
   for (int b = 0; b < 2; b++)
   {
     if ((rc = grow(ctx, m.klo[b], m.klo_cap[b], n))) return rc;
@@ -133,6 +319,35 @@ int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const
   if (!m.total) KMD_CUDA(ctx, cudaMalloc(&m.total, sizeof(uint32_t)));
   for (cudaEvent_t& e : m.ev) if (!e) KMD_CUDA(ctx, cudaEventCreate(&e));
   m.timed = false;
+
+  KMD_CUDA(ctx, cudaMemcpyAsync(m.stream_off, off.data(), (N + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  KMD_CUDA(ctx, cudaMemcpyAsync(m.ab_min, ab_min, N * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = fill_raw())) return rc;
+
+  // the union tree (kmd_union.cuh) unless a record is below its sample's abundance_min or the caller asks for the pairwise tree
+  if (m.algo < 0)
+  {
+    // the knobs are read once per context
+    m.algo = env_u32("KMD_MERGE_PAIRWISE", 0) ? 1 : 0;
+    m.knob_rows = env_u32("KMD_UNION_ROWS", 0);
+    m.knob_smem = std::min<uint32_t>(200, std::max<uint32_t>(8, env_u32("KMD_UNION_SMEM_KB", 56))) << 10;
+    m.knob_scatter_tile = std::max<uint32_t>(16, std::min<uint32_t>(uni::kRowTile, env_u32("KMD_UNION_SCATTER_TILE", 1024) / 16 * 16));
+  }
+  m.last_algo = 1;
+  if (m.algo == 0)
+  {
+    bool used = false;
+    rc = W == 2 ? merge_union<2>(ctx, raw, off, ab_min, n, n_rows, &used) : merge_union<1>(ctx, raw, off, ab_min, n, n_rows, &used);
+    if (rc) return rc;
+    if (used)
+    {
+      KMD_CUDA(ctx, cudaEventRecord(m.ev[3], ctx->stream));
+      m.timed = true;
+      m.last_algo = 0;
+      m.last_records = n;
+      return KMD_OK;
+    }
+  }
 
   // the merge tree: leaves = streams, every pass halves the number of runs
   std::vector<uint32_t> plan;
@@ -164,15 +379,12 @@ int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const
   }
   if ((rc = grow(ctx, m.plan, m.plan_cap, std::max<size_t>(1, plan.size())))) return rc;
 
-  KMD_CUDA(ctx, cudaMemcpyAsync(m.stream_off, off.data(), (N + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  KMD_CUDA(ctx, cudaMemcpyAsync(m.ab_min, ab_min, N * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   if (!plan.empty())
     KMD_CUDA(ctx, cudaMemcpyAsync(m.plan, plan.data(), plan.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  if ((rc = fill_raw())) return rc;
 
   KMD_CUDA(ctx, cudaEventRecord(m.ev[0], ctx->stream));
   mrg::UnpackArgs U{};
-  U.raw = m.raw; U.stream_off = m.stream_off; U.ab_min = m.ab_min; U.n_streams = N; U.n = n;
+  U.raw = raw; U.stream_off = m.stream_off; U.ab_min = m.ab_min; U.n_streams = N; U.n = n;
   U.kmer_words = W; U.count_bytes = B;
   U.klo = m.klo[0]; U.khi = m.khi[0]; U.pay = m.pay[0];
   const uint32_t ublocks = std::max<uint32_t>(1, std::min<uint32_t>((n + 255) / 256, ctx->sm_count * 8));
@@ -388,6 +600,38 @@ int kmd_merge_scan_host(kmd_context* ctx, const void* const* streams, const uint
   if (n_rows) *n_rows = rows;
   if (rows == 0) return KMD_OK;
   return scan_device_impl(ctx, ctx->mrg.rows, rows, row_base, partition);
+}
+
+int kmd_merge_scan_device(kmd_context* ctx, const void* d_records, const uint64_t* n_records, const uint32_t* ab_min,
+                          uint64_t row_base, uint32_t partition, uint64_t* n_rows)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  if (!n_records || !ab_min) return fail(ctx, KMD_ERR_ARG, "null argument");
+  if (reinterpret_cast<uintptr_t>(d_records) & 3u) return fail(ctx, KMD_ERR_ARG, "d_records must be 4-byte aligned");
+  KMD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t N = ctx->cfg.nb_controls + ctx->cfg.nb_cases;
+  if (N > 0xFFFFu) return fail(ctx, KMD_ERR_ARG, "more than 65535 samples");
+  std::vector<uint64_t> off(N + 1, 0);
+  for (uint32_t s = 0; s < N; s++) off[s + 1] = off[s] + n_records[s];
+  if (off[N] && !d_records) return fail(ctx, KMD_ERR_ARG, "null record pointer");
+  uint32_t rows = 0;
+  int rc = merge_from_offsets(ctx, off, ab_min, &rows, []() -> int { return KMD_OK; }, static_cast<const uint8_t*>(d_records));
+  if (rc) return rc;
+  if (n_rows) *n_rows = rows;
+  if (rows == 0) return KMD_OK;
+  return scan_device_impl(ctx, ctx->mrg.rows, rows, row_base, partition);
+}
+
+int kmd_merge_info(kmd_context* ctx, uint32_t* algo, uint32_t* rows_mode, uint64_t* keys_in, uint64_t* keys_out)
+{
+  if (!ctx) return KMD_ERR_ARG;
+  const MergeState& m = ctx->mrg;
+  if (!m.timed) return fail(ctx, KMD_ERR_STATE, "no merge call has completed on this context");
+  if (algo) *algo = static_cast<uint32_t>(m.last_algo);
+  if (rows_mode) *rows_mode = m.last_algo == 0 ? static_cast<uint32_t>(m.last_rows_mode) : 0;
+  if (keys_in) *keys_in = m.last_algo == 0 ? m.last_keys_in : 0;
+  if (keys_out) *keys_out = m.last_algo == 0 ? m.last_keys_out : 0;
+  return KMD_OK;
 }
 
 int kmd_merge_prefetch(kmd_context* ctx, const void* const* blobs, const uint64_t* blob_bytes, int frames)

@@ -197,3 +197,120 @@ def test_prefetched_chunks_merge_like_plain_calls(frames):
     finally:
         for ptr in keep:
             L.kmd_host_free(ptr)
+
+
+# ---- the two merge algorithms (kmd_union.cuh / kmd_merge.cuh) -------------------------------------------------
+
+def _random_streams(rng, n, k, b, m, dens, max_count=12):
+    """n sorted record streams over a universe of m random k-mers; dens(s) = share of the universe sample s holds"""
+    kw = (k + 31) // 32
+    lo = np.unique(rng.integers(0, 2**min(62, 2 * k), size=m, dtype=np.uint64))
+    hi = None
+    if kw == 2:
+        hi = np.sort(rng.integers(0, 3, size=len(lo), dtype=np.uint64))
+        order = np.lexsort((lo, hi))
+        lo, hi = lo[order], hi[order]
+    streams = []
+    for s in range(n):
+        sel = rng.random(len(lo)) < dens(s)
+        rec = np.zeros((int(sel.sum()), 8 * kw + b), dtype=np.uint8)
+        rec[:, :8] = lo[sel].view(np.uint8).reshape(-1, 8)
+        if kw == 2:
+            rec[:, 8:16] = hi[sel].view(np.uint8).reshape(-1, 8)
+        cnt = rng.integers(1, min(2**(8 * b) - 1, max_count), size=int(sel.sum()), dtype=np.uint64)
+        rec[:, 8 * kw:] = cnt.view(np.uint8).reshape(-1, 8)[:, :b]
+        streams.append(rec.ravel())
+    return streams, kw
+
+
+@pytest.mark.parametrize("n,k,b,m,kind", [
+    (20, 31, 4, 300_000, "dense"),       # every sample holds ~90 % of the k-mers: runs hardly grow from level to level
+    (20, 31, 4, 300_000, "sparse"),      # ~1/n each: the union is nearly the concatenation
+    (200, 31, 4, 40_000, "mixed"),       # c3 width, densities 0 .. 0.9, empty streams
+    (7, 63, 2, 120_000, "dense"),        # two key words, 2-byte counts, lone runs on two levels
+    (33, 20, 1, 90_000, "mixed"),        # 1-byte counts (records of 9 bytes: nothing is aligned)
+    (2, 31, 4, 50_000, "one"),           # one stream with records: its keys are the rows
+    (2, 32, 4, 70_000, "dense"),         # k = 32: all 64 key bits in use
+])
+@pytest.mark.parametrize("rows_mode", ["assembled", "scattered"])
+def test_union_tree_equals_pairwise_tree_and_oracle(n, k, b, m, kind, rows_mode, monkeypatch):
+    """every record solid -> the union tree (k-mers merged with duplicates dropped, counts scattered); the pairwise
+    (k-mer, payload) tree on the same streams and the oracle's km::KmerMerger give the same rows, byte for byte"""
+    rng = np.random.default_rng(n * 1000 + k + b)
+    dens = {"dense": lambda s: 0.9, "sparse": lambda s: 1.0 / n, "mixed": lambda s: [0.0, 0.9, 0.02, 0.3, 0.6][s % 5],
+            "one": lambda s: float(s == 1)}[kind]
+    streams, kw = _random_streams(rng, n, k, b, m, dens)
+    want = oracle.kmer_merge(streams, kw, b)
+    # dense cohorts get their rows assembled in shared memory, sparse ones scattered into zeroed rows: force each
+    monkeypatch.setenv("KMD_UNION_ROWS", {"assembled": "1", "scattered": "2"}[rows_mode])
+    with ctx_for(n // 2, n - n // 2, k, b) as ctx:
+        got = ctx.merge_rows_host(streams)
+        info = ctx.merge_info()
+        assert info["algo"] == "union" and info["rows"] == rows_mode
+        assert got.shape == want.shape and np.array_equal(got, want)
+        n_rec = sum(s.size for s in streams) // (8 * kw + b)
+        if n > 1:
+            # level 0 reads every record's key once; the root run is the row set
+            assert info["keys_in"] >= n_rec and info["keys_out"] >= len(want)
+        # the same context again (buffers, look-back words and tickets are reused), streams in another order
+        got1 = ctx.merge_rows_host(streams[::-1])
+        assert np.array_equal(got1, oracle.kmer_merge(streams[::-1], kw, b))
+        assert ctx.counters().rows == 0      # also: no lookup failure flagged by the scatter
+    monkeypatch.setenv("KMD_MERGE_PAIRWISE", "1")
+    with ctx_for(n // 2, n - n // 2, k, b) as ctx:
+        got2 = ctx.merge_rows_host(streams)
+        assert ctx.merge_info()["algo"] == "pairwise"
+    assert np.array_equal(got2, want)
+
+
+def test_union_tree_falls_back_when_a_record_is_not_solid():
+    """a count below its sample's abundance_min is absent as far as the row's existence goes (merge.hpp:204-223,
+    239-240): the union tree notices and the pairwise tree, which carries the solid flags, takes over"""
+    rng = np.random.default_rng(5)
+    streams, kw = _random_streams(rng, 6, 31, 4, 50_000, lambda s: 0.5, max_count=6)
+    ab = np.array([1, 1, 3, 1, 1, 2], dtype=np.uint32)
+    want = oracle.kmer_merge(streams, kw, 4, ab)
+    with ctx_for(3, 3, 31, 4) as ctx:
+        got = ctx.merge_rows_host(streams, ab)
+        assert ctx.merge_info()["algo"] == "pairwise"
+        assert np.array_equal(got, want)
+        # thresholds every count meets -> the union tree again on the same context
+        got = ctx.merge_rows_host(streams, 1)
+        assert ctx.merge_info()["algo"] == "union"
+        assert np.array_equal(got, oracle.kmer_merge(streams, kw, 4))
+        # ab_min = 0 and a zero count: solid (0 >= 0), the row exists with a zero in it
+        z = [s.copy() for s in streams]
+        z[0].reshape(-1, 12)[::7, 8:] = 0
+        zab = np.array([0, 1, 1, 1, 1, 1], dtype=np.uint32)
+        got = ctx.merge_rows_host(z, zab)
+        assert np.array_equal(got, oracle.kmer_merge(z, kw, 4, zab))
+
+
+def test_union_tree_picks_the_row_writer_by_density():
+    rng = np.random.default_rng(9)
+    for kind, dens, want_mode in (("dense", lambda s: 0.8, "assembled"), ("sparse", lambda s: 0.05, "scattered")):
+        streams, kw = _random_streams(rng, 16, 31, 4, 60_000, dens)
+        with ctx_for(8, 8, 31, 4) as ctx:
+            got = ctx.merge_rows_host(streams)
+            assert ctx.merge_info()["rows"] == want_mode, kind
+        assert np.array_equal(got, oracle.kmer_merge(streams, kw, 4))
+
+
+def test_merge_scan_device_equals_merge_scan_host():
+    """records already in HBM (kmd_merge_scan_device): same rows tested, same survivors as from host streams"""
+    import torch
+    spec, rows, totals = make_cohort("c2", 150_000, seed=11)
+    streams = kio.rows_to_streams(rows, 20, 1, 4)
+    want, w_ctl, w_case = oracle.Model(10, 10, totals).diff(rows, 1, 4, THR)
+    d = torch.from_numpy(np.concatenate(streams)).cuda()
+    cnt = [s.size // 12 for s in streams]
+    with ctx_for(10, 10, 31, 4, totals) as ctx:
+        assert ctx.merge_scan_device(d.data_ptr(), cnt, row_base=7, partition=2) == 150_000
+        c = ctx.counters()
+        surv = ctx.survivors()
+        assert (c.rows, c.survivors, c.n_control, c.n_case) == (150_000, len(want), w_ctl, w_case)
+        assert np.array_equal(surv["row"], want["row"] + 7) and np.array_equal(surv["kmer"], want["kmer"])
+        ctx.reset()
+        assert ctx.merge_scan_host(streams, row_base=7, partition=2) == 150_000
+        surv2 = ctx.survivors()
+    assert np.array_equal(surv2["row"], surv["row"]) and np.array_equal(surv2["p_value"], surv["p_value"])
