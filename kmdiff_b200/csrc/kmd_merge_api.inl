@@ -120,6 +120,8 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
   *used = false;
 
   // the tree: a run's start is the sum of the leaf lengths before it (host), its length is the level's output (device)
+  // (two key words and 512 threads would not fit the static shared memory)
+  const uint32_t threads = (W == 2 && m.knob_threads == 512) ? 256 : m.knob_threads, tile = threads * uni::kItems;
   std::vector<uint32_t> plan;
   std::vector<UnionLevel> levels;
   {
@@ -144,7 +146,7 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
         nbase[q] = base[2 * q];
         nub[q] = ub[2 * q] + (2 * q + 1 < n_runs ? ub[2 * q + 1] : 0u);
         plan.push_back(tiles);
-        tiles += (nub[q] + uni::kTile - 1) / uni::kTile;
+        tiles += (nub[q] + tile - 1) / tile;
       }
       plan.push_back(tiles);
       lv.tiles = tiles;
@@ -193,13 +195,18 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
     A.run_len = m.plan + lv.run_len;
     A.pair_tile = m.plan + lv.pair_tile;
     A.out_len = m.plan + lv.out_len;
-    A.n_runs = lv.n_runs; A.n_pairs = lv.n_pairs; A.tiles = lv.tiles;
+    A.n_runs = lv.n_runs; A.n_pairs = lv.n_pairs; A.tiles = lv.tiles; A.tile = tile;
     A.desc = m.udesc;
     A.status = m.ustatus;
     A.ticket = reinterpret_cast<uint32_t*>(m.ustatus + lv.tiles);
     KMD_CUDA(ctx, cudaMemsetAsync(m.ustatus, 0, (static_cast<size_t>(lv.tiles) + 1) * sizeof(unsigned long long), ctx->stream));
-    uni::level_partition_kernel<W><<<(lv.tiles + 127) / 128, 128, 0, ctx->stream>>>(A);
-    uni::union_level_kernel<W><<<lv.tiles, uni::kThreads, 0, ctx->stream>>>(A);
+    uni::level_partition_kernel<W><<<(lv.tiles + 3) / 4, 128, 0, ctx->stream>>>(A);   // one warp per tile
+    switch (threads)
+    {
+      case 128: uni::union_level_kernel<W, 128><<<lv.tiles, 128, 0, ctx->stream>>>(A); break;
+      case 512: if constexpr (W == 1) uni::union_level_kernel<1, 512><<<lv.tiles, 512, 0, ctx->stream>>>(A); break;
+      default: uni::union_level_kernel<W, 256><<<lv.tiles, 256, 0, ctx->stream>>>(A); break;
+    }
     ctx->launches += 2;
     cur = A.out;
     flip ^= 1;
@@ -330,6 +337,8 @@ int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const
     // the knobs are read once per context
     m.algo = env_u32("KMD_MERGE_PAIRWISE", 0) ? 1 : 0;
     m.knob_rows = env_u32("KMD_UNION_ROWS", 0);
+    m.knob_threads = env_u32("KMD_UNION_THREADS", uni::kThreadsDefault);
+    if (m.knob_threads != 128 && m.knob_threads != 512) m.knob_threads = 256;
     m.knob_smem = std::min<uint32_t>(200, std::max<uint32_t>(8, env_u32("KMD_UNION_SMEM_KB", 56))) << 10;
     m.knob_scatter_tile = std::max<uint32_t>(16, std::min<uint32_t>(uni::kRowTile, env_u32("KMD_UNION_SCATTER_TILE", 1024) / 16 * 16));
   }

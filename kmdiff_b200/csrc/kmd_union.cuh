@@ -30,10 +30,8 @@ using mrg::Key;
 using mrg::KeyArrays;
 using mrg::merge_path;
 
-constexpr int kThreads = 256;
-constexpr int kItems = 8;
-constexpr int kTile = kThreads * kItems;        // merged inputs (A slice + B slice) per CTA of a level
-constexpr int kStage = kTile + kTile / kItems;  // shared key slots: inputs (+1 halo), then the skewed outputs
+constexpr int kItems = 8;                       // merged positions per thread of a level: a tile is threads * kItems
+constexpr int kThreadsDefault = 256;            // threads per CTA of a level (KMD_UNION_THREADS: 128, 256 or 512)
 constexpr int kRowTile = 2048;                  // most rows per CTA of the scatter / the row assembly
 constexpr int kMaxFlat = 2048;                  // most streams assemble_rows_kernel keeps a prefix sum for
 
@@ -101,7 +99,7 @@ struct __align__(16) TileDesc
   uint32_t la, lb;    // their lengths
   uint32_t ai0;       // keys of run A before the tile's first merged position
   uint32_t pair;
-  uint32_t lt;        // index of the tile inside its pair: first position = lt * kTile
+  uint32_t lt;        // index of the tile inside its pair: first position = lt * tile size
   uint32_t valid;     // 0: the pair ends before this tile (the host's tile count is an upper bound)
 };
 
@@ -118,17 +116,42 @@ struct LevelArgs
   const uint32_t* pair_tile;
   uint32_t* out_len;             // zero before the launch
   uint32_t n_runs, n_pairs, tiles;
+  uint32_t tile;                 // merged positions per tile = threads per CTA * kItems
   TileDesc* desc;                // [tiles]
   unsigned long long* status;    // [tiles], zero before the launch: flag << 32 | keys (flag 1 = the tile's own count,
                                  // 2 = the count of the tile and of every tile of the pair before it)
   uint32_t* ticket;              // zero before the launch
 };
 
-// one thread per tile: the pair it belongs to and the merge-path split at its first position
+// merge_path by a whole warp: 32 probes per step instead of one (the probes are dependent loads from global memory,
+// ~0.7 us each: 5 steps instead of 21 for runs of a million keys)
+template <int W, class GetA, class GetB>
+__device__ inline uint32_t merge_path_warp(uint32_t diag, uint32_t len_a, uint32_t len_b, GetA a, GetB b)
+{
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t lo = diag > len_b ? diag - len_b : 0, hi = diag < len_a ? diag : len_a;
+  // a(mid) <= b(diag - 1 - mid) holds for every mid below the answer and for none from it on
+  while (lo < hi)
+  {
+    const uint32_t width = hi - lo;
+    const uint32_t mid = width <= 32 ? lo + lane : lo + static_cast<uint32_t>(static_cast<uint64_t>(width) * (lane + 1) / 33);
+    const bool valid = mid < hi;
+    const bool below = valid && (a(mid) <= b(diag - 1 - mid));
+    const uint32_t k = __popc(__ballot_sync(0xFFFFFFFFu, below));       // probes 0 .. k-1 lie below the answer
+    const uint32_t n_valid = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+    const uint32_t p_last = __shfl_sync(0xFFFFFFFFu, mid, k ? k - 1 : 0);
+    const uint32_t p_next = __shfl_sync(0xFFFFFFFFu, mid, k < 32 ? k : 31);
+    if (k < n_valid) hi = p_next;
+    if (k) lo = p_last + 1;
+  }
+  return lo;
+}
+
+// one warp per tile: the pair it belongs to and the merge-path split at its first position
 template <int W>
 __global__ void __launch_bounds__(128) level_partition_kernel(const LevelArgs<W> A)
 {
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= A.tiles) return;
   uint32_t ql = 0, qh = A.n_pairs;
   while (qh - ql > 1)
@@ -145,15 +168,15 @@ __global__ void __launch_bounds__(128) level_partition_kernel(const LevelArgs<W>
   d.la = A.run_len[2 * q];
   d.b0 = has_b ? A.run_base[2 * q + 1] : 0;
   d.lb = has_b ? A.run_len[2 * q + 1] : 0;
-  const uint32_t d0 = d.lt * kTile;
+  const uint32_t d0 = d.lt * A.tile;
   if (d0 < d.la + d.lb)
   {
     d.valid = 1;
     auto ga = [&](uint32_t i) { return A.in.get(d.a0 + i); };
     auto gb = [&](uint32_t i) { return A.in.get(d.b0 + i); };
-    d.ai0 = merge_path<W>(d0, d.la, d.lb, ga, gb);
+    d.ai0 = merge_path_warp<W>(d0, d.la, d.lb, ga, gb);
   }
-  A.desc[t] = d;
+  if ((threadIdx.x & 31) == 0) A.desc[t] = d;
 }
 
 __device__ __forceinline__ uint32_t stage_slot(uint32_t i) { return i + i / kItems; }
@@ -162,9 +185,11 @@ __device__ __forceinline__ uint32_t stage_slot(uint32_t i) { return i + i / kIte
 // registers and keeps a B key only when run A does not hold it (ties put A first, so the twin is the A key right
 // before it), block-wide prefix of the kept counts, look-back for the tile's offset inside the output run, coalesced
 // stores.  Tiles are numbered by a ticket, so a tile that is waited for has already started.
-template <int W>
+template <int W, int kThreads>
 __global__ void __launch_bounds__(kThreads) union_level_kernel(const LevelArgs<W> A)
 {
+  constexpr int kTile = kThreads * kItems;        // merged inputs (A slice + B slice) of the CTA
+  constexpr int kStage = kTile + kTile / kItems;  // shared key slots: inputs (+1 halo), then the skewed outputs
   __shared__ __align__(16) uint64_t s_lo[kStage];
   __shared__ __align__(16) uint64_t s_hi[W == 2 ? kStage : 1];
   __shared__ uint32_t s_warp[kThreads / 32];
@@ -293,7 +318,7 @@ __global__ void __launch_bounds__(kThreads) union_level_kernel(const LevelArgs<W
         const bool in_pair = dist <= d.lt;
         unsigned long long v = 0;
         if (in_pair)
-          do { v = st[tile - dist]; } while ((v >> 32) == 0);
+          while (((v = st[tile - dist]) >> 32) == 0) __nanosleep(64);
         const uint32_t closed = __ballot_sync(0xFFFFFFFFu, in_pair && (v >> 32) == 2);
         const uint32_t upto = closed ? __ffs(closed) - 1 : 31;
         uint32_t part = (in_pair && lane <= upto) ? static_cast<uint32_t>(v) : 0u;
@@ -549,40 +574,73 @@ __global__ void __launch_bounds__(256) assemble_rows_kernel(const ScatterArgs<W>
     return k;
   };
   const uint32_t M = s_pre[N];
-  for (uint32_t m = threadIdx.x; m < M; m += blockDim.x)
+  // kBatch records per thread at a time: their loads are in flight together, then each is placed
+  constexpr int kBatch = 4;
+  uint32_t walk = 0;   // stream of the thread's previous record
+  for (uint32_t m0 = threadIdx.x; m0 < M; m0 += blockDim.x * kBatch)
   {
-    // the stream of flat record m: last s with s_pre[s] <= m (an empty stream shares its prefix with the next one)
-    uint32_t sl = 0, sh = N;
-    while (sh - sl > 1)
+    Key<W> key[kBatch];
+    uint32_t cnt[kBatch], str[kBatch], lo[kBatch], hi[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++)
     {
-      const uint32_t mid = (sl + sh) >> 1;
-      if (s_pre[mid] <= m) sl = mid; else sh = mid;
+      const uint32_t m = m0 + u * blockDim.x;
+      str[u] = 0xFFFFFFFFu;
+      if (m < M)
+      {
+        // the stream of flat record m: last s with s_pre[s] <= m (an empty stream shares its prefix with the next
+        // one).  A thread's records ascend, so it walks on from the stream of its previous record; a long walk
+        // (many short streams) turns into a binary search.
+        uint32_t sl = walk;
+        if (s_pre[sl + 1] <= m)
+        {
+          uint32_t steps = 0;
+          do { sl++; steps++; } while (steps < 4 && s_pre[sl + 1] <= m);
+          if (s_pre[sl + 1] <= m)
+          {
+            uint32_t sh = N;
+            while (sh - sl > 1)
+            {
+              const uint32_t mid = (sl + sh) >> 1;
+              if (s_pre[mid] <= m) sl = mid; else sh = mid;
+            }
+          }
+        }
+        walk = sl;
+        str[u] = sl;
+        const uint32_t j = s_rec[sl] + m;   // record index in the raw buffer
+        if constexpr (B == 4)
+        {
+          const uint32_t* w = reinterpret_cast<const uint32_t*>(A.raw) + static_cast<size_t>(j) * (2 * W + 1);
+          key[u].lo = w[0] | (static_cast<uint64_t>(w[1]) << 32);
+          if constexpr (W == 2) key[u].hi = w[2] | (static_cast<uint64_t>(w[3]) << 32);
+          cnt[u] = w[2 * W];
+        }
+        else
+        {
+          key[u] = A.leaf.get(j);
+          cnt[u] = *reinterpret_cast<const unit_t*>(A.raw + static_cast<size_t>(j) * A.rec + 8 * W);
+        }
+        // the stream's keys are distinct and all among the tile's: m - s_pre[s] of them lie before this one, the rest after
+        lo[u] = m - s_pre[sl];
+        hi[u] = rt - (s_pre[sl + 1] - m);
+      }
     }
-    const uint32_t s = sl, j = s_rec[s] + m;   // record index in the raw buffer
-    Key<W> key;
-    uint32_t c;
-    if constexpr (B == 4)
+#pragma unroll
+    for (int u = 0; u < kBatch; u++)
     {
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(A.raw) + static_cast<size_t>(j) * (2 * W + 1);
-      key.lo = w[0] | (static_cast<uint64_t>(w[1]) << 32);
-      if constexpr (W == 2) key.hi = w[2] | (static_cast<uint64_t>(w[3]) << 32);
-      c = w[2 * W];
+      if (str[u] == 0xFFFFFFFFu) continue;
+      uint32_t l = lo[u], h = hi[u];
+      if (h >= rt || l > h) { atomicOr(A.err, 4u); continue; }
+      while (l < h)
+      {
+        const uint32_t mid = (l + h) >> 1;
+        if (key[u] <= row_key(mid)) h = mid; else l = mid + 1;
+      }
+      if (!(row_key(l) == key[u])) { atomicOr(A.err, 4u); continue; }
+      if (cnt[u] >= A.ab_min[str[u]])
+        reinterpret_cast<unit_t*>(s_rows)[static_cast<size_t>(l) * row_units + kmer_units + str[u]] = static_cast<unit_t>(cnt[u]);
     }
-    else
-    {
-      key = A.leaf.get(j);
-      c = *reinterpret_cast<const unit_t*>(A.raw + static_cast<size_t>(j) * A.rec + 8 * W);
-    }
-    // the stream's keys are distinct and all among the tile's: m - s_pre[s] of them lie before this one, the rest after
-    uint32_t lo = m - s_pre[s], hi = rt - (s_pre[s + 1] - m);
-    if (hi >= rt || lo > hi) { atomicOr(A.err, 4u); continue; }
-    while (lo < hi)
-    {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (key <= row_key(mid)) hi = mid; else lo = mid + 1;
-    }
-    if (!(row_key(lo) == key)) { atomicOr(A.err, 4u); continue; }
-    if (c >= A.ab_min[s]) reinterpret_cast<unit_t*>(s_rows)[static_cast<size_t>(lo) * row_units + kmer_units + s] = static_cast<unit_t>(c);
   }
   __syncthreads();
   // the tile's rows are contiguous in the matrix: whole 16-byte stores (the tile starts on a multiple of 16 rows)
