@@ -56,6 +56,8 @@ CONFIGS = {
     # the c2 cohort as `kmdiff count` leaves it: per-sample sorted (k-mer, count) files, no matrices
     # (BASELINE.json configs[0]'s input layout; km::KmerMerger row of SURVEY.md §8a) — host streams in
     "c2m": (10, 10, 31, 4, 8_000_000, "bonferroni"),
+    # the same for the north-star cohort width: 200 streams, 8 levels of the merge tree
+    "c3m": (100, 100, 31, 4, 1_000_000, "benjamini"),
 }
 HEADLINE = "c3"
 SECONDARY = "c2"
@@ -298,7 +300,7 @@ def bench_merge(args) -> None:
     from kmdiff_b200 import kmtricks_io as kio
 
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        raise SystemExit("bench.py: c2m is a single-GPU bench line")
+        raise SystemExit(f"bench.py: {args.config} is a single-GPU bench line")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — kmdiff_b200 has no CPU fallback")
     cfg_name = args.config
@@ -420,7 +422,7 @@ def bench_merge(args) -> None:
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         try:
-            sample = min(rows, reference_sample_rows("c2", cores) // 4)
+            sample = min(rows, reference_sample_rows(cfg_name[:-1], cores) // 4)
             parts = max(cores, 8)
             run_dir = make_run_dir(cfg_name, sample, parts)
             try:

@@ -148,7 +148,7 @@ struct MergeState
   int algo = -1;            // 0 union tree (pairwise tree when a record is not solid), 1 pairwise tree; -1 = ask KMD_MERGE_PAIRWISE
   int last_algo = 1;        // what the last call ran
   bool asm_attr_set[2] = {false, false};
-  uint32_t knob_threads = 256;   // KMD_UNION_THREADS
+  bool knob_raw_leaf = true;     // KMD_UNION_RAW_LEAF=0: unpack the keys first even with 4-byte counts
   uint32_t knob_rows = 0, knob_smem = 56 << 10, knob_scatter_tile = 1024;   // KMD_UNION_ROWS / _SMEM_KB / _SCATTER_TILE
   int last_rows_mode = 0;   // union tree: 1 rows assembled in shared memory, 2 scattered into zeroed rows
   uint64_t last_keys_in = 0, last_keys_out = 0;   // keys read / written by the levels of the last union tree

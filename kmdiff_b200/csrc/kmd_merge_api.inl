@@ -120,8 +120,7 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
   *used = false;
 
   // the tree: a run's start is the sum of the leaf lengths before it (host), its length is the level's output (device)
-  // (two key words and 512 threads would not fit the static shared memory)
-  const uint32_t threads = (W == 2 && m.knob_threads == 512) ? 256 : m.knob_threads, tile = threads * uni::kItems;
+  const uint32_t tile = uni::kThreads * uni::kItems;
   std::vector<uint32_t> plan;
   std::vector<UnionLevel> levels;
   {
@@ -168,15 +167,20 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
   if (!plan.empty())
     KMD_CUDA(ctx, cudaMemcpyAsync(m.plan, plan.data(), plan.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 
-  // leaves = klo[0] / khi[0]; the levels alternate between klo[1] / khi[1] and pay[0] / pay[1]
+  // leaves = klo[0] / khi[0] (or the records themselves: 4-byte counts, see RawKeys); the levels alternate between
+  // klo[1] / khi[1] and pay[0] / pay[1]
   mrg::KeyArrays<W> leaf{m.klo[0], m.khi[0]};
   mrg::KeyArrays<W> ping{m.klo[1], m.khi[1]}, pong{m.pay[0], m.pay[1]};
+  const uint32_t ab_min_max = *std::max_element(ab_min, ab_min + N);
+  const bool raw_leaf = B == 4 && !levels.empty() && m.knob_raw_leaf;
+  const uni::RawKeys<W> raw_keys{reinterpret_cast<const uint32_t*>(raw)};
   KMD_CUDA(ctx, cudaEventRecord(m.ev[0], ctx->stream));
+  if (!raw_leaf)
   {
     uni::KeysArgs K{};
     K.raw = raw; K.stream_off = m.stream_off; K.ab_min = m.ab_min; K.n_streams = N; K.n = n;
     K.kmer_words = W; K.count_bytes = B;
-    K.ab_min_max = *std::max_element(ab_min, ab_min + N);
+    K.ab_min_max = ab_min_max;
     K.klo = leaf.lo; K.khi = leaf.hi; K.nonsolid = m.uflags;
     const uint32_t blocks = std::max<uint32_t>(1, std::min<uint32_t>((n + 255) / 256, ctx->sm_count * 8));
     uni::keys_kernel<<<blocks, 256, 0, ctx->stream>>>(K);
@@ -185,30 +189,46 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
   KMD_CUDA(ctx, cudaEventRecord(m.ev[1], ctx->stream));
   mrg::KeyArrays<W> cur = leaf;
   int flip = 0;
+  bool first = true;
   for (const UnionLevel& lv : levels)
   {
-    if (lv.tiles == 0) continue;   // nothing but empty runs
-    uni::LevelArgs<W> A{};
-    A.in = cur;
-    A.out = flip ? pong : ping;
-    A.run_base = m.plan + lv.run_base;
-    A.run_len = m.plan + lv.run_len;
-    A.pair_tile = m.plan + lv.pair_tile;
-    A.out_len = m.plan + lv.out_len;
-    A.n_runs = lv.n_runs; A.n_pairs = lv.n_pairs; A.tiles = lv.tiles; A.tile = tile;
-    A.desc = m.udesc;
-    A.status = m.ustatus;
-    A.ticket = reinterpret_cast<uint32_t*>(m.ustatus + lv.tiles);
-    KMD_CUDA(ctx, cudaMemsetAsync(m.ustatus, 0, (static_cast<size_t>(lv.tiles) + 1) * sizeof(unsigned long long), ctx->stream));
-    uni::level_partition_kernel<W><<<(lv.tiles + 3) / 4, 128, 0, ctx->stream>>>(A);   // one warp per tile
-    switch (threads)
+    const bool from_raw = first && raw_leaf;
+    first = false;
+    mrg::KeyArrays<W> out = flip ? pong : ping;
+    if (lv.tiles)   // else: nothing but empty runs
     {
-      case 128: uni::union_level_kernel<W, 128><<<lv.tiles, 128, 0, ctx->stream>>>(A); break;
-      case 512: if constexpr (W == 1) uni::union_level_kernel<1, 512><<<lv.tiles, 512, 0, ctx->stream>>>(A); break;
-      default: uni::union_level_kernel<W, 256><<<lv.tiles, 256, 0, ctx->stream>>>(A); break;
+      KMD_CUDA(ctx, cudaMemsetAsync(m.ustatus, 0, (static_cast<size_t>(lv.tiles) + 1) * sizeof(unsigned long long), ctx->stream));
+      auto fill = [&](auto& A) {
+        A.out = out;
+        A.ab_min = m.ab_min; A.ab_min_max = ab_min_max; A.nonsolid = m.uflags;
+        A.run_base = m.plan + lv.run_base;
+        A.run_len = m.plan + lv.run_len;
+        A.pair_tile = m.plan + lv.pair_tile;
+        A.out_len = m.plan + lv.out_len;
+        A.n_runs = lv.n_runs; A.n_pairs = lv.n_pairs; A.tiles = lv.tiles; A.tile = tile;
+        A.desc = m.udesc;
+        A.status = m.ustatus;
+        A.ticket = reinterpret_cast<uint32_t*>(m.ustatus + lv.tiles);
+      };
+      if (from_raw)
+      {
+        uni::LevelArgs<W, uni::RawKeys<W>> A{};
+        A.in = raw_keys;
+        fill(A);
+        uni::level_partition_kernel<W><<<(lv.tiles + 3) / 4, 128, 0, ctx->stream>>>(A);   // one warp per tile
+        uni::union_level_kernel<W, uni::kThreads><<<lv.tiles, uni::kThreads, 0, ctx->stream>>>(A);
+      }
+      else
+      {
+        uni::LevelArgs<W, uni::SoaKeys<W>> A{};
+        A.in.lo = cur.lo; A.in.hi = cur.hi;
+        fill(A);
+        uni::level_partition_kernel<W><<<(lv.tiles + 3) / 4, 128, 0, ctx->stream>>>(A);
+        uni::union_level_kernel<W, uni::kThreads><<<lv.tiles, uni::kThreads, 0, ctx->stream>>>(A);
+      }
+      ctx->launches += 2;
     }
-    ctx->launches += 2;
-    cur = A.out;
+    cur = out;
     flip ^= 1;
   }
   KMD_CUDA(ctx, cudaGetLastError());
@@ -258,7 +278,8 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
   S.rows = m.rows;
   S.err = &ctx->d_cnt->overflow;
   const uint64_t splits = (static_cast<uint64_t>(row_tiles) + 1) * N;
-  uni::scatter_partition_kernel<W><<<static_cast<uint32_t>((splits + 255) / 256), 256, 0, ctx->stream>>>(S);
+  if (raw_leaf) uni::scatter_partition_kernel<W><<<static_cast<uint32_t>((splits + 255) / 256), 256, 0, ctx->stream>>>(S, raw_keys);
+  else uni::scatter_partition_kernel<W><<<static_cast<uint32_t>((splits + 255) / 256), 256, 0, ctx->stream>>>(S, leaf);
   if (assemble)
   {
     const size_t smem = uni::assemble_smem_bytes<W>(row_tile, S.row_bytes, N);
@@ -337,8 +358,7 @@ int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const
     // the knobs are read once per context
     m.algo = env_u32("KMD_MERGE_PAIRWISE", 0) ? 1 : 0;
     m.knob_rows = env_u32("KMD_UNION_ROWS", 0);
-    m.knob_threads = env_u32("KMD_UNION_THREADS", uni::kThreadsDefault);
-    if (m.knob_threads != 128 && m.knob_threads != 512) m.knob_threads = 256;
+    m.knob_raw_leaf = env_u32("KMD_UNION_RAW_LEAF", 1) != 0;
     m.knob_smem = std::min<uint32_t>(200, std::max<uint32_t>(8, env_u32("KMD_UNION_SMEM_KB", 56))) << 10;
     m.knob_scatter_tile = std::max<uint32_t>(16, std::min<uint32_t>(uni::kRowTile, env_u32("KMD_UNION_SCATTER_TILE", 1024) / 16 * 16));
   }

@@ -31,9 +31,34 @@ using mrg::KeyArrays;
 using mrg::merge_path;
 
 constexpr int kItems = 8;                       // merged positions per thread of a level: a tile is threads * kItems
-constexpr int kThreadsDefault = 256;            // threads per CTA of a level (KMD_UNION_THREADS: 128, 256 or 512)
+constexpr int kThreads = 256;                   // threads per CTA of a level (128 and 512 measured: within 10 %, profiles/r02u)
 constexpr int kRowTile = 2048;                  // most rows per CTA of the scatter / the row assembly
 constexpr int kMaxFlat = 2048;                  // most streams assemble_rows_kernel keeps a prefix sum for
+
+// ---- the k-mer words of record i, read where the record lies (4-byte counts: records are whole 32-bit words) ----
+
+template <int W>
+struct RawKeys
+{
+  static constexpr bool kLeaf = true;
+  const uint32_t* w;   // the streams' records back to back, 2W + 1 words each
+  __device__ Key<W> get(uint32_t i) const
+  {
+    const uint32_t* r = w + static_cast<size_t>(i) * (2 * W + 1);
+    Key<W> k;
+    k.lo = r[0] | (static_cast<uint64_t>(r[1]) << 32);
+    if constexpr (W == 2) k.hi = r[2] | (static_cast<uint64_t>(r[3]) << 32);
+    return k;
+  }
+  __device__ uint32_t count(uint32_t i) const { return w[static_cast<size_t>(i) * (2 * W + 1) + 2 * W]; }
+};
+
+template <int W>
+struct SoaKeys : KeyArrays<W>
+{
+  static constexpr bool kLeaf = false;
+  __device__ uint32_t count(uint32_t) const { return 0; }
+};
 
 // ---- records -> k-mer words ---------------------------------------------------------------------
 
@@ -107,10 +132,16 @@ struct __align__(16) TileDesc
 // the leaf lengths before it), the length is what the level below produced.  Pair q = runs 2q and 2q + 1 (a lone last
 // run is a pair with an empty right side) -> output run q at run_base[2q], length out_len[q].
 // pair_tile[q] = first tile of pair q, from the host's upper bound of the pair's length.
-template <int W>
+// In = RawKeys (the first level reads the k-mers inside the records and checks that every count is solid: the records
+// of run r belong to sample r) or SoaKeys (the output of the level below).
+template <int W, class In>
 struct LevelArgs
 {
-  KeyArrays<W> in, out;
+  In in;
+  KeyArrays<W> out;
+  const uint32_t* ab_min;        // RawKeys only: [n_runs] abundance_min of the samples, their maximum, and the flag
+  uint32_t ab_min_max;           //   that is set when a count lies below its sample's
+  uint32_t* nonsolid;
   const uint32_t* run_base;
   const uint32_t* run_len;
   const uint32_t* pair_tile;
@@ -148,8 +179,8 @@ __device__ inline uint32_t merge_path_warp(uint32_t diag, uint32_t len_a, uint32
 }
 
 // one warp per tile: the pair it belongs to and the merge-path split at its first position
-template <int W>
-__global__ void __launch_bounds__(128) level_partition_kernel(const LevelArgs<W> A)
+template <int W, class In>
+__global__ void __launch_bounds__(128) level_partition_kernel(const LevelArgs<W, In> A)
 {
   const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= A.tiles) return;
@@ -185,8 +216,8 @@ __device__ __forceinline__ uint32_t stage_slot(uint32_t i) { return i + i / kIte
 // registers and keeps a B key only when run A does not hold it (ties put A first, so the twin is the A key right
 // before it), block-wide prefix of the kept counts, look-back for the tile's offset inside the output run, coalesced
 // stores.  Tiles are numbered by a ticket, so a tile that is waited for has already started.
-template <int W, int kThreads>
-__global__ void __launch_bounds__(kThreads) union_level_kernel(const LevelArgs<W> A)
+template <int W, int kThreads, class In>
+__global__ void __launch_bounds__(kThreads) union_level_kernel(const LevelArgs<W, In> A)
 {
   constexpr int kTile = kThreads * kItems;        // merged inputs (A slice + B slice) of the CTA
   constexpr int kStage = kTile + kTile / kItems;  // shared key slots: inputs (+1 halo), then the skewed outputs
@@ -215,14 +246,22 @@ __global__ void __launch_bounds__(kThreads) union_level_kernel(const LevelArgs<W
     if (i < nt)
     {
       const uint32_t src = i < na ? a_src + i : b_src + (i - na);
-      s_lo[1 + i] = A.in.lo[src];
-      if constexpr (W == 2) s_hi[1 + i] = A.in.hi[src];
+      const Key<W> k = A.in.get(src);
+      s_lo[1 + i] = k.lo;
+      if constexpr (W == 2) s_hi[1 + i] = k.hi;
+      if constexpr (In::kLeaf)
+      {
+        // merge.hpp:204-223: a count below the sample's abundance_min makes the record absent — not this tree's case
+        const uint32_t c = A.in.count(src);
+        if (c < A.ab_min_max && c < A.ab_min[2 * d.pair + (i < na ? 0 : 1)]) *A.nonsolid = 1u;
+      }
     }
   }
   if (threadIdx.x == 0 && halo)
   {
-    s_lo[0] = A.in.lo[a_src - 1];
-    if constexpr (W == 2) s_hi[0] = A.in.hi[a_src - 1];
+    const Key<W> k = A.in.get(a_src - 1);
+    s_lo[0] = k.lo;
+    if constexpr (W == 2) s_hi[0] = k.hi;
   }
   __syncthreads();
 
@@ -350,7 +389,7 @@ __global__ void __launch_bounds__(kThreads) union_level_kernel(const LevelArgs<W
 template <int W>
 struct ScatterArgs
 {
-  KeyArrays<W> leaf;           // the streams' keys, back to back (keys_kernel)
+  KeyArrays<W> leaf;           // the streams' keys, back to back (keys_kernel; not with 4-byte counts: they are read in the records)
   KeyArrays<W> rows_key;       // U: the k-mer of every row, ascending
   const uint8_t* raw;
   const uint64_t* stream_off;  // [n_streams + 1]
@@ -364,8 +403,8 @@ struct ScatterArgs
 };
 
 // split[b][s] = lower bound of the first k-mer of row tile b in stream s (b == tiles: the stream's length)
-template <int W>
-__global__ void __launch_bounds__(256) scatter_partition_kernel(const ScatterArgs<W> A)
+template <int W, class Leaf>
+__global__ void __launch_bounds__(256) scatter_partition_kernel(const ScatterArgs<W> A, const Leaf leaf)
 {
   const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<uint64_t>(A.tiles + 1) * A.n_streams) return;
@@ -379,7 +418,7 @@ __global__ void __launch_bounds__(256) scatter_partition_kernel(const ScatterArg
     while (lo < hi)
     {
       const uint32_t mid = (lo + hi) >> 1;
-      if (key <= A.leaf.get(off + mid)) hi = mid; else lo = mid + 1;
+      if (key <= leaf.get(off + mid)) hi = mid; else lo = mid + 1;
     }
   }
   else lo = len;

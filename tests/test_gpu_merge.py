@@ -286,14 +286,21 @@ def test_union_tree_falls_back_when_a_record_is_not_solid():
         assert np.array_equal(got, oracle.kmer_merge(z, kw, 4, zab))
 
 
-def test_union_tree_picks_the_row_writer_by_density():
+def test_union_tree_picks_the_row_writer_by_density(monkeypatch):
     rng = np.random.default_rng(9)
     for kind, dens, want_mode in (("dense", lambda s: 0.8, "assembled"), ("sparse", lambda s: 0.05, "scattered")):
         streams, kw = _random_streams(rng, 16, 31, 4, 60_000, dens)
+        want = oracle.kmer_merge(streams, kw, 4)
         with ctx_for(8, 8, 31, 4) as ctx:
             got = ctx.merge_rows_host(streams)
             assert ctx.merge_info()["rows"] == want_mode, kind
-        assert np.array_equal(got, oracle.kmer_merge(streams, kw, 4))
+        assert np.array_equal(got, want)
+        # 4-byte counts: the first level reads the k-mers inside the records; with the knob off they are unpacked first
+        monkeypatch.setenv("KMD_UNION_RAW_LEAF", "0")
+        with ctx_for(8, 8, 31, 4) as ctx:
+            assert np.array_equal(ctx.merge_rows_host(streams), want)
+            assert ctx.merge_info()["algo"] == "union"
+        monkeypatch.delenv("KMD_UNION_RAW_LEAF")
 
 
 def test_merge_scan_device_equals_merge_scan_host():
