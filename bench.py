@@ -16,7 +16,10 @@ Headline workload at every N: BASELINE.json configs[2], the shape the north-star
 121 GB resident per GPU (2e9 rows = 1.6 TB do not fit 8 x 180 GB; every rank holds its own disjoint
 partition set: weak scaling, no data-path collective).  The line also carries, under "c2", the same
 measurement of configs[1] ("10 control + 10 case, k=31, 1e9 k-mer rows, Poisson LRT + Bonferroni",
-88 GB resident per GPU), the headline of round 1.
+88 GB resident per GPU), the headline of round 1, and at N = 1 under "c2m" the count-file input of
+that cohort (`--config c2m`, `--config c3m` alone: the km::KmerMerger row — per-sample sorted record
+streams -> device N-way merge -> the same scan; `value` from records resident in HBM through
+kmd_merge_scan_device, `e2e` from pinned host streams through kmd_merge_scan_host).
 
 `value`   : rows/s with the rows already resident in HBM (device generated, seeded).
 `e2e`     : rows/s through the C-ABI with HOST buffers (kmd_scan_host from pinned memory, exchange,
@@ -289,7 +292,7 @@ def fasta_kmers(path: str):
 # our arm, per-sample count-file input (km::KmerMerger row): host streams -> device merge -> scan -> correction
 # ------------------------------------------------------------------------------------------------------
 
-def bench_merge(args) -> None:
+def bench_merge(args, cfg_name: str | None = None, emit: bool = True, cpu_baseline: bool = True) -> dict:
     import ctypes
 
     import numpy as np
@@ -303,9 +306,10 @@ def bench_merge(args) -> None:
         raise SystemExit(f"bench.py: {args.config} is a single-GPU bench line")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — kmdiff_b200 has no CPU fallback")
-    cfg_name = args.config
+    standalone = cfg_name is None
+    cfg_name = cfg_name or args.config
     nc, nk, k, b, rows, corr = CONFIGS[cfg_name]
-    if args.rows:
+    if args.rows and standalone:
         rows = args.rows
     n = nc + nk
     spec = K.SynthSpec(nc, nk, kmer_size=k, count_bytes=b, total_rows=CONFIGS[cfg_name][4], seed=SEED, enriched_ppm=ENRICHED_PPM)
@@ -419,7 +423,7 @@ def bench_merge(args) -> None:
     min_bytes = n_records * rec + 2 * rows * spec.row_bytes
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if cpu_baseline and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         try:
             sample = min(rows, reference_sample_rows(cfg_name[:-1], cores) // 4)
@@ -464,10 +468,13 @@ def bench_merge(args) -> None:
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    if emit:
+        print(json.dumps(line))
     ctx.close()
+    del dev_chunks
     for hptr in pinned:
         L.kmd_host_free(hptr)
+    return line
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -943,6 +950,15 @@ def bench_b200(args) -> None:
                                                            "e2e_cli", "cpu_baseline", "parity_on_prefix", "parity_detail",
                                                            "gpu_launches", "clocks") if key in secondary}
         line[SECONDARY]["unit"] = "rows/s"
+    if not args.config and not args.no_secondary and env.world == 1:
+        # the count-file input of the same path (km::KmerMerger row of SURVEY.md §8a): device N-way merge + scan
+        try:
+            env.torch.cuda.empty_cache()
+            m = bench_merge(args, cfg_name="c2m", emit=False, cpu_baseline=True)
+            line["c2m"] = {key: m[key] for key in ("value", "unit", "ms_per_step", "config", "roofline", "e2e", "gpu_launches",
+                                                   "cpu_baseline") if key in m}
+        except BaseException as e:   # SystemExit included: this block must not take the headline line down
+            line["c2m"] = {"failed": str(e)}
     env.emit(line)
     env.close()
 

@@ -201,9 +201,10 @@ int kmd_lz4_decode_host(kmd_context* ctx, const void* const* frames, const uint6
 int kmd_merge_rows_host(kmd_context* ctx, const void* const* streams, const uint64_t* n_records,
                         const uint32_t* ab_min, void* rows_out, uint64_t cap_rows, uint64_t* n_rows);
 
-/* device times (CUDA events on the context's stream) of the last kmd_merge_* call: record unpacking, the
- * merge-tree passes, row numbering + dense-row writing (the latter includes one host round trip for the
- * row count); the number of passes and records of that call.  Any output may be NULL. */
+/* device times (CUDA events on the context's stream) of the last kmd_merge_* call: record unpacking (nothing when
+ * the first level of the union tree reads the k-mers inside the records), the levels / passes of the tree, row
+ * numbering + dense-row writing (the latter includes one host round trip for the row count); the number of levels
+ * and records of that call.  Any output may be NULL. */
 int kmd_merge_ms(kmd_context* ctx, float* unpack_ms, float* passes_ms, float* rows_ms, uint32_t* n_passes,
                  uint64_t* n_records);
 

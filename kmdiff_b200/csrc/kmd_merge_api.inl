@@ -455,6 +455,29 @@ bool take_prefetch(kmd_context* ctx, int kind, const void* const* ptrs, const ui
   return false;
 }
 
+// Host blobs -> device, blob s to dst + at[s]: neighbours that are contiguous on both sides go as one copy (a reader
+// that keeps a range's streams back to back in one pinned buffer pays one copy per range, not one per sample).
+int copy_blobs(kmd_context* ctx, uint8_t* dst, const std::vector<uint64_t>& at, const void* const* blobs, const uint64_t* bytes,
+               uint32_t n, cudaStream_t stream)
+{
+  uint32_t s = 0;
+  while (s < n)
+  {
+    if (!bytes[s]) { s++; continue; }
+    const uint8_t* src = static_cast<const uint8_t*>(blobs[s]);
+    uint64_t len = bytes[s];
+    uint32_t e = s + 1;
+    while (e < n && (!bytes[e] || (static_cast<const uint8_t*>(blobs[e]) == src + len && at[e] == at[s] + len)))
+    {
+      len += bytes[e];
+      e++;
+    }
+    KMD_CUDA(ctx, cudaMemcpyAsync(dst + at[s], src, len, cudaMemcpyHostToDevice, stream));
+    s = e;
+  }
+  return KMD_OK;
+}
+
 // streams[s] = n_records[s] HOST records of sample s
 int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_records, const uint32_t* ab_min, uint32_t* n_rows)
 {
@@ -473,10 +496,9 @@ int merge_impl(kmd_context* ctx, const void* const* streams, const uint64_t* n_r
   const bool prefetched = take_prefetch(ctx, 0, streams, bytes.data(), N, ctx->mrg.raw, ctx->mrg.raw_cap);
   return merge_from_offsets(ctx, off, ab_min, n_rows, [&]() -> int {
     if (prefetched) return KMD_OK;
-    for (uint32_t s = 0; s < N; s++)
-      if (n_records[s])
-        KMD_CUDA(ctx, cudaMemcpyAsync(ctx->mrg.raw + off[s] * rec, streams[s], n_records[s] * rec, cudaMemcpyHostToDevice, ctx->stream));
-    return KMD_OK;
+    std::vector<uint64_t> at(N);
+    for (uint32_t s = 0; s < N; s++) at[s] = off[s] * rec;
+    return copy_blobs(ctx, ctx->mrg.raw, at, streams, bytes.data(), N, ctx->stream);
   });
 }
 
@@ -685,9 +707,7 @@ int kmd_merge_prefetch(kmd_context* ctx, const void* const* blobs, const uint64_
   int rc;
   if ((rc = grow(ctx, f->buf, f->cap, total + 16))) return rc;
   if (!f->done) KMD_CUDA(ctx, cudaEventCreateWithFlags(&f->done, cudaEventDisableTiming));
-  for (uint32_t s = 0; s < N; s++)
-    if (blob_bytes[s])
-      KMD_CUDA(ctx, cudaMemcpyAsync(f->buf + at[s], blobs[s], blob_bytes[s], cudaMemcpyHostToDevice, ctx->copy_stream));
+  if ((rc = copy_blobs(ctx, f->buf, at, blobs, blob_bytes, N, ctx->copy_stream))) return rc;
   KMD_CUDA(ctx, cudaEventRecord(f->done, ctx->copy_stream));
   f->ptrs.assign(blobs, blobs + N);
   f->bytes.assign(blob_bytes, blob_bytes + N);
