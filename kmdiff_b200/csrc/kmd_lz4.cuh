@@ -47,10 +47,9 @@ struct Reader
   uint64_t win_pos;      // stream offset of win[0] (multiple of 16), ~0 = empty
   uint32_t lane;
 
-  // makes [pos, pos + 1) available; warp-collective
-  __device__ __forceinline__ void ensure(uint64_t pos)
+  // the window takes the stream from pos (rounded down to 16) on; bytes past the stream's end read as 0; warp-collective
+  __device__ __forceinline__ void refill(uint64_t pos)
   {
-    if (pos >= win_pos && pos < win_pos + kWindow) return;
     __syncwarp();
     win_pos = pos & ~15ull;
     for (uint32_t o = lane * 16; o < kWindow; o += 32 * 16)
@@ -61,6 +60,18 @@ struct Reader
       *reinterpret_cast<uint4*>(win + o) = v;
     }
     __syncwarp();
+  }
+  // makes [pos, pos + 1) available
+  __device__ __forceinline__ void ensure(uint64_t pos)
+  {
+    if (pos >= win_pos && pos < win_pos + kWindow) return;
+    refill(pos);
+  }
+  // makes [pos, pos + 32) available
+  __device__ __forceinline__ void ensure_span(uint64_t pos)
+  {
+    if (pos >= win_pos && pos + 32 <= win_pos + kWindow) return;
+    refill(pos);
   }
   __device__ __forceinline__ uint32_t byte(uint64_t pos)
   {
@@ -150,6 +161,68 @@ __global__ void __launch_bounds__(kWarps * 32) frames_kernel(const Args A)
         // compressed block: sequences {token, literals, offset, match}
         while (ip < bend)
         {
+          // Short sequences (what sorted records compress into: a few literal bytes + a match of 4..18 bytes a record
+          // or two back) run in a tight loop on 32-bit window / ring indices: token, literals and offset come from one
+          // stretch of the window, the NEXT token is fetched before the current sequence is copied (the parse chain is
+          // one shared-memory load per sequence; the copy runs in its shadow), and ONE warp step writes the literals and
+          // the match.  Lane i produces output byte i: a literal, or byte (i - lit) mod off of the `off` bytes before
+          // the match, which lie in the ring (earlier sequences) or among this sequence's own literals — no lane waits
+          // for another.  Everything else (length extensions, the last sequences of a block, far or long matches,
+          // errors) leaves the loop for the general path below.
+          if (ip + 20 <= bend)
+          {
+            R.ensure_span(ip);
+            uint32_t w = static_cast<uint32_t>(ip - R.win_pos);
+            // last window index a short sequence may start at: its 17 header bytes + the next token lie inside the
+            // window, and 20 bytes before the block's end
+            const uint64_t room = bend - 20 - R.win_pos;
+            const uint32_t w_last = static_cast<uint32_t>(min(room, static_cast<uint64_t>(kWindow - 32)));
+            const uint64_t behind = op - frame_start, ahead = cap - op;
+            uint32_t avail = behind > 0xFFFF0000ull ? 0xFFFF0000u : static_cast<uint32_t>(behind);   // bytes a match may reach back
+            uint32_t budget = ahead > 0xFFFF0000ull ? 0xFFFF0000u : static_cast<uint32_t>(ahead);   // bytes the output may still take
+            uint32_t o32 = static_cast<uint32_t>(op), done = 0;
+            uint8_t* outp = out + op;
+            uint32_t token = R.win[w];
+            while (true)
+            {
+              const uint32_t lit = token >> 4, mcode = token & 15u;
+              if (lit == 15 || mcode == 15) break;
+              const uint8_t* q = R.win + w;
+              const uint32_t off = q[1 + lit] | (static_cast<uint32_t>(q[2 + lit]) << 8);
+              const uint32_t ml = mcode + 4, total = lit + ml;
+              if (off == 0 || off > avail + lit || off + total > kRing || total > budget) break;
+              const uint32_t w_next = w + 3 + lit;
+              const uint32_t token_next = R.win[w_next];   // inside the window: w <= kWindow - 32
+              if (copy)
+              {
+                if (lane < total)
+                {
+                  uint32_t v;
+                  if (lane < lit) v = q[1 + lane];
+                  else
+                  {
+                    const uint32_t j = lane - lit;
+                    const int32_t sp = static_cast<int32_t>(lit) - static_cast<int32_t>(off) + static_cast<int32_t>(off >= ml ? j : j % off);
+                    v = sp >= 0 ? q[1 + sp] : ring[(o32 + static_cast<uint32_t>(sp)) & (kRing - 1)];
+                  }
+                  outp[done + lane] = static_cast<uint8_t>(v);
+                  // ring slots [op, op + total) do not meet the slots read, [op + lit - off, op): off + total <= kRing
+                  ring[(o32 + lane) & (kRing - 1)] = static_cast<uint8_t>(v);
+                }
+                __syncwarp();
+              }
+              o32 += total;
+              done += total;
+              avail = min(avail + total, 0xFFFF0000u);
+              budget -= total;
+              w = w_next;
+              token = token_next;
+              if (w > w_last) break;
+            }
+            ip = R.win_pos + w;
+            op += done;
+            if (done) continue;   // progress was made: come back through the loop head (window refill, block end)
+          }
           const uint32_t token = R.byte(ip++);
           uint64_t lit = token >> 4;
           if (lit == 15)
