@@ -455,26 +455,14 @@ bool take_prefetch(kmd_context* ctx, int kind, const void* const* ptrs, const ui
   return false;
 }
 
-// Host blobs -> device, blob s to dst + at[s]: neighbours that are contiguous on both sides go as one copy (a reader
-// that keeps a range's streams back to back in one pinned buffer pays one copy per range, not one per sample).
+// Host blobs -> device, blob s to dst + at[s].  One copy per blob: neighbours that happen to be adjacent in the address
+// space may still belong to two pinned allocations, and a copy must not span two.
 int copy_blobs(kmd_context* ctx, uint8_t* dst, const std::vector<uint64_t>& at, const void* const* blobs, const uint64_t* bytes,
                uint32_t n, cudaStream_t stream)
 {
-  uint32_t s = 0;
-  while (s < n)
-  {
-    if (!bytes[s]) { s++; continue; }
-    const uint8_t* src = static_cast<const uint8_t*>(blobs[s]);
-    uint64_t len = bytes[s];
-    uint32_t e = s + 1;
-    while (e < n && (!bytes[e] || (static_cast<const uint8_t*>(blobs[e]) == src + len && at[e] == at[s] + len)))
-    {
-      len += bytes[e];
-      e++;
-    }
-    KMD_CUDA(ctx, cudaMemcpyAsync(dst + at[s], src, len, cudaMemcpyHostToDevice, stream));
-    s = e;
-  }
+  for (uint32_t s = 0; s < n; s++)
+    if (bytes[s])
+      KMD_CUDA(ctx, cudaMemcpyAsync(dst + at[s], blobs[s], bytes[s], cudaMemcpyHostToDevice, stream));
   return KMD_OK;
 }
 

@@ -228,6 +228,8 @@ def _random_streams(rng, n, k, b, m, dens, max_count=12):
     (20, 31, 4, 300_000, "sparse"),      # ~1/n each: the union is nearly the concatenation
     (200, 31, 4, 40_000, "mixed"),       # c3 width, densities 0 .. 0.9, empty streams
     (7, 63, 2, 120_000, "dense"),        # two key words, 2-byte counts, lone runs on two levels
+    (5, 63, 4, 80_000, "dense"),         # two key words inside 20-byte records (the first level reads them there)
+    (400, 31, 4, 5_000, "dense"),        # c4 width: 1608-byte rows, 32 of them per assembly tile
     (33, 20, 1, 90_000, "mixed"),        # 1-byte counts (records of 9 bytes: nothing is aligned)
     (2, 31, 4, 50_000, "one"),           # one stream with records: its keys are the rows
     (2, 32, 4, 70_000, "dense"),         # k = 32: all 64 key bits in use
