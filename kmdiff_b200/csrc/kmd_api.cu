@@ -144,6 +144,7 @@ struct MergeState
   uni::TileDesc* udesc = nullptr; size_t udesc_cap = 0;
   unsigned long long* ustatus = nullptr; size_t ustatus_cap = 0;
   uint32_t* usplit = nullptr; size_t usplit_cap = 0;
+  uint32_t* uorder = nullptr; size_t uorder_cap = 0;
   uint32_t* uflags = nullptr;
   int algo = -1;            // 0 union tree (pairwise tree when a record is not solid), 1 pairwise tree; -1 = ask KMD_MERGE_PAIRWISE
   int last_algo = 1;        // what the last call ran

@@ -25,7 +25,7 @@ void merge_free(kmd_context* ctx)
   cudaFree(m.flag); cudaFree(m.tile); cudaFree(m.head_pos); cudaFree(m.rows); cudaFree(m.stream_off);
   cudaFree(m.ab_min); cudaFree(m.plan); cudaFree(m.total); cudaFree(m.split);
   cudaFree(m.lz_in); cudaFree(m.lz_tab); cudaFree(m.lz_status);
-  cudaFree(m.udesc); cudaFree(m.ustatus); cudaFree(m.usplit); cudaFree(m.uflags);
+  cudaFree(m.udesc); cudaFree(m.ustatus); cudaFree(m.usplit); cudaFree(m.uflags); cudaFree(m.uorder);
   for (auto& f : m.pf) { cudaFree(f.buf); if (f.done) cudaEventDestroy(f.done); }
   for (cudaEvent_t e : m.ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : m.lz_ev) if (e) cudaEventDestroy(e);
@@ -161,6 +161,7 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
   int rc;
   if ((rc = grow(ctx, m.plan, m.plan_cap, std::max<size_t>(1, plan.size())))) return rc;
   if ((rc = grow(ctx, m.udesc, m.udesc_cap, std::max<size_t>(1, max_tiles)))) return rc;
+  if ((rc = grow(ctx, m.uorder, m.uorder_cap, std::max<size_t>(1, max_tiles)))) return rc;
   if ((rc = grow(ctx, m.ustatus, m.ustatus_cap, static_cast<size_t>(max_tiles) + 1))) return rc;
   if (!m.uflags) KMD_CUDA(ctx, cudaMalloc(&m.uflags, 4 * sizeof(uint32_t)));
   KMD_CUDA(ctx, cudaMemsetAsync(m.uflags, 0, 4 * sizeof(uint32_t), ctx->stream));
@@ -198,6 +199,13 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
     if (lv.tiles)   // else: nothing but empty runs
     {
       KMD_CUDA(ctx, cudaMemsetAsync(m.ustatus, 0, (static_cast<size_t>(lv.tiles) + 1) * sizeof(unsigned long long), ctx->stream));
+      // tickets go round robin over the pairs (not worth computing for one pair, or for thousands of short ones)
+      const bool round_robin = lv.n_pairs > 1 && lv.n_pairs <= 1024;
+      if (round_robin)
+      {
+        uni::tile_order_kernel<<<(lv.tiles + 255) / 256, 256, 0, ctx->stream>>>(m.plan + lv.pair_tile, lv.n_pairs, lv.tiles, m.uorder);
+        ctx->launches++;
+      }
       auto fill = [&](auto& A) {
         A.out = out;
         A.ab_min = m.ab_min; A.ab_min_max = ab_min_max; A.nonsolid = m.uflags;
@@ -209,6 +217,7 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
         A.desc = m.udesc;
         A.status = m.ustatus;
         A.ticket = reinterpret_cast<uint32_t*>(m.ustatus + lv.tiles);
+        A.order = round_robin ? m.uorder : nullptr;
       };
       if (from_raw)
       {

@@ -152,7 +152,34 @@ struct LevelArgs
   unsigned long long* status;    // [tiles], zero before the launch: flag << 32 | keys (flag 1 = the tile's own count,
                                  // 2 = the count of the tile and of every tile of the pair before it)
   uint32_t* ticket;              // zero before the launch
+  const uint32_t* order;         // [tiles] ticket -> tile (tile_order_kernel): round robin over the pairs, so that the tiles in
+                                 // flight belong to many runs and a tile's predecessors (same run) are long done when it
+                                 // looks back; null = tiles in index order
 };
+
+// order[ticket] = tile: the pairs' first tiles, then their second ones, ... (round robin over the pairs that still have
+// tiles).  One thread per tile; its ticket = the tiles with a smaller index inside their pair, plus the pairs before its
+// own that reach its index.
+__global__ void __launch_bounds__(256) tile_order_kernel(const uint32_t* __restrict__ pair_tile, uint32_t n_pairs, uint32_t tiles,
+                                                         uint32_t* __restrict__ order)
+{
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= tiles) return;
+  uint32_t ql = 0, qh = n_pairs;
+  while (qh - ql > 1)
+  {
+    const uint32_t mid = (ql + qh) >> 1;
+    if (pair_tile[mid] <= g) ql = mid; else qh = mid;
+  }
+  const uint32_t lt = g - pair_tile[ql];
+  uint32_t ticket = 0;
+  for (uint32_t q = 0; q < n_pairs; q++)
+  {
+    const uint32_t cnt = pair_tile[q + 1] - pair_tile[q];
+    ticket += min(cnt, lt) + (q < ql && cnt > lt ? 1u : 0u);
+  }
+  order[ticket] = g;
+}
 
 // merge_path by a whole warp: 32 probes per step instead of one (the probes are dependent loads from global memory,
 // ~0.7 us each: 5 steps instead of 21 for runs of a million keys)
@@ -215,7 +242,8 @@ __device__ __forceinline__ uint32_t stage_slot(uint32_t i) { return i + i / kIte
 // One tile: both slices into shared memory, every thread merges kItems consecutive positions of the merged order in
 // registers and keeps a B key only when run A does not hold it (ties put A first, so the twin is the A key right
 // before it), block-wide prefix of the kept counts, look-back for the tile's offset inside the output run, coalesced
-// stores.  Tiles are numbered by a ticket, so a tile that is waited for has already started.
+// stores.  Tiles are handed out by a ticket, earlier tiles of a run before later ones, so a tile that is waited for
+// has already started.
 template <int W, int kThreads, class In>
 __global__ void __launch_bounds__(kThreads) union_level_kernel(const LevelArgs<W, In> A)
 {
@@ -226,7 +254,11 @@ __global__ void __launch_bounds__(kThreads) union_level_kernel(const LevelArgs<W
   __shared__ uint32_t s_warp[kThreads / 32];
   __shared__ uint32_t s_tile, s_prefix;
 
-  if (threadIdx.x == 0) s_tile = atomicAdd(A.ticket, 1u);
+  if (threadIdx.x == 0)
+  {
+    const uint32_t ticket = atomicAdd(A.ticket, 1u);
+    s_tile = A.order ? A.order[ticket] : ticket;
+  }
   __syncthreads();
   const uint32_t tile = s_tile;
   const TileDesc d = A.desc[tile];
