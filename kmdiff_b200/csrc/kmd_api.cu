@@ -150,7 +150,7 @@ struct MergeState
   int last_algo = 1;        // what the last call ran
   bool asm_attr_set[2] = {false, false};
   bool knob_raw_leaf = true;     // KMD_UNION_RAW_LEAF=0: unpack the keys first even with 4-byte counts
-  uint32_t knob_rows = 0, knob_smem = 56 << 10, knob_scatter_tile = 1024;   // KMD_UNION_ROWS / _SMEM_KB / _SCATTER_TILE
+  uint32_t knob_rows = 0, knob_smem = 0, knob_scatter_tile = 1024;   // KMD_UNION_ROWS / _SMEM_KB / _SCATTER_TILE
   int last_rows_mode = 0;   // union tree: 1 rows assembled in shared memory, 2 scattered into zeroed rows
   uint64_t last_keys_in = 0, last_keys_out = 0;   // keys read / written by the levels of the last union tree
 };

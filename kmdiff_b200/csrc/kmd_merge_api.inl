@@ -269,9 +269,22 @@ int merge_union(kmd_context* ctx, const uint8_t* raw, const std::vector<uint64_t
   // into zeroed rows otherwise (a sparse row is mostly the zeros).  KMD_UNION_ROWS: 0 choose, 1 shared memory, 2 scatter.
   const size_t row_bytes = ctx->plan.row_bytes;
   const uint32_t rows_mode = m.knob_rows, smem_budget = m.knob_smem, scatter_tile = m.knob_scatter_tile;
+  // Rows per assembly tile.  Narrow rows: ~28 KB of them, so that 6-7 CTAs share an SM (c2m: 1.23 ms per step against
+  // 1.42 with 56 KB tiles); wide rows: no fewer than 80 (every tile costs one search per stream: c3m 2.20 ms with 88-row
+  // tiles against 2.39 with 64) as long as the tile stays under 100 KB (profiles/r03d).  KMD_UNION_SMEM_KB fixes the budget.
   uint32_t asm_tile = 0;
-  if (N <= static_cast<uint32_t>(uni::kMaxFlat) && smem_budget > (2ull * N + 2) * 4)
-    asm_tile = static_cast<uint32_t>(std::min<size_t>(uni::kRowTile, (smem_budget - (2ull * N + 2) * 4 - 16) / (row_bytes + 8 * W)) / 16 * 16);
+  if (N <= static_cast<uint32_t>(uni::kMaxFlat))
+  {
+    const size_t per_row = row_bytes + 8 * W, fixed = (2ull * N + 2) * 4 + 16;
+    size_t rows_fit;
+    if (smem_budget) rows_fit = smem_budget > fixed ? (smem_budget - fixed) / per_row : 0;
+    else
+    {
+      rows_fit = (28u << 10) / per_row;
+      if (rows_fit < 80) rows_fit = std::min<size_t>(80, ((100u << 10) - fixed) / per_row);
+    }
+    asm_tile = static_cast<uint32_t>(std::min<size_t>(uni::kRowTile, rows_fit) / 16 * 16);
+  }
   const bool dense = static_cast<uint64_t>(n) * 4 >= static_cast<uint64_t>(n_rows) * N;   // a quarter of the cells or more
   const bool assemble = asm_tile >= 16 && (rows_mode == 1 || (rows_mode == 0 && dense));
   const uint32_t row_tile = assemble ? asm_tile : scatter_tile;
@@ -368,7 +381,7 @@ int merge_from_offsets(kmd_context* ctx, const std::vector<uint64_t>& off, const
     m.algo = env_u32("KMD_MERGE_PAIRWISE", 0) ? 1 : 0;
     m.knob_rows = env_u32("KMD_UNION_ROWS", 0);
     m.knob_raw_leaf = env_u32("KMD_UNION_RAW_LEAF", 1) != 0;
-    m.knob_smem = std::min<uint32_t>(200, std::max<uint32_t>(8, env_u32("KMD_UNION_SMEM_KB", 56))) << 10;
+    m.knob_smem = std::min<uint32_t>(200, env_u32("KMD_UNION_SMEM_KB", 0)) << 10;   // 0: chosen from the row size
     m.knob_scatter_tile = std::max<uint32_t>(16, std::min<uint32_t>(uni::kRowTile, env_u32("KMD_UNION_SCATTER_TILE", 1024) / 16 * 16));
   }
   m.last_algo = 1;
