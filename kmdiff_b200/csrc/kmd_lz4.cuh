@@ -172,6 +172,7 @@ __global__ void __launch_bounds__(kWarps * 32) frames_kernel(const Args A)
           if (ip + 20 <= bend)
           {
             R.ensure_span(ip);
+            __syncwarp();   // ring bytes written by the general path (literals at a block's end, stored blocks) are read below
             uint32_t w = static_cast<uint32_t>(ip - R.win_pos);
             // last window index a short sequence may start at: its 17 header bytes + the next token lie inside the
             // window, and 20 bytes before the block's end
