@@ -6,19 +6,24 @@
 // what `kmtricks count --hard-min` writes).  The pairwise tree of kmd_merge.cuh carries (key, payload) pairs through
 // ceil(log2 N) full passes; but a dense row only needs to know WHERE each k-mer goes.  So:
 //
-//   1. keys_kernel: the k-mer words of every record, SoA (the leaves);
-//   2. union_level_kernel x ceil(log2 N): pairwise merge of sorted DISTINCT key runs that drops the k-mer both sides
-//      hold.  Cohort samples share most k-mers, so a run is hardly longer than its inputs and the levels shrink
-//      (N = 20 streams of ~n keys: 20n keys in, then 10n, 5n, 3n, 2n — 2 full passes' worth instead of 5, keys only);
-//      the root is U, the sorted k-mers of the rows.  Output sizes are data dependent: a tile learns its output
-//      offset inside its run by a decoupled look-back over the tiles before it (single pass, no second read);
-//   3. scatter_rows_kernel: a CTA owns 2048 consecutive rows (their k-mers in shared memory), takes every stream's
-//      records that fall into them (scatter_partition_kernel: one lower bound per tile and stream), finds each
-//      record's row by a binary search in shared memory narrowed by the record's rank in its stream, and stores the
-//      count into the zeroed row — kmtricks matrix layout (matrix_file.hpp:121-127), ready for lrt_scan_kernel.
+//   1. the leaves: the records themselves when the counts have 4 bytes (RawKeys: the first level reads the k-mer words
+//      where they lie), else keys_kernel unpacks the k-mer words first, SoA;
+//   2. level_partition_kernel + union_level_kernel x ceil(log2 N): pairwise merge of sorted DISTINCT key runs that drops
+//      the k-mer both sides hold.  Cohort samples share most k-mers, so a run is hardly longer than its inputs and the
+//      levels shrink (N = 20 streams of ~n keys: 20n keys in, then 10n, 5n, 3n, 2n — 2 full passes' worth instead of 5,
+//      keys only); the root is U, the sorted k-mers of the rows.  Output sizes are data dependent: a run starts where the
+//      host knows (the sum of the leaf lengths before it), is as long as the level below says, and a tile learns its
+//      output offset inside its run by a decoupled look-back over the tiles before it (single pass, no second read);
+//      tiles are handed out by a ticket, round robin over the pairs (tile_order_kernel);
+//   3. scatter_partition_kernel (one lower bound per row tile and stream), then assemble_rows_kernel (dense cohorts: a
+//      CTA assembles its rows in shared memory — their k-mers, zeros, and every stream's counts that fall into them,
+//      each record's row found by a binary search narrowed by the record's rank in its stream — and writes them whole)
+//      or scatter_rows_kernel (sparse cohorts: 4-byte stores into rows zeroed by a memset) — kmtricks matrix layout
+//      (matrix_file.hpp:121-127), ready for lrt_scan_kernel.
 //
 // A record below its sample's abundance_min counts as absent for the row's existence (merge.hpp:204-223, 239-240);
-// keys_kernel reports whether there is one and the caller then takes the pairwise tree of kmd_merge.cuh instead.
+// the leaf level (or keys_kernel) reports whether there is one and the caller then takes the pairwise tree of
+// kmd_merge.cuh instead.
 #pragma once
 
 #include "kmd_merge.cuh"
