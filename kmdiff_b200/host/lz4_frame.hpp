@@ -63,6 +63,36 @@ inline size_t lz4_block_decode(const uint8_t* src, size_t n, uint8_t* dst, size_
   uint8_t* op = dst;
   uint8_t* const oend = dst + cap;
   auto copy16 = [](uint8_t* d, const uint8_t* s_) { uint64_t a, b; memcpy(&a, s_, 8); memcpy(&b, s_ + 8, 8); memcpy(d, &a, 8); memcpy(d + 8, &b, 8); };
+  auto copy8 = [](uint8_t* d, const uint8_t* s_) { uint64_t a; memcpy(&a, s_, 8); memcpy(d, &a, 8); };
+  // Fast zone: while a whole short sequence (token, <= 14 literals, offset; match of <= 18 bytes) can be read and
+  // written without looking at the buffer ends, the per-sequence bounds checks go away and both copies have a fixed
+  // size: 16 literal bytes, and 18 match bytes in 8 + 8 + 2 (for offsets >= 8 every chunk reads only bytes written by
+  // earlier chunks, which is the replication an overlapping LZ4 match means).  Anything else — a length extension, an
+  // offset below 8, an offset before the window — leaves the zone untouched for the general loop below, which also
+  // finishes the block.
+  if (n > 32 && cap > 64)
+  {
+    const uint8_t* const ifast = iend - 18;
+    uint8_t* const ofast = oend - 40;
+    const uint8_t* const lowest = dst - history;
+    while (ip < ifast && op < ofast)
+    {
+      const unsigned token = *ip;
+      const size_t lit = token >> 4, mcode = token & 15;
+      if (lit == 15 || mcode == 15) break;
+      const uint8_t* const lp = ip + 1;
+      const size_t off = lp[lit] | (static_cast<size_t>(lp[lit + 1]) << 8);
+      uint8_t* const mp = op + lit;
+      if (off < 8 || static_cast<size_t>(mp - lowest) < off) break;
+      copy16(op, lp);
+      const uint8_t* m = mp - off;
+      copy8(mp, m);
+      copy8(mp + 8, m + 8);
+      uint16_t t2; memcpy(&t2, m + 16, 2); memcpy(mp + 16, &t2, 2);
+      ip = lp + lit + 2;
+      op = mp + mcode + 4;
+    }
+  }
   while (ip < iend)
   {
     const unsigned token = *ip++;
@@ -119,17 +149,59 @@ class Lz4FrameReader
  public:
   explicit Lz4FrameReader(FILE* f) : m_f(f) {}
 
-  // up to n decoded bytes into dst; 0 at end of stream
+  // Up to n decoded bytes into dst; 0 at end of stream.  A block is decoded straight into dst when dst has room for a
+  // whole one and already holds the 64 KiB a linked block may refer back to (no copy besides the decoder's own);
+  // otherwise — the first blocks of a call, the last one, small reads — through the window, which keeps the history.
   size_t read(uint8_t* dst, size_t n)
   {
     size_t got = 0;
+    bool hist_in_dst = false;   // the last blocks went straight to dst: the window's history is stale
     while (got < n)
     {
-      if (m_pos == m_end && !next_block()) break;
-      const size_t take = std::min(n - got, m_end - m_pos);
-      memcpy(dst + got, m_win.data() + m_pos, take);
-      m_pos += take; got += take;
+      if (m_pos < m_end)
+      {
+        const size_t take = std::min(n - got, m_end - m_pos);
+        memcpy(dst + got, m_win.data() + m_pos, take);
+        m_pos += take; got += take;
+        continue;
+      }
+      bool stored;
+      size_t bs;
+      if (!next_header(stored, bs)) break;
+      const bool direct = n - got >= m_block_max + kLz4Slack && (!m_linked || got >= kHistory);
+      uint8_t* const to = direct ? dst + got : m_win.data() + kHistory;
+      if (!direct)
+      {
+        if (hist_in_dst) { history_from(dst, got); hist_in_dst = false; }
+        else
+        {
+          // slide the last 64 KiB of output in front of the window
+          const size_t produced = m_end - kHistory;
+          if (m_linked && produced)
+          {
+            const size_t keep = std::min(kHistory, m_hist + produced);
+            memmove(m_win.data() + kHistory - keep, m_win.data() + m_end - keep, keep);
+            m_hist = keep;
+          }
+        }
+      }
+      size_t out;
+      if (stored)
+      {
+        if (!fill(to, bs)) throw std::runtime_error("lz4: truncated block");
+        out = bs;
+      }
+      else
+      {
+        if (m_src.size() < bs + kLz4Slack) m_src.resize(bs + kLz4Slack);
+        if (!fill(m_src.data(), bs)) throw std::runtime_error("lz4: truncated block");
+        out = lz4_block_decode(m_src.data(), bs, to, m_block_max, m_linked ? (direct ? got : m_hist) : 0);
+      }
+      if (m_block_checksum) { uint32_t c; fill(&c, 4); }
+      if (direct) { got += out; hist_in_dst = true; }
+      else { m_pos = kHistory; m_end = kHistory + out; }
     }
+    if (hist_in_dst) history_from(dst, got);   // the next call starts through the window
     return got;
   }
 
@@ -137,6 +209,15 @@ class Lz4FrameReader
   static constexpr size_t kHistory = 64 * 1024;
 
   bool fill(void* p, size_t n) { return fread(p, 1, n, m_f) == n; }
+
+  // the window's history := the last 64 KiB of the `got` bytes at dst; the window itself holds nothing
+  void history_from(const uint8_t* dst, size_t got)
+  {
+    const size_t keep = std::min(kHistory, got);
+    memcpy(m_win.data() + kHistory - keep, dst + got - keep, keep);
+    m_hist = keep;
+    m_pos = m_end = kHistory;
+  }
 
   bool open_frame()
   {
@@ -171,7 +252,8 @@ class Lz4FrameReader
     return true;
   }
 
-  bool next_block()
+  // the next data block's header (opening the next frame when the current one has ended); false at end of stream
+  bool next_header(bool& stored, size_t& n)
   {
     for (;;)
     {
@@ -184,32 +266,11 @@ class Lz4FrameReader
         m_in_frame = false;
         continue;
       }
-      const bool stored = hdr & 0x80000000u;
-      const size_t n = hdr & 0x7FFFFFFFu;
+      stored = hdr & 0x80000000u;
+      n = hdr & 0x7FFFFFFFu;
       if (n > m_block_max) throw std::runtime_error("lz4: block larger than the frame's maximum");
-      // slide the last 64 KiB of output in front of the window
-      const size_t produced = m_end - kHistory;
-      if (m_linked && produced)
-      {
-        const size_t keep = std::min(kHistory, m_hist + produced);
-        memmove(m_win.data() + kHistory - keep, m_win.data() + m_end - keep, keep);
-        m_hist = keep;
-      }
-      size_t out;
-      if (stored)
-      {
-        if (!fill(m_win.data() + kHistory, n)) throw std::runtime_error("lz4: truncated block");
-        out = n;
-      }
-      else
-      {
-        if (m_src.size() < n + kLz4Slack) m_src.resize(n + kLz4Slack);
-        if (!fill(m_src.data(), n)) throw std::runtime_error("lz4: truncated block");
-        out = lz4_block_decode(m_src.data(), n, m_win.data() + kHistory, m_block_max, m_linked ? m_hist : 0);
-      }
-      if (m_block_checksum) { uint32_t c; fill(&c, 4); }
-      m_pos = kHistory; m_end = kHistory + out;
-      if (out) return true;
+      if (n == 0) continue;   // an empty stored block
+      return true;
     }
   }
 
