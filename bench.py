@@ -957,7 +957,7 @@ def bench_b200(args) -> None:
             m = bench_merge(args, cfg_name="c2m", emit=False, cpu_baseline=True)
             line["c2m"] = {key: m[key] for key in ("value", "unit", "ms_per_step", "config", "roofline", "e2e", "gpu_launches",
                                                    "cpu_baseline") if key in m}
-        except BaseException as e:   # SystemExit included: this block must not take the headline line down
+        except (Exception, SystemExit) as e:   # this block must not take the headline line down
             line["c2m"] = {"failed": str(e)}
     env.emit(line)
     env.close()
