@@ -68,13 +68,14 @@ inline size_t lz4_block_decode(const uint8_t* src, size_t n, uint8_t* dst, size_
   // written without looking at the buffer ends, the per-sequence bounds checks go away and both copies have a fixed
   // size: 16 literal bytes, and 18 match bytes in 8 + 8 + 2 (for offsets >= 8 every chunk reads only bytes written by
   // earlier chunks, which is the replication an overlapping LZ4 match means).  Anything else — a length extension, an
-  // offset below 8, an offset before the window — leaves the zone untouched for the general loop below, which also
-  // finishes the block.
-  if (n > 32 && cap > 64)
+  // offset below 8, an offset before the window, the ends of the block — is ONE sequence of the general code below,
+  // after which the fast zone is tried again.
+  const bool zone = n > 32 && cap > 64;
+  const uint8_t* const ifast = zone ? iend - 18 : src;
+  uint8_t* const ofast = zone ? oend - 40 : dst;
+  const uint8_t* const lowest = dst - history;
+  while (ip < iend)
   {
-    const uint8_t* const ifast = iend - 18;
-    uint8_t* const ofast = oend - 40;
-    const uint8_t* const lowest = dst - history;
     while (ip < ifast && op < ofast)
     {
       const unsigned token = *ip;
@@ -92,9 +93,6 @@ inline size_t lz4_block_decode(const uint8_t* src, size_t n, uint8_t* dst, size_
       ip = lp + lit + 2;
       op = mp + mcode + 4;
     }
-  }
-  while (ip < iend)
-  {
     const unsigned token = *ip++;
     size_t lit = token >> 4;
     if (lit == 15)
