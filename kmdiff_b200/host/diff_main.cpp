@@ -150,7 +150,7 @@ struct DiffOptions
     "  --count-bytes INT       count width of the matrices: 1, 2 or 4 (the reference's compile-time MAX_C). {4}\n"
     "  --max-survivors INT     capacity of the per-GPU survivor buffers. {4194304}\n"
     "  --max-sampled INT       capacity of the per-GPU sampled k-mer buffer (--pop-correction). {2097152}\n"
-    "  --device-lz4            count files: decode the LZ4 frames on the GPU (default from 1024 samples on).\n",
+    "  --device-lz4            count files: decode the LZ4 frames on the GPU (default from 2048 samples on).\n",
     code ? stderr : stdout);
   exit(code);
 }
@@ -658,11 +658,12 @@ class GpuWorker
   bool merge_whole_partition(const Partition& p, uint32_t N, uint32_t kw, uint32_t B, uint64_t budget)
   {
     // One warp decodes one stream at ~27 MB/s over its two passes (a serial chain of short sequences;
-    // profiles/r02x/dev_lz4_rate.json), a host thread at ~2 GB/s: the device path pays off only with a thousand streams
-    // or more in flight, so it is taken from 1024 samples per partition on (or on request: --device-lz4 /
-    // KMD_DEVICE_LZ4=1); smaller cohorts are decoded by the -t host threads.
+    // profiles/r02x/dev_lz4_rate.json), a host thread at ~3 GB/s (profiles/r03k/host_lz4.jsonl): the device draws level
+    // with 16 host threads at ~1 700 streams in flight, so it is taken from 2048 samples per partition on (or on
+    // request: --device-lz4 / KMD_DEVICE_LZ4=1, e.g. where few host cores feed many GPUs); smaller cohorts are decoded by
+    // the -t host threads.
     const char* force = getenv("KMD_DEVICE_LZ4");
-    const bool on = force ? atoi(force) != 0 : (m_opt.device_lz4 || N >= 1024);
+    const bool on = force ? atoi(force) != 0 : (m_opt.device_lz4 || N >= 2048);
     if (!on) return false;
     const size_t rec = 8ull * kw + B;
     std::vector<uint64_t> fsize(N), foff(N + 1, 0);
